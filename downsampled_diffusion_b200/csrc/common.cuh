@@ -1,0 +1,110 @@
+// Shared device helpers for libddb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/ddb200.h"
+
+namespace dd {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define DD_REQUIRE(cond, ...)                       \
+    do {                                            \
+        if (!(cond)) {                              \
+            dd::set_error(__VA_ARGS__);             \
+            return DD_ERR_ARG;                      \
+        }                                           \
+    } while (0)
+
+// Mish(x) = x * tanh(softplus(x))  (blocks.py:80, convblocks.py:110).
+// tanh(log(1+e^x)) = n/(n+2), n = e^x (e^x + 2): one exp, no cancellation for x << 0.
+__device__ __forceinline__ float mish_f(float x) {
+    if (x > 20.f) return x;
+    float e = expf(x);
+    float n = e * (e + 2.f);
+    return x * (n / (n + 2.f));
+}
+
+// d/dx mish(x) = tanh(sp) + x * sigmoid(x) * (1 - tanh(sp)^2)
+__device__ __forceinline__ float mish_grad_f(float x) {
+    if (x > 20.f) return 1.f;
+    float e = expf(x);
+    float n = e * (e + 2.f);
+    float th = n / (n + 2.f);
+    float sg = e / (1.f + e);
+    return th + x * sg * (1.f - th * th);
+}
+
+template <typename T> struct Vec;   // 16-byte vector of activations
+template <> struct Vec<float> {
+    static constexpr int N = 4;
+    float v[4];
+    __device__ __forceinline__ void load(const float* p) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void store(float* p) const {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    float v[8];
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+        uint4 t = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f = __bfloat1622float2(h[i]);
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+    __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+        uint4 t;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = t;
+    }
+};
+
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+}  // namespace dd
+
+// dispatch on activation dtype
+#define DD_DISPATCH_DTYPE(dtype, T, ...)                                   \
+    do {                                                                   \
+        if ((dtype) == DD_F32) { using T = float; __VA_ARGS__; }           \
+        else if ((dtype) == DD_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+        else { dd::set_error("bad dtype %d", (int)(dtype)); return DD_ERR_ARG; } \
+    } while (0)

@@ -1,0 +1,398 @@
+// HBM-bound elementwise / layout kernels of the dDDPM hot path.
+// Arithmetic mirrors ATen's op-by-op rounding (explicit __fmul_rn/__fadd_rn, no FMA contraction)
+// so the posterior update, q_sample and EMA are bit-identical to the reference's fp32 results.
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace dd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return DD_ERR_CUDA;
+    }
+    return DD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// q_sample  (ddpm.py:270-273)
+// ---------------------------------------------------------------------------------------------
+__global__ void q_sample_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
+                                const int64_t* __restrict__ t, const float* __restrict__ sa,
+                                const float* __restrict__ sb, float4* __restrict__ out, int64_t chw4) {
+    const int b = blockIdx.y;
+    const float a = sa[t[b]], c = sb[t[b]];
+    const int64_t base = (int64_t)b * chw4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < chw4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 xv = x[base + i], ev = eps[base + i], o;
+        o.x = __fadd_rn(__fmul_rn(a, xv.x), __fmul_rn(c, ev.x));
+        o.y = __fadd_rn(__fmul_rn(a, xv.y), __fmul_rn(c, ev.y));
+        o.z = __fadd_rn(__fmul_rn(a, xv.z), __fmul_rn(c, ev.z));
+        o.w = __fadd_rn(__fmul_rn(a, xv.w), __fmul_rn(c, ev.w));
+        out[base + i] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// posterior step (ddpm.py:149-158, 177-185, 217-227): 4 fp32 streams = 16 B / element.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float post1(float xt, float e, float z, float c0, float c1, float c2, float c3,
+                                       float sig, int clip) {
+    float x0 = __fsub_rn(__fmul_rn(c0, xt), __fmul_rn(c1, e));
+    if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    float mean = __fadd_rn(__fmul_rn(c2, x0), __fmul_rn(c3, xt));
+    return __fadd_rn(mean, __fmul_rn(sig, z));
+}
+
+__global__ void posterior_step_kernel(const float4* __restrict__ xt, const float4* __restrict__ eh,
+                                      const float4* __restrict__ noise, const float* __restrict__ coef,
+                                      const int32_t* __restrict__ t_idx, int t_stride, int64_t noise_step_stride4,
+                                      int T, int clip, float4* __restrict__ out, int64_t chw4) {
+    const int b = blockIdx.y;
+    const int t = t_idx[(int64_t)b * t_stride];
+    const float* c = coef + (int64_t)t * 5;
+    const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
+    const float sig = (t == 0) ? 0.f : c[4];   // nonzero_mask * exp(0.5*logvar), ddpm.py:224-227
+    const float4* nz = noise + (int64_t)(T - 1 - t) * noise_step_stride4;
+    const int64_t base = (int64_t)b * chw4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < chw4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 x = xt[base + i], e = eh[base + i], z = nz[base + i], o;
+        o.x = post1(x.x, e.x, z.x, c0, c1, c2, c3, sig, clip);
+        o.y = post1(x.y, e.y, z.y, c0, c1, c2, c3, sig, clip);
+        o.z = post1(x.z, e.z, z.z, c0, c1, c2, c3, sig, clip);
+        o.w = post1(x.w, e.w, z.w, c0, c1, c2, c3, sig, clip);
+        out[base + i] = o;
+    }
+}
+
+__global__ void predict_x0_kernel(const float4* __restrict__ xt, const float4* __restrict__ eps,
+                                  const int64_t* __restrict__ t, const float* __restrict__ ra,
+                                  const float* __restrict__ rb, int clip, float4* __restrict__ out, int64_t chw4) {
+    const int b = blockIdx.y;
+    const float a = ra[t[b]], c = rb[t[b]];
+    const int64_t base = (int64_t)b * chw4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < chw4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 x = xt[base + i], e = eps[base + i], o;
+        o.x = __fsub_rn(__fmul_rn(a, x.x), __fmul_rn(c, e.x));
+        o.y = __fsub_rn(__fmul_rn(a, x.y), __fmul_rn(c, e.y));
+        o.z = __fsub_rn(__fmul_rn(a, x.z), __fmul_rn(c, e.z));
+        o.w = __fsub_rn(__fmul_rn(a, x.w), __fmul_rn(c, e.w));
+        if (clip) {
+            o.x = fminf(fmaxf(o.x, -1.f), 1.f); o.y = fminf(fmaxf(o.y, -1.f), 1.f);
+            o.z = fminf(fmaxf(o.z, -1.f), 1.f); o.w = fminf(fmaxf(o.w, -1.f), 1.f);
+        }
+        out[base + i] = o;
+    }
+}
+
+__global__ void tick_kernel(int32_t* t, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) t[i] -= 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-sample squared error sum (ddpm.py:279-283)
+// ---------------------------------------------------------------------------------------------
+__global__ void mse_rowsum_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                                  float* __restrict__ out, int64_t chw4, float scale) {
+    const int row = blockIdx.x;
+    const int64_t base = (int64_t)row * chw4;
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < chw4; i += blockDim.x) {
+        float4 x = a[base + i], y = b[base + i];
+        float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+        acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    __shared__ double red[32];
+    double v = (double)warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) s += red[w];
+        out[row] = (float)(s * (double)scale);
+    }
+}
+
+__global__ void mse_rowsum_bwd_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                                      const float* __restrict__ w, float4* __restrict__ g, int64_t chw4, float gscale) {
+    const int row = blockIdx.y;
+    const float s = 2.f * gscale * (w ? w[row] : 1.f);
+    const int64_t base = (int64_t)row * chw4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < chw4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 x = a[base + i], y = b[base + i], o;
+        o.x = (y.x - x.x) * s; o.y = (y.y - x.y) * s; o.z = (y.z - x.z) * s; o.w = (y.w - x.w) * s;
+        g[base + i] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-tensor EMA (trainers/ema.py:36-44): 12 B / parameter, one launch for every tensor.
+// ---------------------------------------------------------------------------------------------
+__global__ void ema_update_kernel(const uint64_t* __restrict__ table, const int32_t* __restrict__ chunks,
+                                  int chunk_elems, float decay, float omd) {
+    const int ti = chunks[2 * blockIdx.x], ci = chunks[2 * blockIdx.x + 1];
+    float* __restrict__ s = reinterpret_cast<float*>(table[3 * ti]);
+    const float* __restrict__ p = reinterpret_cast<const float*>(table[3 * ti + 1]);
+    const int64_t n = (int64_t)table[3 * ti + 2];
+    const int64_t lo = (int64_t)ci * chunk_elems;
+    const int64_t hi = min(lo + (int64_t)chunk_elems, n);
+    const bool vec = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(p)) & 15) == 0;
+    if (vec) {
+        const int64_t hi4 = lo + ((hi - lo) & ~(int64_t)3);
+        for (int64_t i = lo + 4 * (int64_t)threadIdx.x; i < hi4; i += 4 * (int64_t)blockDim.x) {
+            float4 sv = *reinterpret_cast<float4*>(s + i);
+            const float4 pv = *reinterpret_cast<const float4*>(p + i);
+            sv.x = __fadd_rn(__fmul_rn(sv.x, decay), __fmul_rn(omd, pv.x));
+            sv.y = __fadd_rn(__fmul_rn(sv.y, decay), __fmul_rn(omd, pv.y));
+            sv.z = __fadd_rn(__fmul_rn(sv.z, decay), __fmul_rn(omd, pv.z));
+            sv.w = __fadd_rn(__fmul_rn(sv.w, decay), __fmul_rn(omd, pv.w));
+            *reinterpret_cast<float4*>(s + i) = sv;
+        }
+        for (int64_t i = hi4 + threadIdx.x; i < hi; i += blockDim.x)
+            s[i] = __fadd_rn(__fmul_rn(s[i], decay), __fmul_rn(omd, p[i]));
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+            s[i] = __fadd_rn(__fmul_rn(s[i], decay), __fmul_rn(omd, p[i]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout kernels
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC T.  One thread per (b, pixel); reads are coalesced per channel plane.
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int C, int HW) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const float* xb = x + (int64_t)b * C * HW + p;
+    T* yb = y + ((int64_t)b * HW + p) * C;
+    for (int c = 0; c < C; ++c) yb[c] = from_f<T>(xb[(int64_t)c * HW]);
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int C, int HW) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const T* xb = x + ((int64_t)b * HW + p) * C;
+    float* yb = y + (int64_t)b * C * HW + p;
+    for (int c = 0; c < C; ++c) yb[(int64_t)c * HW] = to_f(xb[c]);
+}
+
+// NCHW fp32 -> bf16 im2col rows (B*H*W, kpad), 3x3 pad 1.  One thread per (pixel, 8-column group).
+__global__ void im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                 int C, int H, int W, int kpad) {
+    const int b = blockIdx.y;
+    const int groups = kpad >> 3;
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int HW = H * W;
+    if (idx >= (int64_t)HW * groups) return;
+    const int p = (int)(idx / groups), g = (int)(idx % groups);
+    const int h = p / W, w = p % W;
+    const float* xb = x + (int64_t)b * C * HW;
+    Vec<__nv_bfloat16> v;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = g * 8 + j;
+        float val = 0.f;
+        if (k < 9 * C) {
+            const int tap = k / C, c = k % C;
+            const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = xb[(int64_t)c * HW + hh * W + ww];
+        }
+        v.v[j] = val;
+    }
+    v.store(y + ((int64_t)b * HW + p) * kpad + g * 8);
+}
+
+template <typename T>
+__global__ void avgpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, int64_t total_vec) {
+    constexpr int VN = Vec<T>::N;
+    const int Ho = H >> 1, Wo = W >> 1, cv = C / VN;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cv) * VN;
+        int64_t r = i / cv;
+        const int wo = (int)(r % Wo); r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int64_t b = r / Ho;
+        const T* p = x + (((b * H + 2 * ho) * W + 2 * wo) * (int64_t)C) + c;
+        Vec<T> a, bq, cq, d, o;
+        a.load(p); bq.load(p + C); cq.load(p + (int64_t)W * C); d.load(p + (int64_t)W * C + C);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o.v[j] = (a.v[j] + bq.v[j] + cq.v[j] + d.v[j]) * 0.25f;
+        o.store(y + (((b * Ho + ho) * Wo + wo) * (int64_t)C) + c);
+    }
+}
+
+template <typename T>
+__global__ void upsample2_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, int64_t total_vec) {
+    constexpr int VN = Vec<T>::N;
+    const int Ho = H * 2, Wo = W * 2, cv = C / VN;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cv) * VN;
+        int64_t r = i / cv;
+        const int wo = (int)(r % Wo); r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int64_t b = r / Ho;
+        const uint4 v = *reinterpret_cast<const uint4*>(x + (((b * H + (ho >> 1)) * W + (wo >> 1)) * (int64_t)C) + c);
+        *reinterpret_cast<uint4*>(y + (((b * Ho + ho) * Wo + wo) * (int64_t)C) + c) = v;
+    }
+}
+
+// NHWC bf16 -> (4, B, H/2, W/2, C) parity planes.
+__global__ void s2d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                           int B, int H, int W, int C, int64_t total_vec) {
+    const int cv = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cv) * 8;
+        int64_t r = i / cv;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int64_t b = r / H;
+        const int plane = (h & 1) * 2 + (w & 1);
+        const uint4 v = *reinterpret_cast<const uint4*>(x + i * 8);
+        *reinterpret_cast<uint4*>(y + ((((int64_t)plane * B + b) * Ho + (h >> 1)) * Wo + (w >> 1)) * (int64_t)C + c) = v;
+    }
+}
+
+static inline int grid_for(int64_t n, int threads, int cap_mult = 8) {
+    int64_t g = (n + threads - 1) / threads;
+    int64_t cap = (int64_t)num_sms() * cap_mult;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace dd
+
+using namespace dd;
+
+extern "C" {
+
+const char* dd_last_error(void) { return dd::g_err; }
+int dd_version(void) { return 100; }
+
+int dd_device_ok(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+}
+
+int dd_q_sample(const float* x, const float* eps, const int64_t* t, const float* sa, const float* sb,
+                float* out, int B, int64_t chw, void* stream) {
+    DD_REQUIRE(chw % 4 == 0 && B > 0, "q_sample: chw=%lld must be a multiple of 4", (long long)chw);
+    dim3 grid(grid_for(chw / 4, 256, 4), B);
+    q_sample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)eps, t, sa, sb,
+                                                           (float4*)out, chw / 4);
+    return check_launch("q_sample");
+}
+
+int dd_posterior_step(const float* x_t, const float* eps_hat, const float* noise, const float* coef,
+                      const int32_t* t_idx, int t_stride, int64_t noise_step_stride, int T, int clip,
+                      float* x_out, int B, int64_t chw, void* stream) {
+    DD_REQUIRE(chw % 4 == 0 && B > 0 && noise_step_stride % 4 == 0, "posterior_step: chw=%lld must be a multiple of 4",
+               (long long)chw);
+    dim3 grid(grid_for(chw / 4, 256, 4), B);
+    posterior_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)x_t, (const float4*)eps_hat, (const float4*)noise, coef, t_idx, t_stride,
+        noise_step_stride / 4, T, clip, (float4*)x_out, chw / 4);
+    return check_launch("posterior_step");
+}
+
+int dd_predict_x0(const float* x_t, const float* eps, const int64_t* t, const float* ra, const float* rb, int clip,
+                  float* out, int B, int64_t chw, void* stream) {
+    DD_REQUIRE(chw % 4 == 0 && B > 0, "predict_x0: chw=%lld must be a multiple of 4", (long long)chw);
+    dim3 grid(grid_for(chw / 4, 256, 4), B);
+    predict_x0_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x_t, (const float4*)eps, t, ra, rb, clip,
+                                                             (float4*)out, chw / 4);
+    return check_launch("predict_x0");
+}
+
+int dd_tick(int32_t* t_idx, int n, void* stream) {
+    tick_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t_idx, n);
+    return check_launch("tick");
+}
+
+int dd_mse_rowsum(const float* a, const float* b, float* out, int B, int64_t chw, float scale, void* stream) {
+    DD_REQUIRE(chw % 4 == 0 && B > 0, "mse_rowsum: chw=%lld must be a multiple of 4", (long long)chw);
+    mse_rowsum_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, out, chw / 4, scale);
+    return check_launch("mse_rowsum");
+}
+
+int dd_mse_rowsum_bwd(const float* a, const float* b, const float* w, float* grad_b, int B, int64_t chw, float gscale,
+                      void* stream) {
+    DD_REQUIRE(chw % 4 == 0 && B > 0, "mse_rowsum_bwd: chw=%lld must be a multiple of 4", (long long)chw);
+    dim3 grid(grid_for(chw / 4, 256, 4), B);
+    mse_rowsum_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, w,
+                                                                 (float4*)grad_b, chw / 4, gscale);
+    return check_launch("mse_rowsum_bwd");
+}
+
+int dd_ema_update(const uint64_t* table, const int32_t* chunks, int n_chunks, int chunk_elems, float decay,
+                  float one_minus_decay, void* stream) {
+    DD_REQUIRE(n_chunks > 0 && chunk_elems > 0 && chunk_elems % 4 == 0, "ema_update: bad chunking");
+    ema_update_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(table, chunks, chunk_elems, decay, one_minus_decay);
+    return check_launch("ema_update");
+}
+
+int dd_nchw_to_nhwc(const float* x, void* y, int dtype, int B, int C, int H, int W, void* stream) {
+    dim3 grid((H * W + 127) / 128, B);
+    DD_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid, 128, 0, (cudaStream_t)stream>>>(x, (T*)y, C, H * W)));
+    return check_launch("nchw_to_nhwc");
+}
+
+int dd_nhwc_to_nchw(const void* x, int dtype, float* y, int B, int C, int H, int W, void* stream) {
+    dim3 grid((H * W + 127) / 128, B);
+    DD_DISPATCH_DTYPE(dtype, T, (nhwc_to_nchw_kernel<T><<<grid, 128, 0, (cudaStream_t)stream>>>((const T*)x, y, C, H * W)));
+    return check_launch("nhwc_to_nchw");
+}
+
+int dd_im2col3x3_nchw(const float* x, void* y, int B, int C, int H, int W, int kpad, void* stream) {
+    DD_REQUIRE(kpad % 64 == 0 && kpad >= 9 * C, "im2col3x3: kpad=%d must be a multiple of 64 and >= 9*C", kpad);
+    int64_t n = (int64_t)H * W * (kpad / 8);
+    dim3 grid((unsigned)((n + 255) / 256), B);
+    im2col3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, C, H, W, kpad);
+    return check_launch("im2col3x3");
+}
+
+int dd_avgpool2(const void* x, void* y, int dtype, int B, int H, int W, int C, void* stream) {
+    DD_REQUIRE(H % 2 == 0 && W % 2 == 0, "avgpool2: odd spatial size");
+    DD_DISPATCH_DTYPE(dtype, T, {
+        DD_REQUIRE(C % Vec<T>::N == 0, "avgpool2: C=%d not vectorisable", C);
+        int64_t n = (int64_t)B * (H / 2) * (W / 2) * (C / Vec<T>::N);
+        avgpool2_kernel<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, H, W, C, n);
+    });
+    return check_launch("avgpool2");
+}
+
+int dd_upsample_nearest2(const void* x, void* y, int dtype, int B, int H, int W, int C, void* stream) {
+    DD_DISPATCH_DTYPE(dtype, T, {
+        DD_REQUIRE(C % Vec<T>::N == 0, "upsample2: C=%d not vectorisable", C);
+        int64_t n = (int64_t)B * (H * 2) * (W * 2) * (C / Vec<T>::N);
+        upsample2_kernel<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, H, W, C, n);
+    });
+    return check_launch("upsample_nearest2");
+}
+
+int dd_space_to_depth2(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+    DD_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "space_to_depth2: bad shape");
+    int64_t n = (int64_t)B * H * W * (C / 8);
+    s2d_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W,
+                                                                  C, n);
+    return check_launch("space_to_depth2");
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+/*
+ * ddb200.h -- C-ABI of the B200-native dDDPM hot path (libddb200.so).
+ *
+ * The reference (simonamtoft/downsampled-diffusion) has no FFI: every operation below is an
+ * ATen call made from Python.  Each entry point cites the reference call site it replaces
+ * (paths relative to the reference repo root).  A maintainer binds these with ctypes
+ * (see INTEGRATION.md); downsampled_diffusion_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - activations are NHWC ("channels-last") contiguous; `dtype` is DD_F32 or DD_BF16;
+ *     tensors crossing the Python API (x_t, eps_hat, noise, images) are NCHW fp32 like the reference;
+ *   - `stream` is a cudaStream_t passed as void*; every call is stream-ordered and re-entrant,
+ *     the library keeps no global mutable state besides the thread-local error string;
+ *   - return 0 on success, a negative DD_ERR_* otherwise (message: dd_last_error());
+ *   - the library never allocates or frees device memory and never retains a pointer
+ *     past the call (TMA descriptors are built by value into the launch parameters).
+ */
+#ifndef DDB200_H_
+#define DDB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DD_F32  0
+#define DD_BF16 1
+
+#define DD_OK              0
+#define DD_ERR_ARG        -1   /* unsupported shape / bad argument (Python raises ValueError/RuntimeError) */
+#define DD_ERR_CUDA       -2   /* CUDA runtime / driver error */
+#define DD_ERR_NO_DEVICE  -3   /* no sm_100 device */
+
+const char* dd_last_error(void);
+int dd_version(void);
+/* 1 when the current device is compute capability 10.x (tcgen05/TMA kernels usable). */
+int dd_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Diffusion arithmetic (models/diffusion/ddpm.py)
+ * ---------------------------------------------------------------------------------------- */
+
+/* q_sample: ddpm.py:256-273.  out = sqrt_ac[t_b]*x + sqrt_1mac[t_b]*eps, t per sample.
+ * x/eps/out: (B, chw) fp32.  t: int64 (B,).  Separate mul/mul/add roundings like ATen. */
+int dd_q_sample(const float* x, const float* eps, const int64_t* t,
+                const float* sqrt_ac, const float* sqrt_1mac,
+                float* out, int B, int64_t chw, void* stream);
+
+/* One ancestral update given eps_hat: ddpm.py:149-158 (predict_x_from_eps, clamp), :160-185
+ * (q_posterior), :217-227 (noise injection, masked at t==0).
+ * coef: (T,5) fp32 rows {sqrt_recip_ac, sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2,
+ * exp(0.5*post_logvar_clipped)}.  t_idx: int32 device array, sample b uses t_idx[b*t_stride]
+ * (t_stride 0 = one shared step, the sampling loop).  noise_step_stride != 0 selects
+ * noise + (T-1-t)*noise_step_stride, i.e. the pre-drawn chain noise of ddpm.py:223 for this step.
+ * clip != 0 applies clamp(-1,1) to x0 (ddpm.py:156-157). All NCHW fp32, (B, chw). */
+int dd_posterior_step(const float* x_t, const float* eps_hat, const float* noise,
+                      const float* coef, const int32_t* t_idx, int t_stride,
+                      int64_t noise_step_stride, int T, int clip,
+                      float* x_out, int B, int64_t chw, void* stream);
+
+/* predict_x_from_eps alone (ddpm.py:149-158), per-sample int64 t (used by reconstruct / non-AE loss). */
+int dd_predict_x0(const float* x_t, const float* eps, const int64_t* t,
+                  const float* sqrt_recip_ac, const float* sqrt_recipm1_ac, int clip,
+                  float* out, int B, int64_t chw, void* stream);
+
+/* t_idx[i] -= 1 for i < n : advances the device-side step counter between graph replays
+ * (replaces the host-side torch.full of ddpm.py:247). */
+int dd_tick(int32_t* t_idx, int n, void* stream);
+
+/* loss_ddpm's inner part: ddpm.py:279-283 + utils/utils.py:27-40.
+ * out[b] = sum_chw (a-b)^2  (scale=1) or mean (scale=1/chw). */
+int dd_mse_rowsum(const float* a, const float* b, float* out, int B, int64_t chw, float scale, void* stream);
+/* d/d b of mean_b(out[b]*w[b]) :  grad_b = 2*(b-a)*scale*gscale*w[b] (w may be NULL). */
+int dd_mse_rowsum_bwd(const float* a, const float* b, const float* w, float* grad_b,
+                      int B, int64_t chw, float gscale, void* stream);
+
+/* EMA.update: trainers/ema.py:36-44.  For every tensor i: shadow_i = shadow_i*decay + one_minus*param_i.
+ * table: device array of n_tensors*3 uint64 {shadow_ptr, param_ptr, numel}; chunk: device array of
+ * n_chunks*2 int32 {tensor index, chunk index}, each chunk = chunk_elems elements. */
+int dd_ema_update(const uint64_t* table, const int32_t* chunks, int n_chunks, int chunk_elems,
+                  float decay, float one_minus_decay, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * U-Net pieces (models/unet/unet.py, models/unet/blocks.py)
+ * ---------------------------------------------------------------------------------------- */
+
+/* NCHW fp32 -> NHWC dtype (input staging for unet.py:74). */
+int dd_nchw_to_nhwc(const float* x, void* y, int dtype, int B, int C, int H, int W, void* stream);
+/* NHWC dtype -> NCHW fp32. */
+int dd_nhwc_to_nchw(const void* x, int dtype, float* y, int B, int C, int H, int W, void* stream);
+/* NCHW fp32 -> bf16 im2col rows (B*H*W, kpad): column tap*C+c holds x[b,c,h+dy,w+dx] (3x3, zero pad 1),
+ * zero for columns >= 9*C.  Lets the first 3x3 conv (tiny C_in) and its res_conv run as K=kpad GEMMs. */
+int dd_im2col3x3_nchw(const float* x, void* y_bf16, int B, int C, int H, int W, int kpad, void* stream);
+
+/* SinusoidalPosEmb + time_mlp + every ResnetBlock's mlp (blocks.py:22-29, unet.py:30-35, blocks.py:92-95,108):
+ * out[r, j] = Wcat[j,:] . mish(temb(t_r)) + bcat[j], temb = W2 . mish(W1 . sincos(t_r) + b1) + b2.
+ * t: float32 (R,) time values (the reference multiplies the int64 t by fp32 frequencies); freq: (dim/2,)
+ * fp32 = exp(arange(dim/2) * -log(10000)/(dim/2-1)) computed by the host exactly like blocks.py:25-26. */
+int dd_time_bias(const float* t, int R, int dim, const float* freq,
+                 const float* W1, const float* b1, const float* W2, const float* b2,
+                 const float* Wcat, const float* bcat, int J, float* out, void* stream);
+
+/* GroupNorm statistics, blocks.py:79 (biased variance, eps inside sqrt).  x: NHWC (B,HW,C).
+ * stats: (B, G, 2) fp32 = {mean, rstd}. */
+int dd_gn_stats(const void* x, int dtype, int B, int HW, int C, int G, float eps, float* stats, void* stream);
+
+/* GroupNorm apply + Mish (+ time-embedding bias) (+ residual): blocks.py:79-84, 108-109, 115.
+ * stats_mode 0: stats = {mean, rstd}; 1: stats = {sum, sumsq} accumulated by the conv epilogue.
+ * tbias: row table (rows, tb_stride) already offset to this block's first column, or NULL;
+ * sample b uses row trow[b*trow_stride] (trow NULL: row b).  residual: NHWC same dtype, or NULL. */
+int dd_gn_mish(const void* x, void* y, int dtype, int B, int HW, int C, int G,
+               const float* stats, int stats_mode, float eps,
+               const float* gamma, const float* beta,
+               const float* tbias, int tb_stride, const int32_t* trow, int trow_stride,
+               const void* residual, void* stream);
+
+/* Channel LayerNorm of blocks.py:50-60: (x-mean_c)/(sqrt(var_c)+eps)*g+b, per pixel. x,y NHWC (P, C). */
+int dd_layernorm_c(const void* x, void* y, int dtype, int64_t P, int C, const float* g, const float* b,
+                   float eps, void* stream);
+
+/* LinearAttention core, blocks.py:128-133: qkv NHWC (B, n, 3*heads*dh), channel = (qkv, head, c);
+ * k softmax over n, ctx = k v^T, out = ctx^T q.  out NHWC (B, n, heads*dh).  dh must be 32. */
+int dd_linattn_core(const void* qkv, void* out, int dtype, int B, int n, int heads, int dh, void* stream);
+
+/* Generic direct convolution on CUDA cores, fp32 accumulate (validation mode, odd shapes, and the
+ * down/up-sampling nets).  Replaces F.conv2d / F.conv_transpose2d call sites of blocks.py:35,44,78,103,
+ * 123-124, unet.py:71, convblocks.py:29-67.
+ *   x (B,H,W,C1) [+ x2 (B,H,W,C2) concatenated on channels: unet.py:97], w (taps, C1+C2, Cout) fp32,
+ *   mode 0: conv k x k, stride, pad;  mode 1: ConvTranspose2d(k=4,s=2,p=1) (w tap = ky*4+kx).
+ *   flags: DD_CONV_PRE_MISH applies Mish to the input on load (convblocks.py:118-121),
+ *          DD_CONV_TANH applies tanh to the output (dddpm.py:99-100,110-111),
+ *          DD_CONV_OUT_NCHW writes fp32 NCHW, DD_CONV_IN_NCHW reads fp32 NCHW (x2 must be NULL). */
+#define DD_CONV_PRE_MISH  1
+#define DD_CONV_TANH      2
+#define DD_CONV_OUT_NCHW  4
+#define DD_CONV_IN_NCHW   8
+int dd_conv_direct(const void* x, const void* x2, int C1, int C2, int in_dtype,
+                   const float* w, const float* bias, const void* residual,
+                   void* y, int out_dtype, int B, int H, int W, int Cout,
+                   int ksize, int stride, int pad, int mode, int flags, void* stream);
+
+/* avg_pool2d(2,2) (convblocks.py:129) and nearest x2 (convblocks.py:127), NHWC. */
+int dd_avgpool2(const void* x, void* y, int dtype, int B, int H, int W, int C, void* stream);
+int dd_upsample_nearest2(const void* x, void* y, int dtype, int B, int H, int W, int C, void* stream);
+
+/* Space-to-depth: NHWC bf16 (B,H,W,C) -> 4 parity planes (4,B,H/2,W/2,C), plane = (h&1)*2+(w&1).
+ * Feeds the stride-2 Downsample conv (blocks.py:44) as 9 unit-stride taps. */
+int dd_space_to_depth2(const void* x, void* y, int B, int H, int W, int C, void* stream);
+
+/* tcgen05 / TMEM / TMA implicit-GEMM convolution, bf16 operands, fp32 accumulate.
+ * D[pixel, co] = sum_{tap, c} X_tap[pixel, c] * Wp[co, tap*(C1+C2) + c]
+ *   kind DD_TC_CONV3x3 : 3x3 stride 1 pad 1 (blocks.py:78)            x (B,H,W,C)
+ *   kind DD_TC_CONV1x1 : pointwise (blocks.py:103,123,124, unet.py:71) x (B,H,W,C)
+ *   kind DD_TC_DOWN    : 3x3 stride 2 pad 1 (blocks.py:44)  x = space-to-depth planes (4,B,H,W,C), H,W = OUTPUT size
+ *   kind DD_TC_UPT     : ConvTranspose2d(4,2,1) (blocks.py:35) as 4 sub-pixel phases; Wp rows = phase*Cout_pad+co,
+ *                        K = 4 taps * C; output (B,2H,2W,Cout)
+ * x2 (optional, same geometry, C2 channels) is the skip tensor of unet.py:97 (concat-free).
+ * C1, C2 multiples of 64; H, W powers of two; Wp (rows, K) bf16 K-major, rows padded to bn.
+ * Epilogue: + bias, GroupNorm {sum,sumsq} atomics into gn_stats (B, G, 2) when non-NULL (stats of the
+ * fp32 accumulator + bias), + residual (bf16 NHWC, output geometry), store bf16 NHWC or fp32 NCHW
+ * (out_nchw_f32, only the first cout_valid channels). */
+#define DD_TC_CONV3x3 0
+#define DD_TC_CONV1x1 1
+#define DD_TC_DOWN    2
+#define DD_TC_UPT     3
+int dd_conv_tc(int kind, const void* x, const void* x2, int C1, int C2,
+               const void* wp, int w_rows, const float* bias, const void* residual,
+               void* y, int out_nchw_f32, int cout_valid,
+               float* gn_stats, int G,
+               int B, int H, int W, int Cout, void* stream);
+
+/* Pack OIHW fp32 weights into the K-major bf16 matrix dd_conv_tc expects.
+ * kind as above; for DD_TC_UPT the source is ConvTranspose2d's (Cin, Cout, 4, 4).
+ * cin_total = C1+C2; rows_out = padded row count (>= Cout, multiple of 16); for UPT rows_out is per phase. */
+int dd_pack_weights_tc(int kind, const float* w, void* wp, int Cout, int cin_total, int rows_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DDB200_H_ */
