@@ -57,13 +57,15 @@ __device__ __forceinline__ float post1(float xt, float e, float z, float c0, flo
 __global__ void posterior_step_kernel(const float4* __restrict__ xt, const float4* __restrict__ eh,
                                       const float4* __restrict__ noise, const float* __restrict__ coef,
                                       const int32_t* __restrict__ t_idx, int t_stride, int64_t noise_step_stride4,
-                                      int T, int clip, float4* __restrict__ out, int64_t chw4) {
+                                      int T, int noise_period, int clip, float4* __restrict__ out, int64_t chw4) {
     const int b = blockIdx.y;
     const int t = t_idx[(int64_t)b * t_stride];
     const float* c = coef + (int64_t)t * 5;
     const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
     const float sig = (t == 0) ? 0.f : c[4];   // nonzero_mask * exp(0.5*logvar), ddpm.py:224-227
-    const float4* nz = noise + (int64_t)(T - 1 - t) * noise_step_stride4;
+    int step = T - 1 - t;                      // index of this step's pre-drawn noise (ddpm.py:223 draw order)
+    if (noise_period > 0) step %= noise_period;
+    const float4* nz = noise + (int64_t)step * noise_step_stride4;
     const int64_t base = (int64_t)b * chw4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < chw4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 x = xt[base + i], e = eh[base + i], z = nz[base + i], o;
@@ -301,14 +303,14 @@ int dd_q_sample(const float* x, const float* eps, const int64_t* t, const float*
 }
 
 int dd_posterior_step(const float* x_t, const float* eps_hat, const float* noise, const float* coef,
-                      const int32_t* t_idx, int t_stride, int64_t noise_step_stride, int T, int clip,
+                      const int32_t* t_idx, int t_stride, int64_t noise_step_stride, int T, int noise_period, int clip,
                       float* x_out, int B, int64_t chw, void* stream) {
     DD_REQUIRE(chw % 4 == 0 && B > 0 && noise_step_stride % 4 == 0, "posterior_step: chw=%lld must be a multiple of 4",
                (long long)chw);
     dim3 grid(grid_for(chw / 4, 256, 4), B);
     posterior_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const float4*)x_t, (const float4*)eps_hat, (const float4*)noise, coef, t_idx, t_stride,
-        noise_step_stride / 4, T, clip, (float4*)x_out, chw / 4);
+        noise_step_stride / 4, T, noise_period, clip, (float4*)x_out, chw / 4);
     return check_launch("posterior_step");
 }
 

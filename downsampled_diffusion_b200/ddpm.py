@@ -1,0 +1,264 @@
+"""Gaussian diffusion wrapper: schedule buffers, q_sample, posterior, ancestral sampling, training loss.
+
+Drop-in for models/diffusion/ddpm.py:22-457 of the reference: same constructor
+`DDPM(config, latent_model, device, color_channels=3)`, method names, return types and buffers.
+The arithmetic runs in libddb200 kernels; the T-step chain replays ONE captured CUDA graph per step
+(U-Net + posterior update + step-counter tick) with no host synchronisation in between.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Union
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from .engine import EngineCache
+from .schedule import diffusion_buffers, posterior_coef_table
+
+OBJECTIVE_NAMES = ("simple", "vlb", "hybrid")
+NOISE_RING_BYTES = 4 << 30      # pre-drawn chain noise is held in a ring of at most this many bytes
+
+
+class SamplingPlan:
+    """Captured sampling step for one (batch, latent shape, precision)."""
+
+    def __init__(self, ddpm: "DDPM", shape: Sequence[int]):
+        B, C, H, W = shape
+        self.shape = tuple(shape)
+        self.T = ddpm.timesteps
+        dev = next(ddpm.latent_model.parameters()).device
+        self.eng = ddpm.latent_model.engine(B, H, W)
+        self.chw = C * H * W
+        self.t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.coef = posterior_coef_table({k: getattr(ddpm, k) for k in (
+            "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+            "posterior_mean_coef2", "posterior_log_variance_clipped")}).to(dev)
+        per_step = B * self.chw * 4
+        self.period = max(1, min(self.T, NOISE_RING_BYTES // per_step))
+        self.noise = torch.empty(self.period, B, C, H, W, dtype=torch.float32, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.table_version = None
+        self.clip = ddpm.clip_denoised
+
+    def step_eager(self) -> None:
+        e = self.eng
+        e.run()
+        ops.posterior_step_raw(e.x_in, e.eps_out, self.noise, self.coef, self.t_dev, 0, self.shape[0] * self.chw,
+                               self.T, self.period, self.clip, out=e.x_in)
+        L.call("dd_tick", L.ptr(self.t_dev), 1, L.stream())
+
+    def prepare(self) -> None:
+        """(Re)build the time-bias table and the graph when the U-Net's weights changed."""
+        e = self.eng
+        e.refresh_weights()
+        if self.table_version != e.weights_version or e.time_table is None:
+            e.build_time_table(self.T)
+            self.table_version = e.weights_version
+        e.bind_table(e.time_table, self.t_dev, 0)
+        if self.graph is None:
+            # warm-up on a side stream (lazy CUDA initialisation must not happen inside capture)
+            self.t_dev.fill_(self.T - 1)
+            self.noise[0].zero_()
+            e.x_in.zero_()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self.step_eager()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.step_eager()
+            self.graph = g
+            self.launches_per_step = len(e.ops) + 3
+
+
+class DDPM(nn.Module):
+    def __init__(self, config: dict, latent_model: nn.Module, device: str, color_channels: int = 3):
+        super().__init__()
+        self.in_channels = color_channels
+        self.latent_model = latent_model
+        self.device = device
+        self.image_size = config["image_size"]
+        self.timesteps = config["T"]
+        self.sample_shape = [self.in_channels, self.image_size, self.image_size]
+        self.clip_denoised = True
+        self.clip_range = (-1.0, 1.0)
+        self.L = config["loss_type"]
+        self.lambda_ = 0.0001
+        assert self.L in OBJECTIVE_NAMES
+        if config["loss_flat"] not in ("mean", "sum"):
+            raise ValueError(f'Can only do mean or sum for flatten of loss, but {config["loss_flat"]} was desired..')
+        self.loss_flat = config["loss_flat"]
+        for name, buf in diffusion_buffers(config["beta_schedule"], self.timesteps).items():
+            self.register_buffer(name, buf, persistent=(name != "vlb_weights"))
+        assert not torch.isnan(self.vlb_weights).all()
+        self._plans = EngineCache()
+        self.use_graph = config.get("cuda_graph", True)
+
+    # reference spelling of the flatten helpers (ddpm.py:45-52)
+    def flatten_loss(self, per_elem_or_pair):
+        raise NotImplementedError("use mse_rows(a, b); the flatten is fused with the squared error")
+
+    def mse_rows(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        """flatten_loss(get_loss(a, b)): per-sample sum/mean of squared error (ddpm.py:45-52, 279)."""
+        return ops.mse_rows(a, b, self.loss_flat == "mean")
+
+    # ---- forward process ---------------------------------------------------------------------
+    def q_sample(self, x: torch.Tensor, t: torch.Tensor, eps: torch.Tensor) -> torch.Tensor:
+        """x_t ~ q(x_t | x): ddpm.py:256-273."""
+        assert x.shape == eps.shape
+        return ops.q_sample(x, eps, t, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod)
+
+    def q_mean_variance(self, x, t):
+        """ddpm.py:108-124 (evaluation helper; plain gather glue)."""
+        shape = (x.shape[0],) + (1,) * (x.dim() - 1)
+        mean = self.sqrt_alphas_cumprod.gather(-1, t).reshape(shape) * x
+        var = (1.0 - self.alphas_cumprod).gather(-1, t).reshape(shape)
+        logvar = self.log_one_minus_alphas_cumprod.gather(-1, t).reshape(shape)
+        return mean, var, logvar
+
+    # ---- reverse process -----------------------------------------------------------------------
+    def predict_x_from_eps(self, x_t, t, eps, clip: bool = True):
+        """ddpm.py:149-158."""
+        assert x_t.shape == eps.shape
+        return ops.predict_x0(x_t, eps, t, self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod, clip)
+
+    def q_posterior(self, x, x_t, t):
+        """ddpm.py:160-185: mean = c1*x0 + c2*x_t (q_sample's kernel), variance / clipped log-variance gathers."""
+        assert x.shape == x_t.shape
+        mean = ops.q_sample_raw(x, x_t, t, self.posterior_mean_coef1, self.posterior_mean_coef2)
+        shape = (x.shape[0],) + (1,) * (x.dim() - 1)
+        var = self.posterior_variance.gather(-1, t).reshape(shape)
+        logvar = self.posterior_log_variance_clipped.gather(-1, t).reshape(shape)
+        return mean, var, logvar
+
+    def p_mean_variance(self, x_t, t):
+        """ddpm.py:187-201."""
+        eps_hat = self.latent_model(x_t, t)
+        x_recon = self.predict_x_from_eps(x_t, t, eps_hat, clip=True)
+        return self.q_posterior(x_recon, x_t, t)
+
+    def _coef(self) -> torch.Tensor:
+        c = getattr(self, "_coef_cache", None)
+        if c is None or c.device != self.betas.device:
+            c = posterior_coef_table({k: getattr(self, k) for k in (
+                "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                "posterior_mean_coef2", "posterior_log_variance_clipped")}).to(self.betas.device)
+            self._coef_cache = c
+        return c
+
+    @torch.no_grad()
+    def p_sample(self, x_t: torch.Tensor, t: torch.Tensor, repeat_noise: bool = False, noise: torch.Tensor = None):
+        """One ancestral step with a per-sample `t`: ddpm.py:203-227 (U-Net, then one fused posterior kernel)."""
+        x_t = x_t.contiguous().float()
+        eps_hat = self.latent_model(x_t, t)
+        if noise is None:
+            if repeat_noise:
+                noise = torch.randn((1, *x_t.shape[1:]), device=x_t.device).repeat(x_t.shape[0], *((1,) * (x_t.dim() - 1)))
+            else:
+                noise = torch.randn(x_t.shape, device=x_t.device)
+        t32 = t.to(torch.int32).contiguous()
+        return ops.posterior_step_raw(x_t, eps_hat.contiguous(), noise.contiguous().float(), self._coef(), t32, 1, 0,
+                                      self.timesteps, 0, self.clip_denoised)
+
+    def sampling_plan(self, shape) -> SamplingPlan:
+        key = (tuple(shape), getattr(self.latent_model, "precision", None))
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = SamplingPlan(self, shape)
+            self._plans[key] = plan
+        return plan
+
+    @torch.no_grad()
+    def p_sample_loop(self, shape, every: int = 1, early_stop: int = None,
+                      noise: Union[torch.Tensor, Sequence[torch.Tensor], None] = None) -> torch.Tensor:
+        """ddpm.py:229-249.  `every` is accepted and ignored like the reference.
+
+        noise: optional pre-drawn chain noise, (n_steps+1, B, C, H, W) tensor or sequence of tensors
+        (device or pinned host): entry 0 is the start image, entry 1+k the k-th step's z.  When None the
+        same draws are made with torch.randn on the device, in the reference's order (start image, then
+        one draw per step including the masked one at t=0)."""
+        shape = tuple(shape)
+        T = self.timesteps
+        t_end = 0 if early_stop is None else early_stop
+        n_steps = T - t_end
+        plan = self.sampling_plan(shape)
+        plan.prepare()
+        eng = plan.eng
+        dev = eng.device
+
+        def draw(k):      # k = 0: start image; k >= 1: noise of step k-1
+            if noise is None:
+                return torch.randn(shape, device=dev)
+            return noise[k]
+
+        eng.x_in.copy_(draw(0), non_blocking=True)
+        plan.t_dev.fill_(T - 1)
+        done = 0
+        while done < n_steps:
+            chunk = min(plan.period - (done % plan.period), n_steps - done)
+            base = done % plan.period
+            if noise is None:
+                for j in range(chunk):
+                    plan.noise[base + j].copy_(torch.randn(shape, device=dev))
+            elif isinstance(noise, torch.Tensor):
+                plan.noise[base:base + chunk].copy_(noise[1 + done:1 + done + chunk], non_blocking=True)
+            else:
+                for j in range(chunk):
+                    plan.noise[base + j].copy_(noise[1 + done + j], non_blocking=True)
+            for _ in range(chunk):
+                if self.use_graph:
+                    plan.graph.replay()
+                else:
+                    plan.step_eager()
+            L._Counter.n += chunk * plan.launches_per_step if self.use_graph else 0
+            done += chunk
+        return eng.x_in.clone()
+
+    @torch.no_grad()
+    def sample(self, batch_size: int = 16, every: int = 1, early_stop: int = None, noise=None) -> torch.Tensor:
+        """ddpm.py:251-254."""
+        return self.p_sample_loop((batch_size, *self.sample_shape), every, early_stop, noise=noise)
+
+    @torch.no_grad()
+    def reconstruct(self, x: torch.Tensor, n: int) -> torch.Tensor:
+        """ddpm.py:126-147."""
+        assert x.shape[0] >= n
+        x = x[:n]
+        t = torch.linspace(0, self.timesteps - 1, n, device=x.device, dtype=torch.long)
+        eps = torch.randn_like(x)
+        x_0 = self.q_sample(x, t, eps)
+        eps_hat = self.latent_model(x_0, t)
+        return self.predict_x_from_eps(x_0, t, eps_hat, clip=False)
+
+    # ---- training objective --------------------------------------------------------------------
+    def loss_ddpm(self, eps: torch.Tensor, eps_hat: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """ddpm.py:275-288."""
+        loss = self.mse_rows(eps, eps_hat)
+        if self.L == "simple":
+            return loss.mean()
+        if self.L == "vlb":
+            return (self.vlb_weights[t] * loss).mean()
+        return (loss + self.lambda_ * self.vlb_weights[t] * loss).mean()
+
+    def losses(self, x: torch.Tensor, t: torch.Tensor, eps: torch.Tensor = None):
+        """ddpm.py:290-315.  `eps` may be passed in for reproducible parity runs."""
+        if eps is None:
+            eps = torch.randn_like(x)
+        x_t = self.q_sample(x, t, eps)
+        eps_hat = self.latent_model(x_t, t)
+        return self.loss_ddpm(eps, eps_hat, t)
+
+    p_losses = losses      # the name BASELINE.json's north_star uses
+
+    def t_sample(self, n: int) -> torch.Tensor:
+        """ddpm.py:448-450."""
+        return torch.randint(0, self.timesteps, (n,), device=self.device).long()
+
+    def forward(self, x: torch.Tensor):
+        """ddpm.py:452-457."""
+        t = self.t_sample(x.shape[0])
+        return self.losses(x, t)

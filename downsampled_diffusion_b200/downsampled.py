@@ -1,0 +1,209 @@
+"""Down/up-sampling networks of dDDPM: parameter containers + their launch programs.
+
+Drop-in for models/downsampled/convblocks.py:70-159 and models/downsampled/wrapper.py:6-59 of the
+reference (`get_downsampling(config, shape)`, `get_upsampling(config, shape)`, same module tree and
+state_dict keys: `conv.0.weight`, `conv.1.c1.weight`, ...).  The modules hold parameters; forward
+runs a fixed list of libddb200 launches (engine.Program).
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib as L
+from .engine import Act, EngineCache, Program, ensure_lazy
+
+
+class ConvResBlock(nn.Module):
+    """convblocks.py:92-130: x + c4(mish(c3(mish(c2(mish(c1(mish(x)))))))), then avg-pool / nearest x2."""
+
+    def __init__(self, dim: int, in_channels: int, out_channels: int = None, upsample: bool = False,
+                 downsample: bool = False, dropout: float = 0, residual: bool = False):
+        super().__init__()
+        assert not (upsample and downsample), "Does not make sense to both down- and upsample."
+        self.upsample, self.downsample, self.residual = upsample, downsample, residual
+        self.c1 = nn.Conv2d(in_channels, dim, 1)
+        self.c2 = nn.Conv2d(dim, dim, 3, padding=1)
+        self.c3 = nn.Conv2d(dim, dim, 3, padding=1)
+        self.c4 = nn.Conv2d(dim, out_channels, 1)
+        self.drop = nn.Dropout2d(p=dropout)
+
+
+class _ResampleProgram(Program):
+    """Launch list of a ConvResNet / SimpleDownConv / SimpleUpConv for a fixed (B, H, W)."""
+
+    def __init__(self, net: nn.Module, B: int, C: int, H: int, W: int, precision: str, tanh: bool):
+        super().__init__(net, B, precision)
+        ensure_lazy()
+        self.x_in = self.empty(B, C, H, W, dtype=torch.float32)
+        layers = list(net.conv)
+        x = None
+        self.out = None
+        for i, m in enumerate(layers):
+            last = i == len(layers) - 1
+            if isinstance(m, ConvResBlock):
+                if m.drop.p > 0 and net.training:
+                    raise RuntimeError("Dropout2d in the resampling nets is only supported with p=0 (reference default)")
+                h, _ = self.conv(x, m.c1, kind="1x1", pre_mish=True)
+                h, _ = self.conv(h, m.c2, kind="3x3", pre_mish=True)
+                h, _ = self.conv(h, m.c3, kind="3x3", pre_mish=True)
+                x, _ = self.conv(h, m.c4, kind="1x1", pre_mish=True, residual=x if m.residual else None)
+                if m.upsample:
+                    y = self.act(x.H * 2, x.W * 2, x.C, B)
+                    self.add("dd_upsample_nearest2", L.ptr(x.t), L.ptr(y.t), self.dcode, B, x.H, x.W, x.C)
+                    x = y
+                elif m.downsample:
+                    y = self.act(x.H // 2, x.W // 2, x.C, B)
+                    self.add("dd_avgpool2", L.ptr(x.t), L.ptr(y.t), self.dcode, B, x.H, x.W, x.C)
+                    x = y
+                continue
+            # plain nn.Conv2d / nn.ConvTranspose2d layer
+            transposed = isinstance(m, nn.ConvTranspose2d)
+            ks = m.kernel_size[0]
+            stride = m.stride[0]
+            Cin = m.in_channels
+            Cout = m.out_channels
+            first = x is None
+            if first:
+                Hi, Wi = H, W
+            else:
+                Hi, Wi = x.H, x.W
+            if transposed:
+                Ho, Wo, mode, pad = Hi * 2, Wi * 2, 1, 1
+                wd = self.packed((16, Cin, Cout), torch.float32,
+                                 lambda buf, m=m, Cin=Cin, Cout=Cout: buf.copy_(m.weight.detach().permute(2, 3, 0, 1).reshape(16, Cin, Cout)))
+            else:
+                pad = m.padding[0]
+                Ho = (Hi + 2 * pad - ks) // stride + 1
+                Wo = (Wi + 2 * pad - ks) // stride + 1
+                mode = 0
+                wd = self.packed((ks * ks, Cin, Cout), torch.float32,
+                                 lambda buf, m=m, ks=ks, Cin=Cin, Cout=Cout: buf.copy_(m.weight.detach().permute(2, 3, 1, 0).reshape(ks * ks, Cin, Cout)))
+            b_t = self.f32(m.bias) if m.bias is not None else None
+            flags = (L.CONV_IN_NCHW if first else 0)
+            if last:
+                self.out = self.empty(B, Cout, Ho, Wo, dtype=torch.float32)
+                flags |= L.CONV_OUT_NCHW | (L.CONV_TANH if tanh else 0)
+                dst = self.out
+                y = None
+            else:
+                y = self.act(Ho, Wo, Cout, B)
+                dst = y.t
+            self.add("dd_conv_direct", L.ptr(self.x_in) if first else L.ptr(x.t), None, Cin, 0,
+                     L.DD_F32 if first else self.dcode, L.ptr(wd), L.ptr(b_t) if b_t is not None else None, None,
+                     L.ptr(dst), self.dcode, B, Hi, Wi, Cout, ks, stride, pad, mode, flags)
+            x = y
+        if self.out is None:
+            raise ValueError("resampling net must end in a plain convolution")
+        self.refresh_weights()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self.refresh_weights()
+        self.x_in.copy_(x)
+        self.run_ops()
+        return self.out.clone()
+
+
+class _ResampleNet(nn.Module):
+    precision = "bf16"
+
+    def _program(self, x: torch.Tensor, tanh: bool) -> _ResampleProgram:
+        if not hasattr(self, "_programs"):
+            self._programs = EngineCache()
+        B, C, H, W = x.shape
+        key = (B, C, H, W, self.precision, tanh)
+        prog = self._programs.get(key)
+        if prog is None:
+            prog = _ResampleProgram(self, B, C, H, W, self.precision, tanh)
+            self._programs[key] = prog
+        return prog
+
+    def forward(self, x: torch.Tensor, tanh: bool = False) -> torch.Tensor:
+        """NCHW fp32 in / out.  `tanh=True` fuses dddpm.py:99-100 / 110-111's squashing into the last conv."""
+        if not x.is_cuda:
+            raise RuntimeError("downsampled_diffusion_b200 resampling nets run on CUDA only; there is no CPU fallback")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import resample_apply
+            return resample_apply(self, x, tanh)
+        return self._program(x, tanh).forward(x.contiguous().float())
+
+
+class ConvResNet(_ResampleNet):
+    """convblocks.py:133-159."""
+
+    def __init__(self, dim: int, in_channels: int, out_channels: int, n_downsamples: int = 1, upsample: bool = False,
+                 dropout: float = 0, n_blocks: int = 1):
+        super().__init__()
+        downsample = not upsample
+        layers = [nn.Conv2d(in_channels, dim, 1)]
+        for _ in range(n_downsamples):
+            layers.append(ConvResBlock(int(dim / 2), dim, dim, upsample, downsample, dropout, residual=True))
+            for _ in range(max(int(n_blocks) - 1, 0)):
+                layers.append(ConvResBlock(int(dim / 2), dim, dim, False, False, dropout, residual=True))
+        layers.append(nn.Conv2d(dim, out_channels, 1))
+        self.conv = nn.Sequential(*layers)
+
+
+class SimpleDownConv(_ResampleNet):
+    """convblocks.py:70-78: a stack of stride-2 3x3 convolutions."""
+
+    def __init__(self, dim: int = 8, in_channels: int = 3, n_downsamples: int = 1):
+        super().__init__()
+        dims = [in_channels] + [dim] * n_downsamples
+        self.in_out = list(zip(dims[:-1], dims[1:]))
+        self.conv = nn.Sequential(*[nn.Conv2d(i, o, 3, stride=2, padding=1) for i, o in self.in_out])
+
+
+class SimpleUpConv(_ResampleNet):
+    """convblocks.py:81-89: a stack of 4x4 stride-2 transposed convolutions."""
+
+    def __init__(self, dim: int = 8, in_channels: int = 3, n_downsamples: int = 1):
+        super().__init__()
+        dims = [in_channels] + [dim] * n_downsamples
+        self.in_out = list(zip(dims[:-1], dims[1:]))
+        self.conv = nn.Sequential(*[nn.ConvTranspose2d(o, i, 4, stride=2, padding=1) for i, o in self.in_out[::-1]])
+
+
+def get_interpolate(size: tuple, mode: str = None, align: bool = True):
+    """convblocks.py:8-26 ('deterministic' mode): bicubic F.interpolate, a library call kept for API parity
+    only -- it is not part of the BASELINE configurations and has no kernel in libddb200."""
+    align = None if mode == "nearest" else align
+    mode = "bicubic" if mode is None else mode
+    return partial(F.interpolate, size=size, mode=mode, align_corners=align)
+
+
+def get_upsampling(config: dict, shape: tuple):
+    """wrapper.py:6-30."""
+    assert shape[1] == shape[2]
+    assert shape[0] == 1 or shape[0] == 3
+    in_channels, mode = shape[0], config["u_mode"]
+    if mode == "deterministic":
+        return get_interpolate((shape[1], shape[2]))
+    if mode == "convolutional":
+        return SimpleUpConv(config["unet_in"], in_channels, config["n_downsamples"])
+    if mode == "convolutional_res":
+        return ConvResNet(config["d_chans"], config["unet_in"], in_channels, config["n_downsamples"], upsample=True,
+                          dropout=config["d_dropout"], n_blocks=config["u_n_blocks"])
+    raise NotImplementedError(f'Upsampling method for "{mode}" not implemented!')
+
+
+def get_downsampling(config: dict, shape: tuple):
+    """wrapper.py:33-59."""
+    assert shape[1] == shape[2]
+    assert shape[0] == 1 or shape[0] == 3
+    in_channels, mode = shape[0], config["d_mode"]
+    if mode == "deterministic":
+        scale = np.power(2, config["n_downsamples"]).astype(int)
+        size = (int(shape[1] / scale), int(shape[2] / scale))
+        assert size[0] % 2 == 0, "result from downsampling should have even dimensions."
+        return get_interpolate(size)
+    if mode == "convolutional":
+        return SimpleDownConv(config["unet_in"], in_channels, config["n_downsamples"])
+    if mode == "convolutional_res":
+        return ConvResNet(config["d_chans"], in_channels, config["unet_in"], config["n_downsamples"], upsample=False,
+                          dropout=config["d_dropout"], n_blocks=config["d_n_blocks"])
+    raise NotImplementedError(f'Downsampling method for "{mode}" not implemented!')

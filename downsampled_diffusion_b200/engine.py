@@ -1,0 +1,482 @@
+"""Step programs: the U-Net forward (unet.py:74-104 of the reference) and the down/up-sampling nets
+(convblocks.py:133-159) lowered to a fixed list of libddb200 kernel launches.
+
+A program is built once per (module, batch, resolution, precision): every activation buffer is a
+torch tensor allocated up front (Python/torch owns all memory, the C side none), weights are repacked
+into the kernels' layouts, and `run()` is a flat loop of C-ABI calls on the current CUDA stream with
+fixed pointers -- so a whole ancestral step can be captured in one CUDA graph and replayed T times.
+
+precision 'bf16': NHWC bf16 activations, 3x3/1x1/strided/transposed convs on tcgen05 (dd_conv_tc),
+                  GroupNorm statistics accumulated by the conv epilogue.
+precision 'fp32': NHWC fp32 activations, CUDA-core direct convs (dd_conv_direct) -- the validation mode.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+GN_EPS = 1e-5
+
+
+class EngineCache(dict):
+    """Per-module cache of built programs; never copied along with the module (EMA deep-copies models)."""
+
+    def __deepcopy__(self, memo):
+        return EngineCache()
+
+
+class Act:
+    """An NHWC activation tensor of a program."""
+    __slots__ = ("t", "B", "H", "W", "C")
+
+    def __init__(self, t: torch.Tensor, B: int, H: int, W: int, C: int):
+        self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+
+
+def _is_pow2(v: int) -> bool:
+    return v > 0 and (v & (v - 1)) == 0
+
+
+def params_version(module: torch.nn.Module) -> int:
+    """Changes whenever a parameter is written in place (optimizer step, load_state_dict: `_version`) or
+    rebound to new storage (`p.data = ...`: data_ptr).  Raw-pointer writers (EMA.update) call invalidate()."""
+    return hash(tuple((p._version, p.data_ptr()) for p in module.parameters()))
+
+
+class Program:
+    """Shared machinery: buffer allocation, weight repacking, launch list."""
+
+    def __init__(self, module: torch.nn.Module, B: int, precision: str):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.module = module
+        self.B = B
+        self.precision = precision
+        self.device = next(module.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("programs are built for CUDA modules only (no CPU fallback)")
+        self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.dcode = L.dtype_code(self.adt)
+        self.ops: List[Callable[[], None]] = []
+        self.keep: List[torch.Tensor] = []          # packed weights etc. referenced by raw pointer
+        self.packers: List[Callable[[], None]] = [] # re-run when the module's parameters change
+        self.weights_version = None
+        self.n_gn = 0
+        self.gn_slots: List[Tuple[int, int]] = []   # (B*G*2 offset, G) per GroupNorm of a bf16 program
+        self.stats_arena: Optional[torch.Tensor] = None
+
+    # ---- helpers ---------------------------------------------------------------------------
+    def empty(self, *shape, dtype=None) -> torch.Tensor:
+        return torch.empty(*shape, dtype=dtype or self.adt, device=self.device)
+
+    def act(self, H: int, W: int, C: int, B: int = None) -> Act:
+        B = B or self.B
+        return Act(self.empty(B, H, W, C), B, H, W, C)
+
+    def packed(self, shape, dtype, fill: Callable[[torch.Tensor], None]) -> torch.Tensor:
+        """A derived weight buffer: allocated once, (re)filled from the fp32 master parameters."""
+        buf = torch.zeros(*shape, dtype=dtype, device=self.device)
+        self.keep.append(buf)
+
+        def pack():
+            with torch.no_grad():
+                fill(buf)
+        self.packers.append(pack)
+        return buf
+
+    def f32(self, param: torch.Tensor, pad_to: int = None) -> torch.Tensor:
+        """Flat fp32 copy of a parameter (gamma/beta/bias), optionally zero padded."""
+        n = param.numel()
+        return self.packed((pad_to or n,), torch.float32, lambda b: b[:n].copy_(param.detach().reshape(-1)))
+
+    def refresh_weights(self) -> None:
+        v = params_version(self.module)
+        if v != self.weights_version:
+            for pk in self.packers:
+                pk()
+            self.weights_version = v
+
+    def add(self, name: str, *args) -> None:
+        fn = getattr(L.lib(), name)
+
+        def op():
+            L._Counter.n += 1
+            rc = fn(*args, L.stream())
+            if rc != 0:
+                L.check(rc, name)
+        self.ops.append(op)
+
+    def run_ops(self) -> None:
+        for op in self.ops:
+            op()
+
+    # ---- convolution lowering --------------------------------------------------------------
+    def conv(self, x: Act, conv: torch.nn.Module, *, x2: Act = None, kind: str = "3x3", gn: torch.nn.GroupNorm = None,
+             residual: Act = None, pre_mish: bool = False, tanh: bool = False, out_nchw: torch.Tensor = None,
+             bias: bool = True) -> Tuple[Act, Optional[Tuple[torch.Tensor, int]]]:
+        """Lower one nn.Conv2d / nn.ConvTranspose2d.  Returns (output Act, GroupNorm stats handle or None).
+
+        kind: '3x3' (s1 p1), '1x1', 'down' (3x3 s2 p1), 'up' (ConvTranspose2d 4,2,1).
+        gn: when given the conv feeds that GroupNorm: statistics are produced (epilogue atomics in bf16,
+            a dd_gn_stats launch in fp32) and returned as (stats tensor, mode)."""
+        w = conv.weight
+        Cin = x.C + (x2.C if x2 is not None else 0)
+        Cout = w.shape[1] if kind == "up" else w.shape[0]
+        B, H, W = x.B, x.H, x.W
+        if kind == "down":
+            Ho, Wo = H // 2, W // 2
+        elif kind == "up":
+            Ho, Wo = H * 2, W * 2
+        else:
+            Ho, Wo = H, W
+        y = None if out_nchw is not None else self.act(Ho, Wo, Cout, B)
+        b_t = self.f32(conv.bias) if (bias and conv.bias is not None) else None
+        stats = None
+
+        use_tc = self.precision == "bf16" and not pre_mish and not tanh
+        if use_tc:
+            if not (_is_pow2(Ho if kind != "up" else H) and _is_pow2(Wo if kind != "up" else W)):
+                raise ValueError(f"bf16 tensor-core path needs power-of-two feature maps, got {H}x{W}; use precision='fp32'")
+            if x.C % 64 or (x2 is not None and x2.C % 64):
+                raise ValueError(f"bf16 tensor-core path needs channel counts that are multiples of 64, got {x.C}")
+            Cout_p = Cout if Cout % 16 == 0 else (Cout + 15) // 16 * 16
+            rows = Cout_p if Cout_p < 128 else (Cout_p + 127) // 128 * 128
+            if rows != Cout_p:
+                raise ValueError(f"unsupported Cout={Cout} for the tensor-core path")
+            if b_t is not None and Cout_p != Cout:
+                b_t = self.f32(conv.bias, pad_to=Cout_p)
+            if kind in ("3x3", "down"):
+                K = 9 * Cin
+                wp = self.packed((rows, K), torch.bfloat16,
+                                 lambda buf: buf[:Cout].copy_(w.detach().permute(0, 2, 3, 1).reshape(Cout, K)))
+                kcode = L.TC_CONV3x3 if kind == "3x3" else L.TC_DOWN
+            elif kind == "1x1":
+                K = Cin
+                wp = self.packed((rows, K), torch.bfloat16, lambda buf: buf[:Cout].copy_(w.detach().reshape(Cout, K)))
+                kcode = L.TC_CONV1x1
+            else:   # 'up': ConvTranspose2d weight (Cin, Cout, 4, 4) -> 4 sub-pixel phase matrices
+                K = 4 * Cin
+
+                def fill(buf, w=w, Cin=Cin, Cout=Cout, rows=rows):
+                    wd = w.detach()
+                    for ph in range(4):
+                        py, px = ph >> 1, ph & 1
+                        for t in range(4):
+                            a, b = t >> 1, t & 1
+                            ky, kx = 2 * a + 1 - py, 2 * b + 1 - px
+                            buf[ph * rows: ph * rows + Cout, t * Cin:(t + 1) * Cin].copy_(wd[:, :, ky, kx].t())
+                wp = self.packed((4 * rows, K), torch.bfloat16, fill)
+                kcode = L.TC_UPT
+            src, src2 = x.t, (x2.t if x2 is not None else None)
+            gh, gw = (Ho, Wo) if kind == "down" else (H, W)
+            if kind == "down":
+                planes = self.empty(4, B, Ho, Wo, x.C)
+                self.add("dd_space_to_depth2", L.ptr(x.t), L.ptr(planes), B, H, W, x.C)
+                src = planes
+            G = 0
+            st_ptr = None
+            if gn is not None:
+                G = gn.num_groups
+                stats = (self._new_stats_slot(B, G), 1)
+                st_ptr = stats[0]
+            self.add("dd_conv_tc", kcode, L.ptr(src), L.ptr(src2) if src2 is not None else None, x.C,
+                     x2.C if x2 is not None else 0, L.ptr(wp), wp.shape[0], L.ptr(b_t) if b_t is not None else None,
+                     L.ptr(residual.t) if residual is not None else None,
+                     L.ptr(out_nchw) if out_nchw is not None else L.ptr(y.t), 1 if out_nchw is not None else 0,
+                     Cout if out_nchw is not None else 0, st_ptr, G, B, gh, gw, Cout_p)
+            if y is not None and Cout_p != Cout:
+                raise ValueError("padded Cout is only supported with NCHW fp32 output")
+        else:
+            if kind == "up":
+                wd = self.packed((16, Cin, Cout), torch.float32,
+                                 lambda buf: buf.copy_(w.detach().permute(2, 3, 0, 1).reshape(16, Cin, Cout)))
+                ks, stride, pad, mode = 4, 2, 1, 1
+            else:
+                ks = w.shape[2]
+                wd = self.packed((ks * ks, Cin, Cout), torch.float32,
+                                 lambda buf: buf.copy_(w.detach().permute(2, 3, 1, 0).reshape(ks * ks, Cin, Cout)))
+                stride, pad, mode = (2 if kind == "down" else 1), (1 if ks == 3 else 0), 0
+            flags = (L.CONV_PRE_MISH if pre_mish else 0) | (L.CONV_TANH if tanh else 0) | \
+                    (L.CONV_OUT_NCHW if out_nchw is not None else 0)
+            self.add("dd_conv_direct", L.ptr(x.t), L.ptr(x2.t) if x2 is not None else None, x.C,
+                     x2.C if x2 is not None else 0, L.dtype_code(x.t.dtype), L.ptr(wd),
+                     L.ptr(b_t) if b_t is not None else None, L.ptr(residual.t) if residual is not None else None,
+                     L.ptr(out_nchw) if out_nchw is not None else L.ptr(y.t), self.dcode, B, H, W, Cout,
+                     ks, stride, pad, mode, flags)
+            if gn is not None:
+                G = gn.num_groups
+                st = self.empty(B, G, 2, dtype=torch.float32)
+                self.add("dd_gn_stats", L.ptr(y.t), self.dcode, B, Ho * Wo, Cout, G, GN_EPS, L.ptr(st))
+                stats = (st, 0)
+        return y, stats
+
+    def _new_stats_slot(self, B: int, G: int) -> int:
+        """Reserve a (B,G,2) fp32 slot of the statistics arena; returns its device pointer lazily."""
+        off = sum(s for s, _ in self.gn_slots)
+        self.gn_slots.append((B * G * 2, G))
+        return _ArenaPtr(self, off)
+
+    def finalize_arena(self) -> None:
+        total = sum(s for s, _ in self.gn_slots)
+        if total:
+            self.stats_arena = torch.zeros(total, dtype=torch.float32, device=self.device)
+
+    def gn_mish(self, x: Act, stats, gn: torch.nn.GroupNorm, *, tb_col: int = None, tb=None, residual: Act = None) -> Act:
+        y = self.act(x.H, x.W, x.C, x.B)
+        st, mode = stats
+        gamma, beta = self.f32(gn.weight), self.f32(gn.bias)
+        self.add("dd_gn_mish", L.ptr(x.t), L.ptr(y.t), self.dcode, x.B, x.H * x.W, x.C, gn.num_groups,
+                 st if isinstance(st, _ArenaPtr) else L.ptr(st), mode, GN_EPS, L.ptr(gamma), L.ptr(beta),
+                 _TbPtr(self, tb_col) if tb_col is not None else None, tb[0] if tb else 0,
+                 _TrowPtr(self) if tb_col is not None else None, _TrowStride(self) if tb_col is not None else 0,
+                 L.ptr(residual.t) if residual is not None else None)
+        return y
+
+
+class _Lazy:
+    """ctypes argument resolved at launch time (pointers that change between runs)."""
+
+    def __init__(self, prog):
+        self.prog = prog
+
+
+class _ArenaPtr(_Lazy):
+    def __init__(self, prog, off):
+        super().__init__(prog)
+        self.off = off
+
+    @property
+    def _as_parameter_(self):
+        return L.C.c_void_p(self.prog.stats_arena.data_ptr() + 4 * self.off)
+
+
+class _TbPtr(_Lazy):
+    def __init__(self, prog, col):
+        super().__init__(prog)
+        self.col = col
+
+    @property
+    def _as_parameter_(self):
+        return L.C.c_void_p(self.prog.tb_rows.data_ptr() + 4 * self.col)
+
+
+class _TrowPtr(_Lazy):
+    @property
+    def _as_parameter_(self):
+        t = self.prog.trow
+        return L.C.c_void_p(t.data_ptr() if t is not None else None)
+
+
+class _TrowStride(_Lazy):
+    @property
+    def _as_parameter_(self):
+        return L.C.c_int(self.prog.trow_stride)
+
+
+# ctypes calls with argtypes set convert through from_param; teach c_void_p / c_int our lazies
+def _install_lazy_support():
+    lib = L.lib()
+    for name, args in L.SIGNATURES.items():
+        getattr(lib, name).argtypes = [_LazyVoidP if a is L._p else (_LazyInt if a is L._i else a) for a in args]
+
+
+class _LazyVoidP(L.C.c_void_p):
+    @classmethod
+    def from_param(cls, v):
+        if isinstance(v, _Lazy):
+            return v._as_parameter_
+        return L.C.c_void_p.from_param(v)
+
+
+class _LazyInt(L.C.c_int):
+    @classmethod
+    def from_param(cls, v):
+        if isinstance(v, _Lazy):
+            return v._as_parameter_
+        return L.C.c_int(v)
+
+
+_lazy_installed = False
+
+
+def ensure_lazy():
+    global _lazy_installed
+    if not _lazy_installed:
+        _install_lazy_support()
+        _lazy_installed = True
+
+
+class UnetEngine(Program):
+    """The U-Net forward as a launch list (see module docstring).  Inputs/outputs are NCHW fp32."""
+
+    def __init__(self, unet, B: int, H: int, W: int, precision: str):
+        super().__init__(unet, B, precision)
+        ensure_lazy()
+        self.H, self.W = H, W
+        n_levels = len(unet.downs)
+        if H % (1 << (n_levels - 1)) or W % (1 << (n_levels - 1)):
+            raise ValueError(f"input {H}x{W} must be divisible by 2^{n_levels - 1} (unet_dims has {n_levels} levels)")
+        dim, cin = unet.dim, unet.in_channels
+        if dim % 8:
+            raise ValueError("unet_chan must be a multiple of 8 (GroupNorm groups)")
+        self.x_in = self.empty(B, cin, H, W, dtype=torch.float32)      # NCHW staging (graph-stable pointer)
+        self.eps_out = self.empty(B, cin, H, W, dtype=torch.float32)
+        # ---- time-embedding bias columns: one block of dim_out columns per ResnetBlock ----
+        self.res_blocks = [m for m in unet.modules() if type(m).__name__ == "ResnetBlock"]
+        self.tb_off = {}
+        J = 0
+        for rb in self.res_blocks:
+            self.tb_off[id(rb)] = J
+            J += rb.mlp[1].out_features
+        self.J = J
+        Wcat = self.packed((J, dim), torch.float32,
+                           lambda b: b.copy_(torch.cat([rb.mlp[1].weight.detach() for rb in self.res_blocks], 0)))
+        bcat = self.packed((J,), torch.float32,
+                           lambda b: b.copy_(torch.cat([rb.mlp[1].bias.detach() for rb in self.res_blocks], 0)))
+        self.tm = (self.f32(unet.time_mlp[1].weight), self.f32(unet.time_mlp[1].bias),
+                   self.f32(unet.time_mlp[3].weight), self.f32(unet.time_mlp[3].bias), Wcat, bcat)
+        half = dim // 2
+        k = math.log(10000) / (half - 1)
+        self.freq = torch.exp(torch.arange(half) * -k).to(self.device)          # blocks.py:25-26, evaluated on host
+        self.tb_batch = self.empty(B, J, dtype=torch.float32)   # rows for a per-sample `time` argument
+        self.t_float = self.empty(B, dtype=torch.float32)
+        self.tb_rows = self.tb_batch                            # table the gn_mish launches read (rebindable)
+        self.trow: Optional[torch.Tensor] = None                # int32 row index per sample (None: row = b)
+        self.trow_stride = 0
+        self.tb = (J,)
+        self.time_table: Optional[torch.Tensor] = None
+        self._build(unet)
+        self.finalize_arena()
+        self.refresh_weights()
+
+    # ---- program construction --------------------------------------------------------------
+    def _resnet(self, rb, x: Act, x2: Act = None, first: bool = False) -> Act:
+        col = self.tb_off[id(rb)]
+        c1, g1 = rb.block1.block[0], rb.block1.block[1]
+        c2, g2 = rb.block2.block[0], rb.block2.block[1]
+        has_res = not isinstance(rb.res_conv, torch.nn.Identity)
+        if first and self.precision == "bf16":
+            # x is the im2col'd input (B,H,W,kpad): the 3x3 conv and the 1x1 res_conv are K=kpad GEMMs
+            h, st = self._conv_im2col(x, c1, gn=g1, center_only=False)
+            res = self._conv_im2col(x, rb.res_conv, gn=None, center_only=True)[0] if has_res else None
+            if not has_res:
+                raise ValueError("first ResnetBlock without res_conv is not supported on the tensor-core path")
+        else:
+            h, st = self.conv(x, c1, x2=x2, kind="3x3", gn=g1)
+            if has_res:
+                res, _ = self.conv(x, rb.res_conv, x2=x2, kind="1x1")
+            else:
+                assert x2 is None
+                res = x
+        h = self.gn_mish(h, st, g1, tb_col=col, tb=self.tb)
+        h, st = self.conv(h, c2, kind="3x3", gn=g2)
+        return self.gn_mish(h, st, g2, residual=res)
+
+    def _conv_im2col(self, x: Act, conv, gn, center_only: bool):
+        w = conv.weight
+        Cout, Cin = w.shape[0], w.shape[1]
+        kpad = x.C
+
+        def fill(buf):
+            wd = w.detach()
+            if center_only:
+                buf[:, 4 * Cin:5 * Cin].copy_(wd.reshape(Cout, Cin))
+            else:
+                buf[:, :9 * Cin].copy_(wd.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
+        wp = self.packed((Cout, kpad), torch.bfloat16, fill)
+        b_t = self.f32(conv.bias)
+        y = self.act(x.H, x.W, Cout, x.B)
+        stats, st_ptr, G = None, None, 0
+        if gn is not None:
+            G = gn.num_groups
+            stats = (self._new_stats_slot(x.B, G), 1)
+            st_ptr = stats[0]
+        self.add("dd_conv_tc", L.TC_CONV1x1, L.ptr(x.t), None, kpad, 0, L.ptr(wp), Cout, L.ptr(b_t), None, L.ptr(y.t),
+                 0, 0, st_ptr, G, x.B, x.H, x.W, Cout)
+        return y, stats
+
+    def _attn(self, res_mod, x: Act) -> Act:
+        pre = res_mod.fn            # PreNorm
+        attn = pre.fn               # LinearAttention
+        g, b = self.f32(pre.norm.g), self.f32(pre.norm.b)
+        xn = self.act(x.H, x.W, x.C, x.B)
+        self.add("dd_layernorm_c", L.ptr(x.t), L.ptr(xn.t), self.dcode, x.B * x.H * x.W, x.C, L.ptr(g), L.ptr(b),
+                 pre.norm.eps)
+        qkv, _ = self.conv(xn, attn.to_qkv, kind="1x1", bias=False)
+        hid = attn.heads * attn.dim_head
+        o = self.act(x.H, x.W, hid, x.B)
+        self.add("dd_linattn_core", L.ptr(qkv.t), L.ptr(o.t), self.dcode, x.B, x.H * x.W, attn.heads, attn.dim_head)
+        y, _ = self.conv(o, attn.to_out, kind="1x1", residual=x)
+        return y
+
+    def _build(self, unet) -> None:
+        B, H, W, cin = self.B, self.H, self.W, unet.in_channels
+        if self.precision == "bf16":
+            kpad = (9 * cin + 63) // 64 * 64
+            x = self.act(H, W, kpad)
+            self.add("dd_im2col3x3_nchw", L.ptr(self.x_in), L.ptr(x.t), B, cin, H, W, kpad)
+        else:
+            x = self.act(H, W, cin)
+            self.add("dd_nchw_to_nhwc", L.ptr(self.x_in), L.ptr(x.t), self.dcode, B, cin, H, W)
+        skips: List[Act] = []
+        for i, (rb1, rb2, attn, down) in enumerate(unet.downs):
+            x = self._resnet(rb1, x, first=(i == 0))
+            x = self._resnet(rb2, x)
+            x = self._attn(attn, x)
+            skips.append(x)
+            if not isinstance(down, torch.nn.Identity):
+                x, _ = self.conv(x, down.conv, kind="down")
+        x = self._resnet(unet.mid_block1, x)
+        x = self._attn(unet.mid_attn, x)
+        x = self._resnet(unet.mid_block2, x)
+        for rb1, rb2, attn, up in unet.ups:
+            x = self._resnet(rb1, x, x2=skips.pop())        # concat-free: two K ranges (unet.py:97)
+            x = self._resnet(rb2, x)
+            x = self._attn(attn, x)
+            if not isinstance(up, torch.nn.Identity):
+                x, _ = self.conv(x, up.conv, kind="up")
+        blk, last = unet.final_conv[0], unet.final_conv[1]
+        h, st = self.conv(x, blk.block[0], kind="3x3", gn=blk.block[1])
+        h = self.gn_mish(h, st, blk.block[1])
+        self.conv(h, last, kind="1x1", out_nchw=self.eps_out)
+
+    # ---- execution -------------------------------------------------------------------------
+    def run(self) -> None:
+        """x_in -> eps_out with the currently bound time-bias rows.  Pure launch list (graph-capturable)."""
+        if self.stats_arena is not None:
+            L.call("dd_zero", self.stats_arena.data_ptr(), self.stats_arena.numel() * 4, L.stream())
+        self.run_ops()
+
+    def time_bias_rows(self, t_float: torch.Tensor, out: torch.Tensor) -> None:
+        w1, b1, w2, b2, wc, bc = self.tm
+        L.call("dd_time_bias", L.ptr(t_float), t_float.numel(), self.module.dim, L.ptr(self.freq), L.ptr(w1), L.ptr(b1),
+               L.ptr(w2), L.ptr(b2), L.ptr(wc), L.ptr(bc), self.J, L.ptr(out), L.stream())
+
+    def build_time_table(self, T: int) -> torch.Tensor:
+        """(T, J) fp32: every ResnetBlock's time bias for every step -- they depend on t only, so the
+        sampling chain looks them up instead of running the 18 Linear layers per step."""
+        self.refresh_weights()
+        tab = self.empty(T, self.J, dtype=torch.float32)
+        self.time_bias_rows(torch.arange(T, dtype=torch.float32, device=self.device), tab)
+        self.time_table = tab
+        return tab
+
+    def bind_table(self, table: torch.Tensor, trow: torch.Tensor, stride: int) -> None:
+        self.tb_rows, self.trow, self.trow_stride = table, trow, stride
+
+    def bind_batch_rows(self) -> None:
+        self.tb_rows, self.trow, self.trow_stride = self.tb_batch, None, 0
+
+    def forward(self, x: torch.Tensor, time: torch.Tensor) -> torch.Tensor:
+        """Unet.forward(x, time) semantics: per-sample `time`, returns a fresh (B,C,H,W) fp32 tensor."""
+        self.refresh_weights()
+        self.x_in.copy_(x)
+        self.t_float.copy_(time.to(torch.float32))
+        self.bind_batch_rows()
+        self.time_bias_rows(self.t_float, self.tb_batch)
+        self.run()
+        return self.eps_out.clone()

@@ -53,11 +53,12 @@ int dd_q_sample(const float* x, const float* eps, const int64_t* t,
  * coef: (T,5) fp32 rows {sqrt_recip_ac, sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2,
  * exp(0.5*post_logvar_clipped)}.  t_idx: int32 device array, sample b uses t_idx[b*t_stride]
  * (t_stride 0 = one shared step, the sampling loop).  noise_step_stride != 0 selects
- * noise + (T-1-t)*noise_step_stride, i.e. the pre-drawn chain noise of ddpm.py:223 for this step.
+ * noise + ((T-1-t) mod noise_period)*noise_step_stride (no mod when noise_period == 0), i.e. the pre-drawn
+ * chain noise of ddpm.py:223 for this step, held in a ring of noise_period steps.
  * clip != 0 applies clamp(-1,1) to x0 (ddpm.py:156-157). All NCHW fp32, (B, chw). */
 int dd_posterior_step(const float* x_t, const float* eps_hat, const float* noise,
                       const float* coef, const int32_t* t_idx, int t_stride,
-                      int64_t noise_step_stride, int T, int clip,
+                      int64_t noise_step_stride, int T, int noise_period, int clip,
                       float* x_out, int B, int64_t chw, void* stream);
 
 /* predict_x_from_eps alone (ddpm.py:149-158), per-sample int64 t (used by reconstruct / non-AE loss). */
@@ -171,10 +172,8 @@ int dd_conv_tc(int kind, const void* x, const void* x2, int C1, int C2,
                float* gn_stats, int G,
                int B, int H, int W, int Cout, void* stream);
 
-/* Pack OIHW fp32 weights into the K-major bf16 matrix dd_conv_tc expects.
- * kind as above; for DD_TC_UPT the source is ConvTranspose2d's (Cin, Cout, 4, 4).
- * cin_total = C1+C2; rows_out = padded row count (>= Cout, multiple of 16); for UPT rows_out is per phase. */
-int dd_pack_weights_tc(int kind, const float* w, void* wp, int Cout, int cin_total, int rows_out, void* stream);
+/* cudaMemsetAsync(ptr, 0, bytes): clears the GroupNorm {sum,sumsq} arena once per U-Net step. */
+int dd_zero(void* ptr, int64_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

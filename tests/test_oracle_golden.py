@@ -1,0 +1,148 @@
+"""Pins the CPU oracle (oracle/ddpm_oracle.py) against golden vectors produced by the real reference
+(oracle/make_golden.py).  CPU only; the GPU parity tests then use the oracle as their checker."""
+import numpy as np
+import pytest
+import torch
+
+import downsampled_diffusion_b200 as ours
+from oracle import ddpm_oracle as O
+from tests import common as tc
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def sd_of(cfg, kind, seed=0):
+    return {k: v.clone() for k, v in tc.build_model(cfg, ours, kind, seed).state_dict().items()}
+
+
+@pytest.mark.parametrize("sched", ["linear", "cosine"])
+def test_schedule_buffers_bit_exact(golden, sched):
+    buf = O.schedule_buffers(sched, 1000)
+    for k, v in buf.items():
+        assert torch.equal(v, T(golden[f"sched.{sched}.{k}"])), k
+    # the package's own schedule (host-side product code) must match to the bit as well
+    from downsampled_diffusion_b200.schedule import diffusion_buffers
+    for k, v in diffusion_buffers(sched, 1000).items():
+        assert torch.equal(v, T(golden[f"sched.{sched}.{k}"])), k
+
+
+def test_schedule_known_values():
+    buf = O.schedule_buffers("linear", 1000)
+    assert abs(float(buf["betas"][0]) - 1e-4) < 1e-10 and abs(float(buf["betas"][-1]) - 0.02) < 1e-8
+    assert buf["posterior_log_variance_clipped"][0] == buf["posterior_log_variance_clipped"][1]
+    assert float(buf["posterior_mean_coef1"][0]) == 1.0 and float(buf["posterior_mean_coef2"][0]) == 0.0
+    with pytest.raises(ValueError):
+        O.beta_schedule("quadratic", 10)
+
+
+@pytest.mark.parametrize("tag,cfg,hw,seed", [("c3", tc.C3, 32, 11), ("c1", tc.C1, 28, 12), ("cs", tc.CS, 8, 13),
+                                             ("c2", tc.C2, 16, 14)])
+def test_unet_eps(golden, tag, cfg, hw, seed):
+    sd = sd_of(cfg, "unet")
+    x = tc.randn(seed, 2, cfg["unet_in"], hw, hw)
+    for j, t in enumerate((torch.tensor([999, 0]), torch.tensor([500, 37]))):
+        with torch.no_grad():
+            eps = O.unet_forward(sd, cfg, x, t)
+        assert tc.rel_l2(eps, T(golden[f"unet.{tag}.eps{j}"])) < 2e-6
+
+
+def chain_noise(seed, shape, n):
+    torch.manual_seed(seed)
+    return [torch.randn(shape) for _ in range(n + 1)]
+
+
+def test_p_sample_and_chain_c1(golden):
+    cfg = dict(tc.C1, T=50)
+    sd = sd_of(cfg, "ddpm")
+    buf = O.schedule_buffers("linear", 50)
+    x = tc.randn(21, 2, 1, 28, 28)
+    t = torch.tensor([30, 0])
+    torch.manual_seed(22)
+    z = torch.randn(x.shape)
+    with torch.no_grad():
+        out = O.posterior_step(buf, x, t, O.unet_forward(sd, cfg, x, t, "latent_model."), z)
+        assert tc.max_abs(out, T(golden["p_sample.c1.out"])) < 1e-5
+        full = O.p_sample_loop(sd, cfg, buf, chain_noise(5, (2, 1, 28, 28), 50))
+        assert tc.max_abs(full, T(golden["chain.c1.x"])) < 2e-4
+        early = O.p_sample_loop(sd, cfg, buf, chain_noise(6, (2, 1, 28, 28), 10), t_end=40)
+        assert tc.max_abs(early, T(golden["chain.c1.early"])) < 2e-4
+
+
+def test_dddpm_chain_cs(golden):
+    cfg = dict(tc.CS, T=50)
+    sd = sd_of(cfg, "dddpm_ae")
+    buf = O.schedule_buffers("linear", 50)
+    with torch.no_grad():
+        x, z = O.dddpm_sample(sd, cfg, buf, chain_noise(5, (2, 8, 8, 8), 50))
+    assert tc.max_abs(z, T(golden["chain.cs.z"])) < 2e-4
+    assert tc.max_abs(x, T(golden["chain.cs.x"])) < 2e-4
+
+
+def test_resample_nets(golden):
+    sd = sd_of(tc.C2, "dddpm_ae")
+    x = tc.rand_pm1(31, 2, 3, 64, 64)
+    with torch.no_grad():
+        z = O.rescaled_downsample(sd, tc.C2, x)
+        xh = O.rescaled_upsample(sd, tc.C2, z)
+    assert tc.max_abs(z, T(golden["resample.c2.z"])) < 1e-5
+    assert tc.max_abs(xh, T(golden["resample.c2.xhat"])) < 1e-5
+
+
+def test_diffusion_arithmetic_bit_exact(golden):
+    buf = O.schedule_buffers("linear", 1000)
+    x, e = tc.randn(41, 4, 1, 28, 28), tc.randn(42, 4, 1, 28, 28)
+    t = torch.tensor([0, 1, 500, 999])
+    assert torch.equal(O.q_sample(buf, x, t, e), T(golden["ddpm.q_sample"]))
+    assert torch.equal(O.predict_x_from_eps(buf, x, t, e, True), T(golden["ddpm.predict_x0.clip"]))
+    assert torch.equal(O.predict_x_from_eps(buf, x, t, e, False), T(golden["ddpm.predict_x0.noclip"]))
+    mean, var, logvar = O.q_posterior(buf, e.clamp(-1, 1), x, t)
+    assert torch.equal(mean, T(golden["ddpm.q_posterior.mean"]))
+    assert torch.equal(var, T(golden["ddpm.q_posterior.var"]))
+    assert torch.equal(logvar, T(golden["ddpm.q_posterior.logvar"]))
+
+
+@pytest.mark.parametrize("kind", ["dddpm_ae", "dddpm"])
+def test_training_objective(golden, kind):
+    sd = sd_of(tc.CS, kind)
+    buf = O.schedule_buffers("linear", 1000)
+    x = tc.rand_pm1(51, 4, 3, 32, 32)
+    t = torch.tensor([3, 50, 99, 700])
+    torch.manual_seed(7)
+    eps = torch.randn(4, 8, 8, 8)
+    with torch.no_grad():
+        obj, d = O.dddpm_losses(sd, tc.CS, buf, x, t, eps, autoencoder=(kind == "dddpm_ae"))
+    assert abs(float(obj) - float(golden[f"loss.{kind}.obj"])) <= 2e-5 * abs(float(golden[f"loss.{kind}.obj"]))
+    assert abs(float(d["latent"]) - float(golden[f"loss.{kind}.latent"])) <= 2e-5 * abs(float(golden[f"loss.{kind}.latent"]))
+    assert abs(float(d["recon"]) - float(golden[f"loss.{kind}.recon"])) <= 2e-5 * abs(float(golden[f"loss.{kind}.recon"])) + 1e-7
+
+
+@pytest.mark.parametrize("lt,lf", [("vlb", "sum"), ("hybrid", "mean"), ("simple", "mean")])
+def test_ddpm_objective_variants(golden, lt, lf):
+    cfg = dict(tc.C1, loss_type=lt, loss_flat=lf)
+    sd = sd_of(cfg, "ddpm")
+    buf = O.schedule_buffers("linear", 1000)
+    x = tc.rand_pm1(52, 4, 1, 28, 28)
+    t = torch.tensor([0, 10, 400, 999])
+    torch.manual_seed(8)
+    eps = torch.randn(x.shape)
+    with torch.no_grad():
+        obj = O.ddpm_losses(sd, cfg, buf, x, t, eps)
+    ref = float(golden[f"loss.c1.{lt}.{lf}.obj"])
+    assert abs(float(obj) - ref) <= 2e-5 * abs(ref)
+
+
+def test_ema(golden):
+    net = tc.build_model(tc.CS, ours, "unet")
+    shadow = [p.detach().clone() for p in net.parameters()]
+    names = [n for n, _ in net.named_parameters()]
+    for k in range(3):
+        g = torch.Generator().manual_seed(60 + k)
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(0.01 * torch.randn(p.shape, generator=g))
+        shadow = O.ema_update(shadow, [p.detach() for p in net.parameters()], 0.995)
+    got = dict(zip(names, shadow))
+    for n in ("final_conv.1.weight", "downs.0.0.block1.block.0.bias", "mid_attn.fn.norm.g", "time_mlp.3.weight"):
+        assert torch.equal(got[n], T(golden[f"ema.{n}"])), n
