@@ -1,0 +1,92 @@
+"""Multi-GPU drivers: one process per GPU (torchrun), torch.distributed for the plumbing.
+
+Sampling: every sample's chain is independent, so the batch is sharded over ranks with
+NO communication during the T steps and one final gather.  To stay identical to the single-GPU result,
+rank r consumes rows [lo, hi) of the *global* pre-drawn noise tensor.
+Training: data-parallel replicas, one gradient all-reduce (mean) per optimizer step.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [lo, hi) slice of `total` items for `rank` (first total % world ranks get one more)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_noise(noise: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """noise: (n_steps+1, B_global, C, H, W) -> this rank's (n_steps+1, B_local, C, H, W) view."""
+    lo, hi = shard_range(noise.shape[1], rank, world)
+    return noise[:, lo:hi]
+
+
+def gather_batch(local: torch.Tensor, total: int, group=None) -> Optional[torch.Tensor]:
+    """Concatenate per-rank batches along dim 0 on every rank (all_gather; ragged shards are padded)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    rank = dist.get_rank(group)
+    sizes = [shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world)]
+    mx = max(sizes)
+    pad = local
+    if local.shape[0] < mx:
+        pad = torch.cat([local, local.new_zeros((mx - local.shape[0],) + tuple(local.shape[1:]))], 0)
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad.contiguous(), group=group)
+    return torch.cat([b[:n] for b, n in zip(bufs, sizes)], 0)
+
+
+def sample_sharded(model, total_batch: int, noise: Optional[torch.Tensor] = None, early_stop: int = None,
+                   gather: bool = True):
+    """`model.sample(total_batch)` with the batch sharded over the process group.
+
+    noise: optional GLOBAL pre-drawn chain noise (n_steps+1, total_batch, C, H, W), host or device.
+    Returns what model.sample returns (a tensor, or an (x, z) tuple for dDDPM) for the global batch when
+    `gather`, else for the local shard."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    lo, hi = shard_range(total_batch, rank, world)
+    local_noise = None if noise is None else noise[:, lo:hi]
+    out = model.sample(hi - lo, early_stop=early_stop, noise=local_noise)
+    if not gather or world == 1:
+        return out
+    if isinstance(out, tuple):
+        return tuple(gather_batch(o, total_batch) for o in out)
+    return gather_batch(out, total_batch)
+
+
+def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int = 64 << 20) -> None:
+    """DDP-style mean all-reduce of .grad over the default group, in flat fp32 buckets (NCCL over NVLink 5;
+    NVSwitch makes the cost bandwidth-bound, so buckets are sized for launch latency, not link count)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    world = dist.get_world_size()
+    bucket, size = [], 0
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        bucket, size = [], 0
+
+    for p in params:
+        if p.grad is None:
+            continue
+        bucket.append(p.grad)
+        size += p.grad.numel() * 4
+        if size >= bucket_bytes:
+            flush()
+    flush()

@@ -1,0 +1,283 @@
+"""Kernel-level parity on the B200: every C-ABI entry point against the CPU oracle / plain torch-CPU ops
+on the same seeded inputs.  Bit-exact where the arithmetic is op-for-op the reference's (posterior,
+q_sample, EMA); fp32 tolerance 1e-5 for reductions; bf16 tolerances stated per test."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ddpm_oracle as O
+from tests import common as tc
+
+pytestmark = pytest.mark.gpu
+
+
+def L():
+    from downsampled_diffusion_b200 import _lib
+    return _lib
+
+
+def nhwc(x, dtype):
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def from_nhwc(y):
+    return y.float().permute(0, 3, 1, 2).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_library_and_device(cuda):
+    lib = L().lib()
+    assert lib.dd_version() >= 100
+    assert lib.dd_device_ok() == 1, "not an sm_100 device"
+
+
+def test_q_sample_predict_x0_bit_exact(cuda, golden):
+    from downsampled_diffusion_b200 import ops
+    buf = {k: v.to(cuda) for k, v in O.schedule_buffers("linear", 1000).items()}
+    x, e = tc.randn(41, 4, 1, 28, 28).to(cuda), tc.randn(42, 4, 1, 28, 28).to(cuda)
+    t = torch.tensor([0, 1, 500, 999], device=cuda)
+    out = ops.q_sample_raw(x, e, t, buf["sqrt_alphas_cumprod"], buf["sqrt_one_minus_alphas_cumprod"])
+    assert torch.equal(out.cpu(), torch.from_numpy(golden["ddpm.q_sample"]))
+    for clip, key in ((True, "clip"), (False, "noclip")):
+        out = ops.predict_x0_raw(x, e, t, buf["sqrt_recip_alphas_cumprod"], buf["sqrt_recipm1_alphas_cumprod"], clip)
+        assert torch.equal(out.cpu(), torch.from_numpy(golden[f"ddpm.predict_x0.{key}"]))
+
+
+def test_posterior_step_bit_exact(cuda):
+    from downsampled_diffusion_b200 import ops
+    from downsampled_diffusion_b200.schedule import posterior_coef_table
+    bufc = O.schedule_buffers("linear", 1000)
+    coef = posterior_coef_table(bufc).to(cuda)
+    B, shape = 6, (6, 8, 16, 16)
+    x, e, z = tc.randn(1, *shape), tc.randn(2, *shape), tc.randn(3, *shape)
+    t = torch.tensor([0, 1, 2, 500, 998, 999])
+    ref = O.posterior_step(bufc, x, t, e, z)
+    out = ops.posterior_step_raw(x.to(cuda), e.to(cuda), z.to(cuda), coef, t.to(torch.int32).to(cuda), 1, 0, 1000, 0, True)
+    # exp(0.5*logvar) is tabulated on the host with the same torch op the oracle uses -> bit exact
+    assert torch.equal(out.cpu(), ref)
+    # shared-step form used inside the chain graph: t_stride 0, noise ring indexed by (T-1-t) % period
+    ring = torch.stack([tc.randn(10 + i, *shape) for i in range(4)]).to(cuda)
+    tdev = torch.tensor([997], dtype=torch.int32, device=cuda)
+    out = ops.posterior_step_raw(x.to(cuda), e.to(cuda), ring, coef, tdev, 0, x.numel(), 1000, 4, True)
+    ref = O.posterior_step(bufc, x, torch.full((B,), 997), e, ring[(1000 - 1 - 997) % 4].cpu())
+    assert torch.equal(out.cpu(), ref)
+    L().call("dd_tick", L().ptr(tdev), 1, L().stream())
+    assert int(tdev.item()) == 996
+
+
+@pytest.mark.parametrize("mean", [False, True])
+def test_mse_rows_and_backward(cuda, mean):
+    from downsampled_diffusion_b200 import ops
+    a, b = tc.randn(5, 5, 8, 32, 32), tc.randn(6, 5, 8, 32, 32)
+    ref = O.flatten_loss(F.mse_loss(a, b, reduction="none"), "mean" if mean else "sum")
+    out = ops.mse_rowsum_raw(a.to(cuda), b.to(cuda), mean)
+    assert tc.rel_l2(out, ref) < 1e-6
+    ag, bg = a.to(cuda).requires_grad_(), b.to(cuda).requires_grad_()
+    w = tc.randn(7, 5).to(cuda)
+    (ops.mse_rows(ag, bg, mean) * w).sum().backward()
+    ac, bc = a.clone().requires_grad_(), b.clone().requires_grad_()
+    (O.flatten_loss(F.mse_loss(ac, bc, reduction="none"), "mean" if mean else "sum") * w.cpu()).sum().backward()
+    assert tc.rel_l2(ag.grad, ac.grad) < 1e-6 and tc.rel_l2(bg.grad, bc.grad) < 1e-6
+
+
+def test_ema_update_bit_exact(cuda):
+    import downsampled_diffusion_b200 as dd
+    net = tc.build_model(tc.CS, dd, "unet").to(cuda)
+    ema = dd.EMA(net, decay=0.995)
+    shadow = [p.detach().cpu().clone() for p in net.parameters()]
+    for k in range(3):
+        g = torch.Generator().manual_seed(60 + k)
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_((0.01 * torch.randn(p.shape, generator=g)).to(cuda))
+        ema.update(net)
+        shadow = O.ema_update(shadow, [p.detach().cpu() for p in net.parameters()], 0.995)
+    for s, p in zip(shadow, ema.ema_model.parameters()):
+        assert torch.equal(s, p.detach().cpu())
+    # buffers are not averaged and the shadow stays a separate copy
+    assert all(a.data_ptr() != b.data_ptr() for a, b in zip(ema.ema_model.parameters(), net.parameters()))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 8e-3)])
+def test_gn_mish_layernorm(cuda, dtype, tol):
+    lib = L()
+    B, C, H, W, G = 3, 128, 16, 16, 8
+    x = tc.randn(1, B, C, H, W)
+    gamma, beta = tc.randn(2, C), tc.randn(3, C)
+    tb = tc.randn(4, 5, 3 * C)            # table with 5 rows, this block's columns start at C
+    trow = torch.tensor([4, 0, 2], dtype=torch.int32)
+    res = tc.randn(5, B, C, H, W)
+    xd = nhwc(x, dtype).to(cuda)
+    xr = from_nhwc(xd.cpu())              # what the kernel really sees (bf16-rounded in bf16 mode)
+    rd = nhwc(res, dtype).to(cuda)
+    ref = F.mish(F.group_norm(xr, G, gamma, beta, 1e-5)) + tb[trow.long(), C:2 * C][:, :, None, None] + from_nhwc(rd.cpu())
+    stats = torch.empty(B, G, 2, device=cuda)
+    lib.call("dd_gn_stats", lib.ptr(xd), lib.dtype_code(dtype), B, H * W, C, G, 1e-5, lib.ptr(stats), lib.stream())
+    y = torch.empty_like(xd)
+    tbd = tb.to(cuda)
+    lib.call("dd_gn_mish", lib.ptr(xd), lib.ptr(y), lib.dtype_code(dtype), B, H * W, C, G, lib.ptr(stats), 0, 1e-5,
+             lib.ptr(gamma.to(cuda)), lib.ptr(beta.to(cuda)), tbd.data_ptr() + 4 * C, 3 * C, lib.ptr(trow.to(cuda)), 1,
+             lib.ptr(rd), lib.stream())
+    assert tc.rel_l2(from_nhwc(y.cpu()), ref) < tol
+    # {sum, sumsq} statistics form (what the tcgen05 epilogue accumulates)
+    s = xr.reshape(B, G, -1).double()
+    st2 = torch.stack([s.sum(-1), (s * s).sum(-1)], -1).float().to(cuda).contiguous()
+    lib.call("dd_gn_mish", lib.ptr(xd), lib.ptr(y), lib.dtype_code(dtype), B, H * W, C, G, lib.ptr(st2), 1, 1e-5,
+             lib.ptr(gamma.to(cuda)), lib.ptr(beta.to(cuda)), None, 0, None, 0, None, lib.stream())
+    assert tc.rel_l2(from_nhwc(y.cpu()), F.mish(F.group_norm(xr, G, gamma, beta, 1e-5))) < max(tol, 2e-5)
+    # channel LayerNorm (eps added to the std)
+    g, b = tc.randn(6, 1, C, 1, 1), tc.randn(7, 1, C, 1, 1)
+    lib.call("dd_layernorm_c", lib.ptr(xd), lib.ptr(y), lib.dtype_code(dtype), B * H * W, C, lib.ptr(g.reshape(-1).to(cuda)),
+             lib.ptr(b.reshape(-1).to(cuda)), 1e-5, lib.stream())
+    assert tc.rel_l2(from_nhwc(y.cpu()), O.channel_layernorm(xr, g, b)) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 8e-3)])
+@pytest.mark.parametrize("n_side", [4, 32])
+def test_linear_attention_core(cuda, dtype, tol, n_side):
+    lib = L()
+    B, heads, dh = 2, 4, 32
+    qkv = tc.randn(9, B, 3 * heads * dh, n_side, n_side) * 1.5
+    qd = nhwc(qkv, dtype).to(cuda)
+    qr = from_nhwc(qd.cpu()).reshape(B, 3, heads, dh, n_side * n_side)
+    q, k, v = qr[:, 0], qr[:, 1], qr[:, 2]
+    ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(dim=-1), v)
+    ref = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(B, heads * dh, n_side, n_side)
+    out = torch.empty(B, n_side, n_side, heads * dh, dtype=dtype, device=cuda)
+    lib.call("dd_linattn_core", lib.ptr(qd), lib.ptr(out), lib.dtype_code(dtype), B, n_side * n_side, heads, dh, lib.stream())
+    assert tc.rel_l2(from_nhwc(out.cpu()), ref) < tol
+
+
+def test_time_bias(cuda):
+    import downsampled_diffusion_b200 as dd
+    net = tc.build_model(tc.CS, dd, "unet")
+    sd = net.state_dict()
+    eng_net = tc.build_model(tc.CS, dd, "unet").to(cuda)
+    eng = eng_net.engine(2, 8, 8, "fp32")
+    tab = eng.build_time_table(1000).cpu()
+    t = torch.tensor([0, 1, 37, 500, 999])
+    temb = O.time_mlp(sd, "", t, tc.CS["unet_chan"])
+    for rb_name in ("downs.0.0", "mid_block2", "ups.0.1"):
+        rb = dict(eng_net.named_modules())[rb_name]
+        col = eng.tb_off[id(rb)]
+        ref = F.linear(F.mish(temb), sd[rb_name + ".mlp.1.weight"], sd[rb_name + ".mlp.1.bias"])
+        got = tab[t][:, col:col + ref.shape[1]]
+        assert tc.max_abs(got, ref) < 2e-4, rb_name      # fp32 sin/cos of arguments up to 999 rad
+
+
+CONV_CASES = [
+    # kind, Cin, Cin2, Cout, H, W, B
+    ("3x3", 128, 0, 128, 32, 32, 2),
+    ("3x3", 256, 256, 256, 8, 8, 3),      # concat-free two-source, 2 images per M tile (+ a ragged tile)
+    ("3x3", 64, 0, 64, 4, 4, 5),          # 8 images per tile, ragged batch, 8 channels per GN group
+    ("1x1", 256, 0, 384, 16, 16, 2),
+    ("1x1", 128, 0, 256, 2, 2, 3),
+    ("down", 128, 0, 128, 32, 32, 2),
+    ("down", 256, 0, 256, 8, 8, 2),
+    ("up", 256, 0, 256, 4, 4, 2),
+    ("up", 128, 0, 128, 16, 16, 2),
+]
+
+
+@pytest.mark.parametrize("kind,C1,C2,Cout,H,W,B", CONV_CASES)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv_paths(cuda, kind, C1, C2, Cout, H, W, B, precision):
+    """dd_conv_direct (fp32) and dd_conv_tc (tcgen05, bf16) against F.conv2d / F.conv_transpose2d on CPU,
+    including bias, residual add and the GroupNorm {sum,sumsq} epilogue."""
+    from downsampled_diffusion_b200.engine import Act, Program, ensure_lazy
+    torch.manual_seed(0)
+    Cin = C1 + C2
+    if kind == "up":
+        conv = torch.nn.ConvTranspose2d(Cin, Cout, 4, 2, 1)
+    elif kind == "down":
+        conv = torch.nn.Conv2d(Cin, Cout, 3, 2, 1)
+    elif kind == "3x3":
+        conv = torch.nn.Conv2d(Cin, Cout, 3, 1, 1)
+    else:
+        conv = torch.nn.Conv2d(Cin, Cout, 1)
+    gn = torch.nn.GroupNorm(8, Cout) if kind == "3x3" else None
+    holder = torch.nn.ModuleList([conv] + ([gn] if gn else [])).to(cuda)
+    ensure_lazy()
+    prog = Program(holder, B, precision)
+    dt = prog.adt
+    x = tc.randn(1, B, C1, H, W)
+    x2 = tc.randn(2, B, C2, H, W) if C2 else None
+    xa = Act(nhwc(x, dt).to(cuda), B, H, W, C1)
+    x2a = Act(nhwc(x2, dt).to(cuda), B, H, W, C2) if C2 else None
+    Ho, Wo = (H // 2, W // 2) if kind == "down" else ((2 * H, 2 * W) if kind == "up" else (H, W))
+    res = tc.randn(3, B, Cout, Ho, Wo) if kind == "1x1" else None
+    resa = Act(nhwc(res, dt).to(cuda), B, Ho, Wo, Cout) if res is not None else None
+    y, stats = prog.conv(xa, conv, x2=x2a, kind=kind, gn=gn, residual=resa)
+    prog.finalize_arena()
+    prog.refresh_weights()
+    prog.run_ops()
+    torch.cuda.synchronize()
+    # reference on the operands the kernel really consumed
+    xin = from_nhwc(xa.t.cpu())
+    if C2:
+        xin = torch.cat((xin, from_nhwc(x2a.t.cpu())), 1)
+    w = conv.weight.detach().cpu()
+    if precision == "bf16":
+        w = w.bfloat16().float()
+    bias = conv.bias.detach().cpu()
+    if kind == "up":
+        ref = F.conv_transpose2d(xin, w, bias, stride=2, padding=1)
+    else:
+        ref = F.conv2d(xin, w, bias, stride=2 if kind == "down" else 1, padding=0 if kind == "1x1" else 1)
+    pre = ref.clone()
+    if res is not None:
+        ref = ref + from_nhwc(resa.t.cpu())
+    tol = 1e-5 if precision == "fp32" else 6e-3          # bf16: output rounding 2^-9 relative
+    assert tc.rel_l2(from_nhwc(y.t.cpu()), ref) < tol
+    if gn is not None:
+        st, mode = stats
+        if mode == 1:        # {sum, sumsq} of the fp32 accumulator (+bias)
+            arena = prog.stats_arena.cpu().reshape(B, 8, 2)
+            g = pre.reshape(B, 8, -1).double()
+            assert tc.rel_l2(arena[..., 0], g.sum(-1)) < 1e-3 + 1e-2 * (precision == "bf16")
+            assert tc.rel_l2(arena[..., 1], (g * g).sum(-1)) < 1e-4
+        else:
+            g = from_nhwc(y.t.cpu()).reshape(B, 8, -1).double()
+            assert tc.max_abs(st.cpu()[..., 0], g.mean(-1)) < 1e-5
+            assert tc.rel_l2(st.cpu()[..., 1], 1.0 / (g.var(-1, unbiased=False) + 1e-5).sqrt()) < 1e-5
+
+
+def test_conv_tc_rejects_unsupported(cuda):
+    lib = L()
+    x = torch.zeros(1, 28, 28, 64, dtype=torch.bfloat16, device=cuda)
+    w = torch.zeros(64, 9 * 64, dtype=torch.bfloat16, device=cuda)
+    y = torch.zeros(1, 28, 28, 64, dtype=torch.bfloat16, device=cuda)
+    with pytest.raises(RuntimeError, match="powers of two"):
+        lib.call("dd_conv_tc", lib.TC_CONV3x3, lib.ptr(x), None, 64, 0, lib.ptr(w), 64, None, None, lib.ptr(y), 0, 0, None, 0,
+                 1, 28, 28, 64, lib.stream())
+
+
+def test_layout_kernels(cuda):
+    lib = L()
+    x = tc.randn(1, 3, 8, 16, 16).to(cuda)
+    for dt in (torch.float32, torch.bfloat16):
+        y = torch.empty(3, 16, 16, 8, dtype=dt, device=cuda)
+        lib.call("dd_nchw_to_nhwc", lib.ptr(x), lib.ptr(y), lib.dtype_code(dt), 3, 8, 16, 16, lib.stream())
+        assert torch.equal(y, x.permute(0, 2, 3, 1).to(dt))
+        back = torch.empty_like(x)
+        lib.call("dd_nhwc_to_nchw", lib.ptr(y), lib.dtype_code(dt), lib.ptr(back), 3, 8, 16, 16, lib.stream())
+        assert torch.equal(back, y.float().permute(0, 3, 1, 2))
+        yc = torch.randn(2, 8, 8, 64, device=cuda).to(dt)
+        p = torch.empty(2, 4, 4, 64, dtype=dt, device=cuda)
+        lib.call("dd_avgpool2", lib.ptr(yc), lib.ptr(p), lib.dtype_code(dt), 2, 8, 8, 64, lib.stream())
+        ref = F.avg_pool2d(yc.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+        assert tc.max_abs(p.float(), ref) < (1e-6 if dt == torch.float32 else 2e-2)
+        u = torch.empty(2, 16, 16, 64, dtype=dt, device=cuda)
+        lib.call("dd_upsample_nearest2", lib.ptr(yc), lib.ptr(u), lib.dtype_code(dt), 2, 8, 8, 64, lib.stream())
+        assert torch.equal(u, F.interpolate(yc.float().permute(0, 3, 1, 2), scale_factor=2).permute(0, 2, 3, 1).to(dt))
+    col = torch.empty(3 * 16 * 16, 128, dtype=torch.bfloat16, device=cuda)
+    lib.call("dd_im2col3x3_nchw", lib.ptr(x), lib.ptr(col), 3, 8, 16, 16, 128, lib.stream())
+    ref = F.unfold(x, 3, padding=1).reshape(3, 8, 9, 256).permute(0, 3, 2, 1).reshape(3 * 256, 72)   # (pixel, tap, c)
+    assert torch.equal(col[:, :72], ref.to(torch.bfloat16)) and float(col[:, 72:].abs().max()) == 0.0
+    xb = torch.randn(2, 8, 8, 64, device=cuda).to(torch.bfloat16)
+    pl = torch.empty(4, 2, 4, 4, 64, dtype=torch.bfloat16, device=cuda)
+    lib.call("dd_space_to_depth2", lib.ptr(xb), lib.ptr(pl), 2, 8, 8, 64, lib.stream())
+    for py in range(2):
+        for px in range(2):
+            assert torch.equal(pl[py * 2 + px], xb[:, py::2, px::2])
