@@ -13,6 +13,7 @@ precision 'fp32': NHWC fp32 activations, CUDA-core direct convs (dd_conv_direct)
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -62,6 +63,7 @@ class Program:
         self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
         self.dcode = L.dtype_code(self.adt)
         self.ops: List[Callable[[], None]] = []
+        self.op_names: List[str] = []
         self.keep: List[torch.Tensor] = []          # packed weights etc. referenced by raw pointer
         self.packers: List[Callable[[], None]] = [] # re-run when the module's parameters change
         self.weights_version = None
@@ -71,7 +73,10 @@ class Program:
 
     # ---- helpers ---------------------------------------------------------------------------
     def empty(self, *shape, dtype=None) -> torch.Tensor:
-        return torch.empty(*shape, dtype=dtype or self.adt, device=self.device)
+        # launches hold raw pointers: every program buffer must stay alive as long as the program does
+        t = torch.empty(*shape, dtype=dtype or self.adt, device=self.device)
+        self.keep.append(t)
+        return t
 
     def act(self, H: int, W: int, C: int, B: int = None) -> Act:
         B = B or self.B
@@ -102,6 +107,7 @@ class Program:
 
     def add(self, name: str, *args) -> None:
         fn = getattr(L.lib(), name)
+        self.op_names.append(name)
 
         def op():
             L._Counter.n += 1
@@ -111,6 +117,14 @@ class Program:
         self.ops.append(op)
 
     def run_ops(self) -> None:
+        if os.environ.get("DD_DEBUG"):
+            for i, op in enumerate(self.ops):        # synchronise after every launch to localise a fault
+                op()
+                try:
+                    torch.cuda.synchronize()
+                except Exception as e:               # noqa: BLE001
+                    raise RuntimeError(f"op {i} ({self.op_names[i]}) faulted: {e}") from e
+            return
         for op in self.ops:
             op()
 

@@ -115,21 +115,22 @@ def test_gn_mish_layernorm(cuda, dtype, tol):
     stats = torch.empty(B, G, 2, device=cuda)
     lib.call("dd_gn_stats", lib.ptr(xd), lib.dtype_code(dtype), B, H * W, C, G, 1e-5, lib.ptr(stats), lib.stream())
     y = torch.empty_like(xd)
-    tbd = tb.to(cuda)
+    tbd, gd, bd, trd = tb.to(cuda), gamma.to(cuda), beta.to(cuda), trow.to(cuda)     # keep device copies alive
     lib.call("dd_gn_mish", lib.ptr(xd), lib.ptr(y), lib.dtype_code(dtype), B, H * W, C, G, lib.ptr(stats), 0, 1e-5,
-             lib.ptr(gamma.to(cuda)), lib.ptr(beta.to(cuda)), tbd.data_ptr() + 4 * C, 3 * C, lib.ptr(trow.to(cuda)), 1,
+             lib.ptr(gd), lib.ptr(bd), tbd.data_ptr() + 4 * C, 3 * C, lib.ptr(trd), 1,
              lib.ptr(rd), lib.stream())
     assert tc.rel_l2(from_nhwc(y.cpu()), ref) < tol
     # {sum, sumsq} statistics form (what the tcgen05 epilogue accumulates)
     s = xr.reshape(B, G, -1).double()
     st2 = torch.stack([s.sum(-1), (s * s).sum(-1)], -1).float().to(cuda).contiguous()
     lib.call("dd_gn_mish", lib.ptr(xd), lib.ptr(y), lib.dtype_code(dtype), B, H * W, C, G, lib.ptr(st2), 1, 1e-5,
-             lib.ptr(gamma.to(cuda)), lib.ptr(beta.to(cuda)), None, 0, None, 0, None, lib.stream())
+             lib.ptr(gd), lib.ptr(bd), None, 0, None, 0, None, lib.stream())
     assert tc.rel_l2(from_nhwc(y.cpu()), F.mish(F.group_norm(xr, G, gamma, beta, 1e-5))) < max(tol, 2e-5)
     # channel LayerNorm (eps added to the std)
     g, b = tc.randn(6, 1, C, 1, 1), tc.randn(7, 1, C, 1, 1)
-    lib.call("dd_layernorm_c", lib.ptr(xd), lib.ptr(y), lib.dtype_code(dtype), B * H * W, C, lib.ptr(g.reshape(-1).to(cuda)),
-             lib.ptr(b.reshape(-1).to(cuda)), 1e-5, lib.stream())
+    g_d, b_d = g.reshape(-1).to(cuda), b.reshape(-1).to(cuda)
+    lib.call("dd_layernorm_c", lib.ptr(xd), lib.ptr(y), lib.dtype_code(dtype), B * H * W, C, lib.ptr(g_d), lib.ptr(b_d),
+             1e-5, lib.stream())
     assert tc.rel_l2(from_nhwc(y.cpu()), O.channel_layernorm(xr, g, b)) < tol
 
 
