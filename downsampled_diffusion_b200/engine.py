@@ -64,6 +64,7 @@ class Program:
         self.dcode = L.dtype_code(self.adt)
         self.ops: List[Callable[[], None]] = []
         self.op_names: List[str] = []
+        self.conv_tc_flops: List[float] = []        # algorithmic 2*M*N*K of every dd_conv_tc launch, in order
         self.keep: List[torch.Tensor] = []          # packed weights etc. referenced by raw pointer
         self.packers: List[Callable[[], None]] = [] # re-run when the module's parameters change
         self.weights_version = None
@@ -197,6 +198,8 @@ class Program:
                 G = gn.num_groups
                 stats = (self._new_stats_slot(B, G), 1)
                 st_ptr = stats[0]
+            taps = {"3x3": 9, "down": 9, "1x1": 1, "up": 4}[kind]
+            self.conv_tc_flops.append(2.0 * B * Ho * Wo * Cout * taps * Cin)
             self.add("dd_conv_tc", kcode, L.ptr(src), L.ptr(src2) if src2 is not None else None, x.C,
                      x2.C if x2 is not None else 0, L.ptr(wp), wp.shape[0], L.ptr(b_t) if b_t is not None else None,
                      L.ptr(residual.t) if residual is not None else None,
@@ -409,6 +412,7 @@ class UnetEngine(Program):
             G = gn.num_groups
             stats = (self._new_stats_slot(x.B, G), 1)
             st_ptr = stats[0]
+        self.conv_tc_flops.append(2.0 * x.B * x.H * x.W * Cout * Cin * (1 if center_only else 9))
         self.add("dd_conv_tc", L.TC_CONV1x1, L.ptr(x.t), None, kpad, 0, L.ptr(wp), Cout, L.ptr(b_t), None, L.ptr(y.t),
                  0, 0, st_ptr, G, x.B, x.H, x.W, Cout)
         return y, stats
