@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libddb200.so")
 DD_F32, DD_BF16 = 0, 1
 CONV_PRE_MISH, CONV_TANH, CONV_OUT_NCHW, CONV_IN_NCHW = 1, 2, 4, 8
 TC_CONV3x3, TC_CONV1x1, TC_DOWN, TC_UPT = 0, 1, 2, 3
+TC_W_PER_SAMPLE = 1
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -36,15 +37,16 @@ SIGNATURES = {
     "dd_gn_stats": [_p, _i, _i, _i, _i, _i, _f, _p, _p],
     "dd_gn_mish": [_p, _p, _i, _i, _i, _i, _i, _p, _i, _f, _p, _p, _p, _i, _p, _i, _p, _p],
     "dd_layernorm_c": [_p, _p, _i, _i64, _i, _p, _p, _f, _p],
-    "dd_linattn_core": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "dd_linattn_core": [_p, _p, _i, _i, _i, _i, _i, _p, _i64, _p],
+    "dd_linattn_mix": [_p, _i, _i, _i, _i, _i, _p, _i64, _p, _i, _p, _p],
     "dd_conv_direct": [_p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "dd_avgpool2": [_p, _p, _i, _i, _i, _i, _i, _p],
     "dd_upsample_nearest2": [_p, _p, _i, _i, _i, _i, _i, _p],
     "dd_space_to_depth2": [_p, _p, _i, _i, _i, _i, _p],
     "dd_zero": [_p, _i64, _p],
-    "dd_conv_tc": [_i, _p, _p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _p],
+    "dd_conv_tc": [_i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i64, _p, _i, _p],
 }
-PLAIN = {"dd_version": (C.c_int, []), "dd_device_ok": (C.c_int, []), "dd_last_error": (C.c_char_p, [])}
+PLAIN = {"dd_linattn_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_version": (C.c_int, []), "dd_device_ok": (C.c_int, []), "dd_last_error": (C.c_char_p, [])}
 
 _lib: Optional[C.CDLL] = None
 

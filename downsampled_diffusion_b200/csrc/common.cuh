@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "../../include/ddb200.h"
 
 namespace dd {
@@ -27,6 +28,16 @@ __device__ __forceinline__ float mish_f(float x) {
     float n = e * (e + 2.f);
     return x * (n / (n + 2.f));
 }
+
+// fast variant for the bf16 path: ex2/rcp approximations (rel. error ~1e-6, far below bf16 rounding)
+__device__ __forceinline__ float mish_fast(float x) {
+    const float e = __expf(fminf(x, 20.f));
+    const float n = e * (e + 2.f);
+    return x * __fdividef(n, n + 2.f);
+}
+template <typename T> __device__ __forceinline__ float mish_t(float x);
+template <> __device__ __forceinline__ float mish_t<float>(float x) { return mish_f(x); }
+template <> __device__ __forceinline__ float mish_t<__nv_bfloat16>(float x) { return mish_fast(x); }
 
 // d/dx mish(x) = tanh(sp) + x * sigmoid(x) * (1 - tanh(sp)^2)
 __device__ __forceinline__ float mish_grad_f(float x) {
@@ -86,6 +97,33 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every kernel of the library starts with pdl_sync(): wait until the preceding kernel in the stream has
+// completed and flushed its writes, then allow the NEXT kernel to be scheduled.  Launched through
+// launch_pdl(), a kernel's launch latency and prologue (barrier init, TMEM allocation, descriptor
+// prefetch) overlap the tail of its predecessor; inside a captured graph the edges become programmatic
+// dependencies.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+    static const bool on = getenv("DD_NO_PDL") == nullptr;
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 inline int num_sms() {

@@ -45,6 +45,7 @@ __device__ __forceinline__ float conv_fetch(const ConvDirectArgs& a, int b, int 
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) conv_direct_kernel(const ConvDirectArgs a) {
+    pdl_sync();
     constexpr int TM = 64, TN = 64, TK = 16;
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN + 4];
@@ -156,10 +157,10 @@ extern "C" int dd_conv_direct(const void* x, const void* x2, int C1, int C2, int
     dim3 grid((unsigned)((a.M + 63) / 64), (unsigned)((Cout + 63) / 64));
     cudaStream_t st = (cudaStream_t)stream;
     const int odt = (flags & DD_CONV_OUT_NCHW) ? DD_F32 : out_dtype;
-    if (in_dtype == DD_F32 && odt == DD_F32) conv_direct_kernel<float, float><<<grid, 256, 0, st>>>(a);
-    else if (in_dtype == DD_BF16 && odt == DD_BF16) conv_direct_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(a);
-    else if (in_dtype == DD_BF16 && odt == DD_F32) conv_direct_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(a);
-    else if (in_dtype == DD_F32 && odt == DD_BF16) conv_direct_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(a);
+    if (in_dtype == DD_F32 && odt == DD_F32) launch_pdl(conv_direct_kernel<float, float>, dim3(grid), dim3(256), 0, st, a);
+    else if (in_dtype == DD_BF16 && odt == DD_BF16) launch_pdl(conv_direct_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, a);
+    else if (in_dtype == DD_BF16 && odt == DD_F32) launch_pdl(conv_direct_kernel<__nv_bfloat16, float>, dim3(grid), dim3(256), 0, st, a);
+    else if (in_dtype == DD_F32 && odt == DD_BF16) launch_pdl(conv_direct_kernel<float, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, a);
     else { dd::set_error("conv_direct: bad dtypes %d/%d", in_dtype, out_dtype); return DD_ERR_ARG; }
     return check_launch("conv_direct");
 }

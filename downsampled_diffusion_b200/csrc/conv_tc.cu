@@ -16,17 +16,20 @@
 // other's main loop.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace dd {
 
-constexpr int TC_STAGES = 3;
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 16 KB
-constexpr int TC_B_BYTES = 128 * TC_BK * 2;          // 16 KB slot (bn <= 128)
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 192;
+// Pipeline variants <STAGES, BROWS>: BROWS = rows of the weight slot (>= bn).
+//   <3,128>: 96 KB  -> 2 CTAs/SM, for grids that fill the GPU (epilogue of one CTA overlaps the other's loop)
+//   <6,128>: 192 KB -> 1 CTA/SM, grids of at most one wave: twice the loads in flight per CTA
+//   <8, 64>: 192 KB -> 1 CTA/SM, low-resolution layers run with bn = 64 (twice the CTAs) and 8 stages
+constexpr int tc_stage_bytes(int brows) { return TC_A_BYTES + brows * TC_BK * 2; }
+constexpr int tc_smem_bytes(int stages, int brows) { return stages * tc_stage_bytes(brows) + 1024 /*align*/ + 1024 /*barriers + bias*/; }
 constexpr int TC_TMEM_COLS = 128;
 
 struct TcParams {
@@ -40,10 +43,15 @@ struct TcParams {
     int out_mul;            // 1, or 2 for the sub-pixel phases of the transposed conv
     int out_nchw_f32;
     int G, cpg_mask, cpg_shift;
+    int rows_valid;             // tw*th*tn (< 128 when one image has fewer than 128 pixels and tn is forced to 1)
+    int w_per_sample;           // weights are (B, rows, K): every image multiplies its own matrix (fused attention output)
+    int splits, kb_per_split;   // split-K over the (tap, chunk) loop; partial sums meet in splitk_ws
     void* out;
     const float* bias;
     const __nv_bfloat16* residual;
     float* gn_stats;
+    float* splitk_ws;           // (tiles, bn/4, 128, 4) fp32, all zero between launches (self-cleaning)
+    int32_t* splitk_cnt;        // per-tile arrival counters, all zero between launches
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -85,6 +93,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar,
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -111,8 +125,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ TcParams p) {
+template <int TC_STAGES, int BROWS>
+__global__ void __launch_bounds__(TC_THREADS, (TC_STAGES <= 3 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    constexpr int TC_STAGE_BYTES = tc_stage_bytes(BROWS);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;     // full[S], empty[S], tmem_full, tmem_ptr
@@ -123,12 +152,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, n_tile = blockIdx.y, phase = blockIdx.z;
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+    const int phase = p.splits > 1 ? 0 : blockIdx.z;
+    const int split = p.splits > 1 ? blockIdx.z : 0;
     const int w0 = (m_tile % p.tiles_w) * p.tw;
     const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
     const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn;
     const int cpt = p.chunks0 + p.chunks1;
-    const int num_kb = p.ntaps * cpt;
+    const int kb_lo = split * p.kb_per_split;
+    const int num_kb = min(p.ntaps * cpt, kb_lo + p.kb_per_split) - kb_lo;     // k-blocks of this CTA
+    float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));   // 128 floats (barriers use < 160 B)
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA0)) : "memory");
@@ -146,15 +179,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    pdl_sync();      // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const uint32_t stage_tx = TC_A_BYTES + (uint32_t)p.bn * TC_BK * 2;
+            const uint32_t stage_tx = (uint32_t)(p.rows_valid + p.bn) * TC_BK * 2;   // bytes the two TMA boxes deliver
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % TC_STAGES;
                 if (kb >= TC_STAGES) mbar_wait(empty_bar(s), ((kb / TC_STAGES) - 1) & 1);
-                const int tap = kb / cpt, rem = kb - tap * cpt;
+                const int kg = kb_lo + kb;                       // global k-block index
+                const int tap = kg / cpt, rem = kg - tap * cpt;
                 const int ti = phase * p.ntaps + tap;
                 const uint32_t sA = base + s * TC_STAGE_BYTES, sB = sA + TC_A_BYTES;
                 mbar_expect_tx(full_bar(s), stage_tx);
@@ -162,7 +197,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
                     tma_load_5d(&p.tmA0, full_bar(s), sA, rem * 64, w0 + p.tap_dw[ti], h0 + p.tap_dh[ti], n0, p.tap_plane[ti]);
                 else
                     tma_load_5d(&p.tmA1, full_bar(s), sA, (rem - p.chunks0) * 64, w0 + p.tap_dw[ti], h0 + p.tap_dh[ti], n0, p.tap_plane[ti]);
-                tma_load_2d(&p.tmB, full_bar(s), sB, kb * 64, phase * p.rows_per_phase + n_tile * p.bn);
+                if (p.w_per_sample) tma_load_3d(&p.tmB, full_bar(s), sB, kg * 64, n_tile * p.bn, n0);
+                else tma_load_2d(&p.tmB, full_bar(s), sB, kg * 64, phase * p.rows_per_phase + n_tile * p.bn);
             }
         }
     } else if (warp == 1) {
@@ -189,82 +225,137 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
         const int r = q * 32 + lane;
         const int ww = r % p.tw, hh = (r / p.tw) % p.th, nl = r / (p.tw * p.th);
         const int n = n0 + nl;
-        const bool valid = n < p.B;
+        const bool valid = n < p.B && r < p.rows_valid;
         const int mul = p.out_mul;
         const int Ho = p.H * mul, Wo = p.W * mul;
         const int oh = (h0 + hh) * mul + (phase >> 1), ow = (w0 + ww) * mul + (phase & 1);
         const int64_t pix = ((int64_t)n * Ho + oh) * Wo + ow;
         const int cbase = n_tile * p.bn;
         const int seg = min(32, p.tw * p.th);       // lanes of this warp that share a sample
+        const int et = threadIdx.x - 64;            // 0..127
+        if (et < p.bn) s_bias[et] = (p.bias && cbase + et < p.Cout) ? p.bias[cbase + et] : 0.f;
+        const bool use_res = p.residual != nullptr && valid && !p.out_nchw_f32;
+        const uint4* res_ptr = reinterpret_cast<const uint4*>(p.residual + (use_res ? pix * p.Cout + cbase : 0));
+        uint4 res_cur[2], res_nxt[2];
+        if (use_res) { res_cur[0] = res_ptr[0]; res_cur[1] = res_ptr[1]; }
+        epi_bar();
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        float gs = 0.f, gq = 0.f;
-        for (int ch = 0; ch < p.bn; ch += 16) {
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+
+        bool finisher = true;
+        float* wst = nullptr;
+        if (p.splits > 1) {
+            // ---- split-K: add this CTA's partial tile into the fp32 workspace, last arrival finishes ----
+            const int tile_id = m_tile * gridDim.y + n_tile;
+            wst = p.splitk_ws + (int64_t)tile_id * TC_BM * p.bn;
             uint32_t acc[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ch, acc);
-            float v[16];
-            const int c0 = cbase + ch;
+            for (int ch = 0; ch < p.bn; ch += 16) {
+                tmem_ld16_issue(trow + (uint32_t)ch, acc);
+                tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                v[j] = __uint_as_float(acc[j]);
-                if (p.bias && c0 + j < p.Cout) v[j] += p.bias[c0 + j];
+                for (int k4 = 0; k4 < 4; ++k4)
+                    red_add_v4(wst + ((int64_t)((ch >> 2) + k4) * TC_BM + r) * 4, __uint_as_float(acc[4 * k4]),
+                               __uint_as_float(acc[4 * k4 + 1]), __uint_as_float(acc[4 * k4 + 2]), __uint_as_float(acc[4 * k4 + 3]));
             }
-            if (p.gn_stats) {
+            __threadfence();
+            epi_bar();
+            int* s_flag = reinterpret_cast<int*>(s_bias + 128);
+            if (et == 0) {
+                const int ticket = atomicAdd(p.splitk_cnt + tile_id, 1);
+                const int last = (ticket == p.splits - 1);
+                if (last) p.splitk_cnt[tile_id] = 0;                 // self-cleaning for the next launch
+                *s_flag = last;
+            }
+            epi_bar();
+            finisher = (*s_flag != 0);
+            if (finisher) __threadfence();
+        }
+
+        if (finisher) {
+            float gs = 0.f, gq = 0.f;
+            uint32_t acc[16], nxt[16];
+            if (p.splits == 1) { tmem_ld16_issue(trow, acc); tmem_ld_wait(); }
+            for (int ch = 0; ch < p.bn; ch += 16) {
+                const bool more = ch + 16 < p.bn;
+                float v[16];
+                if (p.splits > 1) {
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    float s8 = 0.f, q8 = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { const float t = v[hf * 8 + j]; s8 += t; q8 += t * t; }
-                    if (valid) { gs += s8; gq += q8; }
-                    const int c_end = c0 + hf * 8 + 8;
-                    if ((c_end & p.cpg_mask) == 0) {           // warp-uniform
-                        float a = gs, b = gq;
-                        for (int o = 1; o < seg; o <<= 1) {
-                            a += __shfl_xor_sync(0xffffffffu, a, o);
-                            b += __shfl_xor_sync(0xffffffffu, b, o);
-                        }
-                        if (valid && (lane & (seg - 1)) == 0) {
-                            const int g = (c_end >> p.cpg_shift) - 1;
-                            float* st = p.gn_stats + ((int64_t)n * p.G + g) * 2;
-                            atomicAdd(st, a);
-                            atomicAdd(st + 1, b);
-                        }
-                        gs = 0.f; gq = 0.f;
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        float4* wp4 = reinterpret_cast<float4*>(wst + ((int64_t)((ch >> 2) + k4) * TC_BM + r) * 4);
+                        const float4 t = __ldcg(wp4);
+                        *wp4 = make_float4(0.f, 0.f, 0.f, 0.f);      // leave the workspace zeroed
+                        v[4 * k4] = t.x; v[4 * k4 + 1] = t.y; v[4 * k4 + 2] = t.z; v[4 * k4 + 3] = t.w;
                     }
+                } else {
+                    if (more) tmem_ld16_issue(trow + (uint32_t)(ch + 16), nxt);      // overlaps the math below
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
                 }
-            }
-            if (valid) {
-                if (p.out_nchw_f32) {
-                    float* o = reinterpret_cast<float*>(p.out);
-                    const int64_t hw = (int64_t)Ho * Wo;
+                if (use_res && more) { res_nxt[0] = res_ptr[(ch >> 3) + 2]; res_nxt[1] = res_ptr[(ch >> 3) + 3]; }
+                const int c0 = cbase + ch;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < p.cout_valid) o[((int64_t)n * p.cout_valid + c0 + j) * hw + (int64_t)oh * Wo + ow] = v[j];
-                } else if (c0 < p.Cout) {
-                    const int64_t off = pix * p.Cout + c0;
-                    if (p.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
-#pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            const uint4 rv = rp[hf];
-                            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 f = __bfloat1622float2(rh[j]);
-                                v[hf * 8 + 2 * j] += f.x; v[hf * 8 + 2 * j + 1] += f.y;
-                            }
-                        }
-                    }
-                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+                for (int j = 0; j < 16; ++j) v[j] += s_bias[ch + j];
+                if (p.gn_stats) {
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
-                        uint4 ov;
-                        __nv_bfloat162* oh2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+                        float s8 = 0.f, q8 = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) oh2[j] = __floats2bfloat162_rn(v[hf * 8 + 2 * j], v[hf * 8 + 2 * j + 1]);
-                        op[hf] = ov;
+                        for (int j = 0; j < 8; ++j) { const float t = v[hf * 8 + j]; s8 += t; q8 += t * t; }
+                        if (valid) { gs += s8; gq += q8; }
+                        const int c_end = c0 + hf * 8 + 8;
+                        if ((c_end & p.cpg_mask) == 0) {           // warp-uniform
+                            float a = gs, b = gq;
+                            for (int o = 1; o < seg; o <<= 1) {
+                                a += __shfl_xor_sync(0xffffffffu, a, o);
+                                b += __shfl_xor_sync(0xffffffffu, b, o);
+                            }
+                            if (valid && (lane & (seg - 1)) == 0) {
+                                const int g = (c_end >> p.cpg_shift) - 1;
+                                float* st = p.gn_stats + ((int64_t)n * p.G + g) * 2;
+                                atomicAdd(st, a);
+                                atomicAdd(st + 1, b);
+                            }
+                            gs = 0.f; gq = 0.f;
+                        }
                     }
                 }
+                if (valid) {
+                    if (p.out_nchw_f32) {
+                        float* o = reinterpret_cast<float*>(p.out);
+                        const int64_t hw = (int64_t)Ho * Wo;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < p.cout_valid) o[((int64_t)n * p.cout_valid + c0 + j) * hw + (int64_t)oh * Wo + ow] = v[j];
+                    } else if (c0 < p.Cout) {
+                        if (use_res) {
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) {
+                                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&res_cur[hf]);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 f = __bfloat1622float2(rh[j]);
+                                    v[hf * 8 + 2 * j] += f.x; v[hf * 8 + 2 * j + 1] += f.y;
+                                }
+                            }
+                        }
+                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + c0);
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            uint4 ov;
+                            __nv_bfloat162* oh2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) oh2[j] = __floats2bfloat162_rn(v[hf * 8 + 2 * j], v[hf * 8 + 2 * j + 1]);
+                            op[hf] = ov;
+                        }
+                    }
+                }
+                if (p.splits == 1 && more) {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = nxt[j];
+                }
+                if (use_res && more) { res_cur[0] = res_nxt[0]; res_cur[1] = res_nxt[1]; }
             }
         }
     }
@@ -293,12 +384,12 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int make_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H, int N, int P, int tw, int th, int tn) {
+static int make_act_map(CUtensorMap* tm, const void* ptr, int C, int pitch, int W, int H, int N, int P, int tw, int th, int tn) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
     cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)P};
-    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
-                             (cuuint64_t)N * H * W * C * 2};
+    cuuint64_t strides[4] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2,
+                             (cuuint64_t)N * H * W * pitch * 2};
     cuuint32_t box[5] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -308,14 +399,14 @@ static int make_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H, i
     return DD_OK;
 }
 
-static int make_w_map(CUtensorMap* tm, const void* ptr, int K, int rows, int bn) {
+static int make_w_map(CUtensorMap* tm, const void* ptr, int K, int rows, int bn, int batch) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)bn};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * rows};
+    cuuint32_t box[3] = {64, (cuuint32_t)bn, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, batch > 0 ? 3 : 2, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights K=%d rows=%d bn=%d) failed: %d", K, rows, bn, (int)r); return DD_ERR_CUDA; }
@@ -334,9 +425,10 @@ extern "C" int dd_zero(void* ptr, int64_t bytes, void* stream) {
     return DD_OK;
 }
 
-extern "C" int dd_conv_tc(int kind, const void* x, const void* x2, int C1, int C2, const void* wp, int w_rows,
+extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2, const void* wp, int w_rows,
                           const float* bias, const void* residual, void* y, int out_nchw_f32, int cout_valid,
-                          float* gn_stats, int G, int B, int H, int W, int Cout, void* stream) {
+                          float* gn_stats, int G, int B, int H, int W, int Cout, int flags,
+                          float* splitk_ws, int64_t splitk_ws_floats, int32_t* splitk_cnt, int splitk_cnt_n, void* stream) {
     DD_REQUIRE(kind >= 0 && kind <= 3, "conv_tc: bad kind %d", kind);
     DD_REQUIRE(C1 > 0 && C1 % 64 == 0 && C2 >= 0 && C2 % 64 == 0, "conv_tc: channel counts (%d,%d) must be multiples of 64", C1, C2);
     DD_REQUIRE((C2 == 0) == (x2 == nullptr), "conv_tc: x2/C2 mismatch");
@@ -348,23 +440,32 @@ extern "C" int dd_conv_tc(int kind, const void* x, const void* x2, int C1, int C
 
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(6, 128));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64));
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
         attr_done = true;
     }
+    const bool wps = (flags & DD_TC_W_PER_SAMPLE) != 0;
+    DD_REQUIRE(!wps || kind == DD_TC_CONV1x1, "conv_tc: per-sample weights are for 1x1 convs only");
 
     TcParams p;
     memset(&p, 0, sizeof(p));
     // tile geometry over the GEMM pixel grid
     p.tw = W < 128 ? W : 128;
     p.th = (128 / p.tw) < H ? (128 / p.tw) : H;
-    p.tn = 128 / (p.tw * p.th);
+    p.tn = wps ? 1 : 128 / (p.tw * p.th);      // per-sample weights: one image per tile (rows beyond it are ignored)
+    p.rows_valid = p.tw * p.th * p.tn;
+    p.w_per_sample = wps ? 1 : 0;
     p.tiles_w = W / p.tw; p.tiles_h = H / p.th;
     const int tiles_n = (B + p.tn - 1) / p.tn;
     p.B = B; p.H = H; p.W = W;
     p.chunks0 = C1 / 64; p.chunks1 = C2 / 64;
     p.Cout = Cout; p.cout_valid = out_nchw_f32 ? cout_valid : Cout;
     p.bn = Cout >= 128 ? 128 : Cout;
+    // low-resolution layers (at most half a wave of 128-wide tiles): halve the N tile to double the CTA count
+    const int tiles128 = p.tiles_w * p.tiles_h * tiles_n * ((Cout + 127) / 128);
+    if (tiles128 * 2 <= num_sms() && Cout % 64 == 0 && Cout >= 128) p.bn = 64;
     DD_REQUIRE(Cout % p.bn == 0 && (p.bn == 16 || p.bn == 32 || p.bn == 64 || p.bn == 128), "conv_tc: unsupported Cout=%d", Cout);
     p.out = y; p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.gn_stats = gn_stats; p.G = G; p.out_nchw_f32 = out_nchw_f32; p.out_mul = 1;
@@ -403,14 +504,43 @@ extern "C" int dd_conv_tc(int kind, const void* x, const void* x2, int C1, int C
     p.rows_per_phase = w_rows / phases;
     DD_REQUIRE(w_rows % phases == 0 && p.rows_per_phase >= Cout && p.rows_per_phase % p.bn == 0, "conv_tc: packed weight rows %d do not match", w_rows);
 
-    int rc = make_act_map(&p.tmA0, x, C1, W, H, B, planes, p.tw, p.th, p.tn);
+    if (x_pitch <= 0) x_pitch = C1;
+    DD_REQUIRE(x_pitch >= C1 && x_pitch % 8 == 0, "conv_tc: bad channel pitch %d", x_pitch);
+    int rc = make_act_map(&p.tmA0, x, C1, x_pitch, W, H, B, planes, p.tw, p.th, p.tn);
     if (rc) return rc;
-    rc = make_act_map(&p.tmA1, x2 ? x2 : x, x2 ? C2 : C1, W, H, B, planes, p.tw, p.th, p.tn);
+    rc = make_act_map(&p.tmA1, x2 ? x2 : x, x2 ? C2 : C1, x2 ? C2 : x_pitch, W, H, B, planes, p.tw, p.th, p.tn);
     if (rc) return rc;
-    rc = make_w_map(&p.tmB, wp, K, w_rows, p.bn);
+    rc = make_w_map(&p.tmB, wp, K, w_rows, p.bn, wps ? B : 0);
     if (rc) return rc;
 
-    dim3 grid(p.tiles_w * p.tiles_h * tiles_n, Cout / p.bn, phases);
-    conv_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    // split-K for layers whose output tiles cannot fill the GPU (low-resolution levels): spread the
+    // (tap, chunk) loop over up to 12 CTAs per tile, aiming at ~2 CTAs per SM.
+    const int tiles = p.tiles_w * p.tiles_h * tiles_n * (Cout / p.bn);
+    const int num_kb = p.ntaps * (p.chunks0 + p.chunks1);
+    p.splits = 1; p.kb_per_split = num_kb;
+    p.splitk_ws = splitk_ws; p.splitk_cnt = splitk_cnt;
+    static const bool splitk_on = getenv("DD_SPLITK") != nullptr;   // red.add reduction measured slower than deep pipelines (profiles/README.md)
+    if (splitk_on && splitk_ws && splitk_cnt && phases == 1 && !wps && tiles < num_sms() && num_kb >= 6 &&
+        (int64_t)tiles * TC_BM * p.bn <= splitk_ws_floats && tiles <= splitk_cnt_n) {
+        int sp = (2 * num_sms()) / tiles;
+        if (sp > num_kb / 3) sp = num_kb / 3;
+        if (sp > 12) sp = 12;
+        if (sp >= 2) {
+            p.kb_per_split = (num_kb + sp - 1) / sp;
+            p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+        }
+    }
+    dim3 grid(p.tiles_w * p.tiles_h * tiles_n, Cout / p.bn, phases * p.splits);
+    static const bool verbose = getenv("DD_TC_VERBOSE") != nullptr;
+    if (verbose)
+        fprintf(stderr, "conv_tc kind=%d B=%d H=%d W=%d C=%d+%d Cout=%d grid=(%u,%u,%u) bn=%d num_kb=%d splits=%d kb_per=%d\n", kind, B, H, W,
+                C1, C2, Cout, grid.x, grid.y, grid.z, p.bn, num_kb, p.splits, p.kb_per_split);
+    const int ctas = (int)(grid.x * grid.y * grid.z);
+    if (p.bn <= 64 && ctas <= num_sms())
+        launch_pdl(conv_tc_kernel<8, 64>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64), (cudaStream_t)stream, p);
+    else if (ctas <= num_sms())
+        launch_pdl(conv_tc_kernel<6, 128>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(6, 128), (cudaStream_t)stream, p);
+    else
+        launch_pdl(conv_tc_kernel<3, 128>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128), (cudaStream_t)stream, p);
     return check_launch("conv_tc");
 }

@@ -30,6 +30,7 @@ int check_launch(const char* what) {
 __global__ void q_sample_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
                                 const int64_t* __restrict__ t, const float* __restrict__ sa,
                                 const float* __restrict__ sb, float4* __restrict__ out, int64_t chw4) {
+    pdl_sync();
     const int b = blockIdx.y;
     const float a = sa[t[b]], c = sb[t[b]];
     const int64_t base = (int64_t)b * chw4;
@@ -58,6 +59,7 @@ __global__ void posterior_step_kernel(const float4* __restrict__ xt, const float
                                       const float4* __restrict__ noise, const float* __restrict__ coef,
                                       const int32_t* __restrict__ t_idx, int t_stride, int64_t noise_step_stride4,
                                       int T, int noise_period, int clip, float4* __restrict__ out, int64_t chw4) {
+    pdl_sync();
     const int b = blockIdx.y;
     const int t = t_idx[(int64_t)b * t_stride];
     const float* c = coef + (int64_t)t * 5;
@@ -80,6 +82,7 @@ __global__ void posterior_step_kernel(const float4* __restrict__ xt, const float
 __global__ void predict_x0_kernel(const float4* __restrict__ xt, const float4* __restrict__ eps,
                                   const int64_t* __restrict__ t, const float* __restrict__ ra,
                                   const float* __restrict__ rb, int clip, float4* __restrict__ out, int64_t chw4) {
+    pdl_sync();
     const int b = blockIdx.y;
     const float a = ra[t[b]], c = rb[t[b]];
     const int64_t base = (int64_t)b * chw4;
@@ -98,6 +101,7 @@ __global__ void predict_x0_kernel(const float4* __restrict__ xt, const float4* _
 }
 
 __global__ void tick_kernel(int32_t* t, int n) {
+    pdl_sync();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) t[i] -= 1;
 }
@@ -107,6 +111,7 @@ __global__ void tick_kernel(int32_t* t, int n) {
 // ---------------------------------------------------------------------------------------------
 __global__ void mse_rowsum_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                   float* __restrict__ out, int64_t chw4, float scale) {
+    pdl_sync();
     const int row = blockIdx.x;
     const int64_t base = (int64_t)row * chw4;
     float acc = 0.f;
@@ -128,6 +133,7 @@ __global__ void mse_rowsum_kernel(const float4* __restrict__ a, const float4* __
 
 __global__ void mse_rowsum_bwd_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                       const float* __restrict__ w, float4* __restrict__ g, int64_t chw4, float gscale) {
+    pdl_sync();
     const int row = blockIdx.y;
     const float s = 2.f * gscale * (w ? w[row] : 1.f);
     const int64_t base = (int64_t)row * chw4;
@@ -143,6 +149,7 @@ __global__ void mse_rowsum_bwd_kernel(const float4* __restrict__ a, const float4
 // ---------------------------------------------------------------------------------------------
 __global__ void ema_update_kernel(const uint64_t* __restrict__ table, const int32_t* __restrict__ chunks,
                                   int chunk_elems, float decay, float omd) {
+    pdl_sync();
     const int ti = chunks[2 * blockIdx.x], ci = chunks[2 * blockIdx.x + 1];
     float* __restrict__ s = reinterpret_cast<float*>(table[3 * ti]);
     const float* __restrict__ p = reinterpret_cast<const float*>(table[3 * ti + 1]);
@@ -175,6 +182,7 @@ __global__ void ema_update_kernel(const uint64_t* __restrict__ table, const int3
 // NCHW fp32 -> NHWC T.  One thread per (b, pixel); reads are coalesced per channel plane.
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int C, int HW) {
+    pdl_sync();
     const int b = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= HW) return;
@@ -185,6 +193,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__
 
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int C, int HW) {
+    pdl_sync();
     const int b = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= HW) return;
@@ -196,6 +205,7 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
 // NCHW fp32 -> bf16 im2col rows (B*H*W, kpad), 3x3 pad 1.  One thread per (pixel, 8-column group).
 __global__ void im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                  int C, int H, int W, int kpad) {
+    pdl_sync();
     const int b = blockIdx.y;
     const int groups = kpad >> 3;
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -221,6 +231,7 @@ __global__ void im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 
 template <typename T>
 __global__ void avgpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, int64_t total_vec) {
+    pdl_sync();
     constexpr int VN = Vec<T>::N;
     const int Ho = H >> 1, Wo = W >> 1, cv = C / VN;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -240,6 +251,7 @@ __global__ void avgpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int 
 
 template <typename T>
 __global__ void upsample2_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, int64_t total_vec) {
+    pdl_sync();
     constexpr int VN = Vec<T>::N;
     const int Ho = H * 2, Wo = W * 2, cv = C / VN;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -256,6 +268,7 @@ __global__ void upsample2_kernel(const T* __restrict__ x, T* __restrict__ y, int
 // NHWC bf16 -> (4, B, H/2, W/2, C) parity planes.
 __global__ void s2d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                            int B, int H, int W, int C, int64_t total_vec) {
+    pdl_sync();
     const int cv = C >> 3, Ho = H >> 1, Wo = W >> 1;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % cv) * 8;
@@ -297,7 +310,7 @@ int dd_q_sample(const float* x, const float* eps, const int64_t* t, const float*
                 float* out, int B, int64_t chw, void* stream) {
     DD_REQUIRE(chw % 4 == 0 && B > 0, "q_sample: chw=%lld must be a multiple of 4", (long long)chw);
     dim3 grid(grid_for(chw / 4, 256, 4), B);
-    q_sample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)eps, t, sa, sb,
+    launch_pdl(q_sample_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float4*)x, (const float4*)eps, t, sa, sb,
                                                            (float4*)out, chw / 4);
     return check_launch("q_sample");
 }
@@ -308,7 +321,7 @@ int dd_posterior_step(const float* x_t, const float* eps_hat, const float* noise
     DD_REQUIRE(chw % 4 == 0 && B > 0 && noise_step_stride % 4 == 0, "posterior_step: chw=%lld must be a multiple of 4",
                (long long)chw);
     dim3 grid(grid_for(chw / 4, 256, 4), B);
-    posterior_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(posterior_step_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
         (const float4*)x_t, (const float4*)eps_hat, (const float4*)noise, coef, t_idx, t_stride,
         noise_step_stride / 4, T, noise_period, clip, (float4*)x_out, chw / 4);
     return check_launch("posterior_step");
@@ -318,19 +331,19 @@ int dd_predict_x0(const float* x_t, const float* eps, const int64_t* t, const fl
                   float* out, int B, int64_t chw, void* stream) {
     DD_REQUIRE(chw % 4 == 0 && B > 0, "predict_x0: chw=%lld must be a multiple of 4", (long long)chw);
     dim3 grid(grid_for(chw / 4, 256, 4), B);
-    predict_x0_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x_t, (const float4*)eps, t, ra, rb, clip,
+    launch_pdl(predict_x0_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float4*)x_t, (const float4*)eps, t, ra, rb, clip,
                                                              (float4*)out, chw / 4);
     return check_launch("predict_x0");
 }
 
 int dd_tick(int32_t* t_idx, int n, void* stream) {
-    tick_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t_idx, n);
+    launch_pdl(tick_kernel, dim3((n + 127) / 128), dim3(128), 0, (cudaStream_t)stream, t_idx, n);
     return check_launch("tick");
 }
 
 int dd_mse_rowsum(const float* a, const float* b, float* out, int B, int64_t chw, float scale, void* stream) {
     DD_REQUIRE(chw % 4 == 0 && B > 0, "mse_rowsum: chw=%lld must be a multiple of 4", (long long)chw);
-    mse_rowsum_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, out, chw / 4, scale);
+    launch_pdl(mse_rowsum_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, (const float4*)a, (const float4*)b, out, chw / 4, scale);
     return check_launch("mse_rowsum");
 }
 
@@ -338,7 +351,7 @@ int dd_mse_rowsum_bwd(const float* a, const float* b, const float* w, float* gra
                       void* stream) {
     DD_REQUIRE(chw % 4 == 0 && B > 0, "mse_rowsum_bwd: chw=%lld must be a multiple of 4", (long long)chw);
     dim3 grid(grid_for(chw / 4, 256, 4), B);
-    mse_rowsum_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, w,
+    launch_pdl(mse_rowsum_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float4*)a, (const float4*)b, w,
                                                                  (float4*)grad_b, chw / 4, gscale);
     return check_launch("mse_rowsum_bwd");
 }
@@ -346,19 +359,19 @@ int dd_mse_rowsum_bwd(const float* a, const float* b, const float* w, float* gra
 int dd_ema_update(const uint64_t* table, const int32_t* chunks, int n_chunks, int chunk_elems, float decay,
                   float one_minus_decay, void* stream) {
     DD_REQUIRE(n_chunks > 0 && chunk_elems > 0 && chunk_elems % 4 == 0, "ema_update: bad chunking");
-    ema_update_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(table, chunks, chunk_elems, decay, one_minus_decay);
+    launch_pdl(ema_update_kernel, dim3(n_chunks), dim3(256), 0, (cudaStream_t)stream, table, chunks, chunk_elems, decay, one_minus_decay);
     return check_launch("ema_update");
 }
 
 int dd_nchw_to_nhwc(const float* x, void* y, int dtype, int B, int C, int H, int W, void* stream) {
     dim3 grid((H * W + 127) / 128, B);
-    DD_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid, 128, 0, (cudaStream_t)stream>>>(x, (T*)y, C, H * W)));
+    DD_DISPATCH_DTYPE(dtype, T, (launch_pdl(nchw_to_nhwc_kernel<T>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, x, (T*)y, C, H * W)));
     return check_launch("nchw_to_nhwc");
 }
 
 int dd_nhwc_to_nchw(const void* x, int dtype, float* y, int B, int C, int H, int W, void* stream) {
     dim3 grid((H * W + 127) / 128, B);
-    DD_DISPATCH_DTYPE(dtype, T, (nhwc_to_nchw_kernel<T><<<grid, 128, 0, (cudaStream_t)stream>>>((const T*)x, y, C, H * W)));
+    DD_DISPATCH_DTYPE(dtype, T, (launch_pdl(nhwc_to_nchw_kernel<T>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (const T*)x, y, C, H * W)));
     return check_launch("nhwc_to_nchw");
 }
 
@@ -366,7 +379,7 @@ int dd_im2col3x3_nchw(const float* x, void* y, int B, int C, int H, int W, int k
     DD_REQUIRE(kpad % 64 == 0 && kpad >= 9 * C, "im2col3x3: kpad=%d must be a multiple of 64 and >= 9*C", kpad);
     int64_t n = (int64_t)H * W * (kpad / 8);
     dim3 grid((unsigned)((n + 255) / 256), B);
-    im2col3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, C, H, W, kpad);
+    launch_pdl(im2col3x3_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, C, H, W, kpad);
     return check_launch("im2col3x3");
 }
 
@@ -375,7 +388,7 @@ int dd_avgpool2(const void* x, void* y, int dtype, int B, int H, int W, int C, v
     DD_DISPATCH_DTYPE(dtype, T, {
         DD_REQUIRE(C % Vec<T>::N == 0, "avgpool2: C=%d not vectorisable", C);
         int64_t n = (int64_t)B * (H / 2) * (W / 2) * (C / Vec<T>::N);
-        avgpool2_kernel<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, H, W, C, n);
+        launch_pdl(avgpool2_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (T*)y, H, W, C, n);
     });
     return check_launch("avgpool2");
 }
@@ -384,7 +397,7 @@ int dd_upsample_nearest2(const void* x, void* y, int dtype, int B, int H, int W,
     DD_DISPATCH_DTYPE(dtype, T, {
         DD_REQUIRE(C % Vec<T>::N == 0, "upsample2: C=%d not vectorisable", C);
         int64_t n = (int64_t)B * (H * 2) * (W * 2) * (C / Vec<T>::N);
-        upsample2_kernel<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, H, W, C, n);
+        launch_pdl(upsample2_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (T*)y, H, W, C, n);
     });
     return check_launch("upsample_nearest2");
 }
@@ -392,7 +405,7 @@ int dd_upsample_nearest2(const void* x, void* y, int dtype, int B, int H, int W,
 int dd_space_to_depth2(const void* x, void* y, int B, int H, int W, int C, void* stream) {
     DD_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "space_to_depth2: bad shape");
     int64_t n = (int64_t)B * H * W * (C / 8);
-    s2d_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W,
+    launch_pdl(s2d_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W,
                                                                   C, n);
     return check_launch("space_to_depth2");
 }

@@ -10,6 +10,7 @@ namespace dd {
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x, int HW, int C, int G, float eps, float* __restrict__ stats) {
+    pdl_sync();
     const int b = blockIdx.x / G, g = blockIdx.x % G;
     const int cpg = C / G;
     const T* xb = x + (int64_t)b * HW * C + g * cpg;
@@ -46,48 +47,60 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, int HW, int C, int G, f
 }
 
 // ---------------------------------------------------------------------------------------------
-// y = mish(gn(x)*gamma+beta) [+ tbias[row(b), c]] [+ residual].  16-byte vectors along C.
-// Algorithmic bytes: read x + write y (+ residual read) = 4 (+2) B/element in bf16.
+// y = mish(gn(x)*gamma+beta) [+ tbias[row(b), c]] [+ residual].  One 16-byte vector (8 bf16 / 4 fp32) per
+// thread, every operand fetched with 16-byte loads.  Algorithmic bytes: read x + write y (+ residual read)
+// = 4 (+2) B/element in bf16.
 // ---------------------------------------------------------------------------------------------
+template <int N> struct FVec { float v[N]; };
+template <int N> __device__ __forceinline__ FVec<N> ldg_f(const float* p) {
+    FVec<N> r;
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+        r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w;
+    }
+    return r;
+}
+
 template <typename T>
-__global__ void gn_mish_kernel(const T* __restrict__ x, T* __restrict__ y, int HW, int C, int G,
+__global__ void __launch_bounds__(256) gn_mish_kernel(const T* __restrict__ x, T* __restrict__ y, int HW, int C, int G,
                                const float* __restrict__ stats, int stats_mode, float eps,
                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ tbias, int tb_stride, const int32_t* __restrict__ trow,
                                int trow_stride, const T* __restrict__ residual, int64_t total_vec) {
+    pdl_sync();
     constexpr int VN = Vec<T>::N;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total_vec) return;
     const int cv = C / VN, cpg = C / G;
-    const float inv_n = 1.f / ((float)HW * (float)cpg);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % cv) * VN;
-        const int b = (int)(i / ((int64_t)cv * HW));
-        const int g = c / cpg;
-        float mean, rstd;
-        const float s0 = stats[((int64_t)b * G + g) * 2], s1 = stats[((int64_t)b * G + g) * 2 + 1];
-        if (stats_mode == 0) { mean = s0; rstd = s1; }
-        else {
-            mean = s0 * inv_n;
-            float var = fmaxf(s1 * inv_n - mean * mean, 0.f);
-            rstd = rsqrtf(var + eps);
-        }
-        Vec<T> v, r;
-        v.load(x + i * VN);
-        const float* tb = nullptr;
-        if (tbias) {
-            const int row = trow ? trow[(int64_t)b * trow_stride] : b;
-            tb = tbias + (int64_t)row * tb_stride + c;
-        }
-        if (residual) r.load(residual + i * VN);
-#pragma unroll
-        for (int j = 0; j < VN; ++j) {
-            float h = (v.v[j] - mean) * rstd * gamma[c + j] + beta[c + j];
-            h = mish_f(h);
-            if (tb) h += tb[j];
-            if (residual) h += r.v[j];
-            v.v[j] = h;
-        }
-        v.store(y + i * VN);
+    const int c = (int)(i % cv) * VN;
+    const int b = (int)(i / ((int64_t)cv * HW));
+    const int g = c / cpg;
+    Vec<T> v, r;
+    v.load(x + i * VN);
+    if (residual) r.load(residual + i * VN);
+    const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + (int64_t)b * G + g);
+    float mean, rstd;
+    if (stats_mode == 0) { mean = st.x; rstd = st.y; }
+    else {
+        const float inv_n = 1.f / ((float)HW * (float)cpg);
+        mean = st.x * inv_n;
+        rstd = rsqrtf(fmaxf(st.y * inv_n - mean * mean, 0.f) + eps);
     }
+    const FVec<VN> ga = ldg_f<VN>(gamma + c), be = ldg_f<VN>(beta + c);
+    FVec<VN> tb;
+    if (tbias) {
+        const int row = trow ? trow[(int64_t)b * trow_stride] : b;
+        tb = ldg_f<VN>(tbias + (int64_t)row * tb_stride + c);
+    }
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+        float h = mish_t<T>((v.v[j] - mean) * rstd * ga.v[j] + be.v[j]);
+        if (tbias) h += tb.v[j];
+        if (residual) h += r.v[j];
+        v.v[j] = h;
+    }
+    v.store(y + i * VN);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -96,6 +109,7 @@ __global__ void gn_mish_kernel(const T* __restrict__ x, T* __restrict__ y, int H
 template <typename T, int PER_LANE>
 __global__ void layernorm_c_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t P, int C,
                                    const float* __restrict__ g, const float* __restrict__ bta, float eps) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -129,6 +143,7 @@ __global__ void time_bias_kernel(const float* __restrict__ t, int dim, const flo
                                  const float* __restrict__ b1, const float* __restrict__ W2,
                                  const float* __restrict__ b2, const float* __restrict__ Wcat,
                                  const float* __restrict__ bcat, int J, float* __restrict__ out) {
+    pdl_sync();
     extern __shared__ float sm[];
     float* emb = sm;              // dim
     float* h1 = emb + dim;        // 4*dim
@@ -170,77 +185,188 @@ __global__ void time_bias_kernel(const float* __restrict__ t, int dim, const flo
 }
 
 // ---------------------------------------------------------------------------------------------
-// LinearAttention core (blocks.py:128-133).  One CTA (256 threads) per (b, head), dh = 32.
-//   pass 1: column max / sum-exp of k over n (online, per d)
-//   pass 2: ctx[d][e] = sum_n softmax(k)[d,n] v[e,n]      (tiles of 32 n staged in smem)
-//   pass 3: out[n][e] = sum_d ctx[d][e] q[n][d]           (ctx column in registers, q via shuffles)
+// LinearAttention core (blocks.py:128-133), dh = 32, split over the spatial axis so that (b, head) pairs
+// with many pixels are spread over several CTAs:
+//   ctx kernel : CTA (b, head, split) streams its n-range in 128-row tiles with an online softmax
+//                (running max per d), accumulating un-normalised ctx[d][e] = sum_n exp(k[d,n]-m_d) v[e,n]
+//                and s_d = sum_n exp(k[d,n]-m_d); writes {m, s, ctx} (1088 floats) to the workspace.
+//   out kernel : CTA (b, head, split) merges the S partials (max-rescale), normalises, then
+//                out[n][e] = sum_d ctx[d][e] q[n][d] for its n-range (ctx column in registers, q via shuffles).
 // ---------------------------------------------------------------------------------------------
+constexpr int LA_TILE = 128;
+constexpr int LA_WS = 64 + 32 * 32;      // floats per (b, head, split)
+
+__host__ __device__ inline int la_chunk(int n) {
+    int c = (n + 15) / 16;                                  // at most 16 splits
+    c = (c + LA_TILE - 1) / LA_TILE * LA_TILE;
+    return c < LA_TILE ? LA_TILE : c;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256) linattn_core_kernel(const T* __restrict__ qkv, T* __restrict__ out,
-                                                           int n, int heads) {
+__global__ void __launch_bounds__(256) linattn_ctx_kernel(const T* __restrict__ qkv, float* __restrict__ ws,
+                                                          int n, int heads, int chunk) {
+    pdl_sync();
     constexpr int DH = 32;
-    const int b = blockIdx.x / heads, hd = blockIdx.x % heads;
-    const int C3 = 3 * heads * DH, CO = heads * DH;
-    const T* qb = qkv + (int64_t)b * n * C3 + hd * DH;
-    const T* kb = qb + heads * DH;
+    constexpr int VN = Vec<T>::N;                 // 8 (bf16) / 4 (fp32) channels per 16-byte load
+    constexpr int VPR = DH / VN;                  // vectors per row of one matrix
+    const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
+    const int S = gridDim.y, sp = blockIdx.y;
+    const int C3 = 3 * heads * DH;
+    const T* kb = qkv + (int64_t)b * n * C3 + heads * DH + hd * DH;
     const T* vb = kb + heads * DH;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;   // 8 warps
-
-    __shared__ float s_m[8][DH], s_s[8][DH];
-    __shared__ float s_max[DH], s_inv[DH];
-    __shared__ float s_k[32][DH + 1], s_v[32][DH + 1];
-    __shared__ float s_ctx[DH][DH + 1];
-
-    // pass 1: lane = d, each warp strides over n
-    float m = -INFINITY, s = 0.f;
-    for (int i = warp; i < n; i += 8) {
-        const float kv = to_f(kb[(int64_t)i * C3 + lane]);
-        const float nm = fmaxf(m, kv);
-        s = s * expf(m - nm) + expf(kv - nm);
-        m = nm;
-    }
-    s_m[warp][lane] = m; s_s[warp][lane] = s;
-    __syncthreads();
-    if (warp == 0) {
-        float mm = -INFINITY;
-        for (int w = 0; w < 8; ++w) mm = fmaxf(mm, s_m[w][lane]);
-        float ss = 0.f;
-        for (int w = 0; w < 8; ++w) if (s_m[w][lane] > -INFINITY) ss += s_s[w][lane] * expf(s_m[w][lane] - mm);
-        s_max[lane] = mm; s_inv[lane] = 1.f / ss;
-    }
-    __syncthreads();
-
-    // pass 2: thread (d = lane, e block = warp*4 .. +4)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ float sk[LA_TILE][DH + 1];                    // lane-varying d: conflict free
+    __shared__ __align__(16) float sv[LA_TILE][DH + 4];      // 16-byte aligned rows: float4 broadcasts
+    __shared__ float red[8][DH];
+    __shared__ float s_m[DH], s_scale[DH];
+    const int n_lo = sp * chunk, n_hi = min(n, n_lo + chunk);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int n0 = 0; n0 < n; n0 += 32) {
-        for (int r = warp; r < 32; r += 8) {
-            const int i = n0 + r;
-            float kv = 0.f, vv = 0.f;
-            if (i < n) {
-                kv = expf(to_f(kb[(int64_t)i * C3 + lane]) - s_max[lane]);
-                vv = to_f(vb[(int64_t)i * C3 + lane]);
-            }
-            s_k[r][lane] = kv; s_v[r][lane] = vv;
+    float s_part = 0.f;                 // partial sum over this thread's rows, d = lane
+    if (threadIdx.x < DH) s_m[threadIdx.x] = -INFINITY;
+    __syncthreads();
+    for (int t0 = n_lo; t0 < n_hi; t0 += LA_TILE) {
+        const int rows = min(LA_TILE, n_hi - t0);
+        for (int i = threadIdx.x; i < rows * VPR * 2; i += 256) {
+            const int r = i / (VPR * 2), w = i % (VPR * 2);
+            const int isv = w / VPR, c = (w % VPR) * VN;
+            Vec<T> x;
+            x.load((isv ? vb : kb) + (int64_t)(t0 + r) * C3 + c);
+#pragma unroll
+            for (int j = 0; j < VN; ++j) (isv ? sv[r][c + j] : sk[r][c + j]) = x.v[j];
+        }
+        __syncthreads();
+        float m = -INFINITY;
+        for (int r = warp; r < rows; r += 8) m = fmaxf(m, sk[r][lane]);
+        red[warp][lane] = m;
+        __syncthreads();
+        if (warp == 0) {
+            float mm = s_m[lane];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) mm = fmaxf(mm, red[w][lane]);
+            s_scale[lane] = __expf(s_m[lane] - mm);      // 0 on the first tile (exp(-inf))
+            s_m[lane] = mm;
+        }
+        __syncthreads();
+        const float mcur = s_m[lane], sc = s_scale[lane];
+        s_part *= sc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] *= sc;
+        for (int r = warp; r < rows; r += 8) {
+            const float e = __expf(sk[r][lane] - mcur);
+            sk[r][lane] = e;
+            s_part += e;
         }
         __syncthreads();
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-            const float p = s_k[r][lane];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] += p * s_v[r][warp * 4 + j];
+        for (int r = 0; r < rows; ++r) {
+            const float pe = sk[r][lane];
+            const float4 vv = *reinterpret_cast<const float4*>(&sv[r][warp * 4]);
+            acc[0] += pe * vv.x; acc[1] += pe * vv.y; acc[2] += pe * vv.z; acc[3] += pe * vv.w;
         }
         __syncthreads();
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s_ctx[lane][warp * 4 + j] = acc[j] * s_inv[lane];
+    float* w = ws + ((int64_t)bh * S + sp) * LA_WS;
+    red[warp][lane] = s_part;
     __syncthreads();
+    if (warp == 0) {
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ss += red[k][lane];
+        w[lane] = s_m[lane];
+        w[32 + lane] = ss;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[64 + lane * 32 + warp * 4 + j] = acc[j];
+}
 
-    // pass 3: lane = e
+// Merge the S partial contexts of (b, head) and fold the attention's output projection into them:
+//   M_b[c][h*32+d] = sum_e ctx_h[d][e] * Wout[c][h*32+e]      (bf16, K-major rows of length heads*32)
+// so that  to_out(linattn(q,k,v))[n][c] = sum_{hd} q[n][hd] * M_b[c][hd] + bias[c]  is ONE per-sample GEMM
+// on the tensor cores (dd_conv_tc with DD_TC_W_PER_SAMPLE) instead of a CUDA-core contraction + a GEMM.
+__global__ void __launch_bounds__(256) linattn_mix_kernel(const float* __restrict__ ws, int S, int heads,
+                                                          const float* __restrict__ Wout, int C,
+                                                          __nv_bfloat16* __restrict__ Mb) {
+    pdl_sync();
+    constexpr int DH = 32;
+    const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int HD = heads * DH;
+    __shared__ float s_ctx[DH][DH + 1];
+    const float* w0 = ws + (int64_t)bh * S * LA_WS;
+    float M = -INFINITY;
+    for (int s = 0; s < S; ++s) M = fmaxf(M, w0[s * LA_WS + lane]);
+    float tot = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < S; ++s) {
+        const float* w = w0 + s * LA_WS;
+        const float f = __expf(w[lane] - M);
+        tot += w[32 + lane] * f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += w[64 + lane * 32 + warp * 4 + j] * f;
+    }
+    const float inv = 1.f / tot;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_ctx[lane][warp * 4 + j] = acc[j] * inv;
+    __syncthreads();
+    float ctx[DH];                       // row d = lane of the normalised context
+#pragma unroll
+    for (int e = 0; e < DH; ++e) ctx[e] = s_ctx[lane][e];
+    // stage this head's (C x 32) slice of W_out through shared memory in chunks of 128 output channels:
+    // all loads of a chunk are independent and coalesced, the dot products then read smem broadcasts
+    __shared__ __align__(16) float s_w[128][DH];
+    for (int c0 = 0; c0 < C; c0 += 128) {
+        const int cn = min(128, C - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cn * (DH / 4); i += 256) {
+            const int c = i / (DH / 4), e4 = i % (DH / 4);
+            reinterpret_cast<float4*>(&s_w[c][0])[e4] =
+                __ldg(reinterpret_cast<const float4*>(Wout + (int64_t)(c0 + c) * HD + hd * DH) + e4);
+        }
+        __syncthreads();
+        for (int c = warp; c < cn; c += 8) {
+            float o = 0.f;
+#pragma unroll
+            for (int e4 = 0; e4 < DH / 4; ++e4) {
+                const float4 t = reinterpret_cast<const float4*>(&s_w[c][0])[e4];      // broadcast
+                o += ctx[4 * e4] * t.x + ctx[4 * e4 + 1] * t.y + ctx[4 * e4 + 2] * t.z + ctx[4 * e4 + 3] * t.w;
+            }
+            Mb[((int64_t)b * C + c0 + c) * HD + hd * DH + lane] = __float2bfloat16_rn(o);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) linattn_out_kernel(const T* __restrict__ qkv, T* __restrict__ out,
+                                                          const float* __restrict__ ws, int n, int heads, int chunk) {
+    pdl_sync();
+    constexpr int DH = 32;
+    const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
+    const int S = gridDim.y, sp = blockIdx.y;
+    const int C3 = 3 * heads * DH, CO = heads * DH;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ float s_ctx[DH][DH + 1];
+    // merge the S partials: thread (d = lane, e block = warp)
+    const float* w0 = ws + (int64_t)bh * S * LA_WS;
+    float M = -INFINITY;
+    for (int s = 0; s < S; ++s) M = fmaxf(M, w0[s * LA_WS + lane]);
+    float tot = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < S; ++s) {
+        const float* w = w0 + s * LA_WS;
+        const float f = __expf(w[lane] - M);
+        tot += w[32 + lane] * f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += w[64 + lane * 32 + warp * 4 + j] * f;
+    }
+    const float inv = 1.f / tot;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_ctx[lane][warp * 4 + j] = acc[j] * inv;
+    __syncthreads();
     float ctx[DH];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) ctx[d] = s_ctx[d][lane];
+    for (int d = 0; d < DH; ++d) ctx[d] = s_ctx[d][lane];     // lane = e from here on
+    const T* qb = qkv + (int64_t)b * n * C3 + hd * DH;
     T* ob = out + (int64_t)b * n * CO + hd * DH;
-    for (int i = warp; i < n; i += 8) {
+    const int n_lo = sp * chunk, n_hi = min(n, n_lo + chunk);
+    for (int i = n_lo + warp; i < n_hi; i += 8) {
         const float qv = to_f(qb[(int64_t)i * C3 + lane]);
         float o = 0.f;
 #pragma unroll
@@ -266,13 +392,13 @@ int dd_time_bias(const float* t, int R, int dim, const float* freq, const float*
     DD_REQUIRE(R > 0 && dim >= 4 && dim % 2 == 0 && J > 0 && dim <= 2048, "time_bias: bad sizes R=%d dim=%d J=%d", R, dim, J);
     dim3 grid((J + 127) / 128, R);
     size_t smem = (size_t)6 * dim * sizeof(float);
-    time_bias_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(t, dim, freq, W1, b1, W2, b2, Wcat, bcat, J, out);
+    launch_pdl(time_bias_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, t, dim, freq, W1, b1, W2, b2, Wcat, bcat, J, out);
     return check_launch("time_bias");
 }
 
 int dd_gn_stats(const void* x, int dtype, int B, int HW, int C, int G, float eps, float* stats, void* stream) {
     DD_REQUIRE(C % G == 0 && B > 0 && HW > 0, "gn_stats: C=%d not divisible by G=%d", C, G);
-    DD_DISPATCH_DTYPE(dtype, T, (gn_stats_kernel<T><<<B * G, 256, 0, (cudaStream_t)stream>>>((const T*)x, HW, C, G, eps, stats)));
+    DD_DISPATCH_DTYPE(dtype, T, (launch_pdl(gn_stats_kernel<T>, dim3(B * G), dim3(256), 0, (cudaStream_t)stream, (const T*)x, HW, C, G, eps, stats)));
     return check_launch("gn_stats");
 }
 
@@ -284,7 +410,8 @@ int dd_gn_mish(const void* x, void* y, int dtype, int B, int HW, int C, int G, c
         constexpr int VN = Vec<T>::N;
         DD_REQUIRE(C % VN == 0 && (C / G) % VN == 0, "gn_mish: channels per group (%d) must be a multiple of %d", C / G, VN);
         int64_t n = (int64_t)B * HW * (C / VN);
-        gn_mish_kernel<T><<<grid_cap(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        DD_REQUIRE(tb_stride % 4 == 0, "gn_mish: time-bias row stride must be a multiple of 4 floats");
+        launch_pdl(gn_mish_kernel<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
             (const T*)x, (T*)y, HW, C, G, stats, stats_mode, eps, gamma, beta, tbias, tb_stride, trow, trow_stride,
             (const T*)residual, n);
     });
@@ -298,7 +425,7 @@ int dd_layernorm_c(const void* x, void* y, int dtype, int64_t P, int C, const fl
     const int grid = grid_cap(P * 32, 256);
 #define LN_CASE(N)                                                                                                   \
     case N:                                                                                                          \
-        DD_DISPATCH_DTYPE(dtype, T, (layernorm_c_kernel<T, N><<<grid, 256, 0, (cudaStream_t)stream>>>(               \
+        DD_DISPATCH_DTYPE(dtype, T, (launch_pdl(layernorm_c_kernel<T, N>, dim3(grid), dim3(256), 0, (cudaStream_t)stream,                \
                                         (const T*)x, (T*)y, P, C, g, b, eps)));                                      \
         break;
     switch (per) {
@@ -310,11 +437,34 @@ int dd_layernorm_c(const void* x, void* y, int dtype, int64_t P, int C, const fl
     return check_launch("layernorm_c");
 }
 
-int dd_linattn_core(const void* qkv, void* out, int dtype, int B, int n, int heads, int dh, void* stream) {
+int64_t dd_linattn_ws_floats(int B, int n, int heads) {
+    const int chunk = la_chunk(n);
+    return (int64_t)B * heads * ((n + chunk - 1) / chunk) * LA_WS;
+}
+
+int dd_linattn_core(const void* qkv, void* out, int dtype, int B, int n, int heads, int dh, float* ws, int64_t ws_floats,
+                    void* stream) {
     DD_REQUIRE(dh == 32 && heads > 0 && n > 0, "linattn_core: dim_head must be 32 (got %d)", dh);
-    DD_DISPATCH_DTYPE(dtype, T, (linattn_core_kernel<T><<<B * heads, 256, 0, (cudaStream_t)stream>>>(
-                                    (const T*)qkv, (T*)out, n, heads)));
+    DD_REQUIRE(ws != nullptr && ws_floats >= dd_linattn_ws_floats(B, n, heads), "linattn_core: workspace too small");
+    const int chunk = la_chunk(n);
+    dim3 grid(B * heads, (n + chunk - 1) / chunk);
+    DD_DISPATCH_DTYPE(dtype, T, {
+        launch_pdl(linattn_ctx_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)qkv, ws, n, heads, chunk);
+        launch_pdl(linattn_out_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)qkv, (T*)out, ws, n, heads, chunk);
+    });
     return check_launch("linattn_core");
+}
+
+int dd_linattn_mix(const void* qkv, int dtype, int B, int n, int heads, int dh, float* ws, int64_t ws_floats,
+                   const float* Wout, int C, void* Mb_bf16, void* stream) {
+    DD_REQUIRE(dh == 32 && heads > 0 && n > 0 && C > 0, "linattn_mix: dim_head must be 32 (got %d)", dh);
+    DD_REQUIRE(ws != nullptr && ws_floats >= dd_linattn_ws_floats(B, n, heads), "linattn_mix: workspace too small");
+    const int chunk = la_chunk(n);
+    const int S = (n + chunk - 1) / chunk;
+    dim3 grid(B * heads, S);
+    DD_DISPATCH_DTYPE(dtype, T, (launch_pdl(linattn_ctx_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)qkv, ws, n, heads, chunk)));
+    launch_pdl(linattn_mix_kernel, dim3(B * heads), dim3(256), 0, (cudaStream_t)stream, ws, S, heads, Wout, C, (__nv_bfloat16*)Mb_bf16);
+    return check_launch("linattn_mix");
 }
 
 }  // extern "C"

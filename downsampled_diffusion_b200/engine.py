@@ -200,11 +200,11 @@ class Program:
                 st_ptr = stats[0]
             taps = {"3x3": 9, "down": 9, "1x1": 1, "up": 4}[kind]
             self.conv_tc_flops.append(2.0 * B * Ho * Wo * Cout * taps * Cin)
-            self.add("dd_conv_tc", kcode, L.ptr(src), L.ptr(src2) if src2 is not None else None, x.C,
+            self.add("dd_conv_tc", kcode, L.ptr(src), 0, L.ptr(src2) if src2 is not None else None, x.C,
                      x2.C if x2 is not None else 0, L.ptr(wp), wp.shape[0], L.ptr(b_t) if b_t is not None else None,
                      L.ptr(residual.t) if residual is not None else None,
                      L.ptr(out_nchw) if out_nchw is not None else L.ptr(y.t), 1 if out_nchw is not None else 0,
-                     Cout if out_nchw is not None else 0, st_ptr, G, B, gh, gw, Cout_p)
+                     Cout if out_nchw is not None else 0, st_ptr, G, B, gh, gw, Cout_p, 0, *self.splitk_args())
             if y is not None and Cout_p != Cout:
                 raise ValueError("padded Cout is only supported with NCHW fp32 output")
         else:
@@ -230,6 +230,18 @@ class Program:
                 self.add("dd_gn_stats", L.ptr(y.t), self.dcode, B, Ho * Wo, Cout, G, GN_EPS, L.ptr(st))
                 stats = (st, 0)
         return y, stats
+
+    SPLITK_WS_FLOATS = 148 * 128 * 128        # one full wave of 128x128 fp32 tiles (9.7 MB)
+    SPLITK_COUNTERS = 1024
+
+    def splitk_args(self):
+        """(ws, ws_floats, counters, n_counters) shared by every split-K conv of the program: zero when idle."""
+        if getattr(self, "_splitk", None) is None:
+            ws = torch.zeros(self.SPLITK_WS_FLOATS, dtype=torch.float32, device=self.device)
+            cnt = torch.zeros(self.SPLITK_COUNTERS, dtype=torch.int32, device=self.device)
+            self.keep += [ws, cnt]
+            self._splitk = (L.ptr(ws), self.SPLITK_WS_FLOATS, L.ptr(cnt), self.SPLITK_COUNTERS)
+        return self._splitk
 
     def _new_stats_slot(self, B: int, G: int) -> int:
         """Reserve a (B,G,2) fp32 slot of the statistics arena; returns its device pointer lazily."""
@@ -413,8 +425,8 @@ class UnetEngine(Program):
             stats = (self._new_stats_slot(x.B, G), 1)
             st_ptr = stats[0]
         self.conv_tc_flops.append(2.0 * x.B * x.H * x.W * Cout * Cin * (1 if center_only else 9))
-        self.add("dd_conv_tc", L.TC_CONV1x1, L.ptr(x.t), None, kpad, 0, L.ptr(wp), Cout, L.ptr(b_t), None, L.ptr(y.t),
-                 0, 0, st_ptr, G, x.B, x.H, x.W, Cout)
+        self.add("dd_conv_tc", L.TC_CONV1x1, L.ptr(x.t), 0, None, kpad, 0, L.ptr(wp), Cout, L.ptr(b_t), None, L.ptr(y.t),
+                 0, 0, st_ptr, G, x.B, x.H, x.W, Cout, 0, *self.splitk_args())
         return y, stats
 
     def _attn(self, res_mod, x: Act) -> Act:
@@ -426,8 +438,28 @@ class UnetEngine(Program):
                  pre.norm.eps)
         qkv, _ = self.conv(xn, attn.to_qkv, kind="1x1", bias=False)
         hid = attn.heads * attn.dim_head
+        if self.precision == "bf16":
+            # fused output: per-sample matrices M_b = ctx_b . W_out^T, then ONE tensor-core GEMM q . M_b + bias + x
+            C = x.C
+            if C % 64:
+                raise ValueError("bf16 tensor-core attention needs channel counts that are multiples of 64")
+            need = int(L.lib().dd_linattn_ws_floats(x.B, x.H * x.W, attn.heads))
+            ws = self.empty(need, dtype=torch.float32)
+            wout = self.packed((C, hid), torch.float32, lambda b: b.copy_(attn.to_out.weight.detach().reshape(C, hid)))
+            mb = self.empty(x.B, C, hid, dtype=torch.bfloat16)
+            self.add("dd_linattn_mix", L.ptr(qkv.t), self.dcode, x.B, x.H * x.W, attn.heads, attn.dim_head, L.ptr(ws), need,
+                     L.ptr(wout), C, L.ptr(mb))
+            b_t = self.f32(attn.to_out.bias)
+            y = self.act(x.H, x.W, C, x.B)
+            self.conv_tc_flops.append(2.0 * x.B * x.H * x.W * C * hid)
+            self.add("dd_conv_tc", L.TC_CONV1x1, L.ptr(qkv.t), qkv.C, None, hid, 0, L.ptr(mb), C, L.ptr(b_t), L.ptr(x.t),
+                     L.ptr(y.t), 0, 0, None, 0, x.B, x.H, x.W, C, L.TC_W_PER_SAMPLE, *self.splitk_args())
+            return y
         o = self.act(x.H, x.W, hid, x.B)
-        self.add("dd_linattn_core", L.ptr(qkv.t), L.ptr(o.t), self.dcode, x.B, x.H * x.W, attn.heads, attn.dim_head)
+        need = int(L.lib().dd_linattn_ws_floats(x.B, x.H * x.W, attn.heads))
+        ws = self.empty(need, dtype=torch.float32)
+        self.add("dd_linattn_core", L.ptr(qkv.t), L.ptr(o.t), self.dcode, x.B, x.H * x.W, attn.heads, attn.dim_head,
+                 L.ptr(ws), need)
         y, _ = self.conv(o, attn.to_out, kind="1x1", residual=x)
         return y
 

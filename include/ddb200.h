@@ -122,8 +122,19 @@ int dd_layernorm_c(const void* x, void* y, int dtype, int64_t P, int C, const fl
                    float eps, void* stream);
 
 /* LinearAttention core, blocks.py:128-133: qkv NHWC (B, n, 3*heads*dh), channel = (qkv, head, c);
- * k softmax over n, ctx = k v^T, out = ctx^T q.  out NHWC (B, n, heads*dh).  dh must be 32. */
-int dd_linattn_core(const void* qkv, void* out, int dtype, int B, int n, int heads, int dh, void* stream);
+ * k softmax over n, ctx = k v^T, out = ctx^T q.  out NHWC (B, n, heads*dh).  dh must be 32.
+ * Two launches (partial contexts per n-split, then merge + output); ws: fp32 scratch of at least
+ * dd_linattn_ws_floats(B, n, heads) floats, owned by the caller. */
+int64_t dd_linattn_ws_floats(int B, int n, int heads);
+int dd_linattn_core(const void* qkv, void* out, int dtype, int B, int n, int heads, int dh,
+                    float* ws, int64_t ws_floats, void* stream);
+
+/* Fused form for the tensor-core path: partial contexts (as above), then
+ *   Mb[b][c][h*dh+d] = sum_e ctx_{b,h}[d][e] * Wout[c][h*dh+e]   (bf16, (B, C, heads*dh), K-major)
+ * so that to_out(attention)[n][c] = sum_k q[n][k] * Mb[b][c][k] + bias[c] (blocks.py:132-134) is a single
+ * dd_conv_tc 1x1 launch with DD_TC_W_PER_SAMPLE reading q straight out of the qkv tensor.  Wout: (C, heads*dh) fp32. */
+int dd_linattn_mix(const void* qkv, int dtype, int B, int n, int heads, int dh, float* ws, int64_t ws_floats,
+                   const float* Wout, int C, void* Mb_bf16, void* stream);
 
 /* Generic direct convolution on CUDA cores, fp32 accumulate (validation mode, odd shapes, and the
  * down/up-sampling nets).  Replaces F.conv2d / F.conv_transpose2d call sites of blocks.py:35,44,78,103,
@@ -157,20 +168,28 @@ int dd_space_to_depth2(const void* x, void* y, int B, int H, int W, int C, void*
  *   kind DD_TC_DOWN    : 3x3 stride 2 pad 1 (blocks.py:44)  x = space-to-depth planes (4,B,H,W,C), H,W = OUTPUT size
  *   kind DD_TC_UPT     : ConvTranspose2d(4,2,1) (blocks.py:35) as 4 sub-pixel phases; Wp rows = phase*Cout_pad+co,
  *                        K = 4 taps * C; output (B,2H,2W,Cout)
- * x2 (optional, same geometry, C2 channels) is the skip tensor of unet.py:97 (concat-free).
+ * x_pitch: channels per pixel of the tensor x points into (0 = C1); lets a conv read the first C1 channels of a
+ * wider tensor (q out of qkv).  x2 (optional, same geometry, C2 channels) is the skip tensor of unet.py:97 (concat-free).
  * C1, C2 multiples of 64; H, W powers of two; Wp (rows, K) bf16 K-major, rows padded to bn.
  * Epilogue: + bias, GroupNorm {sum,sumsq} atomics into gn_stats (B, G, 2) when non-NULL (stats of the
  * fp32 accumulator + bias), + residual (bf16 NHWC, output geometry), store bf16 NHWC or fp32 NCHW
- * (out_nchw_f32, only the first cout_valid channels). */
+ * (out_nchw_f32, only the first cout_valid channels).
+ * splitk_ws / splitk_cnt (optional): caller-owned fp32 scratch and int32 counters, ALL ZERO on entry and left all
+ * zero on exit; when given, layers with fewer output tiles than SMs split their K loop over several CTAs that
+ * reduce through the scratch (red.add), the last-arriving CTA running the epilogue. */
 #define DD_TC_CONV3x3 0
 #define DD_TC_CONV1x1 1
 #define DD_TC_DOWN    2
 #define DD_TC_UPT     3
-int dd_conv_tc(int kind, const void* x, const void* x2, int C1, int C2,
+/* flags: DD_TC_W_PER_SAMPLE (1x1 only): wp is (B, w_rows, K), image b multiplies its own matrix -- the fused
+ * LinearAttention output GEMM  out = q . (ctx_b . W_out^T)  (blocks.py:132-134). */
+#define DD_TC_W_PER_SAMPLE 1
+int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2,
                const void* wp, int w_rows, const float* bias, const void* residual,
                void* y, int out_nchw_f32, int cout_valid,
                float* gn_stats, int G,
-               int B, int H, int W, int Cout, void* stream);
+               int B, int H, int W, int Cout, int flags,
+               float* splitk_ws, int64_t splitk_ws_floats, int32_t* splitk_cnt, int splitk_cnt_n, void* stream);
 
 /* cudaMemsetAsync(ptr, 0, bytes): clears the GroupNorm {sum,sumsq} arena once per U-Net step. */
 int dd_zero(void* ptr, int64_t bytes, void* stream);

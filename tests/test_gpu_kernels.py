@@ -135,7 +135,7 @@ def test_gn_mish_layernorm(cuda, dtype, tol):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 8e-3)])
-@pytest.mark.parametrize("n_side", [4, 32])
+@pytest.mark.parametrize("n_side", [4, 32, 80])
 def test_linear_attention_core(cuda, dtype, tol, n_side):
     lib = L()
     B, heads, dh = 2, 4, 32
@@ -146,8 +146,39 @@ def test_linear_attention_core(cuda, dtype, tol, n_side):
     ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(dim=-1), v)
     ref = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(B, heads * dh, n_side, n_side)
     out = torch.empty(B, n_side, n_side, heads * dh, dtype=dtype, device=cuda)
-    lib.call("dd_linattn_core", lib.ptr(qd), lib.ptr(out), lib.dtype_code(dtype), B, n_side * n_side, heads, dh, lib.stream())
+    need = int(lib.lib().dd_linattn_ws_floats(B, n_side * n_side, heads))
+    ws = torch.empty(need, device=cuda)
+    lib.call("dd_linattn_core", lib.ptr(qd), lib.ptr(out), lib.dtype_code(dtype), B, n_side * n_side, heads, dh,
+             lib.ptr(ws), need, lib.stream())
     assert tc.rel_l2(from_nhwc(out.cpu()), ref) < tol
+
+
+@pytest.mark.parametrize("n_side,C", [(32, 128), (8, 256), (4, 256), (2, 64)])
+def test_fused_attention_output(cuda, n_side, C):
+    """dd_linattn_mix + per-sample-weight dd_conv_tc == to_out(linear_attention(qkv)) + bias + residual."""
+    lib = L()
+    B, heads, dh = 3, 4, 32
+    hid = heads * dh
+    n = n_side * n_side
+    qkv = tc.randn(9, B, 3 * hid, n_side, n_side)
+    wout, bias = tc.randn(10, C, hid) * 0.1, tc.randn(11, C)
+    res = tc.randn(12, B, C, n_side, n_side)
+    qd = nhwc(qkv, torch.bfloat16).to(cuda)
+    rd = nhwc(res, torch.bfloat16).to(cuda)
+    qr = from_nhwc(qd.cpu()).reshape(B, 3, heads, dh, n)
+    q, k, v = qr[:, 0], qr[:, 1], qr[:, 2]
+    ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(dim=-1), v)
+    att = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(B, hid, n_side, n_side)
+    ref = F.conv2d(att, wout.reshape(C, hid, 1, 1), bias) + from_nhwc(rd.cpu())
+    need = int(lib.lib().dd_linattn_ws_floats(B, n, heads))
+    ws = torch.empty(need, device=cuda)
+    wd, bd = wout.to(cuda), bias.to(cuda)
+    mb = torch.empty(B, C, hid, dtype=torch.bfloat16, device=cuda)
+    lib.call("dd_linattn_mix", lib.ptr(qd), lib.DD_BF16, B, n, heads, dh, lib.ptr(ws), need, lib.ptr(wd), C, lib.ptr(mb), lib.stream())
+    y = torch.empty(B, n_side, n_side, C, dtype=torch.bfloat16, device=cuda)
+    lib.call("dd_conv_tc", lib.TC_CONV1x1, lib.ptr(qd), 3 * hid, None, hid, 0, lib.ptr(mb), C, lib.ptr(bd), lib.ptr(rd), lib.ptr(y),
+             0, 0, None, 0, B, n_side, n_side, C, lib.TC_W_PER_SAMPLE, None, 0, None, 0, lib.stream())
+    assert tc.rel_l2(from_nhwc(y.cpu()), ref) < 1e-2
 
 
 def test_time_bias(cuda):
@@ -172,6 +203,9 @@ CONV_CASES = [
     ("3x3", 128, 0, 128, 32, 32, 2),
     ("3x3", 256, 256, 256, 8, 8, 3),      # concat-free two-source, 2 images per M tile (+ a ragged tile)
     ("3x3", 64, 0, 64, 4, 4, 5),          # 8 images per tile, ragged batch, 8 channels per GN group
+    ("3x3", 256, 0, 256, 4, 4, 64),       # split-K (16 tiles x 12 splits) with the GroupNorm epilogue in the finisher
+    ("3x3", 256, 256, 256, 8, 8, 64),     # split-K, two sources
+    ("down", 256, 0, 256, 4, 4, 64),      # split-K on the strided conv
     ("1x1", 256, 0, 384, 16, 16, 2),
     ("1x1", 128, 0, 256, 2, 2, 3),
     ("down", 128, 0, 128, 32, 32, 2),
@@ -213,6 +247,13 @@ def test_conv_paths(cuda, kind, C1, C2, Cout, H, W, B, precision):
     prog.finalize_arena()
     prog.refresh_weights()
     prog.run_ops()
+    if precision == "bf16":            # twice: the split-K scratch and counters must come back zeroed
+        first = y.t.clone()
+        prog.stats_arena.zero_() if prog.stats_arena is not None else None
+        prog.run_ops()
+        assert tc.rel_l2(from_nhwc(y.t.cpu()), from_nhwc(first.cpu())) < 1e-3
+        ws_ptr = prog.splitk_args()
+        assert all(float(t.abs().max()) == 0.0 for t in prog.keep if t.dtype in (torch.float32, torch.int32) and t.numel() in (prog.SPLITK_WS_FLOATS, prog.SPLITK_COUNTERS))
     torch.cuda.synchronize()
     # reference on the operands the kernel really consumed
     xin = from_nhwc(xa.t.cpu())
@@ -250,8 +291,8 @@ def test_conv_tc_rejects_unsupported(cuda):
     w = torch.zeros(64, 9 * 64, dtype=torch.bfloat16, device=cuda)
     y = torch.zeros(1, 28, 28, 64, dtype=torch.bfloat16, device=cuda)
     with pytest.raises(RuntimeError, match="powers of two"):
-        lib.call("dd_conv_tc", lib.TC_CONV3x3, lib.ptr(x), None, 64, 0, lib.ptr(w), 64, None, None, lib.ptr(y), 0, 0, None, 0,
-                 1, 28, 28, 64, lib.stream())
+        lib.call("dd_conv_tc", lib.TC_CONV3x3, lib.ptr(x), 0, None, 64, 0, lib.ptr(w), 64, None, None, lib.ptr(y), 0, 0, None, 0,
+                 1, 28, 28, 64, 0, None, 0, None, 0, lib.stream())
 
 
 def test_layout_kernels(cuda):

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "ddb200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(dd_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(dd_\w+)\s*\(", hdr, flags=re.M))
     assert len(declared) >= 20
     lib = _lib.lib()
     for name in declared:
