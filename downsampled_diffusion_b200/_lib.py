@@ -44,6 +44,17 @@ SIGNATURES = {
     "dd_upsample_nearest2": [_p, _p, _i, _i, _i, _i, _i, _p],
     "dd_space_to_depth2": [_p, _p, _i, _i, _i, _i, _p],
     "dd_zero": [_p, _i64, _p],
+    "dd_conv_wgrad": [_p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "dd_colsum": [_p, _p, _i64, _i, _i, _i64, _p],
+    "dd_dropout": [_p, _p, _i64, C.c_uint32, _f, _p],
+    "dd_gn_mish_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p],
+    "dd_layernorm_c_bwd": [_p, _p, _p, _f, _i64, _i, _p, _i, _p, _p, _p],
+    "dd_linattn_save": [_p, _i, _i, _i, _p, _p],
+    "dd_linattn_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "dd_ew": [_i, _p, _p, _p, _i64, _f, _i, _p],
+    "dd_sincos_emb": [_p, _p, _p, _i, _i, _p],
+    "dd_pool2_sum": [_p, _p, _i, _i, _i, _i, _f, _p],
+    "dd_unpool2": [_p, _p, _i, _i, _i, _i, _f, _p],
     "dd_conv_tc": [_i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i64, _p, _i, _p],
 }
 PLAIN = {"dd_linattn_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_version": (C.c_int, []), "dd_device_ok": (C.c_int, []), "dd_last_error": (C.c_char_p, [])}

@@ -1,0 +1,652 @@
+"""Training path: forward + hand-written backward programs behind torch.autograd.Function.
+
+The reference trains through autograd over ATen ops (trainers/trainer_ddpm.py:225-229 calls
+`model(x)` then `.backward()`).  Here the U-Net (unet.py:74-104) and the down/up-sampling nets
+(convblocks.py:133-159) are lowered to an fp32 launch list whose backward is a second launch list of
+libddb200 kernels (backward.cu + dd_conv_direct for input gradients); torch.autograd only sees one
+Function per network.  Activations stay in the program's buffers between forward and backward.
+
+Training programs are fp32 (CUDA-core convolutions): gradients match the reference to ~1e-5; the bf16
+tensor-core backward is the next step.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from .engine import Act, EngineCache, Program, ensure_lazy
+
+GN_EPS = 1e-5
+
+
+class TrainProgram(Program):
+    """fp32 forward launch list + its backward launch list, built together."""
+
+    def __init__(self, module: torch.nn.Module, B: int):
+        super().__init__(module, B, "fp32")
+        ensure_lazy()
+        self.bops: List[Callable[[], None]] = []
+        self.bbuilders: List[Callable[[], None]] = []
+        self.gbuf: Dict[int, torch.Tensor] = {}          # id(act.t) -> gradient tensor (same shape, fp32)
+        self.gwritten = set()
+        self.pg_specs: List[Tuple[torch.nn.Parameter, int, Tuple[int, ...], Callable]] = []
+        self.pg_total = 0
+        self.pg_arena: Optional[torch.Tensor] = None
+        self._emit_bwd = False
+
+    # ---- launch recording -------------------------------------------------------------------
+    def add(self, name: str, *args) -> None:
+        if not self._emit_bwd:
+            return super().add(name, *args)
+        fn = getattr(L.lib(), name)
+
+        def op():
+            L._Counter.n += 1
+            rc = fn(*args, L.stream())
+            if rc != 0:
+                L.check(rc, name)
+        self.bops.append(op)
+
+    def add_host(self, fn: Callable[[], None]) -> None:
+        """A tiny torch-side glue step (slice copy) in the current list."""
+        if self._emit_bwd:
+            self.bops.append(fn)
+        else:
+            self.ops.append(fn)
+            self.op_names.append("host_glue")
+
+    def on_backward(self, builder: Callable[[], None]) -> None:
+        self.bbuilders.append(builder)
+
+    def build_backward(self) -> None:
+        self._emit_bwd = True
+        for b in reversed(self.bbuilders):
+            b()
+        self._emit_bwd = False
+        self.pg_arena = torch.zeros(max(self.pg_total, 1), dtype=torch.float32, device=self.device)
+
+    # ---- gradient buffers ---------------------------------------------------------------------
+    def grad(self, a: Act) -> torch.Tensor:
+        g = self.gbuf.get(id(a.t))
+        if g is None:
+            g = self.empty(*a.t.shape, dtype=torch.float32)
+            self.gbuf[id(a.t)] = g
+        return g
+
+    def has_grad(self, a: Act) -> bool:
+        return id(a.t) in self.gwritten
+
+    def gy(self, a: Act) -> torch.Tensor:
+        if not self.has_grad(a):
+            raise RuntimeError("backward program reads a gradient nobody wrote (internal error)")
+        return self.grad(a)
+
+    def acc(self, a: Act) -> int:
+        """accumulate flag for the next writer of a's gradient (0 = first writer)."""
+        flag = 1 if id(a.t) in self.gwritten else 0
+        self.gwritten.add(id(a.t))
+        return flag
+
+    def add_into(self, a: Act, src: torch.Tensor) -> None:
+        """grad(a) (+)= src"""
+        self.add("dd_ew", 3, L.ptr(src), None, L.ptr(self.grad(a)), src.numel(), 1.0, self.acc(a))
+
+    def pgrad(self, param: torch.nn.Parameter, shape: Tuple[int, ...], to_param: Callable[[torch.Tensor], torch.Tensor]):
+        """Reserve a zero-initialised fp32 accumulation buffer (kernel layout) for `param`'s gradient."""
+        n = 1
+        for s in shape:
+            n *= s
+        off = self.pg_total
+        self.pg_total += (n + 3) // 4 * 4
+        self.pg_specs.append((param, off, tuple(shape), to_param))
+        return _PgPtr(self, off)
+
+    def param_grads(self) -> Dict[int, torch.Tensor]:
+        out: Dict[int, torch.Tensor] = {}
+        for param, off, shape, to_param in self.pg_specs:
+            n = 1
+            for s in shape:
+                n *= s
+            g = to_param(self.pg_arena[off:off + n].view(shape)).reshape(param.shape).clone()
+            out[id(param)] = out[id(param)] + g if id(param) in out else g
+        return out
+
+    def run_backward(self) -> None:
+        L.call("dd_zero", self.pg_arena.data_ptr(), self.pg_arena.numel() * 4, L.stream())
+        for op in self.bops:
+            op()
+
+    # ---- differentiable building blocks --------------------------------------------------------
+    def t_conv(self, x: Optional[Act], conv: torch.nn.Module, *, x2: Act = None, kind: str = "3x3", residual: Act = None,
+               pre_mish: bool = False, tanh: bool = False, out_nchw: torch.Tensor = None, in_nchw: torch.Tensor = None,
+               in_shape: Tuple[int, int, int] = None, bias: bool = True, need_dx: bool = True) -> Act:
+        """conv / transposed conv with optional pre-Mish, residual add, tanh, NCHW input / output (fp32)."""
+        w = conv.weight
+        transposed = kind == "up"
+        if in_nchw is not None:
+            C1, H, W = in_shape
+            B = in_nchw.shape[0]
+        else:
+            C1, H, W, B = x.C, x.H, x.W, x.B
+        C2 = x2.C if x2 is not None else 0
+        Cin = C1 + C2
+        Cout = w.shape[1] if transposed else w.shape[0]
+        ks = w.shape[2]
+        if transposed:
+            stride, pad, mode, Ho, Wo = 2, 1, 1, 2 * H, 2 * W
+            wd = self.packed((ks * ks, Cin, Cout), torch.float32,
+                             lambda buf: buf.copy_(w.detach().permute(2, 3, 0, 1).reshape(ks * ks, Cin, Cout)))
+        else:
+            stride = 2 if kind == "down" else 1
+            pad = 1 if ks == 3 else 0
+            mode = 0
+            Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+            wd = self.packed((ks * ks, Cin, Cout), torch.float32,
+                             lambda buf: buf.copy_(w.detach().permute(2, 3, 1, 0).reshape(ks * ks, Cin, Cout)))
+        has_bias = bias and conv.bias is not None
+        b_t = self.f32(conv.bias) if has_bias else None
+        y = None if out_nchw is not None else self.act(Ho, Wo, Cout, B)
+        flags = (L.CONV_PRE_MISH if pre_mish else 0) | (L.CONV_TANH if tanh else 0) | \
+                (L.CONV_OUT_NCHW if out_nchw is not None else 0) | (L.CONV_IN_NCHW if in_nchw is not None else 0)
+        src = L.ptr(in_nchw) if in_nchw is not None else L.ptr(x.t)
+        self.add("dd_conv_direct", src, L.ptr(x2.t) if x2 is not None else None, C1, C2, L.DD_F32, L.ptr(wd),
+                 L.ptr(b_t) if b_t is not None else None, L.ptr(residual.t) if residual is not None else None,
+                 L.ptr(out_nchw) if out_nchw is not None else L.ptr(y.t), L.DD_F32, B, H, W, Cout, ks, stride, pad, mode, flags)
+
+        # ---- backward -------------------------------------------------------------------------
+        if transposed:
+            to_w = lambda g: g.view(ks, ks, Cin, Cout).permute(2, 3, 0, 1)          # -> (Cin, Cout, k, k)
+        else:
+            to_w = lambda g: g.view(ks, ks, Cin, Cout).permute(3, 2, 0, 1)          # -> (Cout, Cin, k, k)
+        dw = self.pgrad(w, (ks * ks, Cin, Cout), to_w)
+        db = self.pgrad(conv.bias, (Cout,), lambda g: g) if has_bias else None
+        # input-gradient weights per source: wT[tap'][co][ci]
+        srcs = []
+        if need_dx and in_nchw is None:
+            srcs.append((x, 0, C1))
+        if x2 is not None:
+            srcs.append((x2, C1, C2))
+        wts = []
+        for (_, c_lo, c_n) in srcs:
+            def fill(buf, c_lo=c_lo, c_n=c_n):
+                wdt = w.detach()
+                if transposed:                       # (Cin, Cout, k, k): dX = conv(gY, stride 2) with wT[tap][co][ci]
+                    buf.copy_(wdt[c_lo:c_lo + c_n].permute(2, 3, 1, 0).reshape(ks * ks, Cout, c_n))
+                elif kind == "down":                 # dX = transposed conv of gY with wT[tap][co][ci] = W[co][ci][ky][kx]
+                    buf.copy_(wdt[:, c_lo:c_lo + c_n].permute(2, 3, 0, 1).reshape(ks * ks, Cout, c_n))
+                else:                                # stride 1: correlation with the flipped kernel
+                    buf.copy_(wdt[:, c_lo:c_lo + c_n].flip(2, 3).permute(2, 3, 0, 1).reshape(ks * ks, Cout, c_n))
+            wts.append(self.packed((ks * ks, Cout, c_n), torch.float32, fill))
+        ypre = self.empty(*out_nchw.shape, dtype=torch.float32) if (tanh and out_nchw is not None) else None
+
+        def backward():
+            if out_nchw is not None:
+                g = self.out_grad                     # NCHW fp32 gradient handed in by autograd
+                if tanh:
+                    self.add("dd_ew", 2, L.ptr(out_nchw), L.ptr(g), L.ptr(ypre), out_nchw.numel(), 1.0, 0)
+                    g = ypre
+                gflags = L.CONV_OUT_NCHW
+            else:
+                g = self.gy(y)
+                gflags = 0
+            M = B * Ho * Wo
+            if db is not None:
+                self.add("dd_colsum", L.ptr(g), db, M, Cout, 1 if out_nchw is not None else 0, Ho * Wo)
+            self.add("dd_conv_wgrad", src, L.ptr(x2.t) if x2 is not None else None, C1, C2, L.DD_F32, L.ptr(g), dw, B, H, W, Cout,
+                     ks, stride, pad, mode, (flags & (L.CONV_PRE_MISH | L.CONV_IN_NCHW)) | gflags)
+            if residual is not None:
+                self.add_into(residual, g)
+            for (a, c_lo, c_n), wt in zip(srcs, wts):
+                direct = (not pre_mish) and not self.has_grad(a)
+                dst = self.grad(a) if direct else self.empty(*a.t.shape, dtype=torch.float32)
+                gin = L.CONV_IN_NCHW if out_nchw is not None else 0
+                if transposed:        # forward convT(4,2,1): dX = conv(gY, k, stride 2, pad 1)
+                    self.add("dd_conv_direct", L.ptr(g), None, Cout, 0, L.DD_F32, L.ptr(wt), None, None, L.ptr(dst), L.DD_F32,
+                             B, Ho, Wo, c_n, ks, 2, 1, 0, gin)
+                elif kind == "down":  # forward conv(3, stride 2, pad 1): dX = transposed conv of gY
+                    self.add("dd_conv_direct", L.ptr(g), None, Cout, 0, L.DD_F32, L.ptr(wt), None, None, L.ptr(dst), L.DD_F32,
+                             B, Ho, Wo, c_n, ks, 2, 1, 1, gin)
+                else:
+                    self.add("dd_conv_direct", L.ptr(g), None, Cout, 0, L.DD_F32, L.ptr(wt), None, None, L.ptr(dst), L.DD_F32,
+                             B, Ho, Wo, c_n, ks, 1, pad, 0, gin)
+                if direct:
+                    self.acc(a)
+                elif pre_mish:        # d mish(x) / dx
+                    self.add("dd_ew", 1, L.ptr(a.t), L.ptr(dst), L.ptr(self.grad(a)), dst.numel(), 1.0, self.acc(a))
+                else:
+                    self.add_into(a, dst)
+        self.on_backward(backward)
+        return y
+
+    def t_gn_mish(self, x: Act, gn: torch.nn.GroupNorm, *, tb: torch.Tensor = None, tb_col: int = None, dtb: torch.Tensor = None,
+                  residual: Act = None, dropout: float = 0.0) -> Act:
+        B, HW, C, G = x.B, x.H * x.W, x.C, gn.num_groups
+        st = self.empty(B, G, 2, dtype=torch.float32)
+        gamma, beta = self.f32(gn.weight), self.f32(gn.bias)
+        y = self.act(x.H, x.W, C, B)
+        self.add("dd_gn_stats", L.ptr(x.t), L.DD_F32, B, HW, C, G, GN_EPS, L.ptr(st))
+        J = tb.shape[1] if tb is not None else 0
+        self.add("dd_gn_mish", L.ptr(x.t), L.ptr(y.t), L.DD_F32, B, HW, C, G, L.ptr(st), 0, GN_EPS, L.ptr(gamma), L.ptr(beta),
+                 (tb.data_ptr() + 4 * tb_col) if tb is not None else None, J, None, 0,
+                 L.ptr(residual.t) if residual is not None else None)
+        out = y
+        seed_box = None
+        if dropout > 0:
+            out = self.act(x.H, x.W, C, B)
+            seed_box = _SeedArg(self)
+            self.add("dd_dropout", L.ptr(y.t), L.ptr(out.t), y.t.numel(), seed_box, float(dropout))
+        s1, s2, s3 = (self.empty(B, C, dtype=torch.float32) for _ in range(3))
+        dgam = self.pgrad(gn.weight, (C,), lambda g: g)
+        dbet = self.pgrad(gn.bias, (C,), lambda g: g)
+
+        def backward():
+            g = self.gy(out)
+            if dropout > 0:
+                gm = self.grad(y)
+                self.add("dd_dropout", L.ptr(g), L.ptr(gm), g.numel(), seed_box, float(dropout))
+                self.gwritten.add(id(y.t))
+                g = gm
+            if residual is not None:
+                self.add_into(residual, g)
+            self.add("dd_gn_mish_bwd", L.ptr(x.t), L.ptr(g), L.ptr(st), L.ptr(gamma), L.ptr(beta), B, HW, C, G, L.ptr(s1), L.ptr(s2),
+                     L.ptr(s3), L.ptr(self.grad(x)), self.acc(x))
+            self.add("dd_colsum", L.ptr(s1), dgam, B, C, 0, 1)
+            self.add("dd_colsum", L.ptr(s2), dbet, B, C, 0, 1)
+            if tb is not None:
+                self.add_host(lambda: dtb[:, tb_col:tb_col + C].copy_(s3))
+        self.on_backward(backward)
+        return out
+
+    def t_mish(self, x: Act) -> Act:
+        y = self.act(x.H, x.W, x.C, x.B)
+        n = x.t.numel()
+        self.add("dd_ew", 0, L.ptr(x.t), None, L.ptr(y.t), n, 1.0, 0)
+
+        def backward():
+            self.add("dd_ew", 1, L.ptr(x.t), L.ptr(self.gy(y)), L.ptr(self.grad(x)), n, 1.0, self.acc(x))
+        self.on_backward(backward)
+        return y
+
+
+class _PgPtr:
+    """ctypes pointer into the parameter-gradient arena, resolved at launch time."""
+
+    def __init__(self, prog, off):
+        self.prog, self.off = prog, off
+
+    @property
+    def _as_parameter_(self):
+        return int(self.prog.pg_arena.data_ptr() + 4 * self.off)
+
+
+class _SeedArg:
+    """dropout seed drawn per forward call (torch RNG on the host), reused by the backward launch."""
+
+    def __init__(self, prog):
+        self.prog = prog
+
+    @property
+    def _as_parameter_(self):
+        return int(self.prog.dropout_seed & 0xFFFFFFFF)
+
+
+def _ensure_types():
+    """ctypes resolves `_as_parameter_` at call time, so _PgPtr / _SeedArg need no special argtypes."""
+    ensure_lazy()
+
+
+# =====================================================================================================
+class UnetTrainEngine(TrainProgram):
+    """U-Net forward/backward for a fixed (B, H, W) (training: per-sample t, optional dropout)."""
+
+    def __init__(self, unet, B: int, H: int, W: int, need_input_grad: bool):
+        super().__init__(unet, B)
+        _ensure_types()
+        self.H, self.W, self.need_input_grad = H, W, need_input_grad
+        n_levels = len(unet.downs)
+        if H % (1 << (n_levels - 1)) or W % (1 << (n_levels - 1)):
+            raise ValueError(f"input {H}x{W} must be divisible by 2^{n_levels - 1}")
+        dim, cin = unet.dim, unet.in_channels
+        self.dropout_seed = 0
+        self.x_in = self.empty(B, cin, H, W, dtype=torch.float32)
+        self.eps_out = self.empty(B, cin, H, W, dtype=torch.float32)
+        self.out_grad = self.empty(B, cin, H, W, dtype=torch.float32)
+        self.dx_in = self.empty(B, cin, H, W, dtype=torch.float32) if need_input_grad else None
+        self.t_float = self.empty(B, dtype=torch.float32)
+        half = dim // 2
+        self.freq = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1))).to(self.device)
+        self.keep.append(self.freq)
+        # ---- time path: sincos -> Linear -> Mish -> Linear -> Mish -> [all block MLPs as one Linear] ----
+        res_blocks = [m for m in unet.modules() if type(m).__name__ == "ResnetBlock"]
+        self.tb_off, J = {}, 0
+        for rb in res_blocks:
+            self.tb_off[id(rb)] = J
+            J += rb.mlp[1].out_features
+        emb = self.act(1, 1, dim)
+        self.add("dd_sincos_emb", L.ptr(self.t_float), L.ptr(self.freq), L.ptr(emb.t), B, dim)
+        h1 = self.t_linear(emb, unet.time_mlp[1], need_dx=False)
+        a1 = self.t_mish(h1)
+        temb = self.t_linear(a1, unet.time_mlp[3])
+        a2 = self.t_mish(temb)
+        tb = self.act(1, 1, J)
+        self.tb_rows = tb.t.view(B, J)
+        self.dtb = self.grad(tb).view(B, J)
+        col = 0
+        outs = []
+        for rb in res_blocks:          # one small GEMM per block keeps each mlp.1 parameter's gradient separate
+            o = self.t_linear(a2, rb.mlp[1])
+            outs.append((rb, o))
+        # gather the per-block outputs into one (B, J) row table read by the GroupNorm kernels
+        def gather():
+            for rb, o in outs:
+                c0 = self.tb_off[id(rb)]
+                self.tb_rows[:, c0:c0 + o.C].copy_(o.t.view(B, o.C))
+        self.add_host(gather)
+
+        def scatter_back():
+            for rb, o in outs:
+                c0 = self.tb_off[id(rb)]
+                self.grad(o).view(B, o.C).copy_(self.dtb[:, c0:c0 + o.C])
+                self.gwritten.add(id(o.t))
+        # executed in the backward pass after every GroupNorm wrote its dtb slice
+        def scatter_builder():
+            for rb, o in outs:
+                self.gwritten.add(id(o.t))
+            self.add_host(scatter_back)
+        self._build_main(unet, scatter_builder)
+        self.build_backward()
+        self.refresh_weights()
+
+    def t_linear(self, x: Act, lin: torch.nn.Linear, need_dx: bool = True) -> Act:
+        """nn.Linear on (B, C) rows, as a 1x1 convolution over a 1x1 image."""
+        shim = _LinearAsConv(lin)
+        return self.t_conv(x, shim, kind="1x1", need_dx=need_dx)
+
+    def _resnet(self, rb, x: Act, x2: Act = None, need_dx: bool = True) -> Act:
+        col = self.tb_off[id(rb)]
+        c1, g1 = rb.block1.block[0], rb.block1.block[1]
+        c2, g2 = rb.block2.block[0], rb.block2.block[1]
+        h = self.t_conv(x, c1, x2=x2, kind="3x3", need_dx=need_dx)
+        if not isinstance(rb.res_conv, torch.nn.Identity):
+            res = self.t_conv(x, rb.res_conv, x2=x2, kind="1x1", need_dx=need_dx)
+        else:
+            res = x
+        p = rb.dropout.p if (self.module.training and rb.dropout.p > 0) else 0.0
+        h = self.t_gn_mish(h, g1, tb=self.tb_rows, tb_col=col, dtb=self.dtb, dropout=p)
+        h = self.t_conv(h, c2, kind="3x3")
+        return self.t_gn_mish(h, g2, residual=res)
+
+    def _attn(self, res_mod, x: Act) -> Act:
+        pre, attn = res_mod.fn, res_mod.fn.fn
+        B, n, C = x.B, x.H * x.W, x.C
+        g, b = self.f32(pre.norm.g), self.f32(pre.norm.b)
+        xn = self.act(x.H, x.W, C, B)
+        self.add("dd_layernorm_c", L.ptr(x.t), L.ptr(xn.t), L.DD_F32, B * n, C, L.ptr(g), L.ptr(b), pre.norm.eps)
+        dg = self.pgrad(pre.norm.g, (C,), lambda t: t.view(1, C, 1, 1))
+        dbb = self.pgrad(pre.norm.b, (C,), lambda t: t.view(1, C, 1, 1))
+
+        def ln_backward():
+            self.add("dd_layernorm_c_bwd", L.ptr(x.t), L.ptr(self.gy(xn)), L.ptr(g), pre.norm.eps, B * n, C, L.ptr(self.grad(x)),
+                     self.acc(x), dg, dbb)
+        self.on_backward(ln_backward)                 # registration order = forward order (walked in reverse)
+        qkv = self.t_conv(xn, attn.to_qkv, kind="1x1", bias=False)
+        hid = attn.heads * attn.dim_head
+        o = self.act(x.H, x.W, hid, B)
+        need = int(L.lib().dd_linattn_ws_floats(B, n, attn.heads))
+        ws = self.empty(need, dtype=torch.float32)
+        saved = self.empty(B * attn.heads * 1088, dtype=torch.float32)
+        dctx = self.empty(B * attn.heads * 1024, dtype=torch.float32)
+        self.add("dd_linattn_core", L.ptr(qkv.t), L.ptr(o.t), L.DD_F32, B, n, attn.heads, attn.dim_head, L.ptr(ws), need)
+        self.add("dd_linattn_save", L.ptr(ws), B, n, attn.heads, L.ptr(saved))
+
+        def core_backward():
+            self.add("dd_linattn_bwd", L.ptr(qkv.t), L.ptr(self.gy(o)), L.ptr(saved), L.ptr(dctx), L.ptr(self.grad(qkv)), B, n,
+                     attn.heads, attn.dim_head)
+            self.gwritten.add(id(qkv.t))
+        self.on_backward(core_backward)
+        y = self.t_conv(o, attn.to_out, kind="1x1", residual=x)
+        return y
+
+    def _build_main(self, unet, scatter_builder) -> None:
+        B, H, W, cin = self.B, self.H, self.W, unet.in_channels
+        x = self.act(H, W, cin)
+        self.add("dd_nchw_to_nhwc", L.ptr(self.x_in), L.ptr(x.t), L.DD_F32, B, cin, H, W)
+        x0 = x
+
+        def input_backward():
+            if self.need_input_grad:
+                self.add("dd_nhwc_to_nchw", L.ptr(self.gy(x0)), L.DD_F32, L.ptr(self.dx_in), B, cin, H, W)
+        # the time-path scatter must run after all GroupNorm backwards, i.e. be registered BEFORE them
+        self.on_backward(scatter_builder)
+        self.on_backward(input_backward)
+        skips: List[Act] = []
+        first = True
+        for rb1, rb2, attn, down in unet.downs:
+            x = self._resnet(rb1, x, need_dx=(self.need_input_grad or not first))
+            first = False
+            x = self._resnet(rb2, x)
+            x = self._attn(attn, x)
+            skips.append(x)
+            if not isinstance(down, torch.nn.Identity):
+                x = self.t_conv(x, down.conv, kind="down")
+        x = self._resnet(unet.mid_block1, x)
+        x = self._attn(unet.mid_attn, x)
+        x = self._resnet(unet.mid_block2, x)
+        for rb1, rb2, attn, up in unet.ups:
+            x = self._resnet(rb1, x, x2=skips.pop())
+            x = self._resnet(rb2, x)
+            x = self._attn(attn, x)
+            if not isinstance(up, torch.nn.Identity):
+                x = self.t_conv(x, up.conv, kind="up")
+        blk, last = unet.final_conv[0], unet.final_conv[1]
+        h = self.t_conv(x, blk.block[0], kind="3x3")
+        h = self.t_gn_mish(h, blk.block[1])
+        self.t_conv(h, last, kind="1x1", out_nchw=self.eps_out)
+
+    def forward(self, x: torch.Tensor, time: torch.Tensor) -> torch.Tensor:
+        self.refresh_weights()
+        self.x_in.copy_(x)
+        self.t_float.copy_(time.to(torch.float32))
+        self.dropout_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        self.run_ops()
+        return self.eps_out.clone()
+
+    def backward(self, grad_out: torch.Tensor):
+        self.out_grad.copy_(grad_out)
+        self.dtb.zero_()
+        self.run_backward()
+        return self.dx_in.clone() if self.need_input_grad else None
+
+
+class _LinearAsConv:
+    """Presents an nn.Linear as a 1x1 convolution module (weight (out, in, 1, 1)) to t_conv."""
+
+    def __init__(self, lin: torch.nn.Linear):
+        self.lin = lin
+        self.bias = lin.bias
+
+    @property
+    def weight(self):
+        return _W4(self.lin.weight)
+
+
+class _W4:
+    """(out, in) parameter viewed as (out, in, 1, 1); identity-hashable as the underlying parameter."""
+
+    def __init__(self, p):
+        self.p = p
+        self.shape = (p.shape[0], p.shape[1], 1, 1)
+
+    def detach(self):
+        return self.p.detach().view(*self.shape)
+
+
+# make pgrad accept the _W4 wrapper: gradients are registered against the real parameter
+_orig_pgrad = TrainProgram.pgrad
+
+
+def _pgrad(self, param, shape, to_param):
+    if isinstance(param, _W4):
+        real = param.p
+        return _orig_pgrad(self, real, shape, lambda g, f=to_param, r=real: f(g).reshape(r.shape))
+    return _orig_pgrad(self, param, shape, to_param)
+
+
+TrainProgram.pgrad = _pgrad
+
+
+# =====================================================================================================
+class ResampleTrainProgram(TrainProgram):
+    """ConvResNet / SimpleDownConv / SimpleUpConv forward + backward (fp32), NCHW in / out."""
+
+    def __init__(self, net, B: int, C: int, H: int, W: int, tanh: bool, need_input_grad: bool):
+        super().__init__(net, B)
+        _ensure_types()
+        from .downsampled import ConvResBlock
+        self.need_input_grad = need_input_grad
+        self.x_in = self.empty(B, C, H, W, dtype=torch.float32)
+        layers = list(net.conv)
+        x: Optional[Act] = None
+        self.out = None
+        self.dx_in = None
+        for i, m in enumerate(layers):
+            last = i == len(layers) - 1
+            if isinstance(m, ConvResBlock):
+                if m.drop.p > 0 and net.training:
+                    raise RuntimeError("Dropout2d in the resampling nets is only supported with p=0 (reference default)")
+                h = self.t_conv(x, m.c1, kind="1x1", pre_mish=True)
+                h = self.t_conv(h, m.c2, kind="3x3", pre_mish=True)
+                h = self.t_conv(h, m.c3, kind="3x3", pre_mish=True)
+                x = self.t_conv(h, m.c4, kind="1x1", pre_mish=True, residual=x if m.residual else None)
+                if m.upsample:
+                    x = self.t_resample(x, up=True)
+                elif m.downsample:
+                    x = self.t_resample(x, up=False)
+                continue
+            transposed = isinstance(m, torch.nn.ConvTranspose2d)
+            kind = "up" if transposed else ("down" if m.stride[0] == 2 else ("3x3" if m.kernel_size[0] == 3 else "1x1"))
+            first = x is None
+            if last:
+                Cout = m.out_channels
+                Hi, Wi = (H, W) if first else (x.H, x.W)
+                Ho, Wo = (2 * Hi, 2 * Wi) if transposed else ((Hi // 2, Wi // 2) if kind == "down" else (Hi, Wi))
+                self.out = self.empty(B, Cout, Ho, Wo, dtype=torch.float32)
+                self.out_grad = self.empty(B, Cout, Ho, Wo, dtype=torch.float32)
+            if first:
+                if need_input_grad:
+                    # materialise the NHWC copy so the input gradient has a home
+                    x = self.act(H, W, C)
+                    self.add("dd_nchw_to_nhwc", L.ptr(self.x_in), L.ptr(x.t), L.DD_F32, B, C, H, W)
+                    x0 = x
+                    self.dx_in = self.empty(B, C, H, W, dtype=torch.float32)
+
+                    def input_backward(x0=x0):
+                        self.add("dd_nhwc_to_nchw", L.ptr(self.gy(x0)), L.DD_F32, L.ptr(self.dx_in), B, C, H, W)
+                    self.on_backward(input_backward)
+                    x = self.t_conv(x, m, kind=kind, out_nchw=self.out if last else None, tanh=tanh and last)
+                else:
+                    x = self.t_conv(None, m, kind=kind, in_nchw=self.x_in, in_shape=(C, H, W),
+                                    out_nchw=self.out if last else None, tanh=tanh and last)
+            else:
+                x = self.t_conv(x, m, kind=kind, out_nchw=self.out if last else None, tanh=tanh and last)
+        if self.out is None:
+            raise ValueError("resampling net must end in a plain convolution")
+        self.build_backward()
+        self.refresh_weights()
+
+    def t_resample(self, x: Act, up: bool) -> Act:
+        B, H, W, C = x.B, x.H, x.W, x.C
+        if up:      # nearest x2 (convblocks.py:127); backward = 2x2 block sum
+            y = self.act(2 * H, 2 * W, C, B)
+            self.add("dd_unpool2", L.ptr(x.t), L.ptr(y.t), B, H, W, C, 1.0)
+
+            def backward():
+                tmp_needed = self.has_grad(x)
+                dst = self.empty(*x.t.shape, dtype=torch.float32) if tmp_needed else self.grad(x)
+                self.add("dd_pool2_sum", L.ptr(self.gy(y)), L.ptr(dst), B, 2 * H, 2 * W, C, 1.0)
+                if tmp_needed:
+                    self.add_into(x, dst)
+                else:
+                    self.acc(x)
+        else:       # avg_pool2d(2,2) (convblocks.py:129); backward = 0.25 * nearest x2
+            y = self.act(H // 2, W // 2, C, B)
+            self.add("dd_pool2_sum", L.ptr(x.t), L.ptr(y.t), B, H, W, C, 0.25)
+
+            def backward():
+                tmp_needed = self.has_grad(x)
+                dst = self.empty(*x.t.shape, dtype=torch.float32) if tmp_needed else self.grad(x)
+                self.add("dd_unpool2", L.ptr(self.gy(y)), L.ptr(dst), B, H // 2, W // 2, C, 0.25)
+                if tmp_needed:
+                    self.add_into(x, dst)
+                else:
+                    self.acc(x)
+        self.on_backward(backward)
+        return y
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self.refresh_weights()
+        self.x_in.copy_(x)
+        self.run_ops()
+        return self.out.clone()
+
+    def backward(self, grad_out: torch.Tensor):
+        self.out_grad.copy_(grad_out)
+        self.run_backward()
+        return self.dx_in.clone() if self.need_input_grad else None
+
+
+# =====================================================================================================
+class _NetFn(torch.autograd.Function):
+    """One autograd node per network: forward/backward are the program's two launch lists."""
+
+    @staticmethod
+    def forward(ctx, prog, x, extra, *params):
+        ctx.prog = prog
+        ctx.n_params = len(params)
+        ctx.params = params
+        with torch.no_grad():
+            return prog.forward(x, extra) if extra is not None else prog.forward(x)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        prog = ctx.prog
+        with torch.no_grad():
+            dx = prog.backward(grad_out.contiguous().float())
+            pg = prog.param_grads()
+        grads = tuple(pg.get(id(p)) if ctx.needs_input_grad[3 + i] else None for i, p in enumerate(ctx.params))
+        return (None, dx if ctx.needs_input_grad[1] else None, None) + grads
+
+
+def _train_cache(module) -> EngineCache:
+    if not hasattr(module, "_train_programs"):
+        module._train_programs = EngineCache()
+    return module._train_programs
+
+
+def unet_apply(unet, eng_unused, x: torch.Tensor, time: torch.Tensor) -> torch.Tensor:
+    B, _, H, W = x.shape
+    need_dx = bool(x.requires_grad)
+    key = (B, H, W, need_dx, unet.training)
+    cache = _train_cache(unet)
+    prog = cache.get(key)
+    if prog is None:
+        prog = UnetTrainEngine(unet, B, H, W, need_dx)
+        cache[key] = prog
+    params = tuple(unet.parameters())
+    return _NetFn.apply(prog, x.contiguous().float(), time, *params)
+
+
+def resample_apply(net, x: torch.Tensor, tanh: bool) -> torch.Tensor:
+    B, C, H, W = x.shape
+    need_dx = bool(x.requires_grad)
+    key = (B, C, H, W, bool(tanh), need_dx, net.training)
+    cache = _train_cache(net)
+    prog = cache.get(key)
+    if prog is None:
+        prog = ResampleTrainProgram(net, B, C, H, W, bool(tanh), need_dx)
+        cache[key] = prog
+    params = tuple(net.parameters())
+    return _NetFn.apply(prog, x.contiguous().float(), None, *params)

@@ -24,11 +24,11 @@ __device__ __forceinline__ float conv_fetch(const ConvDirectArgs& a, int b, int 
         const int ky = tap / a.ksize, kx = tap - ky * a.ksize;
         ih = oh * a.stride - a.pad + ky;
         iw = ow * a.stride - a.pad + kx;
-    } else {   // ConvTranspose2d(4, 2, 1): oh = 2*ih - 1 + ky
-        const int ky = tap >> 2, kx = tap & 3;
-        const int th = oh + 1 - ky, tw = ow + 1 - kx;
-        if ((th | tw) < 0 || (th & 1) || (tw & 1)) return 0.f;
-        ih = th >> 1; iw = tw >> 1;
+    } else {   // transposed convolution: oh = ih*stride - pad + ky  (ConvTranspose2d(4,2,1); dgrad of a strided conv)
+        const int ky = tap / a.ksize, kx = tap - ky * a.ksize;
+        const int th = oh + a.pad - ky, tw = ow + a.pad - kx;
+        if ((th | tw) < 0 || (th % a.stride) || (tw % a.stride)) return 0.f;
+        ih = th / a.stride; iw = tw / a.stride;
     }
     if (ih < 0 || ih >= a.H || iw < 0 || iw >= a.W) return 0.f;
     float v;
@@ -149,9 +149,9 @@ extern "C" int dd_conv_direct(const void* x, const void* x2, int C1, int C2, int
         a.Wo = (W + 2 * pad - ksize) / stride + 1;
         a.K = ksize * ksize * (C1 + C2);
     } else {
-        DD_REQUIRE(ksize == 4 && stride == 2 && pad == 1, "conv_direct: transposed mode is ConvTranspose2d(4,2,1) only");
-        a.Ho = 2 * H; a.Wo = 2 * W;
-        a.K = 16 * (C1 + C2);
+        DD_REQUIRE(stride >= 1 && ksize >= stride, "conv_direct: bad transposed geometry");
+        a.Ho = stride * H; a.Wo = stride * W;          // output_padding chosen so the size is exactly stride*H
+        a.K = ksize * ksize * (C1 + C2);
     }
     a.M = (int64_t)B * a.Ho * a.Wo;
     dim3 grid((unsigned)((a.M + 63) / 64), (unsigned)((Cout + 63) / 64));

@@ -111,4 +111,3 @@ class DownsampleDDPMAutoencoder(DownsampleDDPM):
         obj = (L_ddpm + L_rec).mean()
         return obj, {"latent": L_ddpm.mean(), "recon": L_rec.mean()}
 
-    p_losses = losses

@@ -140,7 +140,8 @@ int dd_linattn_mix(const void* qkv, int dtype, int B, int n, int heads, int dh, 
  * down/up-sampling nets).  Replaces F.conv2d / F.conv_transpose2d call sites of blocks.py:35,44,78,103,
  * 123-124, unet.py:71, convblocks.py:29-67.
  *   x (B,H,W,C1) [+ x2 (B,H,W,C2) concatenated on channels: unet.py:97], w (taps, C1+C2, Cout) fp32,
- *   mode 0: conv k x k, stride, pad;  mode 1: ConvTranspose2d(k=4,s=2,p=1) (w tap = ky*4+kx).
+ *   mode 0: conv k x k, stride, pad;  mode 1: transposed conv, oh = ih*stride - pad + ky, output size stride*H
+ *           (ConvTranspose2d(4,2,1) of blocks.py:35, and the input gradient of a strided conv); w tap = ky*k+kx.
  *   flags: DD_CONV_PRE_MISH applies Mish to the input on load (convblocks.py:118-121),
  *          DD_CONV_TANH applies tanh to the output (dddpm.py:99-100,110-111),
  *          DD_CONV_OUT_NCHW writes fp32 NCHW, DD_CONV_IN_NCHW reads fp32 NCHW (x2 must be NULL). */
@@ -190,6 +191,42 @@ int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int
                float* gn_stats, int G,
                int B, int H, int W, int Cout, int flags,
                float* splitk_ws, int64_t splitk_ws_floats, int32_t* splitk_cnt, int splitk_cnt_n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward of the training denoising step (fp32 programs): autograd of ddpm.py:290-315 / dddpm.py:122-177.
+ * Input gradients of convolutions are dd_conv_direct launches with transposed / flipped weights.
+ * ---------------------------------------------------------------------------------------- */
+/* dW[tap][ci][co] += sum_pixels X_tap[pixel][ci] * dY[pixel][co]; geometry and flags as dd_conv_direct
+ * (DD_CONV_OUT_NCHW: dy is fp32 NCHW; DD_CONV_PRE_MISH / DD_CONV_IN_NCHW apply to x).  dw fp32 (taps, C1+C2, Cout). */
+int dd_conv_wgrad(const void* x, const void* x2, int C1, int C2, int in_dtype, const float* dy, float* dw,
+                  int B, int H, int W, int Cout, int ksize, int stride, int pad, int mode, int flags, void* stream);
+/* out[c] += sum_m x[m][c]  (x: (M, C) fp32, or NCHW with M = B*HW when nchw != 0): bias gradients. */
+int dd_colsum(const float* x, float* out, int64_t M, int C, int nchw, int64_t HW, void* stream);
+/* y = x * mask / (1-p), mask from a counter-based hash of (seed, index): nn.Dropout of blocks.py:111 (the same
+ * call with the same seed masks the gradient in the backward pass). */
+int dd_dropout(const float* x, float* y, int64_t n, uint32_t seed, float p, void* stream);
+/* GroupNorm+Mish backward (blocks.py:79-84): x pre-norm conv output, stats {mean,rstd}; writes per-(b,c) sums
+ * s_dhxh, s_dh, s_dy ((B, C) fp32: reduce over b for dgamma, dbeta; s_dy is the time-bias gradient) and dx. */
+int dd_gn_mish_bwd(const float* x, const float* dy, const float* stats, const float* gamma, const float* beta,
+                   int B, int HW, int C, int G, float* s_dhxh, float* s_dh, float* s_dy, float* dx, int accumulate,
+                   void* stream);
+/* channel LayerNorm backward (blocks.py:57-60); dg, db accumulate (+=). */
+int dd_layernorm_c_bwd(const float* x, const float* dy, const float* g, float eps, int64_t P, int C, float* dx,
+                       int accumulate, float* dg, float* db, void* stream);
+/* merged attention state {max_d, sum_d, ctx[d][e]} per (b, head) from the partials dd_linattn_core left in ws. */
+int dd_linattn_save(const float* ws, int B, int n, int heads, float* saved, void* stream);
+/* LinearAttention core backward (blocks.py:128-133): dqkv from dout; dctx: (B*heads*1024) fp32 scratch. */
+int dd_linattn_bwd(const float* qkv, const float* dout, const float* saved, float* dctx, float* dqkv,
+                   int B, int n, int heads, int dh, void* stream);
+/* elementwise: mode 0 y=mish(x); 1 y=g*mish'(x); 2 y=g*(1-x^2) (tanh backward, x = tanh output); 3 y=alpha*x;
+ * accumulate != 0 adds into y. */
+int dd_ew(int mode, const float* x, const float* g, float* y, int64_t n, float alpha, int accumulate, void* stream);
+/* SinusoidalPosEmb (blocks.py:22-29): out (R, dim) = [sin(t*freq), cos(t*freq)]. */
+int dd_sincos_emb(const float* t, const float* freq, float* out, int R, int dim, void* stream);
+/* y[b,h/2,w/2,c] = scale * (2x2 block sum of x)  and  y[b,2h,2w,c] = scale * x[b,h,w,c]  (fp32 NHWC): the
+ * forward/backward pair of avg_pool2d(2,2) and nearest x2 (convblocks.py:127-129). */
+int dd_pool2_sum(const float* x, float* y, int B, int H, int W, int C, float scale, void* stream);
+int dd_unpool2(const float* x, float* y, int B, int H, int W, int C, float scale, void* stream);
 
 /* cudaMemsetAsync(ptr, 0, bytes): clears the GroupNorm {sum,sumsq} arena once per U-Net step. */
 int dd_zero(void* ptr, int64_t bytes, void* stream);

@@ -1,0 +1,220 @@
+"""Training denoising step on the B200: objectives and gradients of DDPM.losses / DownsampleDDPM(.Autoencoder).losses
+against the golden vectors the real reference produced with torch autograd on CPU (oracle/make_golden.py), plus
+kernel-level backward checks against torch-CPU autograd.  Training programs are fp32: tolerance 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import downsampled_diffusion_b200 as dd
+from oracle import ddpm_oracle as O
+from tests import common as tc
+
+pytestmark = pytest.mark.gpu
+
+
+def G(golden, key):
+    return torch.from_numpy(np.asarray(golden[key]))
+
+
+@pytest.mark.parametrize("kind", ["dddpm_ae", "dddpm"])
+def test_dddpm_losses_and_gradients(cuda, golden, kind):
+    m = tc.build_model(dict(tc.CS, precision="fp32"), dd, kind, device="cuda").to(cuda)
+    m.train()
+    x = tc.rand_pm1(51, 4, 3, 32, 32).to(cuda)
+    t = torch.tensor([3, 50, 99, 700], device=cuda)
+    torch.manual_seed(7)
+    eps = torch.randn(4, 8, 8, 8).to(cuda)           # the draw the reference made with randn_like(z) on CPU
+    obj, d = m.losses(x, t, eps=eps)
+    obj.backward()
+    for key, val in (("obj", obj), ("latent", d["latent"]), ("recon", d["recon"])):
+        ref = float(golden[f"loss.{kind}.{key}"])
+        assert abs(float(val) - ref) <= 1e-4 * abs(ref) + 1e-7, key
+    names = [n for n, _ in m.named_parameters()]
+    norms = np.asarray(golden[f"loss.{kind}.grad_norms"])
+    worst = 0.0
+    for (n, p), ref in zip(m.named_parameters(), norms):
+        got = 0.0 if p.grad is None else float(p.grad.double().norm())
+        err = abs(got - ref) / max(ref, 1e-6)
+        worst = max(worst, err)
+        assert err < 2e-3, f"{n}: |grad| {got} vs reference {ref}"
+    print(f"{kind}: worst relative gradient-norm error over {len(names)} parameters: {worst:.2e}")
+    params = dict(m.named_parameters())
+    for n in ("latent_model.final_conv.1.weight", "latent_model.downs.0.0.block1.block.1.weight",
+              "latent_model.mid_attn.fn.norm.g", "latent_model.time_mlp.1.bias", "upsample.conv.0.weight",
+              "downsample.conv.7.bias", "latent_model.ups.0.3.conv.bias", "latent_model.downs.0.3.conv.bias"):
+        ref = G(golden, f"loss.{kind}.grad.{n}")
+        g = params[n].grad
+        if ref.numel() == 1 and g is None:
+            continue
+        assert tc.rel_l2(g, ref) < 2e-4, n
+
+
+@pytest.mark.parametrize("lt,lf", [("vlb", "sum"), ("hybrid", "mean"), ("simple", "mean")])
+def test_ddpm_objective_variants(cuda, golden, lt, lf):
+    cfg = dict(tc.C1, loss_type=lt, loss_flat=lf, precision="fp32")
+    m = tc.build_model(cfg, dd, "ddpm", device="cuda").to(cuda)
+    m.train()
+    x = tc.rand_pm1(52, 4, 1, 28, 28).to(cuda)
+    t = torch.tensor([0, 10, 400, 999], device=cuda)
+    torch.manual_seed(8)
+    eps = torch.randn(x.shape).to(cuda)
+    obj = m.p_losses(x, t, eps=eps)
+    obj.backward()
+    ref = float(golden[f"loss.c1.{lt}.{lf}.obj"])
+    assert abs(float(obj) - ref) <= 1e-4 * abs(ref)
+    g = dict(m.named_parameters())["latent_model.final_conv.1.weight"].grad
+    assert tc.rel_l2(g, G(golden, f"loss.c1.{lt}.{lf}.grad_final")) < 2e-4
+
+
+def test_forward_draws_t_and_eps_like_the_reference(cuda):
+    """DDPM.forward = t_sample (randint) then losses (randn_like): ddpm.py:448-457."""
+    cfg = dict(tc.CS, precision="fp32")
+    m = tc.build_model(cfg, dd, "dddpm_ae", device="cuda").to(cuda)
+    x = tc.rand_pm1(3, 2, 3, 32, 32).to(cuda)
+    torch.manual_seed(11)
+    obj, d = m(x)
+    torch.manual_seed(11)
+    t = torch.randint(0, 1000, (2,), device=cuda).long()
+    with torch.no_grad():
+        z = m.rescaled_downsample(x)
+    eps = torch.randn_like(z)
+    obj2, _ = m.losses(x, t, eps=eps)
+    assert abs(float(obj) - float(obj2)) <= 1e-5 * abs(float(obj2))
+    assert set(d.keys()) == {"latent", "recon"}
+
+
+def test_dropout_training_mode_runs_and_masks(cuda):
+    cfg = dict(tc.CS, precision="fp32", unet_dropout=0.5)
+    m = tc.build_model(cfg, dd, "ddpm", device="cuda").to(cuda)
+    m.train()
+    x = tc.randn(1, 2, 8, 8, 8).to(cuda)
+    t = torch.tensor([5, 500], device=cuda)
+    a = m.latent_model(x, t)
+    b = m.latent_model(x, t)
+    assert torch.isfinite(a).all() and not torch.equal(a, b)          # a fresh mask per call
+    a.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.latent_model.parameters())
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m.latent_model(x, t), m.latent_model(x, t))
+
+
+def test_training_step_with_ema_and_grad_accumulation(cuda):
+    """Two micro-batches (gradient_accumulate_every=2, trainer_ddpm.py:35,219-229), Adam step, EMA update."""
+    cfg = dict(tc.CS, precision="fp32")
+    m = tc.build_model(cfg, dd, "dddpm_ae", device="cuda").to(cuda)
+    m.train()
+    ema = dd.EMA(m, decay=0.995)
+    opt = torch.optim.Adam(m.parameters(), lr=2e-4)
+    before = [p.detach().clone() for p in m.parameters()]
+    losses = []
+    for step in range(2):
+        for k in range(2):
+            x = tc.rand_pm1(70 + 2 * step + k, 4, 3, 32, 32).to(cuda)
+            obj, _ = m(x)
+            (obj / 2).backward()
+            losses.append(float(obj))
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+        ema.update(m)
+    assert all(np.isfinite(losses))
+    assert any(not torch.equal(a, b) for a, b in zip(before, m.parameters()))
+    with torch.no_grad():                                  # the updated weights are what the next forward uses
+        x = tc.rand_pm1(99, 4, 3, 32, 32).to(cuda)
+        t = torch.tensor([1, 2, 3, 4], device=cuda)
+        eps = tc.randn(98, 4, 8, 8, 8).to(cuda)
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        ref, _ = O.dddpm_losses(sd, cfg, O.schedule_buffers("linear", 1000), x.cpu(), t.cpu(), eps.cpu(), autoencoder=True)
+        m.eval()
+        got, _ = m.losses(x, t, eps=eps)
+    assert abs(float(got) - float(ref)) <= 2e-4 * abs(float(ref))
+
+
+# ---- kernel-level backward checks -------------------------------------------------------------------
+def test_backward_kernels_against_torch_autograd(cuda):
+    from downsampled_diffusion_b200 import _lib as L
+    torch.manual_seed(0)
+    B, C, H, W, G_ = 2, 32, 6, 6, 8
+    # GroupNorm + Mish
+    x = torch.randn(B, C, H, W, requires_grad=True)
+    gamma, beta = torch.randn(C, requires_grad=True), torch.randn(C, requires_grad=True)
+    dy = torch.randn(B, C, H, W)
+    F.mish(F.group_norm(x, G_, gamma, beta, 1e-5)).backward(dy)
+    nh = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().to(cuda)
+    xd, dyd = nh(x), nh(dy)
+    st = torch.empty(B, G_, 2, device=cuda)
+    L.call("dd_gn_stats", L.ptr(xd), L.DD_F32, B, H * W, C, G_, 1e-5, L.ptr(st), L.stream())
+    s1, s2, s3 = (torch.empty(B, C, device=cuda) for _ in range(3))
+    dx = torch.empty_like(xd)
+    gd, bd = gamma.detach().to(cuda), beta.detach().to(cuda)
+    L.call("dd_gn_mish_bwd", L.ptr(xd), L.ptr(dyd), L.ptr(st), L.ptr(gd), L.ptr(bd), B, H * W, C, G_, L.ptr(s1), L.ptr(s2),
+           L.ptr(s3), L.ptr(dx), 0, L.stream())
+    assert tc.rel_l2(dx.permute(0, 3, 1, 2), x.grad) < 1e-5
+    assert tc.rel_l2(s1.sum(0), gamma.grad) < 1e-5 and tc.rel_l2(s2.sum(0), beta.grad) < 1e-5
+    assert tc.rel_l2(s3.sum(0), dy.sum((0, 2, 3))) < 1e-5
+    # channel LayerNorm (eps on the std)
+    x = torch.randn(B, 64, H, W, requires_grad=True)
+    g, b = torch.randn(1, 64, 1, 1, requires_grad=True), torch.randn(1, 64, 1, 1, requires_grad=True)
+    dy = torch.randn(B, 64, H, W)
+    O.channel_layernorm(x, g, b).backward(dy)
+    xd, dyd = nh(x), nh(dy)
+    dx, dg, db = torch.empty_like(xd), torch.zeros(64, device=cuda), torch.zeros(64, device=cuda)
+    gdev = g.detach().reshape(-1).to(cuda)
+    L.call("dd_layernorm_c_bwd", L.ptr(xd), L.ptr(dyd), L.ptr(gdev), 1e-5, B * H * W, 64, L.ptr(dx), 0, L.ptr(dg), L.ptr(db), L.stream())
+    assert tc.rel_l2(dx.permute(0, 3, 1, 2), x.grad) < 1e-5
+    assert tc.rel_l2(dg, g.grad.reshape(-1)) < 1e-5 and tc.rel_l2(db, b.grad.reshape(-1)) < 1e-5
+    # LinearAttention core
+    heads, dh, n = 4, 32, H * W
+    qkv = torch.randn(B, 3 * heads * dh, H, W, requires_grad=True)
+    dout = torch.randn(B, heads * dh, H, W)
+    q, k, v = qkv.reshape(B, 3, heads, dh, n).unbind(1)
+    ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(dim=-1), v)
+    torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(B, heads * dh, H, W).backward(dout)
+    qd, dod = nh(qkv), nh(dout)
+    need = int(L.lib().dd_linattn_ws_floats(B, n, heads))
+    ws = torch.empty(need, device=cuda)
+    out = torch.empty(B, H, W, heads * dh, device=cuda)
+    L.call("dd_linattn_core", L.ptr(qd), L.ptr(out), L.DD_F32, B, n, heads, dh, L.ptr(ws), need, L.stream())
+    saved = torch.empty(B * heads * 1088, device=cuda)
+    L.call("dd_linattn_save", L.ptr(ws), B, n, heads, L.ptr(saved), L.stream())
+    dctx, dqkv = torch.empty(B * heads * 1024, device=cuda), torch.empty_like(qd)
+    L.call("dd_linattn_bwd", L.ptr(qd), L.ptr(dod), L.ptr(saved), L.ptr(dctx), L.ptr(dqkv), B, n, heads, dh, L.stream())
+    assert tc.rel_l2(dqkv.permute(0, 3, 1, 2), qkv.grad) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["3x3", "1x1", "down", "up"])
+def test_conv_weight_and_input_gradients(cuda, kind):
+    from downsampled_diffusion_b200.autograd import TrainProgram
+    from downsampled_diffusion_b200.engine import Act
+    torch.manual_seed(1)
+    B, C1, C2, Cout, H, W = 2, 16, 8 if kind == "3x3" else 0, 24, 8, 8
+    Cin = C1 + C2
+    conv = {"3x3": lambda: torch.nn.Conv2d(Cin, Cout, 3, 1, 1), "1x1": lambda: torch.nn.Conv2d(Cin, Cout, 1),
+            "down": lambda: torch.nn.Conv2d(Cin, Cout, 3, 2, 1), "up": lambda: torch.nn.ConvTranspose2d(Cin, Cout, 4, 2, 1)}[kind]()
+    x = torch.randn(B, Cin, H, W, requires_grad=True)
+    y = conv(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    holder = torch.nn.ModuleList([conv]).to(cuda)
+    prog = TrainProgram(holder, B)
+    nh = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().to(cuda)
+    xa = Act(nh(x[:, :C1]), B, H, W, C1)
+    x2a = Act(nh(x[:, C1:]), B, H, W, C2) if C2 else None
+    ya = prog.t_conv(xa, holder[0], x2=x2a, kind=kind)
+
+    prog.gwritten.add(id(ya.t))             # the test plays the role of the consumer that wrote dL/dy
+    prog.build_backward()
+    prog.refresh_weights()
+    prog.run_ops()
+    assert tc.rel_l2(ya.t.permute(0, 3, 1, 2), y) < 1e-5
+    prog.grad(ya).copy_(nh(dy))
+    prog.run_backward()
+    pg = prog.param_grads()
+    ref = {n: p.grad for n, p in conv.named_parameters()}
+    assert tc.rel_l2(pg[id(holder[0].weight)], ref["weight"]) < 1e-5
+    assert tc.rel_l2(pg[id(holder[0].bias)], ref["bias"]) < 1e-5
+    assert tc.rel_l2(prog.grad(xa).permute(0, 3, 1, 2), x.grad[:, :C1]) < 1e-5
+    if C2:
+        assert tc.rel_l2(prog.grad(x2a).permute(0, 3, 1, 2), x.grad[:, C1:]) < 1e-5
