@@ -28,12 +28,13 @@ constexpr int TC_THREADS = 192;
 //   <3,128>: 96 KB  -> 2 CTAs/SM, for grids that fill the GPU (epilogue of one CTA overlaps the other's loop)
 //   <6,128>: 192 KB -> 1 CTA/SM, grids of at most one wave: twice the loads in flight per CTA
 //   <8, 64>: 192 KB -> 1 CTA/SM, low-resolution layers run with bn = 64 (twice the CTAs) and 8 stages
-constexpr int tc_stage_bytes(int brows) { return TC_A_BYTES + brows * TC_BK * 2; }
+constexpr int tc_stage_bytes(int brows) { return TC_A_BYTES + brows * TC_BK * 2 + 1024 /* slack: descriptor-phase experiment */; }
 constexpr int tc_smem_bytes(int stages, int brows) { return stages * tc_stage_bytes(brows) + 1024 /*align*/ + 1024 /*barriers + bias*/; }
 constexpr int TC_TMEM_COLS = 128;
 
 struct TcParams {
     CUtensorMap tmA0, tmA1, tmB;
+    CUtensorMap tmH0, tmH1;      // halo boxes (64 ch, tw+2, th+2, 1, 1) of source 0 / 1 (halo kernel only)
     int8_t tap_dw[16], tap_dh[16], tap_plane[16];
     int ntaps;              // taps per phase
     int chunks0, chunks1;   // 64-channel chunks of source 0 / 1
@@ -43,8 +44,10 @@ struct TcParams {
     int out_mul;            // 1, or 2 for the sub-pixel phases of the transposed conv
     int out_nchw_f32;
     int G, cpg_mask, cpg_shift;
+    int tw_sh, th_sh;           // log2(tw), log2(th): tile geometry is all powers of two
     int rows_valid;             // tw*th*tn (< 128 when one image has fewer than 128 pixels and tn is forced to 1)
     int w_per_sample;           // weights are (B, rows, K): every image multiplies its own matrix (fused attention output)
+    int exp_shift, exp_bo;      // experiment: A tile placed exp_shift rows (128 B) past the 1024-B aligned slot; base_offset on/off
     int splits, kb_per_split;   // split-K over the (tap, chunk) loop; partial sums meet in splitk_ws
     void* out;
     const float* bias;
@@ -52,6 +55,7 @@ struct TcParams {
     float* gn_stats;
     float* splitk_ws;           // (tiles, bn/4, 128, 4) fp32, all zero between launches (self-cleaning)
     int32_t* splitk_cnt;        // per-tile arrival counters, all zero between launches
+    long long* dbg;             // optional per-CTA timeline (8 clock64 stamps per CTA), NULL in production
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -99,6 +103,14 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar,
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// One elected lane of a converged warp.  The producer / MMA warps run their loops with all 32 lanes so every
+// loop variable stays warp-uniform (uniform registers feed UTMALDG / UTCHMMA directly); wrapping the loops in
+// `if (lane == 0)` instead costs ~25 R2UR/ELECT/vote instructions per TMA issue (profiles/README.md).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -136,7 +148,298 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ void tstamp(const TcParams& p, int slot) {
+    if (p.dbg) p.dbg[((int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z))) * 16 + slot] = clock64();
+}
+__device__ __forceinline__ void tstore(const TcParams& p, int slot, long long v) {
+    if (p.dbg) p.dbg[((int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z))) * 16 + slot] = v;
+}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+
+// ---- epilogue shared by every pipeline variant: 4 warps, TMEM lane quadrant = warp % 4 ----
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, uint32_t tmem_full_bar, float* s_bias,
+                                            int m_tile, int n_tile, int phase, int w0, int h0, int n0, int warp, int lane) {
+    // ===== epilogue: 4 warps, TMEM lane quadrant = warp % 4 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int ww = r % p.tw, hh = (r / p.tw) % p.th, nl = r / (p.tw * p.th);
+    const int n = n0 + nl;
+    const bool valid = n < p.B && r < p.rows_valid;
+    const int mul = p.out_mul;
+    const int Ho = p.H * mul, Wo = p.W * mul;
+    const int oh = (h0 + hh) * mul + (phase >> 1), ow = (w0 + ww) * mul + (phase & 1);
+    const int64_t pix = ((int64_t)n * Ho + oh) * Wo + ow;
+    const int cbase = n_tile * p.bn;
+    const int seg = min(32, p.tw * p.th);       // lanes of this warp that share a sample
+    const int et = threadIdx.x - 64;            // 0..127
+    if (et < p.bn) s_bias[et] = (p.bias && cbase + et < p.Cout) ? p.bias[cbase + et] : 0.f;
+    const bool use_res = p.residual != nullptr && valid && !p.out_nchw_f32;
+    const uint4* res_ptr = reinterpret_cast<const uint4*>(p.residual + (use_res ? pix * p.Cout + cbase : 0));
+    uint4 res_cur[2], res_nxt[2];
+    if (use_res) { res_cur[0] = res_ptr[0]; res_cur[1] = res_ptr[1]; }
+    epi_bar();
+    mbar_wait(tmem_full_bar, 0);
+    if (et == 0) tstamp(p, 5);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    bool finisher = true;
+    float* wst = nullptr;
+    if (p.splits > 1) {
+        // ---- split-K: add this CTA's partial tile into the fp32 workspace, last arrival finishes ----
+        const int tile_id = m_tile * gridDim.y + n_tile;
+        wst = p.splitk_ws + (int64_t)tile_id * TC_BM * p.bn;
+        uint32_t acc[16];
+        for (int ch = 0; ch < p.bn; ch += 16) {
+            tmem_ld16_issue(trow + (uint32_t)ch, acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+                red_add_v4(wst + ((int64_t)((ch >> 2) + k4) * TC_BM + r) * 4, __uint_as_float(acc[4 * k4]),
+                           __uint_as_float(acc[4 * k4 + 1]), __uint_as_float(acc[4 * k4 + 2]), __uint_as_float(acc[4 * k4 + 3]));
+        }
+        __threadfence();
+        epi_bar();
+        int* s_flag = reinterpret_cast<int*>(s_bias + 128);
+        if (et == 0) {
+            const int ticket = atomicAdd(p.splitk_cnt + tile_id, 1);
+            const int last = (ticket == p.splits - 1);
+            if (last) p.splitk_cnt[tile_id] = 0;                 // self-cleaning for the next launch
+            *s_flag = last;
+        }
+        epi_bar();
+        finisher = (*s_flag != 0);
+        if (finisher) __threadfence();
+    }
+
+    if (finisher) {
+        float gs = 0.f, gq = 0.f;
+        uint32_t acc[16], nxt[16];
+        if (p.splits == 1) { tmem_ld16_issue(trow, acc); tmem_ld_wait(); }
+        for (int ch = 0; ch < p.bn; ch += 16) {
+            const bool more = ch + 16 < p.bn;
+            float v[16];
+            if (p.splits > 1) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    float4* wp4 = reinterpret_cast<float4*>(wst + ((int64_t)((ch >> 2) + k4) * TC_BM + r) * 4);
+                    const float4 t = __ldcg(wp4);
+                    *wp4 = make_float4(0.f, 0.f, 0.f, 0.f);      // leave the workspace zeroed
+                    v[4 * k4] = t.x; v[4 * k4 + 1] = t.y; v[4 * k4 + 2] = t.z; v[4 * k4 + 3] = t.w;
+                }
+            } else {
+                if (more) tmem_ld16_issue(trow + (uint32_t)(ch + 16), nxt);      // overlaps the math below
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+            }
+            if (use_res && more) { res_nxt[0] = res_ptr[(ch >> 3) + 2]; res_nxt[1] = res_ptr[(ch >> 3) + 3]; }
+            const int c0 = cbase + ch;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += s_bias[ch + j];
+            if (p.gn_stats && !(p.exp_bo & 4)) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    float s8 = 0.f, q8 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const float t = v[hf * 8 + j]; s8 += t; q8 += t * t; }
+                    if (valid) { gs += s8; gq += q8; }
+                    const int c_end = c0 + hf * 8 + 8;
+                    if ((c_end & p.cpg_mask) == 0) {           // warp-uniform
+                        float a = gs, b = gq;
+                        for (int o = 1; o < seg; o <<= 1) {
+                            a += __shfl_xor_sync(0xffffffffu, a, o);
+                            b += __shfl_xor_sync(0xffffffffu, b, o);
+                        }
+                        if (valid && (lane & (seg - 1)) == 0) {
+                            const int g = (c_end >> p.cpg_shift) - 1;
+                            float* st = p.gn_stats + ((int64_t)n * p.G + g) * 2;
+                            atomicAdd(st, a);
+                            atomicAdd(st + 1, b);
+                        }
+                        gs = 0.f; gq = 0.f;
+                    }
+                }
+            }
+            if (valid && !(p.exp_bo & 2)) {
+                if (p.out_nchw_f32) {
+                    float* o = reinterpret_cast<float*>(p.out);
+                    const int64_t hw = (int64_t)Ho * Wo;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < p.cout_valid) o[((int64_t)n * p.cout_valid + c0 + j) * hw + (int64_t)oh * Wo + ow] = v[j];
+                } else if (c0 < p.Cout) {
+                    if (use_res) {
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&res_cur[hf]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = __bfloat1622float2(rh[j]);
+                                v[hf * 8 + 2 * j] += f.x; v[hf * 8 + 2 * j + 1] += f.y;
+                            }
+                        }
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + c0);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint4 ov;
+                        __nv_bfloat162* oh2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) oh2[j] = __floats2bfloat162_rn(v[hf * 8 + 2 * j], v[hf * 8 + 2 * j + 1]);
+                        op[hf] = ov;
+                    }
+                }
+            }
+            if (p.splits == 1 && more) {
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = nxt[j];
+            }
+            if (use_res && more) { res_cur[0] = res_nxt[0]; res_cur[1] = res_nxt[1]; }
+        }
+    }
+    if (et == 0) tstamp(p, 6);
+}
+
+
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+// ---- staged epilogue (bf16 NHWC output, bn >= 32) -------------------------------------------------
+// Phase A: each of the 128 epilogue threads drains its accumulator row from TMEM (32-column loads, two in
+//          flight), adds the bias, keeps per-8-channel {sum, sumsq} partials in registers and writes the bf16
+//          row into a padded shared-memory tile (the pipeline stages are free once the accumulator is complete).
+// Phase B: GroupNorm partials are reduced through shared memory (16 lanes per (sample, group), one atomic
+//          pair each), and the tile is written out with fully coalesced 16-byte stores (+ coalesced residual
+//          reads).  The first version did both per row with warp shuffles and 16-byte scattered stores and took
+//          as long as the main loop (profiles/README.md).
+__device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t tmem_base, uint32_t tmem_full_bar, float* s_bias,
+                                                   uint8_t* stage, int n_tile, int phase, int w0, int h0, int n0, int warp,
+                                                   int lane) {
+    const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 64;
+    const int bn = p.bn, cbase = n_tile * bn;
+    const int rps = p.tw * p.th;                       // rows of this tile that belong to one image
+    const int pitch = bn * 2 + 16;                     // bytes; +16 keeps 16-byte row accesses conflict free
+    if (et < bn) s_bias[et] = (p.bias && cbase + et < p.Cout) ? p.bias[cbase + et] : 0.f;
+    const bool valid = (n0 + (r >> (p.tw_sh + p.th_sh))) < p.B && r < p.rows_valid;
+    const bool do_stats = p.gn_stats != nullptr;
+    epi_bar();
+    mbar_wait(tmem_full_bar, 0);
+    if (et == 0) tstamp(p, 5);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    float s8[16], q8[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { s8[k] = 0.f; q8[k] = 0.f; }
+    uint32_t a0[32], a1[32];
+    auto process = [&](const int c32, uint32_t (&acc)[32]) {
+        uint8_t* dst = stage + r * pitch + c32 * 64;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+            float v[8];
+            float sa = 0.f, qa = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j] = __uint_as_float(acc[g8 * 8 + j]) + s_bias[c32 * 32 + g8 * 8 + j];
+                sa += v[j]; qa = fmaf(v[j], v[j], qa);
+            }
+            if (valid) { s8[c32 * 4 + g8] = sa; q8[c32 * 4 + g8] = qa; }
+            uint4 pk;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            *reinterpret_cast<uint4*>(dst + g8 * 16) = pk;
+        }
+    };
+    tmem_ld32_issue(trow, a0);
+    tmem_ld_wait();
+    if (bn > 32) tmem_ld32_issue(trow + 32u, a1);
+    process(0, a0);
+    if (bn > 32) {
+        tmem_ld_wait();
+        if (bn > 64) tmem_ld32_issue(trow + 64u, a0);
+        process(1, a1);
+        if (bn > 64) {
+            tmem_ld_wait();
+            tmem_ld32_issue(trow + 96u, a1);
+            process(2, a0);
+            tmem_ld_wait();
+            process(3, a1);
+        }
+    }
+    float* s_part = reinterpret_cast<float*>(stage + TC_BM * pitch);      // [(sub*2 + {sum,sq})][128 rows]
+    if (do_stats) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k * 8 < bn) { s_part[(2 * k) * TC_BM + r] = s8[k]; s_part[(2 * k + 1) * TC_BM + r] = q8[k]; }
+    }
+    epi_bar();
+    if (do_stats) {
+        const int cpg = p.cpg_mask + 1, spg = cpg >> 3;                   // 8-channel partials per group
+        const int ngroups = bn / cpg, nsamp = TC_BM / rps, nout = ngroups * nsamp;
+        const int hw = et >> 4, l16 = et & 15;
+        for (int o0 = 0; o0 < nout; o0 += 8) {
+            const int o = o0 + hw;
+            const bool act = o < nout;
+            const int gl = act ? o % ngroups : 0, sl = act ? o / ngroups : 0;
+            float sa = 0.f, qa = 0.f;
+            if (act)
+                for (int k = 0; k < spg; ++k) {
+                    const float* ps = s_part + (2 * (gl * spg + k)) * TC_BM + sl * rps;
+                    for (int i = l16; i < rps; i += 16) { sa += ps[i]; qa += ps[TC_BM + i]; }
+                }
+#pragma unroll
+            for (int d = 8; d > 0; d >>= 1) {
+                sa += __shfl_xor_sync(0xffffffffu, sa, d);
+                qa += __shfl_xor_sync(0xffffffffu, qa, d);
+            }
+            if (act && l16 == 0 && n0 + sl < p.B) {
+                float* st = p.gn_stats + ((int64_t)(n0 + sl) * p.G + (cbase / cpg + gl)) * 2;
+                atomicAdd(st, sa);
+                atomicAdd(st + 1, qa);
+            }
+        }
+    }
+    // coalesced write-out: 16 bytes per thread, consecutive threads walk along a row (shifts only: every
+    // tile dimension is a power of two)
+    const int ppr_sh = 31 - __clz(bn >> 3);        // log2(16-byte pieces per row)
+    const int rps_sh = p.tw_sh + p.th_sh;
+    const int pc = et & ((1 << ppr_sh) - 1);
+    const int row_step = TC_BM >> ppr_sh;
+    const int mul = p.out_mul, Ho = p.H * mul, Wo = p.W * mul;
+    const int py = phase >> 1, px = phase & 1;
+    __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+    const __nv_bfloat16* resp = p.residual;
+    const int rows_valid = p.rows_valid, Bn = p.B, Cout = p.Cout;
+    for (int row = et >> ppr_sh; row < TC_BM; row += row_step) {
+        const int n = n0 + (row >> rps_sh);
+        if (row >= rows_valid || n >= Bn) continue;
+        const int ww = row & (p.tw - 1), hh = (row >> p.tw_sh) & (p.th - 1);
+        const int oh = (h0 + hh) * mul + py, ow = (w0 + ww) * mul + px;
+        const int64_t off = (((int64_t)n * Ho + oh) * Wo + ow) * Cout + cbase + pc * 8;
+        uint4 v = *reinterpret_cast<const uint4*>(stage + row * pitch + pc * 16);
+        if (resp) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(resp + off);
+            __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&v);
+            const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 x = __bfloat1622float2(a[j]), y = __bfloat1622float2(b[j]);
+                a[j] = __floats2bfloat162_rn(x.x + y.x, x.y + y.y);
+            }
+        }
+        *reinterpret_cast<uint4*>(outp + off) = v;
+    }
+    if (et == 0) tstamp(p, 6);
+}
 
 // ---------------------------------------------------------------------------------------------
 template <int TC_STAGES, int BROWS>
@@ -152,6 +455,7 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES <= 3 ? 2 : 1)) conv_tc_
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) tstamp(p, 0);
     const int m_tile = blockIdx.x, n_tile = blockIdx.y;
     const int phase = p.splits > 1 ? 0 : blockIdx.z;
     const int split = p.splits > 1 ? blockIdx.z : 0;
@@ -179,185 +483,220 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES <= 3 ? 2 : 1)) conv_tc_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    if (threadIdx.x == 0) tstamp(p, 1);
     pdl_sync();      // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+    if (threadIdx.x == 0) tstamp(p, 2);
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            const uint32_t stage_tx = (uint32_t)(p.rows_valid + p.bn) * TC_BK * 2;   // bytes the two TMA boxes deliver
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % TC_STAGES;
-                if (kb >= TC_STAGES) mbar_wait(empty_bar(s), ((kb / TC_STAGES) - 1) & 1);
-                const int kg = kb_lo + kb;                       // global k-block index
-                const int tap = kg / cpt, rem = kg - tap * cpt;
-                const int ti = phase * p.ntaps + tap;
-                const uint32_t sA = base + s * TC_STAGE_BYTES, sB = sA + TC_A_BYTES;
-                mbar_expect_tx(full_bar(s), stage_tx);
-                if (rem < p.chunks0)
-                    tma_load_5d(&p.tmA0, full_bar(s), sA, rem * 64, w0 + p.tap_dw[ti], h0 + p.tap_dh[ti], n0, p.tap_plane[ti]);
-                else
-                    tma_load_5d(&p.tmA1, full_bar(s), sA, (rem - p.chunks0) * 64, w0 + p.tap_dw[ti], h0 + p.tap_dh[ti], n0, p.tap_plane[ti]);
-                if (p.w_per_sample) tma_load_3d(&p.tmB, full_bar(s), sB, kg * 64, n_tile * p.bn, n0);
-                else tma_load_2d(&p.tmB, full_bar(s), sB, kg * 64, phase * p.rows_per_phase + n_tile * p.bn);
+        // ===== TMA producer: whole warp runs the (uniform) loop, one elected lane issues =====
+        const uint32_t stage_tx = (uint32_t)(p.rows_valid + p.bn) * TC_BK * 2;   // bytes the two TMA boxes deliver
+        const int chunks0 = p.chunks0, wps = p.w_per_sample;
+        int tap = kb_lo / cpt, rem = kb_lo - tap * cpt;
+        int ti = phase * p.ntaps + tap;
+        int cx = w0 + p.tap_dw[ti], cy = h0 + p.tap_dh[ti], cp = p.tap_plane[ti];
+        int kcoord = kb_lo * 64;
+        const int brow = wps ? n_tile * p.bn : phase * p.rows_per_phase + n_tile * p.bn;
+        uint32_t sA = base + 128u * p.exp_shift;
+        int st = 0, round = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const uint32_t fb = full_bar(st);
+            if (round > 0) mbar_wait(empty_bar(st), (round - 1) & 1);
+            if (elect_one()) {
+                mbar_expect_tx(fb, stage_tx);
+                if (rem < chunks0) tma_load_5d(&p.tmA0, fb, sA, rem * 64, cx, cy, n0, cp);
+                else tma_load_5d(&p.tmA1, fb, sA, (rem - chunks0) * 64, cx, cy, n0, cp);
+                const uint32_t sB = sA - 128u * p.exp_shift + TC_A_BYTES + 1024;
+                if (wps) tma_load_3d(&p.tmB, fb, sB, kcoord, brow, n0);
+                else tma_load_2d(&p.tmB, fb, sB, kcoord, brow);
+            }
+            __syncwarp();
+            kcoord += 64;
+            sA += TC_STAGE_BYTES;
+            if (++st == TC_STAGES) { st = 0; ++round; sA -= TC_STAGES * TC_STAGE_BYTES; }
+            if (++rem == cpt) {
+                rem = 0; ++ti;
+                if (kb + 1 < num_kb) { cx = w0 + p.tap_dw[ti]; cy = h0 + p.tap_dh[ti]; cp = p.tap_plane[ti]; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % TC_STAGES;
-                mbar_wait(full_bar(s), (kb / TC_STAGES) & 1);
-                tc_fence_after();
-                const uint32_t sA = base + s * TC_STAGE_BYTES, sB = sA + TC_A_BYTES;
-                const uint64_t ad = umma_desc(sA), bd = umma_desc(sB);
+        // ===== MMA issuer: whole warp loops, one elected lane issues tcgen05.mma / commit =====
+        // instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        uint32_t sA = base + 128u * p.exp_shift;
+        int st = 0;
+        uint32_t par = 0;
+        const uint32_t bo = p.exp_bo;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(full_bar(st), par);
+            if (kb == 0 && lane == 0) tstamp(p, 3);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t ad = umma_desc(sA) | (bo ? ((uint64_t)((sA >> 7) & 7) << 49) : 0ull);
+                const uint64_t bd = umma_desc(sA - 128u * p.exp_shift + TC_A_BYTES + 1024);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k)
                     umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-                umma_commit(empty_bar(s));          // frees this smem stage when the MMAs retire
+                umma_commit(empty_bar(st));          // frees this smem stage when the MMAs retire
             }
-            umma_commit(tmem_full_bar);             // accumulator complete
+            __syncwarp();
+            sA += TC_STAGE_BYTES;
+            if (++st == TC_STAGES) { st = 0; par ^= 1u; sA -= TC_STAGES * TC_STAGE_BYTES; }
         }
+        if (lane == 0) tstamp(p, 4);
+        if (elect_one()) umma_commit(tmem_full_bar);             // accumulator complete
+        __syncwarp();
     } else {
-        // ===== epilogue: 4 warps, TMEM lane quadrant = warp % 4 =====
-        const int q = warp & 3;
-        const int r = q * 32 + lane;
-        const int ww = r % p.tw, hh = (r / p.tw) % p.th, nl = r / (p.tw * p.th);
-        const int n = n0 + nl;
-        const bool valid = n < p.B && r < p.rows_valid;
-        const int mul = p.out_mul;
-        const int Ho = p.H * mul, Wo = p.W * mul;
-        const int oh = (h0 + hh) * mul + (phase >> 1), ow = (w0 + ww) * mul + (phase & 1);
-        const int64_t pix = ((int64_t)n * Ho + oh) * Wo + ow;
-        const int cbase = n_tile * p.bn;
-        const int seg = min(32, p.tw * p.th);       // lanes of this warp that share a sample
-        const int et = threadIdx.x - 64;            // 0..127
-        if (et < p.bn) s_bias[et] = (p.bias && cbase + et < p.Cout) ? p.bias[cbase + et] : 0.f;
-        const bool use_res = p.residual != nullptr && valid && !p.out_nchw_f32;
-        const uint4* res_ptr = reinterpret_cast<const uint4*>(p.residual + (use_res ? pix * p.Cout + cbase : 0));
-        uint4 res_cur[2], res_nxt[2];
-        if (use_res) { res_cur[0] = res_ptr[0]; res_cur[1] = res_ptr[1]; }
-        epi_bar();
-        mbar_wait(tmem_full_bar, 0);
+        if (p.splits == 1 && !p.out_nchw_f32 && p.bn >= 32 && !(p.exp_bo & 8))
+            tc_epilogue_staged(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, phase, w0, h0, n0,
+                               warp, lane);
+        else
+            tc_epilogue(p, tmem_base, tmem_full_bar, s_bias, m_tile, n_tile, phase, w0, h0, n0, warp, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+    }
+}
 
-        bool finisher = true;
-        float* wst = nullptr;
-        if (p.splits > 1) {
-            // ---- split-K: add this CTA's partial tile into the fp32 workspace, last arrival finishes ----
-            const int tile_id = m_tile * gridDim.y + n_tile;
-            wst = p.splitk_ws + (int64_t)tile_id * TC_BM * p.bn;
-            uint32_t acc[16];
-            for (int ch = 0; ch < p.bn; ch += 16) {
-                tmem_ld16_issue(trow + (uint32_t)ch, acc);
-                tmem_ld_wait();
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                    red_add_v4(wst + ((int64_t)((ch >> 2) + k4) * TC_BM + r) * 4, __uint_as_float(acc[4 * k4]),
-                               __uint_as_float(acc[4 * k4 + 1]), __uint_as_float(acc[4 * k4 + 2]), __uint_as_float(acc[4 * k4 + 3]));
-            }
-            __threadfence();
-            epi_bar();
-            int* s_flag = reinterpret_cast<int*>(s_bias + 128);
-            if (et == 0) {
-                const int ticket = atomicAdd(p.splitk_cnt + tile_id, 1);
-                const int last = (ticket == p.splits - 1);
-                if (last) p.splitk_cnt[tile_id] = 0;                 // self-cleaning for the next launch
-                *s_flag = last;
-            }
-            epi_bar();
-            finisher = (*s_flag != 0);
-            if (finisher) __threadfence();
-        }
 
-        if (finisher) {
-            float gs = 0.f, gq = 0.f;
-            uint32_t acc[16], nxt[16];
-            if (p.splits == 1) { tmem_ld16_issue(trow, acc); tmem_ld_wait(); }
-            for (int ch = 0; ch < p.bn; ch += 16) {
-                const bool more = ch + 16 < p.bn;
-                float v[16];
-                if (p.splits > 1) {
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        float4* wp4 = reinterpret_cast<float4*>(wst + ((int64_t)((ch >> 2) + k4) * TC_BM + r) * 4);
-                        const float4 t = __ldcg(wp4);
-                        *wp4 = make_float4(0.f, 0.f, 0.f, 0.f);      // leave the workspace zeroed
-                        v[4 * k4] = t.x; v[4 * k4 + 1] = t.y; v[4 * k4 + 2] = t.z; v[4 * k4 + 3] = t.w;
-                    }
-                } else {
-                    if (more) tmem_ld16_issue(trow + (uint32_t)(ch + 16), nxt);      // overlaps the math below
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+// =============================================================================================
+// Halo variant for 3x3 stride-1 convolutions on maps of at least 16x8 pixels.
+// The CTA tile is 16 rows x 8 columns of one image.  For every 64-channel chunk the (18 x 10)-pixel
+// input halo is loaded ONCE (one TMA box, 23 KB) and all nine filter taps read it in place: the tap
+// (r, s) operand is the same shared-memory tile addressed (r*10 + s) rows further on, with an 8-row
+// group stride of 10 rows (SBO = 1280 B).  The 128-byte swizzle is a function of the absolute
+// shared-memory address on both the TMA and the UMMA side (measured: profiles/README.md), so the
+// shifted descriptors see exactly the bytes TMA wrote.  A-operand traffic drops from 9 x 16 KB to
+// 23 KB per chunk -- these layers are bound by the L2 -> SM path, not by the tensor pipe.
+// =============================================================================================
+constexpr int HALO_TH = 16, HALO_TW = 8;
+constexpr int HALO_ROWS = (HALO_TH + 2) * (HALO_TW + 2);            // 180 pixels
+constexpr int HALO_TX = HALO_ROWS * TC_BK * 2;                      // 23040 bytes per TMA box
+constexpr int HALO_SLOT = (HALO_TX + 1023) / 1024 * 1024;           // 23552
+constexpr int HALO_NH = 2, HALO_NB = 4;
+constexpr int HALO_B_BYTES = 128 * TC_BK * 2;
+constexpr int HALO_SMEM = HALO_NH * HALO_SLOT + HALO_NB * HALO_B_BYTES + 1024 + 1024;
+
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bbase = base + HALO_NH * HALO_SLOT;
+    const uint32_t bars = bbase + HALO_NB * HALO_B_BYTES;
+    auto hfull = [&](int s) { return bars + 8u * s; };
+    auto hempty = [&](int s) { return bars + 8u * (HALO_NH + s); };
+    auto bfull = [&](int s) { return bars + 8u * (2 * HALO_NH + s); };
+    auto bempty = [&](int s) { return bars + 8u * (2 * HALO_NH + HALO_NB + s); };
+    const uint32_t tmem_full_bar = bars + 8u * (2 * HALO_NH + 2 * HALO_NB);
+    const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) tstamp(p, 0);
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+    const int w0 = (m_tile % p.tiles_w) * p.tw;
+    const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+    const int n0 = m_tile / (p.tiles_w * p.tiles_h);
+    const int nchunks = p.chunks0 + p.chunks1;
+    const int cin = nchunks * 64;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmH0)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB)) : "memory");
+        for (int s = 0; s < HALO_NH; ++s) { mbar_init(hfull(s), 1); mbar_init(hempty(s), 1); }
+        for (int s = 0; s < HALO_NB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+    if (threadIdx.x == 0) tstamp(p, 1);
+    pdl_sync();
+    if (threadIdx.x == 0) tstamp(p, 2);
+
+    if (warp == 0) {
+        const uint32_t b_tx = (uint32_t)p.bn * TC_BK * 2;
+        const int brow = n_tile * p.bn, chunks0 = p.chunks0;
+        int bs = 0, bround = 0, hs = 0, hround = 0;
+        uint32_t sB = bbase;
+        for (int c = 0; c < nchunks; ++c) {
+            if (hround > 0) mbar_wait(hempty(hs), (hround - 1) & 1);
+            if (elect_one()) {
+                mbar_expect_tx(hfull(hs), HALO_TX);
+                if (c < chunks0) tma_load_5d(&p.tmH0, hfull(hs), base + hs * HALO_SLOT, c * 64, w0 - 1, h0 - 1, n0, 0);
+                else tma_load_5d(&p.tmH1, hfull(hs), base + hs * HALO_SLOT, (c - chunks0) * 64, w0 - 1, h0 - 1, n0, 0);
+            }
+            __syncwarp();
+            if (++hs == HALO_NH) { hs = 0; ++hround; }
+            int kcoord = c * 64;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t fb = bfull(bs);
+                if (bround > 0) mbar_wait(bempty(bs), (bround - 1) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(fb, b_tx);
+                    tma_load_2d(&p.tmB, fb, sB, kcoord, brow);
                 }
-                if (use_res && more) { res_nxt[0] = res_ptr[(ch >> 3) + 2]; res_nxt[1] = res_ptr[(ch >> 3) + 3]; }
-                const int c0 = cbase + ch;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += s_bias[ch + j];
-                if (p.gn_stats) {
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        float s8 = 0.f, q8 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { const float t = v[hf * 8 + j]; s8 += t; q8 += t * t; }
-                        if (valid) { gs += s8; gq += q8; }
-                        const int c_end = c0 + hf * 8 + 8;
-                        if ((c_end & p.cpg_mask) == 0) {           // warp-uniform
-                            float a = gs, b = gq;
-                            for (int o = 1; o < seg; o <<= 1) {
-                                a += __shfl_xor_sync(0xffffffffu, a, o);
-                                b += __shfl_xor_sync(0xffffffffu, b, o);
-                            }
-                            if (valid && (lane & (seg - 1)) == 0) {
-                                const int g = (c_end >> p.cpg_shift) - 1;
-                                float* st = p.gn_stats + ((int64_t)n * p.G + g) * 2;
-                                atomicAdd(st, a);
-                                atomicAdd(st + 1, b);
-                            }
-                            gs = 0.f; gq = 0.f;
-                        }
-                    }
-                }
-                if (valid) {
-                    if (p.out_nchw_f32) {
-                        float* o = reinterpret_cast<float*>(p.out);
-                        const int64_t hw = (int64_t)Ho * Wo;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c0 + j < p.cout_valid) o[((int64_t)n * p.cout_valid + c0 + j) * hw + (int64_t)oh * Wo + ow] = v[j];
-                    } else if (c0 < p.Cout) {
-                        if (use_res) {
-#pragma unroll
-                            for (int hf = 0; hf < 2; ++hf) {
-                                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&res_cur[hf]);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 f = __bfloat1622float2(rh[j]);
-                                    v[hf * 8 + 2 * j] += f.x; v[hf * 8 + 2 * j + 1] += f.y;
-                                }
-                            }
-                        }
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + c0);
-#pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            uint4 ov;
-                            __nv_bfloat162* oh2 = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) oh2[j] = __floats2bfloat162_rn(v[hf * 8 + 2 * j], v[hf * 8 + 2 * j + 1]);
-                            op[hf] = ov;
-                        }
-                    }
-                }
-                if (p.splits == 1 && more) {
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = nxt[j];
-                }
-                if (use_res && more) { res_cur[0] = res_nxt[0]; res_cur[1] = res_nxt[1]; }
+                __syncwarp();
+                kcoord += cin;
+                sB += HALO_B_BYTES;
+                if (++bs == HALO_NB) { bs = 0; ++bround; sB = bbase; }
             }
         }
+    } else if (warp == 1) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        // A: 8-row groups (one tile row of 8 pixels) are (HALO_TW + 2) halo rows apart
+        const uint64_t a_hi = ((uint64_t)(((HALO_TW + 2) * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        int bs = 0, hs = 0;
+        uint32_t bpar = 0, hpar = 0, acc = 0;
+        uint32_t sB = bbase;
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(hfull(hs), hpar);
+            uint32_t rowA = base + hs * HALO_SLOT;                  // tap (0,0)
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll 1
+                for (int sx = 0; sx < 3; ++sx) {
+                    mbar_wait(bfull(bs), bpar);
+                    if (acc == 0 && lane == 0) tstamp(p, 3);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t ad = (uint64_t)(((rowA + 128u * sx) & 0x3FFFFu) >> 4) | a_hi;
+                        const uint64_t bd = umma_desc(sB);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k)
+                            umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (acc | k) ? 1u : 0u);
+                        umma_commit(bempty(bs));
+                    }
+                    __syncwarp();
+                    acc = 1u;
+                    sB += HALO_B_BYTES;
+                    if (++bs == HALO_NB) { bs = 0; bpar ^= 1u; sB = bbase; }
+                }
+                rowA += (HALO_TW + 2) * 128u;
+            }
+            if (elect_one()) umma_commit(hempty(hs));           // halo slot free once its nine taps have retired
+            __syncwarp();
+            if (++hs == HALO_NH) { hs = 0; hpar ^= 1u; }
+        }
+        if (lane == 0) tstamp(p, 4);
+        if (elect_one()) umma_commit(tmem_full_bar);
+        __syncwarp();
+    } else {
+        if (p.bn >= 32 && !(p.exp_bo & 8))
+            tc_epilogue_staged(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, 0, w0, h0, n0, warp,
+                               lane);
+        else
+            tc_epilogue(p, tmem_base, tmem_full_bar, s_bias, m_tile, n_tile, 0, w0, h0, n0, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -384,7 +723,8 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int make_act_map(CUtensorMap* tm, const void* ptr, int C, int pitch, int W, int H, int N, int P, int tw, int th, int tn) {
+static int make_act_map(CUtensorMap* tm, const void* ptr, int C, int pitch, int W, int H, int N, int P, int tw, int th, int tn,
+                        CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
     cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)P};
@@ -393,7 +733,7 @@ static int make_act_map(CUtensorMap* tm, const void* ptr, int C, int pitch, int 
     cuuint32_t box[5] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation C=%d W=%d H=%d N=%d P=%d box %d,%d,%d) failed: %d", C, W, H, N, P, tw, th, tn, (int)r); return DD_ERR_CUDA; }
     return DD_OK;
@@ -419,6 +759,9 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 using namespace dd;
 
+static long long* g_tc_dbg = nullptr;
+extern "C" int dd_debug_set_timeline(long long* buf) { g_tc_dbg = buf; return DD_OK; }
+
 extern "C" int dd_zero(void* ptr, int64_t bytes, void* stream) {
     cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream);
     if (e != cudaSuccess) { set_error("dd_zero: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
@@ -443,6 +786,7 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(6, 128));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM);
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
         attr_done = true;
     }
@@ -452,10 +796,15 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     TcParams p;
     memset(&p, 0, sizeof(p));
     // tile geometry over the GEMM pixel grid
+    static const bool halo_off = getenv("DD_NO_HALO") != nullptr;
+    const bool halo = !halo_off && kind == DD_TC_CONV3x3 && H >= HALO_TH && W >= HALO_TW && Cout >= 64;
     p.tw = W < 128 ? W : 128;
     p.th = (128 / p.tw) < H ? (128 / p.tw) : H;
+    if (halo) { p.tw = HALO_TW; p.th = HALO_TH; }
     p.tn = wps ? 1 : 128 / (p.tw * p.th);      // per-sample weights: one image per tile (rows beyond it are ignored)
     p.rows_valid = p.tw * p.th * p.tn;
+    p.tw_sh = 0; while ((1 << p.tw_sh) < p.tw) ++p.tw_sh;
+    p.th_sh = 0; while ((1 << p.th_sh) < p.th) ++p.th_sh;
     p.w_per_sample = wps ? 1 : 0;
     p.tiles_w = W / p.tw; p.tiles_h = H / p.th;
     const int tiles_n = (B + p.tn - 1) / p.tn;
@@ -512,6 +861,13 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     if (rc) return rc;
     rc = make_w_map(&p.tmB, wp, K, w_rows, p.bn, wps ? B : 0);
     if (rc) return rc;
+    if (halo) {
+        rc = make_act_map(&p.tmH0, x, C1, x_pitch, W, H, B, 1, HALO_TW + 2, HALO_TH + 2, 1, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+        rc = make_act_map(&p.tmH1, x2 ? x2 : x, x2 ? C2 : C1, x2 ? C2 : x_pitch, W, H, B, 1, HALO_TW + 2, HALO_TH + 2, 1,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+    }
 
     // split-K for layers whose output tiles cannot fill the GPU (low-resolution levels): spread the
     // (tap, chunk) loop over up to 12 CTAs per tile, aiming at ~2 CTAs per SM.
@@ -519,6 +875,9 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     const int num_kb = p.ntaps * (p.chunks0 + p.chunks1);
     p.splits = 1; p.kb_per_split = num_kb;
     p.splitk_ws = splitk_ws; p.splitk_cnt = splitk_cnt;
+    p.dbg = g_tc_dbg;
+    { const char* e1 = getenv("DD_EXP_SHIFT"); const char* e2 = getenv("DD_EXP_BO");
+      p.exp_shift = e1 ? atoi(e1) : 0; p.exp_bo = e2 ? atoi(e2) : 0; }
     static const bool splitk_on = getenv("DD_SPLITK") != nullptr;   // red.add reduction measured slower than deep pipelines (profiles/README.md)
     if (splitk_on && splitk_ws && splitk_cnt && phases == 1 && !wps && tiles < num_sms() && num_kb >= 6 &&
         (int64_t)tiles * TC_BM * p.bn <= splitk_ws_floats && tiles <= splitk_cnt_n) {
@@ -536,7 +895,9 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
         fprintf(stderr, "conv_tc kind=%d B=%d H=%d W=%d C=%d+%d Cout=%d grid=(%u,%u,%u) bn=%d num_kb=%d splits=%d kb_per=%d\n", kind, B, H, W,
                 C1, C2, Cout, grid.x, grid.y, grid.z, p.bn, num_kb, p.splits, p.kb_per_split);
     const int ctas = (int)(grid.x * grid.y * grid.z);
-    if (p.bn <= 64 && ctas <= num_sms())
+    if (halo)
+        launch_pdl(conv_tc_halo_kernel, dim3(grid), dim3(TC_THREADS), HALO_SMEM, (cudaStream_t)stream, p);
+    else if (p.bn <= 64 && ctas <= num_sms())
         launch_pdl(conv_tc_kernel<8, 64>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64), (cudaStream_t)stream, p);
     else if (ctas <= num_sms())
         launch_pdl(conv_tc_kernel<6, 128>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(6, 128), (cudaStream_t)stream, p);

@@ -228,6 +228,10 @@ int dd_sincos_emb(const float* t, const float* freq, float* out, int R, int dim,
 int dd_pool2_sum(const float* x, float* y, int B, int H, int W, int C, float scale, void* stream);
 int dd_unpool2(const float* x, float* y, int B, int H, int W, int C, float scale, void* stream);
 
+/* Debug only: when buf != NULL every dd_conv_tc CTA writes 8 clock64() stamps (start, prologue done, dependency
+ * wait done, first operands landed, last MMA issued, accumulator visible, epilogue done) to buf[cta*8 + i]. */
+int dd_debug_set_timeline(long long* buf);
+
 /* cudaMemsetAsync(ptr, 0, bytes): clears the GroupNorm {sum,sumsq} arena once per U-Net step. */
 int dd_zero(void* ptr, int64_t bytes, void* stream);
 

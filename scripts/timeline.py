@@ -1,0 +1,32 @@
+"""In-kernel timeline of single conv_tc launches (clock64 stamps per CTA)."""
+import os, sys, torch, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import downsampled_diffusion_b200 as dd
+from downsampled_diffusion_b200 import _lib as L
+from tests import common as tc
+dev = torch.device("cuda:0")
+m = tc.build_model(dict(tc.C3, precision="bf16"), dd, "dddpm_ae", device="cuda:0").to(dev).eval()
+plan = m.sampling_plan((64, 8, 32, 32)); plan.prepare()
+eng = plan.eng
+idx = [i for i, n in enumerate(eng.op_names) if n == "dd_conv_tc"]
+buf = torch.zeros(4096 * 16, dtype=torch.int64, device=dev)
+names = ["start", "prologue", "pdl_wait", "first_data", "last_mma", "acc_ready", "epi_done"]
+for which in (2, 5):          # 3x3@32 (halo), 3x3@16 (halo), 3x3@8, 3x3@4
+    op = eng.ops[idx[which]]
+    for _ in range(3): op()
+    torch.cuda.synchronize()
+    buf.zero_()
+    L.lib().dd_debug_set_timeline(buf.data_ptr())
+    op()
+    torch.cuda.synchronize()
+    L.lib().dd_debug_set_timeline(None)
+    t = buf.cpu().numpy().reshape(-1, 16)
+    t = t[t[:, 0] > 0]
+    t0 = t[:, 0].min()
+    rel = t[:, :7] - t[:, [0]]
+    print(f"conv #{which}: {len(t)} CTAs; kernel span {int(t[:, 6].max() - t0)} clk")
+    print("   median per-CTA offsets from its own start:", {n: int(np.median(rel[:, i])) for i, n in enumerate(names)})
+    print("   CTA start offsets (from first CTA): p50 %d p90 %d max %d" % tuple(np.percentile(t[:, 0] - t0, [50, 90, 100])))
+    print("   MMA-thread wait-on-data total: median %d clk; producer wait-on-empty total: median %d clk; producer last issue at %d" % (np.median(t[:, 7]), np.median(t[:, 8]), np.median(t[:, 9] - t[:, 0])))
+    d = rel[:, 4] - rel[:, 3]
+    print("   mainloop (first_data -> last_mma): median %d clk, epilogue (acc_ready -> done): median %d clk" % (np.median(d), np.median(rel[:, 6] - rel[:, 5])))

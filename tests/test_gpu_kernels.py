@@ -200,7 +200,10 @@ def test_time_bias(cuda):
 
 CONV_CASES = [
     # kind, Cin, Cin2, Cout, H, W, B
-    ("3x3", 128, 0, 128, 32, 32, 2),
+    ("3x3", 128, 0, 128, 32, 32, 2),      # halo kernel (16x8 tiles)
+    ("3x3", 256, 256, 128, 16, 16, 3),    # halo kernel, two sources (skip concat), odd batch
+    ("3x3", 256, 0, 256, 16, 16, 2),      # halo kernel, 2 n-tiles
+    ("3x3", 64, 0, 64, 16, 8, 1),         # halo kernel, exactly one tile, bn = 64
     ("3x3", 256, 256, 256, 8, 8, 3),      # concat-free two-source, 2 images per M tile (+ a ragged tile)
     ("3x3", 64, 0, 64, 4, 4, 5),          # 8 images per tile, ragged batch, 8 channels per GN group
     ("3x3", 256, 0, 256, 4, 4, 64),       # split-K (16 tiles x 12 splits) with the GroupNorm epilogue in the finisher
