@@ -375,6 +375,7 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
             process(3, a1);
         }
     }
+    if (et == 0) tstamp(p, 10);
     float* s_part = reinterpret_cast<float*>(stage + TC_BM * pitch);      // [(sub*2 + {sum,sq})][128 rows]
     if (do_stats) {
 #pragma unroll
@@ -383,31 +384,46 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
     }
     epi_bar();
     if (do_stats) {
-        const int cpg = p.cpg_mask + 1, spg = cpg >> 3;                   // 8-channel partials per group
-        const int ngroups = bn / cpg, nsamp = TC_BM / rps, nout = ngroups * nsamp;
+        // (sample, group) outputs: 16 lanes each, rows of the sample split across the lanes; all sizes are
+        // powers of two, so only shifts and masks appear below
+        const int cpg_sh = p.cpg_shift, spg = 1 << (cpg_sh - 3);           // 8-channel partials per group
+        const int ng_sh = (31 - __clz(bn)) - cpg_sh;                        // log2(groups in this tile)
+        const int rps_sh2 = p.tw_sh + p.th_sh;
+        const int nout = (1 << ng_sh) * (TC_BM >> rps_sh2);
         const int hw = et >> 4, l16 = et & 15;
+        const int gbase = cbase >> cpg_sh;
         for (int o0 = 0; o0 < nout; o0 += 8) {
             const int o = o0 + hw;
             const bool act = o < nout;
-            const int gl = act ? o % ngroups : 0, sl = act ? o / ngroups : 0;
-            float sa = 0.f, qa = 0.f;
-            if (act)
-                for (int k = 0; k < spg; ++k) {
-                    const float* ps = s_part + (2 * (gl * spg + k)) * TC_BM + sl * rps;
-                    for (int i = l16; i < rps; i += 16) { sa += ps[i]; qa += ps[TC_BM + i]; }
+            const int gl = o & ((1 << ng_sh) - 1), sl = o >> ng_sh;
+            float sa0 = 0.f, qa0 = 0.f, sa1 = 0.f, qa1 = 0.f;
+            if (act) {
+                const float* ps = s_part + (2 * (gl * spg)) * TC_BM + (sl << rps_sh2) + l16;
+                const int cnt = rps >> 4;                                   // rows per lane (0 when rps < 16)
+                for (int k = 0; k < spg; ++k, ps += 2 * TC_BM) {
+                    if (cnt == 0) { if (l16 < rps) { sa0 += ps[0]; qa0 += ps[TC_BM]; } continue; }
+                    int i = 0;
+                    for (; i + 1 < cnt; i += 2) {
+                        sa0 += ps[16 * i]; qa0 += ps[TC_BM + 16 * i];
+                        sa1 += ps[16 * i + 16]; qa1 += ps[TC_BM + 16 * i + 16];
+                    }
+                    if (i < cnt) { sa0 += ps[16 * i]; qa0 += ps[TC_BM + 16 * i]; }
                 }
+            }
+            float sa = sa0 + sa1, qa = qa0 + qa1;
 #pragma unroll
             for (int d = 8; d > 0; d >>= 1) {
                 sa += __shfl_xor_sync(0xffffffffu, sa, d);
                 qa += __shfl_xor_sync(0xffffffffu, qa, d);
             }
             if (act && l16 == 0 && n0 + sl < p.B) {
-                float* st = p.gn_stats + ((int64_t)(n0 + sl) * p.G + (cbase / cpg + gl)) * 2;
+                float* st = p.gn_stats + ((int64_t)(n0 + sl) * p.G + (gbase + gl)) * 2;
                 atomicAdd(st, sa);
                 atomicAdd(st + 1, qa);
             }
         }
     }
+    if (et == 0) tstamp(p, 11);
     // coalesced write-out: 16 bytes per thread, consecutive threads walk along a row (shifts only: every
     // tile dimension is a power of two)
     const int ppr_sh = 31 - __clz(bn >> 3);        // log2(16-byte pieces per row)
@@ -419,24 +435,38 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
     const __nv_bfloat16* resp = p.residual;
     const int rows_valid = p.rows_valid, Bn = p.B, Cout = p.Cout;
-    for (int row = et >> ppr_sh; row < TC_BM; row += row_step) {
-        const int n = n0 + (row >> rps_sh);
-        if (row >= rows_valid || n >= Bn) continue;
-        const int ww = row & (p.tw - 1), hh = (row >> p.tw_sh) & (p.th - 1);
-        const int oh = (h0 + hh) * mul + py, ow = (w0 + ww) * mul + px;
-        const int64_t off = (((int64_t)n * Ho + oh) * Wo + ow) * Cout + cbase + pc * 8;
-        uint4 v = *reinterpret_cast<const uint4*>(stage + row * pitch + pc * 16);
-        if (resp) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(resp + off);
-            __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&v);
-            const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&rv);
+    // four rows per trip: all shared/global loads first, then the stores (independent -> latencies overlap)
+    for (int row0 = et >> ppr_sh; row0 < TC_BM; row0 += 4 * row_step) {
+        uint4 v[4], rv[4];
+        int64_t off[4];
+        bool ok[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 x = __bfloat1622float2(a[j]), y = __bfloat1622float2(b[j]);
-                a[j] = __floats2bfloat162_rn(x.x + y.x, x.y + y.y);
+        for (int u = 0; u < 4; ++u) {
+            const int row = row0 + u * row_step;
+            const int n = n0 + (row >> rps_sh);
+            ok[u] = row < TC_BM && row < rows_valid && n < Bn;
+            const int ww = row & (p.tw - 1), hh = (row >> p.tw_sh) & (p.th - 1);
+            const int oh = (h0 + hh) * mul + py, ow = (w0 + ww) * mul + px;
+            off[u] = (((int64_t)n * Ho + oh) * Wo + ow) * Cout + cbase + pc * 8;
+            if (ok[u]) {
+                v[u] = *reinterpret_cast<const uint4*>(stage + row * pitch + pc * 16);
+                if (resp) rv[u] = *reinterpret_cast<const uint4*>(resp + off[u]);
             }
         }
-        *reinterpret_cast<uint4*>(outp + off) = v;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            if (resp) {
+                __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&v[u]);
+                const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&rv[u]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 x = __bfloat1622float2(a[j]), y = __bfloat1622float2(b[j]);
+                    a[j] = __floats2bfloat162_rn(x.x + y.x, x.y + y.y);
+                }
+            }
+            *reinterpret_cast<uint4*>(outp + off[u]) = v[u];
+        }
     }
     if (et == 0) tstamp(p, 6);
 }
@@ -895,7 +925,12 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
         fprintf(stderr, "conv_tc kind=%d B=%d H=%d W=%d C=%d+%d Cout=%d grid=(%u,%u,%u) bn=%d num_kb=%d splits=%d kb_per=%d\n", kind, B, H, W,
                 C1, C2, Cout, grid.x, grid.y, grid.z, p.bn, num_kb, p.splits, p.kb_per_split);
     const int ctas = (int)(grid.x * grid.y * grid.z);
-    if (halo)
+    static const int force_variant = getenv("DD_FORCE_VARIANT") ? atoi(getenv("DD_FORCE_VARIANT")) : 0;   // experiments only
+    if (force_variant == 3 && !halo)
+        launch_pdl(conv_tc_kernel<3, 128>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128), (cudaStream_t)stream, p);
+    else if (force_variant == 6 && !halo)
+        launch_pdl(conv_tc_kernel<6, 128>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(6, 128), (cudaStream_t)stream, p);
+    else if (halo)
         launch_pdl(conv_tc_halo_kernel, dim3(grid), dim3(TC_THREADS), HALO_SMEM, (cudaStream_t)stream, p);
     else if (p.bn <= 64 && ctas <= num_sms())
         launch_pdl(conv_tc_kernel<8, 64>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64), (cudaStream_t)stream, p);
