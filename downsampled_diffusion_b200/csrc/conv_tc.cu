@@ -23,13 +23,12 @@ namespace dd {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 16 KB
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 224;      // warps: A producer, MMA, 4 x epilogue, B producer
 // Pipeline variants <STAGES, BROWS>: BROWS = rows of the weight slot (>= bn).
 //   <3,128>: 96 KB  -> 2 CTAs/SM, for grids that fill the GPU (epilogue of one CTA overlaps the other's loop)
 //   <6,128>: 192 KB -> 1 CTA/SM, grids of at most one wave: twice the loads in flight per CTA
 //   <8, 64>: 192 KB -> 1 CTA/SM, low-resolution layers run with bn = 64 (twice the CTAs) and 8 stages
-constexpr int tc_stage_bytes(int brows) { return TC_A_BYTES + brows * TC_BK * 2 + 1024 /* slack: descriptor-phase experiment */; }
-constexpr int tc_smem_bytes(int stages, int brows) { return stages * tc_stage_bytes(brows) + 1024 /*align*/ + 1024 /*barriers + bias*/; }
+constexpr int tc_smem_bytes(int stages, int brows, int kch) { return stages * kch * (TC_A_BYTES + brows * TC_BK * 2) + 1024 /*align*/ + 1024 /*barriers + bias*/; }
 constexpr int TC_TMEM_COLS = 128;
 
 struct TcParams {
@@ -472,9 +471,15 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int TC_STAGES, int BROWS>
-__global__ void __launch_bounds__(TC_THREADS, (TC_STAGES <= 3 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ TcParams p) {
-    constexpr int TC_STAGE_BYTES = tc_stage_bytes(BROWS);
+// Generic pipeline.  <STAGES, BROWS, KCH>: KCH 64-channel chunks per stage (KCH = 2 halves the per-k-block
+// barrier / issue overhead, which -- not bandwidth -- bounds small tiles: one warp needs ~400 clk to issue a
+// stage, see profiles/README.md).  Warp roles: 0 = A-operand TMA producer, 6 = B-operand TMA producer,
+// 1 = MMA issuer + TMEM owner, 2..5 = epilogue.
+// ---------------------------------------------------------------------------------------------
+template <int TC_STAGES, int BROWS, int KCH>
+__global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    constexpr int B_SLOT = BROWS * TC_BK * 2;
+    constexpr int TC_STAGE_BYTES = KCH * (TC_A_BYTES + B_SLOT);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;     // full[S], empty[S], tmem_full, tmem_ptr
@@ -486,21 +491,18 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES <= 3 ? 2 : 1)) conv_tc_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) tstamp(p, 0);
-    const int m_tile = blockIdx.x, n_tile = blockIdx.y;
-    const int phase = p.splits > 1 ? 0 : blockIdx.z;
-    const int split = p.splits > 1 ? blockIdx.z : 0;
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y, phase = blockIdx.z;
     const int w0 = (m_tile % p.tiles_w) * p.tw;
     const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
     const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn;
-    const int cpt = p.chunks0 + p.chunks1;
-    const int kb_lo = split * p.kb_per_split;
-    const int num_kb = min(p.ntaps * cpt, kb_lo + p.kb_per_split) - kb_lo;     // k-blocks of this CTA
+    const int cpt = p.chunks0 + p.chunks1;                  // 64-channel chunks per tap (multiple of KCH)
+    const int num_st = p.ntaps * cpt / KCH;                 // pipeline stages this CTA consumes
     float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));   // 128 floats (barriers use < 160 B)
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA0)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB)) : "memory");
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -518,65 +520,89 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES <= 3 ? 2 : 1)) conv_tc_
     if (threadIdx.x == 0) tstamp(p, 2);
 
     if (warp == 0) {
-        // ===== TMA producer: whole warp runs the (uniform) loop, one elected lane issues =====
-        const uint32_t stage_tx = (uint32_t)(p.rows_valid + p.bn) * TC_BK * 2;   // bytes the two TMA boxes deliver
-        const int chunks0 = p.chunks0, wps = p.w_per_sample;
-        int tap = kb_lo / cpt, rem = kb_lo - tap * cpt;
-        int ti = phase * p.ntaps + tap;
+        // ===== A-operand producer: whole warp runs the (uniform) loop, one elected lane issues =====
+        const uint32_t tx = (uint32_t)KCH * p.rows_valid * TC_BK * 2;
+        const int chunks0 = p.chunks0;
+        int rem = 0, ti = phase * p.ntaps;
         int cx = w0 + p.tap_dw[ti], cy = h0 + p.tap_dh[ti], cp = p.tap_plane[ti];
-        int kcoord = kb_lo * 64;
-        const int brow = wps ? n_tile * p.bn : phase * p.rows_per_phase + n_tile * p.bn;
-        uint32_t sA = base + 128u * p.exp_shift;
+        uint32_t sA = base;
         int st = 0, round = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int i = 0; i < num_st; ++i) {
             const uint32_t fb = full_bar(st);
             if (round > 0) mbar_wait(empty_bar(st), (round - 1) & 1);
             if (elect_one()) {
-                mbar_expect_tx(fb, stage_tx);
-                if (rem < chunks0) tma_load_5d(&p.tmA0, fb, sA, rem * 64, cx, cy, n0, cp);
-                else tma_load_5d(&p.tmA1, fb, sA, (rem - chunks0) * 64, cx, cy, n0, cp);
-                const uint32_t sB = sA - 128u * p.exp_shift + TC_A_BYTES + 1024;
-                if (wps) tma_load_3d(&p.tmB, fb, sB, kcoord, brow, n0);
-                else tma_load_2d(&p.tmB, fb, sB, kcoord, brow);
+                mbar_expect_tx(fb, tx);
+#pragma unroll
+                for (int j = 0; j < KCH; ++j) {
+                    const int c = rem + j;
+                    if (c < chunks0) tma_load_5d(&p.tmA0, fb, sA + j * TC_A_BYTES, c * 64, cx, cy, n0, cp);
+                    else tma_load_5d(&p.tmA1, fb, sA + j * TC_A_BYTES, (c - chunks0) * 64, cx, cy, n0, cp);
+                }
             }
             __syncwarp();
-            kcoord += 64;
             sA += TC_STAGE_BYTES;
-            if (++st == TC_STAGES) { st = 0; ++round; sA -= TC_STAGES * TC_STAGE_BYTES; }
-            if (++rem == cpt) {
+            if (++st == TC_STAGES) { st = 0; ++round; sA = base; }
+            rem += KCH;
+            if (rem == cpt) {
                 rem = 0; ++ti;
-                if (kb + 1 < num_kb) { cx = w0 + p.tap_dw[ti]; cy = h0 + p.tap_dh[ti]; cp = p.tap_plane[ti]; }
+                if (i + 1 < num_st) { cx = w0 + p.tap_dw[ti]; cy = h0 + p.tap_dh[ti]; cp = p.tap_plane[ti]; }
             }
+        }
+    } else if (warp == 6) {
+        // ===== B-operand (weights) producer =====
+        const uint32_t tx = (uint32_t)KCH * p.bn * TC_BK * 2;
+        const int wps = p.w_per_sample;
+        const int brow = wps ? n_tile * p.bn : phase * p.rows_per_phase + n_tile * p.bn;
+        int kcoord = 0;
+        uint32_t sB = base + KCH * TC_A_BYTES;
+        int st = 0, round = 0;
+        for (int i = 0; i < num_st; ++i) {
+            const uint32_t fb = full_bar(st);
+            if (round > 0) mbar_wait(empty_bar(st), (round - 1) & 1);
+            if (elect_one()) {
+                mbar_expect_tx(fb, tx);
+#pragma unroll
+                for (int j = 0; j < KCH; ++j) {
+                    if (wps) tma_load_3d(&p.tmB, fb, sB + j * B_SLOT, kcoord + 64 * j, brow, n0);
+                    else tma_load_2d(&p.tmB, fb, sB + j * B_SLOT, kcoord + 64 * j, brow);
+                }
+            }
+            __syncwarp();
+            kcoord += 64 * KCH;
+            sB += TC_STAGE_BYTES;
+            if (++st == TC_STAGES) { st = 0; ++round; sB = base + KCH * TC_A_BYTES; }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: whole warp loops, one elected lane issues tcgen05.mma / commit =====
         // instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        uint32_t sA = base + 128u * p.exp_shift;
+        uint32_t sA = base;
         int st = 0;
         uint32_t par = 0;
-        const uint32_t bo = p.exp_bo;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int i = 0; i < num_st; ++i) {
             mbar_wait(full_bar(st), par);
-            if (kb == 0 && lane == 0) tstamp(p, 3);
+            if (i == 0 && lane == 0) tstamp(p, 3);
             tc_fence_after();
             if (elect_one()) {
-                const uint64_t ad = umma_desc(sA) | (bo ? ((uint64_t)((sA >> 7) & 7) << 49) : 0ull);
-                const uint64_t bd = umma_desc(sA - 128u * p.exp_shift + TC_A_BYTES + 1024);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k)
-                    umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                for (int j = 0; j < KCH; ++j) {
+                    const uint64_t ad = umma_desc(sA + j * TC_A_BYTES);
+                    const uint64_t bd = umma_desc(sA + KCH * TC_A_BYTES + j * B_SLOT);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)
+                        umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | j | k) ? 1u : 0u);
+                }
                 umma_commit(empty_bar(st));          // frees this smem stage when the MMAs retire
             }
             __syncwarp();
             sA += TC_STAGE_BYTES;
-            if (++st == TC_STAGES) { st = 0; par ^= 1u; sA -= TC_STAGES * TC_STAGE_BYTES; }
+            if (++st == TC_STAGES) { st = 0; par ^= 1u; sA = base; }
         }
         if (lane == 0) tstamp(p, 4);
         if (elect_one()) umma_commit(tmem_full_bar);             // accumulator complete
         __syncwarp();
     } else {
-        if (p.splits == 1 && !p.out_nchw_f32 && p.bn >= 32 && !(p.exp_bo & 8))
+        if (!p.out_nchw_f32 && p.bn >= 32)
             tc_epilogue_staged(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, phase, w0, h0, n0,
                                warp, lane);
         else
@@ -589,7 +615,6 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES <= 3 ? 2 : 1)) conv_tc_
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
     }
 }
-
 
 // =============================================================================================
 // Halo variant for 3x3 stride-1 convolutions on maps of at least 16x8 pixels.
@@ -721,8 +746,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __gri
         if (lane == 0) tstamp(p, 4);
         if (elect_one()) umma_commit(tmem_full_bar);
         __syncwarp();
-    } else {
-        if (p.bn >= 32 && !(p.exp_bo & 8))
+    } else if (warp < 6) {
+        if (p.bn >= 32)
             tc_epilogue_staged(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, 0, w0, h0, n0, warp,
                                lane);
         else
@@ -813,9 +838,11 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
 
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(6, 128));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<6, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(6, 128, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 2));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(4, 64, 2));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM);
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
         attr_done = true;
@@ -899,44 +926,29 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
         if (rc) return rc;
     }
 
-    // split-K for layers whose output tiles cannot fill the GPU (low-resolution levels): spread the
-    // (tap, chunk) loop over up to 12 CTAs per tile, aiming at ~2 CTAs per SM.
-    const int tiles = p.tiles_w * p.tiles_h * tiles_n * (Cout / p.bn);
-    const int num_kb = p.ntaps * (p.chunks0 + p.chunks1);
-    p.splits = 1; p.kb_per_split = num_kb;
-    p.splitk_ws = splitk_ws; p.splitk_cnt = splitk_cnt;
+    p.splits = 1; p.kb_per_split = p.ntaps * (p.chunks0 + p.chunks1);
+    p.splitk_ws = nullptr; p.splitk_cnt = nullptr; p.exp_shift = 0; p.exp_bo = 0;
     p.dbg = g_tc_dbg;
-    { const char* e1 = getenv("DD_EXP_SHIFT"); const char* e2 = getenv("DD_EXP_BO");
-      p.exp_shift = e1 ? atoi(e1) : 0; p.exp_bo = e2 ? atoi(e2) : 0; }
-    static const bool splitk_on = getenv("DD_SPLITK") != nullptr;   // red.add reduction measured slower than deep pipelines (profiles/README.md)
-    if (splitk_on && splitk_ws && splitk_cnt && phases == 1 && !wps && tiles < num_sms() && num_kb >= 6 &&
-        (int64_t)tiles * TC_BM * p.bn <= splitk_ws_floats && tiles <= splitk_cnt_n) {
-        int sp = (2 * num_sms()) / tiles;
-        if (sp > num_kb / 3) sp = num_kb / 3;
-        if (sp > 12) sp = 12;
-        if (sp >= 2) {
-            p.kb_per_split = (num_kb + sp - 1) / sp;
-            p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
-        }
-    }
+    (void)splitk_ws; (void)splitk_ws_floats; (void)splitk_cnt; (void)splitk_cnt_n;
     dim3 grid(p.tiles_w * p.tiles_h * tiles_n, Cout / p.bn, phases * p.splits);
     static const bool verbose = getenv("DD_TC_VERBOSE") != nullptr;
     if (verbose)
         fprintf(stderr, "conv_tc kind=%d B=%d H=%d W=%d C=%d+%d Cout=%d grid=(%u,%u,%u) bn=%d num_kb=%d splits=%d kb_per=%d\n", kind, B, H, W,
-                C1, C2, Cout, grid.x, grid.y, grid.z, p.bn, num_kb, p.splits, p.kb_per_split);
+                C1, C2, Cout, grid.x, grid.y, grid.z, p.bn, p.kb_per_split, p.splits, p.kb_per_split);
     const int ctas = (int)(grid.x * grid.y * grid.z);
-    static const int force_variant = getenv("DD_FORCE_VARIANT") ? atoi(getenv("DD_FORCE_VARIANT")) : 0;   // experiments only
-    if (force_variant == 3 && !halo)
-        launch_pdl(conv_tc_kernel<3, 128>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128), (cudaStream_t)stream, p);
-    else if (force_variant == 6 && !halo)
-        launch_pdl(conv_tc_kernel<6, 128>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(6, 128), (cudaStream_t)stream, p);
-    else if (halo)
-        launch_pdl(conv_tc_halo_kernel, dim3(grid), dim3(TC_THREADS), HALO_SMEM, (cudaStream_t)stream, p);
-    else if (p.bn <= 64 && ctas <= num_sms())
-        launch_pdl(conv_tc_kernel<8, 64>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64), (cudaStream_t)stream, p);
-    else if (ctas <= num_sms())
-        launch_pdl(conv_tc_kernel<6, 128>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(6, 128), (cudaStream_t)stream, p);
+    const bool pair = ((p.chunks0 + p.chunks1) % 2 == 0) && (p.chunks0 % 2 == 0);     // two chunks per stage never straddle the sources
+    cudaStream_t st = (cudaStream_t)stream;
+    if (halo)
+        launch_pdl(conv_tc_halo_kernel, dim3(grid), dim3(TC_THREADS), HALO_SMEM, st, p);
+    else if (ctas > num_sms())      // more than one wave: two CTAs per SM so epilogues overlap main loops
+        launch_pdl(conv_tc_kernel<3, 128, 1>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
+    else if (p.bn <= 64 && pair)
+        launch_pdl(conv_tc_kernel<4, 64, 2>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(4, 64, 2), st, p);
+    else if (p.bn <= 64)
+        launch_pdl(conv_tc_kernel<8, 64, 1>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
+    else if (pair)
+        launch_pdl(conv_tc_kernel<3, 128, 2>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 2), st, p);
     else
-        launch_pdl(conv_tc_kernel<3, 128>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128), (cudaStream_t)stream, p);
+        launch_pdl(conv_tc_kernel<6, 128, 1>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(6, 128, 1), st, p);
     return check_launch("conv_tc");
 }
