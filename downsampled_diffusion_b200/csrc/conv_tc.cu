@@ -80,7 +80,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) { printf("conv_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+        if (clock64() - t0 > 4000000000LL) __trap();      // ~2 s: surfaces as a launch failure on the host
     }
 }
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
@@ -147,11 +147,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+#ifndef DD_TC_TIMELINE
+#define DD_TC_TIMELINE 0          // build with -DDD_TC_TIMELINE=1 to record per-CTA clock64 stamps (scripts/timeline.py)
+#endif
 __device__ __forceinline__ void tstamp(const TcParams& p, int slot) {
-    if (p.dbg) p.dbg[((int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z))) * 16 + slot] = clock64();
+    if (DD_TC_TIMELINE && p.dbg) p.dbg[((int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z))) * 16 + slot] = clock64();
 }
 __device__ __forceinline__ void tstore(const TcParams& p, int slot, long long v) {
-    if (p.dbg) p.dbg[((int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z))) * 16 + slot] = v;
+    if (DD_TC_TIMELINE && p.dbg) p.dbg[((int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z))) * 16 + slot] = v;
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 
@@ -182,55 +185,18 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 
-    bool finisher = true;
-    float* wst = nullptr;
-    if (p.splits > 1) {
-        // ---- split-K: add this CTA's partial tile into the fp32 workspace, last arrival finishes ----
-        const int tile_id = m_tile * gridDim.y + n_tile;
-        wst = p.splitk_ws + (int64_t)tile_id * TC_BM * p.bn;
-        uint32_t acc[16];
-        for (int ch = 0; ch < p.bn; ch += 16) {
-            tmem_ld16_issue(trow + (uint32_t)ch, acc);
-            tmem_ld_wait();
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-                red_add_v4(wst + ((int64_t)((ch >> 2) + k4) * TC_BM + r) * 4, __uint_as_float(acc[4 * k4]),
-                           __uint_as_float(acc[4 * k4 + 1]), __uint_as_float(acc[4 * k4 + 2]), __uint_as_float(acc[4 * k4 + 3]));
-        }
-        __threadfence();
-        epi_bar();
-        int* s_flag = reinterpret_cast<int*>(s_bias + 128);
-        if (et == 0) {
-            const int ticket = atomicAdd(p.splitk_cnt + tile_id, 1);
-            const int last = (ticket == p.splits - 1);
-            if (last) p.splitk_cnt[tile_id] = 0;                 // self-cleaning for the next launch
-            *s_flag = last;
-        }
-        epi_bar();
-        finisher = (*s_flag != 0);
-        if (finisher) __threadfence();
-    }
-
+    const bool finisher = true;
     if (finisher) {
         float gs = 0.f, gq = 0.f;
         uint32_t acc[16], nxt[16];
-        if (p.splits == 1) { tmem_ld16_issue(trow, acc); tmem_ld_wait(); }
+        tmem_ld16_issue(trow, acc);
+        tmem_ld_wait();
         for (int ch = 0; ch < p.bn; ch += 16) {
             const bool more = ch + 16 < p.bn;
             float v[16];
-            if (p.splits > 1) {
+            if (more) tmem_ld16_issue(trow + (uint32_t)(ch + 16), nxt);      // overlaps the math below
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    float4* wp4 = reinterpret_cast<float4*>(wst + ((int64_t)((ch >> 2) + k4) * TC_BM + r) * 4);
-                    const float4 t = __ldcg(wp4);
-                    *wp4 = make_float4(0.f, 0.f, 0.f, 0.f);      // leave the workspace zeroed
-                    v[4 * k4] = t.x; v[4 * k4 + 1] = t.y; v[4 * k4 + 2] = t.z; v[4 * k4 + 3] = t.w;
-                }
-            } else {
-                if (more) tmem_ld16_issue(trow + (uint32_t)(ch + 16), nxt);      // overlaps the math below
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-            }
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
             if (use_res && more) { res_nxt[0] = res_ptr[(ch >> 3) + 2]; res_nxt[1] = res_ptr[(ch >> 3) + 3]; }
             const int c0 = cbase + ch;
 #pragma unroll
@@ -289,7 +255,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
                     }
                 }
             }
-            if (p.splits == 1 && more) {
+            if (more) {
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc[j] = nxt[j];
