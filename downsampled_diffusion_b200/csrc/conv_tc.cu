@@ -442,7 +442,7 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
 // stage, see profiles/README.md).  Warp roles: 0 = A-operand TMA producer, 6 = B-operand TMA producer,
 // 1 = MMA issuer + TMEM owner, 2..5 = epilogue.
 // ---------------------------------------------------------------------------------------------
-template <int TC_STAGES, int BROWS, int KCH>
+template <int TC_STAGES, int BROWS, int KCH, bool LEGACY_EPI>
 __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ TcParams p) {
     constexpr int B_SLOT = BROWS * TC_BK * 2;
     constexpr int TC_STAGE_BYTES = KCH * (TC_A_BYTES + B_SLOT);
@@ -568,11 +568,11 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
         if (elect_one()) umma_commit(tmem_full_bar);             // accumulator complete
         __syncwarp();
     } else {
-        if (!p.out_nchw_f32 && p.bn >= 32)
+        if constexpr (LEGACY_EPI)       // fp32 NCHW output / tiles narrower than 32 channels (the final 1x1 conv)
+            tc_epilogue(p, tmem_base, tmem_full_bar, s_bias, m_tile, n_tile, phase, w0, h0, n0, warp, lane);
+        else
             tc_epilogue_staged(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, phase, w0, h0, n0,
                                warp, lane);
-        else
-            tc_epilogue(p, tmem_base, tmem_full_bar, s_bias, m_tile, n_tile, phase, w0, h0, n0, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -713,11 +713,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __gri
         if (elect_one()) umma_commit(tmem_full_bar);
         __syncwarp();
     } else if (warp < 6) {
-        if (p.bn >= 32)
-            tc_epilogue_staged(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, 0, w0, h0, n0, warp,
-                               lane);
-        else
-            tc_epilogue(p, tmem_base, tmem_full_bar, s_bias, m_tile, n_tile, 0, w0, h0, n0, warp, lane);
+        tc_epilogue_staged(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, 0, w0, h0, n0, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -804,11 +800,12 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
 
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 1));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<6, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(6, 128, 1));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64, 1));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 2));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(4, 64, 2));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<6, 128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(6, 128, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 2));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, 64, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(4, 64, 2));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 1));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM);
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
         attr_done = true;
@@ -820,7 +817,7 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     memset(&p, 0, sizeof(p));
     // tile geometry over the GEMM pixel grid
     static const bool halo_off = getenv("DD_NO_HALO") != nullptr;
-    const bool halo = !halo_off && kind == DD_TC_CONV3x3 && H >= HALO_TH && W >= HALO_TW && Cout >= 64;
+    const bool halo = !halo_off && kind == DD_TC_CONV3x3 && H >= HALO_TH && W >= HALO_TW && Cout >= 64 && !out_nchw_f32;
     p.tw = W < 128 ? W : 128;
     p.th = (128 / p.tw) < H ? (128 / p.tw) : H;
     if (halo) { p.tw = HALO_TW; p.th = HALO_TH; }
@@ -904,17 +901,19 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     const int ctas = (int)(grid.x * grid.y * grid.z);
     const bool pair = ((p.chunks0 + p.chunks1) % 2 == 0) && (p.chunks0 % 2 == 0);     // two chunks per stage never straddle the sources
     cudaStream_t st = (cudaStream_t)stream;
-    if (halo)
+    if (out_nchw_f32 || p.bn < 32)
+        launch_pdl(conv_tc_kernel<3, 128, 1, true>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
+    else if (halo)
         launch_pdl(conv_tc_halo_kernel, dim3(grid), dim3(TC_THREADS), HALO_SMEM, st, p);
     else if (ctas > num_sms())      // more than one wave: two CTAs per SM so epilogues overlap main loops
-        launch_pdl(conv_tc_kernel<3, 128, 1>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
+        launch_pdl(conv_tc_kernel<3, 128, 1, false>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
     else if (p.bn <= 64 && pair)
-        launch_pdl(conv_tc_kernel<4, 64, 2>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(4, 64, 2), st, p);
+        launch_pdl(conv_tc_kernel<4, 64, 2, false>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(4, 64, 2), st, p);
     else if (p.bn <= 64)
-        launch_pdl(conv_tc_kernel<8, 64, 1>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
+        launch_pdl(conv_tc_kernel<8, 64, 1, false>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
     else if (pair)
-        launch_pdl(conv_tc_kernel<3, 128, 2>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 2), st, p);
+        launch_pdl(conv_tc_kernel<3, 128, 2, false>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 2), st, p);
     else
-        launch_pdl(conv_tc_kernel<6, 128, 1>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(6, 128, 1), st, p);
+        launch_pdl(conv_tc_kernel<6, 128, 1, false>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(6, 128, 1), st, p);
     return check_launch("conv_tc");
 }
