@@ -58,7 +58,7 @@ SIGNATURES = {
     "dd_unpool2": [_p, _p, _i, _i, _i, _i, _f, _p],
     "dd_conv_tc": [_i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i64, _p, _i, _p],
 }
-PLAIN = {"dd_linattn_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_version": (C.c_int, []), "dd_device_ok": (C.c_int, []), "dd_last_error": (C.c_char_p, [])}
+PLAIN = {"dd_linattn_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_linattn_mix_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_version": (C.c_int, []), "dd_device_ok": (C.c_int, []), "dd_last_error": (C.c_char_p, [])}
 
 _lib: Optional[C.CDLL] = None
 

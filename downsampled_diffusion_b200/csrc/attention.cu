@@ -1,0 +1,297 @@
+// LinearAttention context on warp-level tensor-core MMA (bf16 in, fp32 accumulate), fused with the fold of the
+// attention's output projection into per-sample matrices (reference: models/unet/blocks.py:118-134).
+//
+//   k, v : (n, 32) slices of the NHWC qkv tensor for one (b, head)
+//   ctx[d][e] = sum_n softmax_n(k)[n][d] * v[n][e]                           (blocks.py:129-130)
+//   Mb[b][c][h*32+d] = sum_e Wout[c][h*32+e] * ctx[d][e]                     (blocks.py:131-133 folded)
+// so that to_out(attention)[n][c] = sum_k q[n][k] Mb[b][c][k] + bias[c] is one per-sample tcgen05 GEMM (dd_conv_tc
+// with DD_TC_W_PER_SAMPLE).  The op is bound by reading k and v once (128 B per pixel and head); the 32x32x n
+// contraction runs on mma.sync.m16n8k16 because a 32x32 output per (b, head) is far too small for a tcgen05 tile.
+//
+// CTA (b, head, split) = 8 warps; a warp owns 32-row slabs of the split's pixel range, keeps an online softmax
+// (running max per d, rescaled fp32 accumulators) in registers, operands via ldmatrix.trans from a warp-private
+// shared-memory slab.  Warps merge through shared memory, splits through a workspace + self-resetting arrival
+// ticket: the last CTA of a (b, head) normalises the context and does the projection fold, also on mma.sync.
+#include "common.cuh"
+
+namespace dd {
+
+constexpr int LA_WS = 64 + 32 * 32;      // floats per (b, head, split): max_d[32], sum_d[32], ctx[32][32]
+constexpr int LM_SLAB = 32;              // rows per warp slab
+constexpr int LM_PITCH = 40;             // bf16 elements per smem row (80 B: conflict-free ldmatrix)
+constexpr int LM_ROWS = 8 * LM_SLAB;     // rows per CTA iteration
+
+__host__ __device__ inline int lm_chunk(int n) {           // rows per split: >= 256, at most 16 splits
+    int c = (n + 15) / 16;
+    c = (c + LM_ROWS - 1) / LM_ROWS * LM_ROWS;
+    return c < LM_ROWS ? LM_ROWS : c;
+}
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float2 unpack_bf2(uint32_t u) {
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256) linattn_ctxmix_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws,
+                                                             int* __restrict__ tickets, int n, int heads, int chunk,
+                                                             const __nv_bfloat16* __restrict__ Wout, int C,
+                                                             __nv_bfloat16* __restrict__ Mb) {
+    pdl_sync();
+    constexpr int DH = 32;
+    const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
+    const int S = gridDim.y, sp = blockIdx.y;
+    const int HD = heads * DH, C3 = 3 * HD;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    __shared__ __align__(16) __nv_bfloat16 s_kv[8][2][LM_SLAB][LM_PITCH];     // 40 KB, later reused (fold stage)
+    __shared__ float s_ctx[DH][DH + 1];
+    __shared__ float s_mw[8][DH];
+    __shared__ float s_s[DH], s_M[DH];
+    __shared__ int s_last;
+
+    for (int i = threadIdx.x; i < DH * (DH + 1); i += 256) (&s_ctx[0][0])[i] = 0.f;
+    if (threadIdx.x < DH) s_s[threadIdx.x] = 0.f;
+
+    const __nv_bfloat16* kb = qkv + (int64_t)b * n * C3 + HD + hd * DH;      // v = k + HD
+    const int n_lo = sp * chunk, n_hi = min(n, n_lo + chunk);
+
+    // per-thread state: d rows {g, g+8, g+16, g+24} (index mt*2+half), e columns nt*8 + 2t, +1
+    float m_run[4], s_run[4], acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m_run[i] = -INFINITY; s_run[i] = 0.f; }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
+
+    __nv_bfloat16 (*sk)[LM_PITCH] = s_kv[warp][0];
+    __nv_bfloat16 (*sv)[LM_PITCH] = s_kv[warp][1];
+    for (int r0 = n_lo + warp * LM_SLAB; r0 < n_hi; r0 += LM_ROWS) {
+        // ---- slab load: 32 rows x (64 B of k + 64 B of v), 8 x 16-byte vectors per lane, all issued before use
+        uint4 ld[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = lane + 32 * u, isv = idx >> 7, r = (idx & 127) >> 2, c16 = idx & 3;
+            if (r0 + r < n_hi) ld[u] = __ldg(reinterpret_cast<const uint4*>(kb + (int64_t)(r0 + r) * C3 + isv * HD) + c16);
+            else ld[u] = isv ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);  // k = -inf
+        }
+        __syncwarp();                     // previous slab's ldmatrix reads are done
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = lane + 32 * u, isv = idx >> 7, r = (idx & 127) >> 2, c16 = idx & 3;
+            *reinterpret_cast<uint4*>(&s_kv[warp][isv][r][c16 * 8]) = ld[u];
+        }
+        __syncwarp();
+        // ---- A = exp(k - m)^T fragments (d x n): ldmatrix.trans of the [n][d] slab
+        uint32_t a[2][2][4];
+        const int mi = lane >> 3, li = lane & 7;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+                ldsm_x4_t(a[mt][ks], &sk[ks * 16 + li + (mi >> 1) * 8][mt * 16 + (mi & 1) * 8]);
+        float fac[4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float2 f = unpack_bf2(a[mt][ks][h + 2 * q]);
+                        mx = fmaxf(mx, fmaxf(f.x, f.y));
+                    }
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                const int i = mt * 2 + h;
+                const float mn = fmaxf(m_run[i], mx);            // finite: the slab has at least one valid row
+                fac[i] = __expf(m_run[i] - mn);                  // 0 on the first slab
+                m_run[i] = mn;
+                float ssum = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float2 f = unpack_bf2(a[mt][ks][h + 2 * q]);
+                        const uint32_t p = pack_bf2(__expf(f.x - mn), __expf(f.y - mn));
+                        const float2 pr = unpack_bf2(p);         // the sum uses the rounded weights the MMA sees
+                        ssum += pr.x + pr.y;
+                        a[mt][ks][h + 2 * q] = p;
+                    }
+                s_run[i] = s_run[i] * fac[i] + ssum;
+            }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                acc[mt][nt][0] *= fac[mt * 2]; acc[mt][nt][1] *= fac[mt * 2];
+                acc[mt][nt][2] *= fac[mt * 2 + 1]; acc[mt][nt][3] *= fac[mt * 2 + 1];
+            }
+        // ---- B = v fragments (n x e) and the MMAs
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                uint32_t bb[4];
+                ldsm_x4_t(bb, &sv[ks * 16 + li + (mi & 1) * 8][np * 16 + (mi >> 1) * 8]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mma_bf16(acc[mt][np * 2], a[mt][ks], bb[0], bb[1]);
+                    mma_bf16(acc[mt][np * 2 + 1], a[mt][ks], bb[2], bb[3]);
+                }
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        s_run[i] += __shfl_xor_sync(0xffffffffu, s_run[i], 1);
+        s_run[i] += __shfl_xor_sync(0xffffffffu, s_run[i], 2);
+    }
+    // ---- merge the 8 warps: CTA max, rescale, shared-memory accumulation
+    if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_mw[warp][g + 8 * i] = m_run[i];
+    }
+    __syncthreads();
+    float f_own[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) M = fmaxf(M, s_mw[w][g + 8 * i]);
+        f_own[i] = (m_run[i] == -INFINITY) ? 0.f : __expf(m_run[i] - M);       // a warp without rows contributes nothing
+        if (warp == 0 && t == 0) s_M[g + 8 * i] = M;
+        if (t == 0 && f_own[i] != 0.f) atomicAdd(&s_s[g + 8 * i], s_run[i] * f_own[i]);
+    }
+    if (m_run[0] != -INFINITY) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    atomicAdd(&s_ctx[mt * 16 + g + 8 * (j >> 1)][nt * 8 + 2 * t + (j & 1)], acc[mt][nt][j] * f_own[mt * 2 + (j >> 1)]);
+    }
+    __syncthreads();
+
+    // normalised context as bf16 [d][e] (pitch 40) for the fold; reuses the slab memory
+    __nv_bfloat16 (*s_cb)[LM_PITCH] = reinterpret_cast<__nv_bfloat16 (*)[LM_PITCH]>(&s_kv[0][0][0][0]);
+    float* s_fac = reinterpret_cast<float*>(&s_kv[1][0][0][0]);              // [S][32] split factors, then 1/total at [16][32]
+    if (S == 1) {
+        for (int i = threadIdx.x; i < DH * DH; i += 256) {
+            const int d = i >> 5, e = i & 31;
+            s_cb[d][e] = __float2bfloat16_rn(s_ctx[d][e] / s_s[d]);
+        }
+    } else {
+        float* w = ws + ((int64_t)bh * S + sp) * LA_WS;
+        if (threadIdx.x < DH) { w[threadIdx.x] = s_M[threadIdx.x]; w[32 + threadIdx.x] = s_s[threadIdx.x]; }
+        for (int i = threadIdx.x; i < DH * DH; i += 256) w[64 + i] = s_ctx[i >> 5][i & 31];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int tk = atomicAdd(tickets + bh, 1);
+            s_last = (tk == S - 1);
+            if (s_last) tickets[bh] = 0;                  // self-resetting: zero again for the next launch
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const float* w0 = ws + (int64_t)bh * S * LA_WS;
+        if (threadIdx.x < DH) {
+            const int d = threadIdx.x;
+            float M = -INFINITY;
+            for (int s = 0; s < S; ++s) M = fmaxf(M, __ldcg(w0 + s * LA_WS + d));
+            float tot = 0.f;
+            for (int s = 0; s < S; ++s) {
+                const float f = __expf(__ldcg(w0 + s * LA_WS + d) - M);
+                s_fac[s * DH + d] = f;
+                tot += __ldcg(w0 + s * LA_WS + 32 + d) * f;
+            }
+            s_fac[16 * DH + d] = 1.f / tot;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < DH * DH; i += 256) {
+            const int d = i >> 5, e = i & 31;
+            float o = 0.f;
+            for (int s = 0; s < S; ++s) o += __ldcg(w0 + s * LA_WS + 64 + i) * s_fac[s * DH + d];
+            s_cb[d][e] = __float2bfloat16_rn(o * s_fac[16 * DH + d]);
+        }
+    }
+    __syncthreads();
+
+    // ---- projection fold: Mb[c][hd*32 + d] = sum_e Wout[c][hd*32 + e] * ctx[d][e]   (M = c, N = d, K = e)
+    uint32_t bf[2][4][2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            bf[ks][nt][0] = *reinterpret_cast<const uint32_t*>(&s_cb[nt * 8 + g][ks * 16 + 2 * t]);
+            bf[ks][nt][1] = *reinterpret_cast<const uint32_t*>(&s_cb[nt * 8 + g][ks * 16 + 2 * t + 8]);
+        }
+    const __nv_bfloat16* wh = Wout + hd * DH;
+    __nv_bfloat16* mb = Mb + (int64_t)b * C * HD + hd * DH;
+    for (int c0 = warp * 16; c0 < C; c0 += 128) {
+        uint32_t aw[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const __nv_bfloat16* p0 = wh + (int64_t)(c0 + g) * HD + ks * 16 + 2 * t;
+            const __nv_bfloat16* p1 = p0 + 8 * HD;
+            aw[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(p0));
+            aw[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(p1));
+            aw[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 8));
+            aw[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(p1 + 8));
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_bf16(o, aw[0], bf[0][nt][0], bf[0][nt][1]);
+            mma_bf16(o, aw[1], bf[1][nt][0], bf[1][nt][1]);
+            *reinterpret_cast<uint32_t*>(mb + (int64_t)(c0 + g) * HD + nt * 8 + 2 * t) = pack_bf2(o[0], o[1]);
+            *reinterpret_cast<uint32_t*>(mb + (int64_t)(c0 + g + 8) * HD + nt * 8 + 2 * t) = pack_bf2(o[2], o[3]);
+        }
+    }
+}
+
+}  // namespace dd
+
+using namespace dd;
+
+extern "C" {
+
+int64_t dd_linattn_mix_ws_floats(int B, int n, int heads) {
+    const int chunk = lm_chunk(n);
+    return (int64_t)B * heads * ((n + chunk - 1) / chunk) * LA_WS + (int64_t)B * heads;
+}
+
+int dd_linattn_mix(const void* qkv, int dtype, int B, int n, int heads, int dh, float* ws, int64_t ws_floats,
+                   const void* Wout_bf16, int C, void* Mb_bf16, void* stream) {
+    DD_REQUIRE(dtype == DD_BF16, "linattn_mix: bf16 tensor-core path only (dtype %d)", dtype);
+    DD_REQUIRE(dh == 32 && heads > 0 && n > 0, "linattn_mix: dim_head must be 32 (got %d)", dh);
+    DD_REQUIRE(C > 0 && C % 16 == 0, "linattn_mix: C=%d must be a multiple of 16", C);
+    const int chunk = lm_chunk(n);
+    const int S = (n + chunk - 1) / chunk;
+    DD_REQUIRE(ws != nullptr && ws_floats >= dd_linattn_mix_ws_floats(B, n, heads), "linattn_mix: workspace too small");
+    int* tickets = reinterpret_cast<int*>(ws + (int64_t)B * heads * S * LA_WS);
+    launch_pdl(linattn_ctxmix_kernel, dim3(B * heads, S), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)qkv, ws,
+               tickets, n, heads, chunk, (const __nv_bfloat16*)Wout_bf16, C, (__nv_bfloat16*)Mb_bf16);
+    return check_launch("linattn_mix");
+}
+
+}  // extern "C"

@@ -62,23 +62,34 @@ template <int N> __device__ __forceinline__ FVec<N> ldg_f(const float* p) {
     return r;
 }
 
+constexpr int GN_UNR = 2;
+// grid = (vector blocks within one image, B): no division to find the image, 32-bit index math only
+// (the first version spent ~25 of its 36 instructions per element on 64-bit index divisions -- profiles/README.md).
 template <typename T>
-__global__ void __launch_bounds__(256) gn_mish_kernel(const T* __restrict__ x, T* __restrict__ y, int HW, int C, int G,
+__global__ void __launch_bounds__(256, 4) gn_mish_kernel(const T* __restrict__ x, T* __restrict__ y, int HW, int C, int G,
                                const float* __restrict__ stats, int stats_mode, float eps,
                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ tbias, int tb_stride, const int32_t* __restrict__ trow,
-                               int trow_stride, const T* __restrict__ residual, int64_t total_vec) {
+                               int trow_stride, const T* __restrict__ residual, int vec_per_img) {
     pdl_sync();
     constexpr int VN = Vec<T>::N;
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= total_vec) return;
-    const int cv = C / VN, cpg = C / G;
-    const int c = (int)(i % cv) * VN;
-    const int b = (int)(i / ((int64_t)cv * HW));
-    const int g = c / cpg;
-    Vec<T> v, r;
-    v.load(x + i * VN);
-    if (residual) r.load(residual + i * VN);
+    constexpr int UNR = GN_UNR;                      // independent 16-byte vectors per thread: loads first, math after
+    const int b = blockIdx.y;
+    const unsigned cv = (unsigned)C / VN, cpg = (unsigned)C / G;   // cv divides 256: a thread's vectors share their channels
+    const unsigned i0 = blockIdx.x * (256u * UNR) + threadIdx.x;
+    if (i0 >= (unsigned)vec_per_img) return;
+    const int c = (int)(i0 % cv) * VN;
+    const int g = c / (int)cpg;
+    const int64_t base = (int64_t)b * vec_per_img;
+    Vec<T> v[UNR], r[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+        const unsigned i = i0 + u * 256u;
+        if (i < (unsigned)vec_per_img) {
+            v[u].load(x + (base + i) * VN);
+            if (residual) r[u].load(residual + (base + i) * VN);
+        }
+    }
     const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + (int64_t)b * G + g);
     float mean, rstd;
     if (stats_mode == 0) { mean = st.x; rstd = st.y; }
@@ -87,20 +98,28 @@ __global__ void __launch_bounds__(256) gn_mish_kernel(const T* __restrict__ x, T
         mean = st.x * inv_n;
         rstd = rsqrtf(fmaxf(st.y * inv_n - mean * mean, 0.f) + eps);
     }
-    const FVec<VN> ga = ldg_f<VN>(gamma + c), be = ldg_f<VN>(beta + c);
-    FVec<VN> tb;
+    FVec<VN> sc = ldg_f<VN>(gamma + c), sh = ldg_f<VN>(beta + c), tb;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) { sc.v[j] *= rstd; sh.v[j] -= mean * sc.v[j]; }     // h = x * sc + sh
     if (tbias) {
         const int row = trow ? trow[(int64_t)b * trow_stride] : b;
         tb = ldg_f<VN>(tbias + (int64_t)row * tb_stride + c);
+    } else {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) tb.v[j] = 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < VN; ++j) {
-        float h = mish_t<T>((v.v[j] - mean) * rstd * ga.v[j] + be.v[j]);
-        if (tbias) h += tb.v[j];
-        if (residual) h += r.v[j];
-        v.v[j] = h;
+    for (int u = 0; u < UNR; ++u) {
+        const unsigned i = i0 + u * 256u;
+        if (i >= (unsigned)vec_per_img) break;
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+            float h = mish_t<T>(fmaf(v[u].v[j], sc.v[j], sh.v[j])) + tb.v[j];
+            if (residual) h += r[u].v[j];
+            v[u].v[j] = h;
+        }
+        v[u].store(y + (base + i) * VN);
     }
-    v.store(y + i * VN);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -132,6 +151,41 @@ __global__ void layernorm_c_kernel(const T* __restrict__ x, T* __restrict__ y, i
             yp[c] = from_f<T>((v[j] - mean) * inv * g[c] + bta[c]);
         }
     }
+}
+
+// bf16 fast path: 16-byte loads, C/8 lanes per pixel (8, 16 or 32), several pixels per warp.
+template <int LPP>
+__global__ void __launch_bounds__(256) layernorm_c_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                               int64_t P, const float* __restrict__ g,
+                                                               const float* __restrict__ bta, float eps) {
+    pdl_sync();
+    constexpr int C = LPP * 8, PPW = 32 / LPP;       // pixels per warp
+    const int lane = threadIdx.x & 31, sub = lane / LPP, l = lane % LPP;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t p = warp * PPW + sub;
+    const bool ok = p < P;
+    Vec<__nv_bfloat16> v;
+    if (ok) v.load(x + p * C + l * 8);
+    else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] = 0.f;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v.v[j];
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v.v[j] -= mean; q += v.v[j] * v.v[j]; }
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float inv = 1.f / (sqrtf(q * (1.f / C)) + eps);
+    const FVec<8> gg = ldg_f<8>(g + l * 8), bb = ldg_f<8>(bta + l * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] = v.v[j] * inv * gg.v[j] + bb.v[j];
+    if (ok) v.store(y + p * C + l * 8);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -226,13 +280,26 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const T* __restrict__ 
     __syncthreads();
     for (int t0 = n_lo; t0 < n_hi; t0 += LA_TILE) {
         const int rows = min(LA_TILE, n_hi - t0);
-        for (int i = threadIdx.x; i < rows * VPR * 2; i += 256) {
-            const int r = i / (VPR * 2), w = i % (VPR * 2);
-            const int isv = w / VPR, c = (w % VPR) * VN;
-            Vec<T> x;
-            x.load((isv ? vb : kb) + (int64_t)(t0 + r) * C3 + c);
+        {   // all global loads of the tile are issued before the first use (the kernel is load-latency bound)
+            constexpr int NV = LA_TILE * VPR * 2 / 256;          // vectors per thread for a full tile
+            Vec<T> xv[NV];
 #pragma unroll
-            for (int j = 0; j < VN; ++j) (isv ? sv[r][c + j] : sk[r][c + j]) = x.v[j];
+            for (int u = 0; u < NV; ++u) {
+                const int i = threadIdx.x + u * 256;
+                const int r = i / (VPR * 2), w = i % (VPR * 2);
+                const int isv = w / VPR, c = (w % VPR) * VN;
+                if (r < rows) xv[u].load((isv ? vb : kb) + (int64_t)(t0 + r) * C3 + c);
+            }
+#pragma unroll
+            for (int u = 0; u < NV; ++u) {
+                const int i = threadIdx.x + u * 256;
+                const int r = i / (VPR * 2), w = i % (VPR * 2);
+                const int isv = w / VPR, c = (w % VPR) * VN;
+                if (r < rows) {
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) (isv ? sv[r][c + j] : sk[r][c + j]) = xv[u].v[j];
+                }
+            }
         }
         __syncthreads();
         float m = -INFINITY;
@@ -277,61 +344,6 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const T* __restrict__ 
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) w[64 + lane * 32 + warp * 4 + j] = acc[j];
-}
-
-// Merge the S partial contexts of (b, head) and fold the attention's output projection into them:
-//   M_b[c][h*32+d] = sum_e ctx_h[d][e] * Wout[c][h*32+e]      (bf16, K-major rows of length heads*32)
-// so that  to_out(linattn(q,k,v))[n][c] = sum_{hd} q[n][hd] * M_b[c][hd] + bias[c]  is ONE per-sample GEMM
-// on the tensor cores (dd_conv_tc with DD_TC_W_PER_SAMPLE) instead of a CUDA-core contraction + a GEMM.
-__global__ void __launch_bounds__(256) linattn_mix_kernel(const float* __restrict__ ws, int S, int heads,
-                                                          const float* __restrict__ Wout, int C,
-                                                          __nv_bfloat16* __restrict__ Mb) {
-    pdl_sync();
-    constexpr int DH = 32;
-    const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int HD = heads * DH;
-    __shared__ float s_ctx[DH][DH + 1];
-    const float* w0 = ws + (int64_t)bh * S * LA_WS;
-    float M = -INFINITY;
-    for (int s = 0; s < S; ++s) M = fmaxf(M, w0[s * LA_WS + lane]);
-    float tot = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < S; ++s) {
-        const float* w = w0 + s * LA_WS;
-        const float f = __expf(w[lane] - M);
-        tot += w[32 + lane] * f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] += w[64 + lane * 32 + warp * 4 + j] * f;
-    }
-    const float inv = 1.f / tot;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s_ctx[lane][warp * 4 + j] = acc[j] * inv;
-    __syncthreads();
-    float ctx[DH];                       // row d = lane of the normalised context
-#pragma unroll
-    for (int e = 0; e < DH; ++e) ctx[e] = s_ctx[lane][e];
-    // stage this head's (C x 32) slice of W_out through shared memory in chunks of 128 output channels:
-    // all loads of a chunk are independent and coalesced, the dot products then read smem broadcasts
-    __shared__ __align__(16) float s_w[128][DH];
-    for (int c0 = 0; c0 < C; c0 += 128) {
-        const int cn = min(128, C - c0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < cn * (DH / 4); i += 256) {
-            const int c = i / (DH / 4), e4 = i % (DH / 4);
-            reinterpret_cast<float4*>(&s_w[c][0])[e4] =
-                __ldg(reinterpret_cast<const float4*>(Wout + (int64_t)(c0 + c) * HD + hd * DH) + e4);
-        }
-        __syncthreads();
-        for (int c = warp; c < cn; c += 8) {
-            float o = 0.f;
-#pragma unroll
-            for (int e4 = 0; e4 < DH / 4; ++e4) {
-                const float4 t = reinterpret_cast<const float4*>(&s_w[c][0])[e4];      // broadcast
-                o += ctx[4 * e4] * t.x + ctx[4 * e4 + 1] * t.y + ctx[4 * e4 + 2] * t.z + ctx[4 * e4 + 3] * t.w;
-            }
-            Mb[((int64_t)b * C + c0 + c) * HD + hd * DH + lane] = __float2bfloat16_rn(o);
-        }
-    }
 }
 
 template <typename T>
@@ -409,11 +421,12 @@ int dd_gn_mish(const void* x, void* y, int dtype, int B, int HW, int C, int G, c
     DD_DISPATCH_DTYPE(dtype, T, {
         constexpr int VN = Vec<T>::N;
         DD_REQUIRE(C % VN == 0 && (C / G) % VN == 0, "gn_mish: channels per group (%d) must be a multiple of %d", C / G, VN);
-        int64_t n = (int64_t)B * HW * (C / VN);
+        const int vpi = HW * (C / VN);                       // vectors per image
         DD_REQUIRE(tb_stride % 4 == 0, "gn_mish: time-bias row stride must be a multiple of 4 floats");
-        launch_pdl(gn_mish_kernel<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
+        DD_REQUIRE(256 % (C / VN) == 0, "gn_mish: C=%d must divide 256 vectors", C);
+        launch_pdl(gn_mish_kernel<T>, dim3((unsigned)((vpi + 256 * GN_UNR - 1) / (256 * GN_UNR)), (unsigned)B), dim3(256), 0, (cudaStream_t)stream,
             (const T*)x, (T*)y, HW, C, G, stats, stats_mode, eps, gamma, beta, tbias, tb_stride, trow, trow_stride,
-            (const T*)residual, n);
+            (const T*)residual, vpi);
     });
     return check_launch("gn_mish");
 }
@@ -421,6 +434,15 @@ int dd_gn_mish(const void* x, void* y, int dtype, int B, int HW, int C, int G, c
 int dd_layernorm_c(const void* x, void* y, int dtype, int64_t P, int C, const float* g, const float* b, float eps,
                    void* stream) {
     DD_REQUIRE(C % 32 == 0 && C <= 512, "layernorm_c: C=%d must be a multiple of 32 and <= 512", C);
+    if (dtype == DD_BF16 && (C == 64 || C == 128 || C == 256)) {
+        const int lpp = C / 8, ppw = 32 / lpp;
+        const int64_t warps = (P + ppw - 1) / ppw;
+        const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+        if (lpp == 8) launch_pdl(layernorm_c_bf16_kernel<8>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, P, g, b, eps);
+        else if (lpp == 16) launch_pdl(layernorm_c_bf16_kernel<16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, P, g, b, eps);
+        else launch_pdl(layernorm_c_bf16_kernel<32>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, P, g, b, eps);
+        return check_launch("layernorm_c");
+    }
     const int per = C / 32;
     const int grid = grid_cap(P * 32, 256);
 #define LN_CASE(N)                                                                                                   \
@@ -453,18 +475,6 @@ int dd_linattn_core(const void* qkv, void* out, int dtype, int B, int n, int hea
         launch_pdl(linattn_out_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)qkv, (T*)out, ws, n, heads, chunk);
     });
     return check_launch("linattn_core");
-}
-
-int dd_linattn_mix(const void* qkv, int dtype, int B, int n, int heads, int dh, float* ws, int64_t ws_floats,
-                   const float* Wout, int C, void* Mb_bf16, void* stream) {
-    DD_REQUIRE(dh == 32 && heads > 0 && n > 0 && C > 0, "linattn_mix: dim_head must be 32 (got %d)", dh);
-    DD_REQUIRE(ws != nullptr && ws_floats >= dd_linattn_ws_floats(B, n, heads), "linattn_mix: workspace too small");
-    const int chunk = la_chunk(n);
-    const int S = (n + chunk - 1) / chunk;
-    dim3 grid(B * heads, S);
-    DD_DISPATCH_DTYPE(dtype, T, (launch_pdl(linattn_ctx_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)qkv, ws, n, heads, chunk)));
-    launch_pdl(linattn_mix_kernel, dim3(B * heads), dim3(256), 0, (cudaStream_t)stream, ws, S, heads, Wout, C, (__nv_bfloat16*)Mb_bf16);
-    return check_launch("linattn_mix");
 }
 
 }  // extern "C"

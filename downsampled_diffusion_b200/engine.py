@@ -443,9 +443,10 @@ class UnetEngine(Program):
             C = x.C
             if C % 64:
                 raise ValueError("bf16 tensor-core attention needs channel counts that are multiples of 64")
-            need = int(L.lib().dd_linattn_ws_floats(x.B, x.H * x.W, attn.heads))
-            ws = self.empty(need, dtype=torch.float32)
-            wout = self.packed((C, hid), torch.float32, lambda b: b.copy_(attn.to_out.weight.detach().reshape(C, hid)))
+            need = int(L.lib().dd_linattn_mix_ws_floats(x.B, x.H * x.W, attn.heads))    # partials + arrival tickets
+            ws = torch.zeros(need, dtype=torch.float32, device=self.device)
+            self.keep.append(ws)
+            wout = self.packed((C, hid), torch.bfloat16, lambda b: b.copy_(attn.to_out.weight.detach().reshape(C, hid)))
             mb = self.empty(x.B, C, hid, dtype=torch.bfloat16)
             self.add("dd_linattn_mix", L.ptr(qkv.t), self.dcode, x.B, x.H * x.W, attn.heads, attn.dim_head, L.ptr(ws), need,
                      L.ptr(wout), C, L.ptr(mb))

@@ -129,12 +129,15 @@ int64_t dd_linattn_ws_floats(int B, int n, int heads);
 int dd_linattn_core(const void* qkv, void* out, int dtype, int B, int n, int heads, int dh,
                     float* ws, int64_t ws_floats, void* stream);
 
-/* Fused form for the tensor-core path: partial contexts (as above), then
- *   Mb[b][c][h*dh+d] = sum_e ctx_{b,h}[d][e] * Wout[c][h*dh+e]   (bf16, (B, C, heads*dh), K-major)
+/* Fused form for the tensor-core path (bf16 only): context on warp-level MMA with an online softmax, then
+ *   Mb[b][c][h*dh+d] = sum_e Wout[c][h*dh+e] * ctx_{b,h}[d][e]   (bf16, (B, C, heads*dh), K-major)
  * so that to_out(attention)[n][c] = sum_k q[n][k] * Mb[b][c][k] + bias[c] (blocks.py:132-134) is a single
- * dd_conv_tc 1x1 launch with DD_TC_W_PER_SAMPLE reading q straight out of the qkv tensor.  Wout: (C, heads*dh) fp32. */
+ * dd_conv_tc 1x1 launch with DD_TC_W_PER_SAMPLE reading q straight out of the qkv tensor.  Wout: (C, heads*dh) bf16.
+ * One launch: the last split CTA of each (b, head) merges and folds.  ws: dd_linattn_mix_ws_floats(B, n, heads) floats
+ * that must be ZERO before the first call (the trailing B*heads arrival tickets reset themselves). */
+int64_t dd_linattn_mix_ws_floats(int B, int n, int heads);
 int dd_linattn_mix(const void* qkv, int dtype, int B, int n, int heads, int dh, float* ws, int64_t ws_floats,
-                   const float* Wout, int C, void* Mb_bf16, void* stream);
+                   const void* Wout_bf16, int C, void* Mb_bf16, void* stream);
 
 /* Generic direct convolution on CUDA cores, fp32 accumulate (validation mode, odd shapes, and the
  * down/up-sampling nets).  Replaces F.conv2d / F.conv_transpose2d call sites of blocks.py:35,44,78,103,

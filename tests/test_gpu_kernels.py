@@ -170,9 +170,9 @@ def test_fused_attention_output(cuda, n_side, C):
     ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(dim=-1), v)
     att = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(B, hid, n_side, n_side)
     ref = F.conv2d(att, wout.reshape(C, hid, 1, 1), bias) + from_nhwc(rd.cpu())
-    need = int(lib.lib().dd_linattn_ws_floats(B, n, heads))
-    ws = torch.empty(need, device=cuda)
-    wd, bd = wout.to(cuda), bias.to(cuda)
+    need = int(lib.lib().dd_linattn_mix_ws_floats(B, n, heads))               # partials + arrival tickets (zeroed)
+    ws = torch.zeros(need, device=cuda)
+    wd, bd = wout.to(cuda).to(torch.bfloat16), bias.to(cuda)
     mb = torch.empty(B, C, hid, dtype=torch.bfloat16, device=cuda)
     lib.call("dd_linattn_mix", lib.ptr(qd), lib.DD_BF16, B, n, heads, dh, lib.ptr(ws), need, lib.ptr(wd), C, lib.ptr(mb), lib.stream())
     y = torch.empty(B, n_side, n_side, C, dtype=torch.bfloat16, device=cuda)
