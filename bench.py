@@ -292,6 +292,143 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# -------------------------------------------------------------------------------------------------
+# Training workload (BASELINE.json configs[3], C4): dDDPM x3 256x256, p_losses forward + backward, gradient
+# all-reduce (N > 1), clip, Adam, EMA.  `python bench.py --workload train [--gpus N]`; the driver's default run
+# is the sampling workload above.
+TRAIN_GFLOP = 57.5          # per sample, forward + backward (torch flop counter on the reference)
+
+
+def cpu_train_rate(batch: int, threads: int):
+    """Reference algorithm of one training step (dddpm.py:155-177 through the oracle port + torch autograd) on the host."""
+    from oracle import ddpm_oracle as O
+    from tests import common as tc
+    import downsampled_diffusion_b200 as dd
+    torch.set_num_threads(threads)
+    cfg = dict(tc.C3, unet_dropout=0.0)
+    model = tc.build_model(cfg, dd, "dddpm_ae")
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and k in dict(model.named_parameters())) for k, v in model.state_dict().items()}
+    buf = O.schedule_buffers("linear", T_STEPS)
+    x = tc.rand_pm1(5, batch, *IMAGE)
+    t = torch.randint(0, T_STEPS, (batch,), generator=torch.Generator().manual_seed(6))
+    eps = tc.randn(7, batch, *LATENT)
+    t0 = time.perf_counter()
+    obj, _ = O.dddpm_losses(sd, cfg, buf, x, t, eps, autoencoder=True)
+    obj.backward()
+    return batch / (time.perf_counter() - t0)
+
+
+def run_train(args):
+    import torch.distributed as dist
+    import downsampled_diffusion_b200 as dd
+    from downsampled_diffusion_b200 import _lib, parallel
+    from tests import common as tc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            threads = os.cpu_count() or 1
+            rate = cpu_train_rate(args.cpu_batch_train, threads)
+            print(json.dumps({"impl": "reference", "metric": "samples/sec, dDDPM x3 256x256 training step", "value": rate, "unit": "samples/s",
+                              "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "dtype": "f32",
+                              "data": "synthetic", "config": {"workload": "C4 (CPU sample)", "cpu_batch": args.cpu_batch_train},
+                              "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+                                               "sample": f"one forward+backward on {args.cpu_batch_train} images"},
+                              "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    pk = peaks()
+    B = args.train_batch
+    cfg = dict(tc.C3, unet_dropout=0.1, precision="fp32" if args.train_precision == "fp32" else "bf16")
+    model = tc.build_model(cfg, dd, "dddpm_ae", device=str(dev)).to(dev).train()
+    model.downsample.precision = model.upsample.precision = cfg["precision"]
+    ema = dd.EMA(model, decay=0.995)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    params = [p for p in model.parameters()]
+    x_host = torch.empty(B, *IMAGE, dtype=torch.float32, pin_memory=True)
+    x_host.copy_(tc.rand_pm1(100 + rank, B, *IMAGE))
+    x_dev = x_host.to(dev)
+
+    def step(x):
+        obj, _ = model(x)
+        obj.backward()
+        parallel.allreduce_gradients(params)
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=False)
+        ema.update(model)
+        return obj
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(x_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launches() - n0
+    sampler.stop_flag.set()
+    sampler.join(timeout=3)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e2.record()
+    loss = 0.0
+    for _ in range(args.steps):
+        loss = float(step(x_host.to(dev, non_blocking=True)))        # H2D of the batch, D2H of the loss, every step
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        total = world * B * args.steps
+        value, e2e = total / (ms / 1e3), total / (ms_e2e / 1e3)
+        tf = TRAIN_GFLOP * B / (ms / args.steps)           # per GPU, GFLOP/ms = TFLOP/s
+        line = {"metric": "samples/sec, dDDPM x3 256x256 training step (p_losses fwd+bwd, clip, Adam, EMA)", "value": value,
+                "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.train_precision == "fp32" else "tf32",
+                "data": "synthetic",
+                "config": {"workload": "C4 (BASELINE configs[3]): dDDPM x3 256x256 training, x ~ U(-1,1), dropout 0.1",
+                           "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"data-parallel x{world}, bucketed NCCL gradient all-reduce",
+                           "l2": "activations of one step (tens of GB) exceed L2"},
+                "gpu_launches": launches, "last_loss": loss,
+                "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 4},
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
+                             "traffic": None, "kernel": "whole step; forward + input-gradient convolutions on tcgen05 kind::tf32, weight gradients on CUDA cores" if args.train_precision != "fp32" else "whole step (fp32 CUDA-core convolutions)",
+                             "peak_source": pk["src"] + " sustained bf16"},
+                "clocks": sampler.summary()}
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            rate = cpu_train_rate(args.cpu_batch_train, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+                                    "sample": f"one forward+backward (oracle port + torch autograd) on {args.cpu_batch_train} images"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -303,8 +440,14 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"])
+    ap.add_argument("--train-batch", type=int, default=32, help="images per GPU per training step")
+    ap.add_argument("--train-precision", default="tf32", choices=["tf32", "fp32"], help="tf32: tcgen05 kind::tf32 convolutions; fp32: CUDA-core validation mode")
+    ap.add_argument("--cpu-batch-train", type=int, default=2)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "train":
+        run_train(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

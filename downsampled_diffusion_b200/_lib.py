@@ -12,12 +12,13 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libddb200.so")
+LIB_PATH = os.environ.get("DD_LIB_PATH") or os.path.join(_HERE, "libddb200.so")      # DD_LIB_PATH: instrumented builds (scripts/timeline.py)
 
 DD_F32, DD_BF16 = 0, 1
 CONV_PRE_MISH, CONV_TANH, CONV_OUT_NCHW, CONV_IN_NCHW = 1, 2, 4, 8
 TC_CONV3x3, TC_CONV1x1, TC_DOWN, TC_UPT = 0, 1, 2, 3
 TC_W_PER_SAMPLE = 1
+TC_SPLITK = 2
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -36,6 +37,7 @@ SIGNATURES = {
     "dd_time_bias": [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p],
     "dd_gn_stats": [_p, _i, _i, _i, _i, _i, _f, _p, _p],
     "dd_gn_mish": [_p, _p, _i, _i, _i, _i, _i, _p, _i, _f, _p, _p, _p, _i, _p, _i, _p, _p],
+    "dd_gn_mish_sum": [_p, _i, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p, _i, _p, _p],
     "dd_layernorm_c": [_p, _p, _i, _i64, _i, _p, _p, _f, _p],
     "dd_linattn_core": [_p, _p, _i, _i, _i, _i, _i, _p, _i64, _p],
     "dd_linattn_mix": [_p, _i, _i, _i, _i, _i, _p, _i64, _p, _i, _p, _p],
@@ -56,9 +58,12 @@ SIGNATURES = {
     "dd_sincos_emb": [_p, _p, _p, _i, _i, _p],
     "dd_pool2_sum": [_p, _p, _i, _i, _i, _i, _f, _p],
     "dd_unpool2": [_p, _p, _i, _i, _i, _i, _f, _p],
+    "dd_conv_tc32": [_i, _p, _p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _p],
+    "dd_conv_wgrad_tc32": [_i, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p],
+    "dd_nhwc_to_chw_pad": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "dd_conv_tc": [_i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i64, _p, _i, _p],
 }
-PLAIN = {"dd_linattn_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_linattn_mix_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_version": (C.c_int, []), "dd_device_ok": (C.c_int, []), "dd_last_error": (C.c_char_p, [])}
+PLAIN = {"dd_conv_tc_splits": (C.c_int, [_i, _i, _i, _i, _i, _i]), "dd_linattn_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_linattn_mix_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_version": (C.c_int, []), "dd_device_ok": (C.c_int, []), "dd_last_error": (C.c_char_p, [])}
 
 _lib: Optional[C.CDLL] = None
 

@@ -25,9 +25,12 @@ GN_EPS = 1e-5
 class TrainProgram(Program):
     """fp32 forward launch list + its backward launch list, built together."""
 
-    def __init__(self, module: torch.nn.Module, B: int):
+    def __init__(self, module: torch.nn.Module, B: int, tf32: bool = False):
         super().__init__(module, B, "fp32")
         ensure_lazy()
+        self.scratch_need: Dict[str, int] = {}
+        self.scratch_buf: Dict[str, torch.Tensor] = {}
+        self.tf32 = tf32                                  # 3x3 / 1x1 convolutions (forward + input gradient) on tcgen05 kind::tf32
         self.bops: List[Callable[[], None]] = []
         self.bbuilders: List[Callable[[], None]] = []
         self.gbuf: Dict[int, torch.Tensor] = {}          # id(act.t) -> gradient tensor (same shape, fp32)
@@ -58,6 +61,11 @@ class TrainProgram(Program):
             self.ops.append(fn)
             self.op_names.append("host_glue")
 
+    def scratch(self, key: str, numel: int) -> "_ScratchPtr":
+        """fp32 scratch shared by every launch that asks for `key` (launches are stream-ordered); sized at the end of the build."""
+        self.scratch_need[key] = max(self.scratch_need.get(key, 0), int(numel))
+        return _ScratchPtr(self, key)
+
     def on_backward(self, builder: Callable[[], None]) -> None:
         self.bbuilders.append(builder)
 
@@ -67,6 +75,8 @@ class TrainProgram(Program):
             b()
         self._emit_bwd = False
         self.pg_arena = torch.zeros(max(self.pg_total, 1), dtype=torch.float32, device=self.device)
+        for key, n in self.scratch_need.items():
+            self.scratch_buf[key] = torch.empty(n, dtype=torch.float32, device=self.device)
 
     # ---- gradient buffers ---------------------------------------------------------------------
     def grad(self, a: Act) -> torch.Tensor:
@@ -152,9 +162,26 @@ class TrainProgram(Program):
         flags = (L.CONV_PRE_MISH if pre_mish else 0) | (L.CONV_TANH if tanh else 0) | \
                 (L.CONV_OUT_NCHW if out_nchw is not None else 0) | (L.CONV_IN_NCHW if in_nchw is not None else 0)
         src = L.ptr(in_nchw) if in_nchw is not None else L.ptr(x.t)
-        self.add("dd_conv_direct", src, L.ptr(x2.t) if x2 is not None else None, C1, C2, L.DD_F32, L.ptr(wd),
-                 L.ptr(b_t) if b_t is not None else None, L.ptr(residual.t) if residual is not None else None,
-                 L.ptr(out_nchw) if out_nchw is not None else L.ptr(y.t), L.DD_F32, B, H, W, Cout, ks, stride, pad, mode, flags)
+        pow2 = lambda v: v > 0 and (v & (v - 1)) == 0
+        use_tc = (self.tf32 and kind in ("3x3", "1x1") and in_nchw is None and out_nchw is None and not tanh and C1 % 32 == 0
+                  and C2 % 32 == 0 and Cout % 32 == 0 and pow2(H) and pow2(W) and H * W >= 16)
+        kcode = L.TC_CONV3x3 if ks == 3 else L.TC_CONV1x1
+        xm = None
+        if use_tc:
+            K = ks * ks * Cin
+            wp = self.packed((Cout, K), torch.float32, lambda buf: buf.copy_(w.detach().permute(0, 2, 3, 1).reshape(Cout, K)))
+            xin = x
+            if pre_mish:       # the activated copy feeds the tensor-core forward (TMA -> UMMA has no place for a pre-activation)
+                xm = self.act(H, W, C1, B)
+                self.add("dd_ew", 0, L.ptr(x.t), None, L.ptr(xm.t), x.t.numel(), 1.0, 0)
+                xin = xm
+            self.add("dd_conv_tc32", kcode, L.ptr(xin.t), L.ptr(x2.t) if x2 is not None else None, C1, C2, L.ptr(wp), Cout,
+                     L.ptr(b_t) if b_t is not None else None, L.ptr(residual.t) if residual is not None else None, L.ptr(y.t),
+                     B, H, W, Cout)
+        else:
+            self.add("dd_conv_direct", src, L.ptr(x2.t) if x2 is not None else None, C1, C2, L.DD_F32, L.ptr(wd),
+                     L.ptr(b_t) if b_t is not None else None, L.ptr(residual.t) if residual is not None else None,
+                     L.ptr(out_nchw) if out_nchw is not None else L.ptr(y.t), L.DD_F32, B, H, W, Cout, ks, stride, pad, mode, flags)
 
         # ---- backward -------------------------------------------------------------------------
         if transposed:
@@ -179,7 +206,11 @@ class TrainProgram(Program):
                     buf.copy_(wdt[:, c_lo:c_lo + c_n].permute(2, 3, 0, 1).reshape(ks * ks, Cout, c_n))
                 else:                                # stride 1: correlation with the flipped kernel
                     buf.copy_(wdt[:, c_lo:c_lo + c_n].flip(2, 3).permute(2, 3, 0, 1).reshape(ks * ks, Cout, c_n))
-            wts.append(self.packed((ks * ks, Cout, c_n), torch.float32, fill))
+            if use_tc:          # rows = input channels of this source, K = tap * Cout + co, flipped taps
+                wts.append(self.packed((c_n, ks * ks * Cout), torch.float32, lambda buf, c_lo=c_lo, c_n=c_n: buf.copy_(
+                    w.detach()[:, c_lo:c_lo + c_n].flip(2, 3).permute(1, 2, 3, 0).reshape(c_n, ks * ks * Cout))))
+            else:
+                wts.append(self.packed((ks * ks, Cout, c_n), torch.float32, fill))
         ypre = self.empty(*out_nchw.shape, dtype=torch.float32) if (tanh and out_nchw is not None) else None
 
         def backward():
@@ -195,11 +226,35 @@ class TrainProgram(Program):
             M = B * Ho * Wo
             if db is not None:
                 self.add("dd_colsum", L.ptr(g), db, M, Cout, 1 if out_nchw is not None else 0, Ho * Wo)
-            self.add("dd_conv_wgrad", src, L.ptr(x2.t) if x2 is not None else None, C1, C2, L.DD_F32, L.ptr(g), dw, B, H, W, Cout,
-                     ks, stride, pad, mode, (flags & (L.CONV_PRE_MISH | L.CONV_IN_NCHW)) | gflags)
+            if use_tc:
+                # tensor-core weight gradient: K-major TF32 operands = padded channel-major copies of the input and of dY
+                xin = xm if xm is not None else x
+                Wp = max(32, W)
+                ns = 3 if ks == 3 else 1                  # column shifts are baked into copies (TMA origin alignment)
+                xT, gT = self.scratch("wg_x", ns * B * C1 * (H + 2) * Wp), self.scratch("wg_g", B * Cout * H * Wp)
+                self.add("dd_nhwc_to_chw_pad", L.ptr(xin.t), xT, B, C1, H, W, Wp, 1, ns)
+                x2T = None
+                if x2 is not None:
+                    x2T = self.scratch("wg_x2", ns * B * C2 * (H + 2) * Wp)
+                    self.add("dd_nhwc_to_chw_pad", L.ptr(x2.t), x2T, B, C2, H, W, Wp, 1, ns)
+                self.add("dd_nhwc_to_chw_pad", L.ptr(g), gT, B, Cout, H, W, Wp, 0, 1)
+                self.add("dd_conv_wgrad_tc32", kcode, xT, x2T, C1, C2, gT, dw, B, H, W, Wp, Cout)
+            else:
+                self.add("dd_conv_wgrad", src, L.ptr(x2.t) if x2 is not None else None, C1, C2, L.DD_F32, L.ptr(g), dw, B, H, W, Cout,
+                         ks, stride, pad, mode, (flags & (L.CONV_PRE_MISH | L.CONV_IN_NCHW)) | gflags)
             if residual is not None:
                 self.add_into(residual, g)
             for (a, c_lo, c_n), wt in zip(srcs, wts):
+                if use_tc:
+                    if pre_mish:
+                        dst = self.empty(*a.t.shape, dtype=torch.float32)
+                        self.add("dd_conv_tc32", kcode, L.ptr(g), None, Cout, 0, L.ptr(wt), c_n, None, None, L.ptr(dst), B, Ho, Wo, c_n)
+                        self.add("dd_ew", 1, L.ptr(a.t), L.ptr(dst), L.ptr(self.grad(a)), dst.numel(), 1.0, self.acc(a))
+                    else:       # accumulate in the epilogue when the gradient already has a writer
+                        ga = self.grad(a)
+                        self.add("dd_conv_tc32", kcode, L.ptr(g), None, Cout, 0, L.ptr(wt), c_n, None, L.ptr(ga) if self.acc(a) else None,
+                                 L.ptr(ga), B, Ho, Wo, c_n)
+                    continue
                 direct = (not pre_mish) and not self.has_grad(a)
                 dst = self.grad(a) if direct else self.empty(*a.t.shape, dtype=torch.float32)
                 gin = L.CONV_IN_NCHW if out_nchw is not None else 0
@@ -271,6 +326,15 @@ class TrainProgram(Program):
         return y
 
 
+class _ScratchPtr:
+    def __init__(self, prog, key):
+        self.prog, self.key = prog, key
+
+    @property
+    def _as_parameter_(self):
+        return int(self.prog.scratch_buf[self.key].data_ptr())
+
+
 class _PgPtr:
     """ctypes pointer into the parameter-gradient arena, resolved at launch time."""
 
@@ -302,8 +366,8 @@ def _ensure_types():
 class UnetTrainEngine(TrainProgram):
     """U-Net forward/backward for a fixed (B, H, W) (training: per-sample t, optional dropout)."""
 
-    def __init__(self, unet, B: int, H: int, W: int, need_input_grad: bool):
-        super().__init__(unet, B)
+    def __init__(self, unet, B: int, H: int, W: int, need_input_grad: bool, tf32: bool = False):
+        super().__init__(unet, B, tf32)
         _ensure_types()
         self.H, self.W, self.need_input_grad = H, W, need_input_grad
         n_levels = len(unet.downs)
@@ -502,8 +566,8 @@ TrainProgram.pgrad = _pgrad
 class ResampleTrainProgram(TrainProgram):
     """ConvResNet / SimpleDownConv / SimpleUpConv forward + backward (fp32), NCHW in / out."""
 
-    def __init__(self, net, B: int, C: int, H: int, W: int, tanh: bool, need_input_grad: bool):
-        super().__init__(net, B)
+    def __init__(self, net, B: int, C: int, H: int, W: int, tanh: bool, need_input_grad: bool, tf32: bool = False):
+        super().__init__(net, B, tf32)
         _ensure_types()
         from .downsampled import ConvResBlock
         self.need_input_grad = need_input_grad
@@ -620,6 +684,13 @@ class _NetFn(torch.autograd.Function):
         return (None, dx if ctx.needs_input_grad[1] else None, None) + grads
 
 
+def train_math(module) -> str:
+    """'fp32' (CUDA-core convolutions, bit-faithful validation mode) when the module runs in precision='fp32', else
+    'tf32': convolutions on the tensor cores with TF32 operands / fp32 accumulate -- the arithmetic torch's default
+    `cudnn.allow_tf32 = True` gives the reference on a GPU."""
+    return "fp32" if getattr(module, "precision", "bf16") == "fp32" else "tf32"
+
+
 def _train_cache(module) -> EngineCache:
     if not hasattr(module, "_train_programs"):
         module._train_programs = EngineCache()
@@ -629,11 +700,12 @@ def _train_cache(module) -> EngineCache:
 def unet_apply(unet, eng_unused, x: torch.Tensor, time: torch.Tensor) -> torch.Tensor:
     B, _, H, W = x.shape
     need_dx = bool(x.requires_grad)
-    key = (B, H, W, need_dx, unet.training)
+    tf32 = train_math(unet) == "tf32"
+    key = (B, H, W, need_dx, unet.training, tf32)
     cache = _train_cache(unet)
     prog = cache.get(key)
     if prog is None:
-        prog = UnetTrainEngine(unet, B, H, W, need_dx)
+        prog = UnetTrainEngine(unet, B, H, W, need_dx, tf32)
         cache[key] = prog
     params = tuple(unet.parameters())
     return _NetFn.apply(prog, x.contiguous().float(), time, *params)
@@ -642,11 +714,12 @@ def unet_apply(unet, eng_unused, x: torch.Tensor, time: torch.Tensor) -> torch.T
 def resample_apply(net, x: torch.Tensor, tanh: bool) -> torch.Tensor:
     B, C, H, W = x.shape
     need_dx = bool(x.requires_grad)
-    key = (B, C, H, W, bool(tanh), need_dx, net.training)
+    tf32 = train_math(net) == "tf32"
+    key = (B, C, H, W, bool(tanh), need_dx, net.training, tf32)
     cache = _train_cache(net)
     prog = cache.get(key)
     if prog is None:
-        prog = ResampleTrainProgram(net, B, C, H, W, bool(tanh), need_dx)
+        prog = ResampleTrainProgram(net, B, C, H, W, bool(tanh), need_dx, tf32)
         cache[key] = prog
     params = tuple(net.parameters())
     return _NetFn.apply(prog, x.contiguous().float(), None, *params)

@@ -45,26 +45,27 @@ __device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(256) linattn_ctxmix_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws,
+__global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws,
                                                              int* __restrict__ tickets, int n, int heads, int chunk,
                                                              const __nv_bfloat16* __restrict__ Wout, int C,
                                                              __nv_bfloat16* __restrict__ Mb) {
-    pdl_sync();
     constexpr int DH = 32;
     const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
     const int S = gridDim.y, sp = blockIdx.y;
     const int HD = heads * DH, C3 = 3 * HD;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
+    // the projection weights do not depend on the previous kernel: pull this warp's rows of the head's (C x 32) slice
+    // towards the SM while the grid dependency is still pending (the fold at the end is otherwise two exposed L2 trips)
+    for (int c0 = warp * 16; c0 < C; c0 += 128)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(Wout + (int64_t)(c0 + (lane & 15)) * HD + hd * DH + (lane >> 4) * 16));
+    pdl_sync();
 
     __shared__ __align__(16) __nv_bfloat16 s_kv[8][2][LM_SLAB][LM_PITCH];     // 40 KB, later reused (fold stage)
     __shared__ float s_ctx[DH][DH + 1];
     __shared__ float s_mw[8][DH];
     __shared__ float s_s[DH], s_M[DH];
     __shared__ int s_last;
-
-    for (int i = threadIdx.x; i < DH * (DH + 1); i += 256) (&s_ctx[0][0])[i] = 0.f;
-    if (threadIdx.x < DH) s_s[threadIdx.x] = 0.f;
 
     const __nv_bfloat16* kb = qkv + (int64_t)b * n * C3 + HD + hd * DH;      // v = k + HD
     const int n_lo = sp * chunk, n_hi = min(n, n_lo + chunk);
@@ -178,16 +179,46 @@ __global__ void __launch_bounds__(256) linattn_ctxmix_kernel(const __nv_bfloat16
         for (int w = 0; w < 8; ++w) M = fmaxf(M, s_mw[w][g + 8 * i]);
         f_own[i] = (m_run[i] == -INFINITY) ? 0.f : __expf(m_run[i] - M);       // a warp without rows contributes nothing
         if (warp == 0 && t == 0) s_M[g + 8 * i] = M;
-        if (t == 0 && f_own[i] != 0.f) atomicAdd(&s_s[g + 8 * i], s_run[i] * f_own[i]);
     }
-    if (m_run[0] != -INFINITY) {
+    // each warp parks its rescaled partial in its own (now idle) slab: [32][33] context + 32 sums, then a tree-free
+    // sum over the 8 warps (shared-memory float atomics would be CAS loops under 8-way contention)
+    float* my = reinterpret_cast<float*>(&s_kv[warp][0][0][0]);          // 5120 B per warp >= (32*33 + 32) * 4
+    __syncwarp();
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    atomicAdd(&s_ctx[mt * 16 + g + 8 * (j >> 1)][nt * 8 + 2 * t + (j & 1)], acc[mt][nt][j] * f_own[mt * 2 + (j >> 1)]);
+            for (int j = 0; j < 4; ++j)
+                my[(mt * 16 + g + 8 * (j >> 1)) * 33 + nt * 8 + 2 * t + (j & 1)] = acc[mt][nt][j] * f_own[mt * 2 + (j >> 1)];
+    if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) my[32 * 33 + g + 8 * i] = s_run[i] * f_own[i];
+    }
+    __syncthreads();
+    {
+        constexpr int WSTRIDE = 2 * LM_SLAB * LM_PITCH / 2;                 // floats between warp regions
+        const float* w0 = reinterpret_cast<const float*>(&s_kv[0][0][0][0]);
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = threadIdx.x + 256 * k;
+                part[k] += w0[w * WSTRIDE + (i >> 5) * 33 + (i & 31)];
+            }
+        float ssum = 0.f;
+        if (threadIdx.x < DH) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) ssum += w0[w * WSTRIDE + 32 * 33 + threadIdx.x];
+        }
+        __syncthreads();                                                 // slab memory is reused below
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = threadIdx.x + 256 * k;
+            s_ctx[i >> 5][i & 31] = part[k];
+        }
+        if (threadIdx.x < DH) s_s[threadIdx.x] = ssum;
     }
     __syncthreads();
 
@@ -203,16 +234,16 @@ __global__ void __launch_bounds__(256) linattn_ctxmix_kernel(const __nv_bfloat16
         float* w = ws + ((int64_t)bh * S + sp) * LA_WS;
         if (threadIdx.x < DH) { w[threadIdx.x] = s_M[threadIdx.x]; w[32 + threadIdx.x] = s_s[threadIdx.x]; }
         for (int i = threadIdx.x; i < DH * DH; i += 256) w[64 + i] = s_ctx[i >> 5][i & 31];
-        __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence();                              // release: cumulative over the CTA's writes ordered by the barrier
             const int tk = atomicAdd(tickets + bh, 1);
             s_last = (tk == S - 1);
             if (s_last) tickets[bh] = 0;                  // self-resetting: zero again for the next launch
+            __threadfence();                              // acquire side for the reads below
         }
         __syncthreads();
         if (!s_last) return;
-        __threadfence();
         const float* w0 = ws + (int64_t)bh * S * LA_WS;
         if (threadIdx.x < DH) {
             const int d = threadIdx.x;

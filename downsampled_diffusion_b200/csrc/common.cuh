@@ -60,6 +60,12 @@ template <> struct Vec<float> {
     __device__ __forceinline__ void store(float* p) const {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
+    __device__ __forceinline__ void from_raw(const uint4& t) {
+        v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+    }
+    __device__ __forceinline__ uint4 to_raw() const {
+        return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    }
 };
 template <> struct Vec<__nv_bfloat16> {
     static constexpr int N = 8;
@@ -79,6 +85,18 @@ template <> struct Vec<__nv_bfloat16> {
 #pragma unroll
         for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
         *reinterpret_cast<uint4*>(p) = t;
+    }
+    __device__ __forceinline__ void from_raw(const uint4& t) {
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    }
+    __device__ __forceinline__ uint4 to_raw() const {
+        uint4 t;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        return t;
     }
 };
 

@@ -33,6 +33,7 @@ constexpr int TC_TMEM_COLS = 128;
 
 struct TcParams {
     CUtensorMap tmA0, tmA1, tmB;
+    CUtensorMap tmB3;            // weights as (c, row, tap): one box = a filter row of three taps (8x8 halo form)
     CUtensorMap tmH0, tmH1;      // halo boxes (64 ch, tw+2, th+2, 1, 1) of source 0 / 1 (halo kernel only)
     int8_t tap_dw[16], tap_dh[16], tap_plane[16];
     int ntaps;              // taps per phase
@@ -45,6 +46,7 @@ struct TcParams {
     int G, cpg_mask, cpg_shift;
     int tw_sh, th_sh;           // log2(tw), log2(th): tile geometry is all powers of two
     int rows_valid;             // tw*th*tn (< 128 when one image has fewer than 128 pixels and tn is forced to 1)
+    int interleave;             // 8x8 halo variant: GEMM row r = (h = r >> 4, image = (r >> 3) & 1, w = r & 7)
     int w_per_sample;           // weights are (B, rows, K): every image multiplies its own matrix (fused attention output)
     int exp_shift, exp_bo;      // experiment: A tile placed exp_shift rows (128 B) past the 1024-B aligned slot; base_offset on/off
     int splits, kb_per_split;   // split-K over the (tap, chunk) loop; partial sums meet in splitk_ws
@@ -122,6 +124,12 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -294,7 +302,8 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
     const int rps = p.tw * p.th;                       // rows of this tile that belong to one image
     const int pitch = bn * 2 + 16;                     // bytes; +16 keeps 16-byte row accesses conflict free
     if (et < bn) s_bias[et] = (p.bias && cbase + et < p.Cout) ? p.bias[cbase + et] : 0.f;
-    const bool valid = (n0 + (r >> (p.tw_sh + p.th_sh))) < p.B && r < p.rows_valid;
+    const bool il = p.interleave != 0;
+    const bool valid = (n0 + (il ? ((r >> 3) & 1) : (r >> (p.tw_sh + p.th_sh)))) < p.B && r < p.rows_valid;
     const bool do_stats = p.gn_stats != nullptr;
     epi_bar();
     mbar_wait(tmem_full_bar, 0);
@@ -363,16 +372,19 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
             const int gl = o & ((1 << ng_sh) - 1), sl = o >> ng_sh;
             float sa0 = 0.f, qa0 = 0.f, sa1 = 0.f, qa1 = 0.f;
             if (act) {
-                const float* ps = s_part + (2 * (gl * spg)) * TC_BM + (sl << rps_sh2) + l16;
+                // rows of sample sl: contiguous, or (interleaved) 8-row groups alternating between the two images
+                const int rbase = il ? (8 * sl + (l16 & 7) + 16 * (l16 >> 3)) : ((sl << rps_sh2) + l16);
+                const int rs = il ? 32 : 16;                                // row stride between a lane's rows
+                const float* ps = s_part + (2 * (gl * spg)) * TC_BM + rbase;
                 const int cnt = rps >> 4;                                   // rows per lane (0 when rps < 16)
                 for (int k = 0; k < spg; ++k, ps += 2 * TC_BM) {
                     if (cnt == 0) { if (l16 < rps) { sa0 += ps[0]; qa0 += ps[TC_BM]; } continue; }
                     int i = 0;
                     for (; i + 1 < cnt; i += 2) {
-                        sa0 += ps[16 * i]; qa0 += ps[TC_BM + 16 * i];
-                        sa1 += ps[16 * i + 16]; qa1 += ps[TC_BM + 16 * i + 16];
+                        sa0 += ps[rs * i]; qa0 += ps[TC_BM + rs * i];
+                        sa1 += ps[rs * i + rs]; qa1 += ps[TC_BM + rs * i + rs];
                     }
-                    if (i < cnt) { sa0 += ps[16 * i]; qa0 += ps[TC_BM + 16 * i]; }
+                    if (i < cnt) { sa0 += ps[rs * i]; qa0 += ps[TC_BM + rs * i]; }
                 }
             }
             float sa = sa0 + sa1, qa = qa0 + qa1;
@@ -408,9 +420,9 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int row = row0 + u * row_step;
-            const int n = n0 + (row >> rps_sh);
+            const int n = n0 + (il ? ((row >> 3) & 1) : (row >> rps_sh));
             ok[u] = row < TC_BM && row < rows_valid && n < Bn;
-            const int ww = row & (p.tw - 1), hh = (row >> p.tw_sh) & (p.th - 1);
+            const int ww = row & (p.tw - 1), hh = il ? (row >> 4) : ((row >> p.tw_sh) & (p.th - 1));
             const int oh = (h0 + hh) * mul + py, ow = (w0 + ww) * mul + px;
             off[u] = (((int64_t)n * Ho + oh) * Wo + ow) * Cout + cbase + pc * 8;
             if (ok[u]) {
@@ -436,14 +448,99 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
     if (et == 0) tstamp(p, 6);
 }
 
+// ---- split-K partial epilogue ------------------------------------------------------------------------
+// The CTA's fp32 accumulator goes, unreduced and without bias, to ws[split][pixel][Cout].  dd_gn_mish_sum adds the
+// splits (+ bias) while it computes the GroupNorm statistics: no atomics, no counters, deterministic, and the
+// low-resolution layers (8 - 32 tiles per launch) spread their operand streams over 4x as many SMs.
+__device__ __forceinline__ void tc_epilogue_partial(const TcParams& p, uint32_t tmem_base, uint32_t tmem_full_bar, int n_tile, int split,
+                                                    int w0, int h0, int n0, int warp, int lane) {
+    const int q = warp & 3, r = q * 32 + lane;
+    const int ww = r & (p.tw - 1), hh = (r >> p.tw_sh) & (p.th - 1), n = n0 + (r >> (p.tw_sh + p.th_sh));
+    const bool valid = n < p.B && r < p.rows_valid;
+    const int64_t pix = ((int64_t)n * p.H + (h0 + hh)) * p.W + (w0 + ww);
+    float* dst = p.splitk_ws + (((int64_t)split * p.B * p.H * p.W + pix) * p.Cout + n_tile * p.bn);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t a0[32], a1[32];
+    tmem_ld32_issue(trow, a0);
+    for (int c = 0; c < p.bn; c += 64) {
+        tmem_ld_wait();
+        if (c + 32 < p.bn) tmem_ld32_issue(trow + (uint32_t)(c + 32), a1);
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                reinterpret_cast<uint4*>(dst + c)[j] = make_uint4(a0[4 * j], a0[4 * j + 1], a0[4 * j + 2], a0[4 * j + 3]);
+        }
+        if (c + 32 < p.bn) {
+            tmem_ld_wait();
+            if (c + 64 < p.bn) tmem_ld32_issue(trow + (uint32_t)(c + 64), a0);
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    reinterpret_cast<uint4*>(dst + c + 32)[j] = make_uint4(a1[4 * j], a1[4 * j + 1], a1[4 * j + 2], a1[4 * j + 3]);
+            }
+        }
+    }
+}
+
+// ---- fp32 NHWC epilogue (training form) -----------------------------------------------------------------
+// y[pixel][c] = acc + bias [+ addend[pixel][c]] (addend may alias y: gradient accumulation).  Each thread owns one
+// output row; 16-byte stores of a row are completed to full sectors by the next column group.
+__device__ __forceinline__ void tc_epilogue_f32(const TcParams& p, uint32_t tmem_base, uint32_t tmem_full_bar, float* s_bias, int n_tile,
+                                                int w0, int h0, int n0, int warp, int lane) {
+    const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 64;
+    const int bn = p.bn, cbase = n_tile * bn;
+    if (et < bn) s_bias[et] = (p.bias && cbase + et < p.Cout) ? p.bias[cbase + et] : 0.f;
+    const int ww = r & (p.tw - 1), hh = (r >> p.tw_sh) & (p.th - 1), n = n0 + (r >> (p.tw_sh + p.th_sh));
+    const bool valid = n < p.B && r < p.rows_valid;
+    const int64_t off = (((int64_t)n * p.H + (h0 + hh)) * p.W + (w0 + ww)) * p.Cout + cbase;
+    float* dst = reinterpret_cast<float*>(p.out) + off;
+    const float* add = p.residual ? reinterpret_cast<const float*>(p.residual) + off : nullptr;
+    epi_bar();
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t a0[32], a1[32];
+    auto emit = [&](int c, uint32_t (&acc)[32]) {
+        if (!valid) return;
+        float4 ad[8];
+        if (add) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ad[j] = reinterpret_cast<const float4*>(add + c)[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 v = make_float4(__uint_as_float(acc[4 * j]) + s_bias[c + 4 * j], __uint_as_float(acc[4 * j + 1]) + s_bias[c + 4 * j + 1],
+                                   __uint_as_float(acc[4 * j + 2]) + s_bias[c + 4 * j + 2], __uint_as_float(acc[4 * j + 3]) + s_bias[c + 4 * j + 3]);
+            if (add) { v.x += ad[j].x; v.y += ad[j].y; v.z += ad[j].z; v.w += ad[j].w; }
+            reinterpret_cast<float4*>(dst + c)[j] = v;
+        }
+    };
+    tmem_ld32_issue(trow, a0);
+    for (int c = 0; c < bn; c += 64) {
+        tmem_ld_wait();
+        if (c + 32 < bn) tmem_ld32_issue(trow + (uint32_t)(c + 32), a1);
+        emit(c, a0);
+        if (c + 32 < bn) {
+            tmem_ld_wait();
+            if (c + 64 < bn) tmem_ld32_issue(trow + (uint32_t)(c + 64), a0);
+            emit(c + 32, a1);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Generic pipeline.  <STAGES, BROWS, KCH>: KCH 64-channel chunks per stage (KCH = 2 halves the per-k-block
 // barrier / issue overhead, which -- not bandwidth -- bounds small tiles: one warp needs ~400 clk to issue a
 // stage, see profiles/README.md).  Warp roles: 0 = A-operand TMA producer, 6 = B-operand TMA producer,
 // 1 = MMA issuer + TMEM owner, 2..5 = epilogue.
 // ---------------------------------------------------------------------------------------------
-template <int TC_STAGES, int BROWS, int KCH, bool LEGACY_EPI>
+// TF32 = the fp32 training form: operands are fp32 NHWC / fp32 packed weights, a pipeline chunk is 32 channels (the same
+// 128-byte rows), tcgen05.mma.kind::tf32 consumes 8 channels per instruction, EPI = 3 writes fp32 NHWC.
+template <int TC_STAGES, int BROWS, int KCH, int EPI, bool TF32 = false>      // EPI: 0 staged bf16, 1 legacy (fp32 NCHW / narrow), 2 split-K partial, 3 fp32 NHWC
 __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    constexpr int CH = TF32 ? 32 : 64;                   // channels per 128-byte operand row
     constexpr int B_SLOT = BROWS * TC_BK * 2;
     constexpr int TC_STAGE_BYTES = KCH * (TC_A_BYTES + B_SLOT);
     extern __shared__ uint8_t smem_raw[];
@@ -457,12 +554,14 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) tstamp(p, 0);
-    const int m_tile = blockIdx.x, n_tile = blockIdx.y, phase = blockIdx.z;
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+    const int phase = EPI == 2 ? 0 : blockIdx.z, split = EPI == 2 ? blockIdx.z : 0;     // split-K: blockIdx.z walks the K ranges
     const int w0 = (m_tile % p.tiles_w) * p.tw;
     const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
     const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn;
     const int cpt = p.chunks0 + p.chunks1;                  // 64-channel chunks per tap (multiple of KCH)
-    const int num_st = p.ntaps * cpt / KCH;                 // pipeline stages this CTA consumes
+    const int num_st = p.kb_per_split / KCH;                // pipeline stages this CTA consumes
+    const int kb0 = split * p.kb_per_split;                 // first (tap, chunk) block of this CTA's K range
     float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));   // 128 floats (barriers use < 160 B)
 
     if (warp == 0 && lane == 0) {
@@ -489,7 +588,7 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
         // ===== A-operand producer: whole warp runs the (uniform) loop, one elected lane issues =====
         const uint32_t tx = (uint32_t)KCH * p.rows_valid * TC_BK * 2;
         const int chunks0 = p.chunks0;
-        int rem = 0, ti = phase * p.ntaps;
+        int rem = kb0 % cpt, ti = phase * p.ntaps + kb0 / cpt;
         int cx = w0 + p.tap_dw[ti], cy = h0 + p.tap_dh[ti], cp = p.tap_plane[ti];
         uint32_t sA = base;
         int st = 0, round = 0;
@@ -501,8 +600,8 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
 #pragma unroll
                 for (int j = 0; j < KCH; ++j) {
                     const int c = rem + j;
-                    if (c < chunks0) tma_load_5d(&p.tmA0, fb, sA + j * TC_A_BYTES, c * 64, cx, cy, n0, cp);
-                    else tma_load_5d(&p.tmA1, fb, sA + j * TC_A_BYTES, (c - chunks0) * 64, cx, cy, n0, cp);
+                    if (c < chunks0) tma_load_5d(&p.tmA0, fb, sA + j * TC_A_BYTES, c * CH, cx, cy, n0, cp);
+                    else tma_load_5d(&p.tmA1, fb, sA + j * TC_A_BYTES, (c - chunks0) * CH, cx, cy, n0, cp);
                 }
             }
             __syncwarp();
@@ -519,7 +618,7 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
         const uint32_t tx = (uint32_t)KCH * p.bn * TC_BK * 2;
         const int wps = p.w_per_sample;
         const int brow = wps ? n_tile * p.bn : phase * p.rows_per_phase + n_tile * p.bn;
-        int kcoord = 0;
+        int kcoord = kb0 * CH;
         uint32_t sB = base + KCH * TC_A_BYTES;
         int st = 0, round = 0;
         for (int i = 0; i < num_st; ++i) {
@@ -529,19 +628,20 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
                 mbar_expect_tx(fb, tx);
 #pragma unroll
                 for (int j = 0; j < KCH; ++j) {
-                    if (wps) tma_load_3d(&p.tmB, fb, sB + j * B_SLOT, kcoord + 64 * j, brow, n0);
-                    else tma_load_2d(&p.tmB, fb, sB + j * B_SLOT, kcoord + 64 * j, brow);
+                    if (wps) tma_load_3d(&p.tmB, fb, sB + j * B_SLOT, kcoord + CH * j, brow, n0);
+                    else tma_load_2d(&p.tmB, fb, sB + j * B_SLOT, kcoord + CH * j, brow);
                 }
             }
             __syncwarp();
-            kcoord += 64 * KCH;
+            kcoord += CH * KCH;
             sB += TC_STAGE_BYTES;
             if (++st == TC_STAGES) { st = 0; ++round; sB = base + KCH * TC_A_BYTES; }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: whole warp loops, one elected lane issues tcgen05.mma / commit =====
         // instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        const uint32_t fmt = TF32 ? 2u : 1u;             // operand format field: 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32)
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
         uint32_t sA = base;
         int st = 0;
         uint32_t par = 0;
@@ -556,7 +656,8 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
                     const uint64_t bd = umma_desc(sA + KCH * TC_A_BYTES + j * B_SLOT);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k)
-                        umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | j | k) ? 1u : 0u);
+                        if (TF32) umma_tf32(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | j | k) ? 1u : 0u);
+                        else umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | j | k) ? 1u : 0u);
                 }
                 umma_commit(empty_bar(st));          // frees this smem stage when the MMAs retire
             }
@@ -568,8 +669,12 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
         if (elect_one()) umma_commit(tmem_full_bar);             // accumulator complete
         __syncwarp();
     } else {
-        if constexpr (LEGACY_EPI)       // fp32 NCHW output / tiles narrower than 32 channels (the final 1x1 conv)
+        if constexpr (EPI == 1)         // fp32 NCHW output / tiles narrower than 32 channels (the final 1x1 conv)
             tc_epilogue(p, tmem_base, tmem_full_bar, s_bias, m_tile, n_tile, phase, w0, h0, n0, warp, lane);
+        else if constexpr (EPI == 2)
+            tc_epilogue_partial(p, tmem_base, tmem_full_bar, n_tile, split, w0, h0, n0, warp, lane);
+        else if constexpr (EPI == 3)
+            tc_epilogue_f32(p, tmem_base, tmem_full_bar, s_bias, n_tile, w0, h0, n0, warp, lane);
         else
             tc_epilogue_staged(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, phase, w0, h0, n0,
                                warp, lane);
@@ -599,12 +704,39 @@ constexpr int HALO_SLOT = (HALO_TX + 1023) / 1024 * 1024;           // 23552
 constexpr int HALO_NH = 2, HALO_NB = 4;
 constexpr int HALO_B_BYTES = 128 * TC_BK * 2;
 constexpr int HALO_SMEM = HALO_NH * HALO_SLOT + HALO_NB * HALO_B_BYTES + 1024 + 1024;
+constexpr int HALO8_TX = 2 * 10 * 10 * TC_BK * 2;                   // 8x8 maps: (10 x 2 images x 10) halo rows, 25600 bytes
+constexpr int HALO8_SLOT = (HALO8_TX + 1023) / 1024 * 1024;         // 26624
+constexpr int HALO8_B_RING = 160 * 1024;                            // weight ring of the 8x8 form (1 CTA per SM)
+constexpr int HALO8_SMEM = HALO_NH * HALO8_SLOT + HALO8_B_RING + 1024 + 1024;
 
-__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __grid_constant__ TcParams p) {
+// NT = output tiles per CTA.  NT = 2 ("dual tile"): the two halo slots hold the halos of two consecutive tiles of the
+// SAME 64-channel chunk (single-buffered), every weight tile is loaded once and multiplied into two TMEM accumulators:
+// weight traffic per output pixel halves.  These layers sit on the L2 -> SM throughput cap (~6.3 KB/clk chip-wide),
+// 85 % of their operand bytes being weight re-reads (profiles/README.md), and the grid becomes a single wave.
+// PERM = the 8x8-map form: a tile is all 64 pixels of TWO images.  The halo box is taken from a (C, W, N, H) view of
+// the activation, i.e. it lands as rows (h, image, w) -- 10 x 2 x 10 -- so that the 8-pixel row groups of the tile
+// (row h of image 0, row h of image 1, row h+1 of image 0, ...) are a uniform 10 smem rows apart and ONE M=128 UMMA
+// descriptor covers both images; a filter row further down is 20 smem rows on.
+template <int NT, bool PERM>
+__global__ void __launch_bounds__(TC_THREADS, PERM ? 1 : 2) conv_tc_halo_kernel(const __grid_constant__ TcParams p) {
+    static_assert(!(PERM && NT != 1), "the 8x8 form has one tile per CTA");
+    constexpr int NSTG = HALO_NH / NT;                  // halo pipeline depth: 2 (one tile) or 1 (two tiles)
+    constexpr uint32_t HALO_SLOT = PERM ? HALO8_SLOT : dd::HALO_SLOT;
+    constexpr uint32_t HALO_TX = PERM ? HALO8_TX : dd::HALO_TX;
+    constexpr uint32_t DY_BYTES = (PERM ? 2 : 1) * (HALO_TW + 2) * 128u;      // smem bytes between filter rows
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    // weight ring: 4 x 16 KB next to two resident CTAs; the 8x8 form owns the SM and runs 160 KB of bn-row slots (10 or
+    // 20 stages) -- with 4 stages it had ~80 KB in flight per ~2300-clk L2 round trip and was latency-bound (11.5 us
+    // against 10.1 us for the generic path, profiles/README.md)
+    // One weight TMA per TAPS_PER_LOAD taps: a producer iteration (wait, expect_tx, issue) costs ~400 clk, more than the
+    // four N=64 MMAs of a tap, so the 8x8 form loads a whole filter row (3 taps, 3-D box of the (c, row, tap) view).
+    constexpr int TAPS_PER_LOAD = PERM ? 3 : 1;
+    const uint32_t B_TAP_BYTES = PERM ? (uint32_t)(p.bn * TC_BK * 2) : (uint32_t)dd::HALO_B_BYTES;
+    const uint32_t HALO_B_BYTES = TAPS_PER_LOAD * B_TAP_BYTES;
+    const int HALO_NB = PERM ? (int)(HALO8_B_RING / HALO_B_BYTES) : dd::HALO_NB;
     const uint32_t bbase = base + HALO_NH * HALO_SLOT;
-    const uint32_t bars = bbase + HALO_NB * HALO_B_BYTES;
+    const uint32_t bars = bbase + (PERM ? (uint32_t)HALO8_B_RING : (uint32_t)(dd::HALO_NB * dd::HALO_B_BYTES));
     auto hfull = [&](int s) { return bars + 8u * s; };
     auto hempty = [&](int s) { return bars + 8u * (HALO_NH + s); };
     auto bfull = [&](int s) { return bars + 8u * (2 * HALO_NH + s); };
@@ -612,14 +744,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __gri
     const uint32_t tmem_full_bar = bars + 8u * (2 * HALO_NH + 2 * HALO_NB);
     const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
-    float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));
+    float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 512u - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) tstamp(p, 0);
-    const int m_tile = blockIdx.x, n_tile = blockIdx.y;
-    const int w0 = (m_tile % p.tiles_w) * p.tw;
-    const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
-    const int n0 = m_tile / (p.tiles_w * p.tiles_h);
+    const int n_tile = blockIdx.y;
+    int w0[NT], h0[NT], n0[NT];
+#pragma unroll
+    for (int s = 0; s < NT; ++s) {
+        const int m_tile = blockIdx.x * NT + s;
+        w0[s] = (m_tile % p.tiles_w) * p.tw;
+        h0[s] = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+        n0[s] = (m_tile / (p.tiles_w * p.tiles_h)) * (PERM ? 2 : 1);
+    }
     const int nchunks = p.chunks0 + p.chunks1;
     const int cin = nchunks * 64;
 
@@ -633,7 +770,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __gri
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(TC_TMEM_COLS * NT) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -645,27 +782,34 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __gri
     if (threadIdx.x == 0) tstamp(p, 2);
 
     if (warp == 0) {
-        const uint32_t b_tx = (uint32_t)p.bn * TC_BK * 2;
+        const uint32_t b_tx = (uint32_t)p.bn * TC_BK * 2 * TAPS_PER_LOAD;
         const int brow = n_tile * p.bn, chunks0 = p.chunks0;
         int bs = 0, bround = 0, hs = 0, hround = 0;
         uint32_t sB = bbase;
         for (int c = 0; c < nchunks; ++c) {
             if (hround > 0) mbar_wait(hempty(hs), (hround - 1) & 1);
             if (elect_one()) {
-                mbar_expect_tx(hfull(hs), HALO_TX);
-                if (c < chunks0) tma_load_5d(&p.tmH0, hfull(hs), base + hs * HALO_SLOT, c * 64, w0 - 1, h0 - 1, n0, 0);
-                else tma_load_5d(&p.tmH1, hfull(hs), base + hs * HALO_SLOT, (c - chunks0) * 64, w0 - 1, h0 - 1, n0, 0);
+                mbar_expect_tx(hfull(hs), NT * HALO_TX);
+#pragma unroll
+                for (int s = 0; s < NT; ++s) {
+                    const uint32_t dst = base + (hs * NT + s) * HALO_SLOT;
+                    const CUtensorMap* tm = c < chunks0 ? &p.tmH0 : &p.tmH1;
+                    const int cc = (c < chunks0 ? c : c - chunks0) * 64;
+                    if (PERM) tma_load_5d(tm, hfull(hs), dst, cc, w0[s] - 1, n0[s], h0[s] - 1, 0);     // (C, W, N, H, P) view
+                    else tma_load_5d(tm, hfull(hs), dst, cc, w0[s] - 1, h0[s] - 1, n0[s], 0);
+                }
             }
             __syncwarp();
-            if (++hs == HALO_NH) { hs = 0; ++hround; }
+            if (++hs == NSTG) { hs = 0; ++hround; }
             int kcoord = c * 64;
 #pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < 9; tap += TAPS_PER_LOAD) {
                 const uint32_t fb = bfull(bs);
                 if (bround > 0) mbar_wait(bempty(bs), (bround - 1) & 1);
                 if (elect_one()) {
                     mbar_expect_tx(fb, b_tx);
-                    tma_load_2d(&p.tmB, fb, sB, kcoord, brow);
+                    if (PERM) tma_load_3d(&p.tmB3, fb, sB, c * 64, brow, tap);
+                    else tma_load_2d(&p.tmB, fb, sB, kcoord, brow);
                 }
                 __syncwarp();
                 kcoord += cin;
@@ -682,44 +826,53 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __gri
         uint32_t sB = bbase;
         for (int c = 0; c < nchunks; ++c) {
             mbar_wait(hfull(hs), hpar);
-            uint32_t rowA = base + hs * HALO_SLOT;                  // tap (0,0)
+            uint32_t rowA = base + hs * NT * HALO_SLOT;             // tap (0,0) of the first tile
 #pragma unroll 1
             for (int r = 0; r < 3; ++r) {
 #pragma unroll 1
                 for (int sx = 0; sx < 3; ++sx) {
-                    mbar_wait(bfull(bs), bpar);
+                    if (!PERM || sx == 0) mbar_wait(bfull(bs), bpar);
                     if (acc == 0 && lane == 0) tstamp(p, 3);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t ad = (uint64_t)(((rowA + 128u * sx) & 0x3FFFFu) >> 4) | a_hi;
-                        const uint64_t bd = umma_desc(sB);
+                        const uint64_t bd = umma_desc(sB + (PERM ? sx * B_TAP_BYTES : 0u));
 #pragma unroll
-                        for (int k = 0; k < TC_BK / 16; ++k)
-                            umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (acc | k) ? 1u : 0u);
-                        umma_commit(bempty(bs));
+                        for (int s = 0; s < NT; ++s) {
+                            const uint64_t ad = (uint64_t)(((rowA + s * HALO_SLOT + 128u * sx) & 0x3FFFFu) >> 4) | a_hi;
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 16; ++k)
+                                umma_f16(tmem_base + (uint32_t)(s * TC_TMEM_COLS), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
+                                         (acc | k) ? 1u : 0u);
+                        }
+                        if (!PERM || sx == 2) umma_commit(bempty(bs));
                     }
                     __syncwarp();
                     acc = 1u;
-                    sB += HALO_B_BYTES;
-                    if (++bs == HALO_NB) { bs = 0; bpar ^= 1u; sB = bbase; }
+                    if (!PERM || sx == 2) {
+                        sB += HALO_B_BYTES;
+                        if (++bs == HALO_NB) { bs = 0; bpar ^= 1u; sB = bbase; }
+                    }
                 }
-                rowA += (HALO_TW + 2) * 128u;
+                rowA += DY_BYTES;
             }
-            if (elect_one()) umma_commit(hempty(hs));           // halo slot free once its nine taps have retired
+            if (elect_one()) umma_commit(hempty(hs));           // halo slot(s) free once their nine taps have retired
             __syncwarp();
-            if (++hs == HALO_NH) { hs = 0; hpar ^= 1u; }
+            if (++hs == NSTG) { hs = 0; hpar ^= 1u; }
         }
         if (lane == 0) tstamp(p, 4);
         if (elect_one()) umma_commit(tmem_full_bar);
         __syncwarp();
     } else if (warp < 6) {
-        tc_epilogue_staged(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, 0, w0, h0, n0, warp, lane);
+#pragma unroll
+        for (int s = 0; s < NT; ++s)
+            tc_epilogue_staged(p, tmem_base + (uint32_t)(s * TC_TMEM_COLS), tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, 0,
+                               w0[s], h0[s], n0[s], warp, lane);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS * NT) : "memory");
     }
 }
 
@@ -741,32 +894,65 @@ static EncodeTiledFn get_encode() {
 }
 
 static int make_act_map(CUtensorMap* tm, const void* ptr, int C, int pitch, int W, int H, int N, int P, int tw, int th, int tn,
-                        CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
+                        CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B, bool f32 = false) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
     cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)P};
-    cuuint64_t strides[4] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2,
-                             (cuuint64_t)N * H * W * pitch * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn, 1};
+    const cuuint64_t es = f32 ? 4 : 2;
+    cuuint64_t strides[4] = {(cuuint64_t)pitch * es, (cuuint64_t)W * pitch * es, (cuuint64_t)H * W * pitch * es,
+                             (cuuint64_t)N * H * W * pitch * es};
+    cuuint32_t box[5] = {f32 ? 32u : 64u, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation C=%d W=%d H=%d N=%d P=%d box %d,%d,%d) failed: %d", C, W, H, N, P, tw, th, tn, (int)r); return DD_ERR_CUDA; }
     return DD_OK;
 }
 
-static int make_w_map(CUtensorMap* tm, const void* ptr, int K, int rows, int bn, int batch) {
+// (C, W, N, H, 1) view of an NHWC activation for the 8x8 halo form: box (64, W + 2, 2, H + 2, 1)
+static int make_act_map_perm(CUtensorMap* tm, const void* ptr, int C, int pitch, int W, int H, int N) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)N, (cuuint64_t)H, 1};
+    cuuint64_t strides[4] = {(cuuint64_t)pitch * 2, (cuuint64_t)H * W * pitch * 2, (cuuint64_t)W * pitch * 2,
+                             (cuuint64_t)N * H * W * pitch * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)(W + 2), 2, (cuuint32_t)(H + 2), 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(permuted activation C=%d W=%d H=%d N=%d) failed: %d", C, W, H, N, (int)r); return DD_ERR_CUDA; }
+    return DD_OK;
+}
+
+static int make_w_map(CUtensorMap* tm, const void* ptr, int K, int rows, int bn, int batch, bool f32 = false) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
+    const cuuint64_t es = f32 ? 4 : 2;
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
-    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * rows};
-    cuuint32_t box[3] = {64, (cuuint32_t)bn, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)K * es * rows};
+    cuuint32_t box[3] = {f32 ? 32u : 64u, (cuuint32_t)bn, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, batch > 0 ? 3 : 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, batch > 0 ? 3 : 2, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights K=%d rows=%d bn=%d) failed: %d", K, rows, bn, (int)r); return DD_ERR_CUDA; }
+    return DD_OK;
+}
+
+// (c, row, tap) view of the packed [row][tap*Cin + c] 3x3 weights: box (64, bn, 3) = the three taps of one filter row
+static int make_w_map_taps(CUtensorMap* tm, const void* ptr, int Cin, int rows, int bn) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)rows, 9};
+    cuuint64_t strides[2] = {(cuuint64_t)9 * Cin * 2, (cuuint64_t)Cin * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)bn, 3};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weight taps Cin=%d rows=%d bn=%d) failed: %d", Cin, rows, bn, (int)r); return DD_ERR_CUDA; }
     return DD_OK;
 }
 
@@ -785,6 +971,19 @@ extern "C" int dd_zero(void* ptr, int64_t bytes, void* stream) {
     return DD_OK;
 }
 
+// Split-K policy: 3x3 stride-1 convs on maps of at most 4x4 pixels whose 64-wide tiles would occupy less than a
+// third of the SMs.  Each CTA streams its whole K range through one SM's L2 port (~64 B/clk), so 32 CTAs take ~7 us
+// for 27 MB of operands while 116 SMs idle; S splits cut that stream S-fold.  Returns S (>= 2) or 1.
+extern "C" int dd_conv_tc_splits(int kind, int B, int H, int W, int Cin, int Cout) {
+    if (kind != DD_TC_CONV3x3 || H * W > 16 || Cout < 128 || Cout % 64 || Cin % 64 || getenv("DD_NO_SPLITK")) return 1;
+    const int rows = B * H * W, tiles = (rows + 127) / 128 * (Cout / 64), num_kb = 9 * (Cin / 64);
+    if (tiles * 3 > dd::num_sms()) return 1;
+    int S = dd::num_sms() / tiles;
+    if (S > 8) S = 8;
+    while (S > 1 && (num_kb % S != 0 || num_kb / S < 4)) --S;
+    return S;
+}
+
 extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2, const void* wp, int w_rows,
                           const float* bias, const void* residual, void* y, int out_nchw_f32, int cout_valid,
                           float* gn_stats, int G, int B, int H, int W, int Cout, int flags,
@@ -800,13 +999,16 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
 
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 1));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<6, 128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(6, 128, 1));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64, 1));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 2));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, 64, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(4, 64, 2));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 1));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<6, 128, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(6, 128, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 2));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, 64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(4, 64, 2));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO8_SMEM);
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
         attr_done = true;
     }
@@ -821,6 +1023,13 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     p.tw = W < 128 ? W : 128;
     p.th = (128 / p.tw) < H ? (128 / p.tw) : H;
     if (halo) { p.tw = HALO_TW; p.th = HALO_TH; }
+    // The 8x8 halo form is an opt-in experiment too: it cuts the A-operand L2 traffic 9x and batches three taps per weight
+    // load, yet measures 12.0 us against 10.1 us for the generic path (profiles/README.md): with bn = 64 every MMA takes
+    // ~100 clk whatever feeds it -- cta_group::1 reads its shared-memory operands at ~64 B/clk, which caps M128 x N64 x K16 at
+    // 25 % and N128 at 50 % of the tensor pipe.  The lever that is left is cta_group::2 (half of B per SM), not less traffic.
+    static const bool halo8_on = getenv("DD_HALO8") != nullptr;
+    const bool halo8 = halo8_on && !halo_off && kind == DD_TC_CONV3x3 && H == 8 && W == 8 && Cout >= 64 && !out_nchw_f32 && !wps;
+    p.interleave = halo8 ? 1 : 0;
     p.tn = wps ? 1 : 128 / (p.tw * p.th);      // per-sample weights: one image per tile (rows beyond it are ignored)
     p.rows_valid = p.tw * p.th * p.tn;
     p.tw_sh = 0; while ((1 << p.tw_sh) < p.tw) ++p.tw_sh;
@@ -835,6 +1044,7 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     // low-resolution layers (at most half a wave of 128-wide tiles): halve the N tile to double the CTA count
     const int tiles128 = p.tiles_w * p.tiles_h * tiles_n * ((Cout + 127) / 128);
     if (tiles128 * 2 <= num_sms() && Cout % 64 == 0 && Cout >= 128) p.bn = 64;
+    if (flags & DD_TC_SPLITK) p.bn = 64;
     DD_REQUIRE(Cout % p.bn == 0 && (p.bn == 16 || p.bn == 32 || p.bn == 64 || p.bn == 128), "conv_tc: unsupported Cout=%d", Cout);
     p.out = y; p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.gn_stats = gn_stats; p.G = G; p.out_nchw_f32 = out_nchw_f32; p.out_mul = 1;
@@ -881,6 +1091,14 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     if (rc) return rc;
     rc = make_w_map(&p.tmB, wp, K, w_rows, p.bn, wps ? B : 0);
     if (rc) return rc;
+    if (halo8) {
+        rc = make_w_map_taps(&p.tmB3, wp, Cin, w_rows, p.bn);
+        if (rc) return rc;
+        rc = make_act_map_perm(&p.tmH0, x, C1, x_pitch, W, H, B);
+        if (rc) return rc;
+        rc = make_act_map_perm(&p.tmH1, x2 ? x2 : x, x2 ? C2 : C1, x2 ? C2 : x_pitch, W, H, B);
+        if (rc) return rc;
+    }
     if (halo) {
         rc = make_act_map(&p.tmH0, x, C1, x_pitch, W, H, B, 1, HALO_TW + 2, HALO_TH + 2, 1, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
@@ -892,28 +1110,327 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     p.splits = 1; p.kb_per_split = p.ntaps * (p.chunks0 + p.chunks1);
     p.splitk_ws = nullptr; p.splitk_cnt = nullptr; p.exp_shift = 0; p.exp_bo = 0;
     p.dbg = g_tc_dbg;
-    (void)splitk_ws; (void)splitk_ws_floats; (void)splitk_cnt; (void)splitk_cnt_n;
+    (void)splitk_cnt; (void)splitk_cnt_n;
+    if (flags & DD_TC_SPLITK) {
+        const int S = dd_conv_tc_splits(kind, B, H, W, Cin, Cout);
+        DD_REQUIRE(S > 1, "conv_tc: DD_TC_SPLITK on a shape dd_conv_tc_splits() does not split");
+        DD_REQUIRE(splitk_ws != nullptr && splitk_ws_floats >= (int64_t)S * B * H * W * Cout, "conv_tc: split-K workspace too small");
+        DD_REQUIRE(residual == nullptr && !out_nchw_f32, "conv_tc: split-K writes raw partials only");
+        p.splits = S; p.kb_per_split /= S; p.splitk_ws = splitk_ws; p.gn_stats = nullptr;
+    }
     dim3 grid(p.tiles_w * p.tiles_h * tiles_n, Cout / p.bn, phases * p.splits);
     static const bool verbose = getenv("DD_TC_VERBOSE") != nullptr;
     if (verbose)
         fprintf(stderr, "conv_tc kind=%d B=%d H=%d W=%d C=%d+%d Cout=%d grid=(%u,%u,%u) bn=%d num_kb=%d splits=%d kb_per=%d\n", kind, B, H, W,
                 C1, C2, Cout, grid.x, grid.y, grid.z, p.bn, p.kb_per_split, p.splits, p.kb_per_split);
     const int ctas = (int)(grid.x * grid.y * grid.z);
+    // dual-tile halo CTAs (two accumulators per weight load) are an opt-in experiment: measured on B200 they do not
+    // help (3x3 128->128 @32x32: 22.2 -> 22.7 us, 256->256 @16x16: 17.5 -> 24.0 us; profiles/README.md) -- these layers
+    // are bound by tensor-pipe occupancy per wave, not by weight re-reads, and the single-buffered halo costs more.
+    static const bool dual_on = getenv("DD_HALO_DUAL") != nullptr;
+    const bool halo_dual = halo && dual_on && grid.x % 2 == 0 && 2 * ctas >= 3 * num_sms();
     const bool pair = ((p.chunks0 + p.chunks1) % 2 == 0) && (p.chunks0 % 2 == 0);     // two chunks per stage never straddle the sources
     cudaStream_t st = (cudaStream_t)stream;
-    if (out_nchw_f32 || p.bn < 32)
-        launch_pdl(conv_tc_kernel<3, 128, 1, true>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
+    if (p.splits > 1)
+        launch_pdl(conv_tc_kernel<8, 64, 1, 2>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
+    else if (out_nchw_f32 || p.bn < 32)
+        launch_pdl(conv_tc_kernel<3, 128, 1, 1>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
+    else if (halo8)
+        launch_pdl(conv_tc_halo_kernel<1, true>, dim3(grid), dim3(TC_THREADS), HALO8_SMEM, st, p);
+    else if (halo && halo_dual)
+        launch_pdl(conv_tc_halo_kernel<2, false>, dim3(grid.x / 2, grid.y, 1), dim3(TC_THREADS), HALO_SMEM, st, p);
     else if (halo)
-        launch_pdl(conv_tc_halo_kernel, dim3(grid), dim3(TC_THREADS), HALO_SMEM, st, p);
+        launch_pdl(conv_tc_halo_kernel<1, false>, dim3(grid), dim3(TC_THREADS), HALO_SMEM, st, p);
     else if (ctas > num_sms())      // more than one wave: two CTAs per SM so epilogues overlap main loops
-        launch_pdl(conv_tc_kernel<3, 128, 1, false>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
+        launch_pdl(conv_tc_kernel<3, 128, 1, 0>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
     else if (p.bn <= 64 && pair)
-        launch_pdl(conv_tc_kernel<4, 64, 2, false>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(4, 64, 2), st, p);
+        launch_pdl(conv_tc_kernel<4, 64, 2, 0>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(4, 64, 2), st, p);
     else if (p.bn <= 64)
-        launch_pdl(conv_tc_kernel<8, 64, 1, false>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
+        launch_pdl(conv_tc_kernel<8, 64, 1, 0>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
     else if (pair)
-        launch_pdl(conv_tc_kernel<3, 128, 2, false>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 2), st, p);
+        launch_pdl(conv_tc_kernel<3, 128, 2, 0>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 2), st, p);
     else
-        launch_pdl(conv_tc_kernel<6, 128, 1, false>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(6, 128, 1), st, p);
+        launch_pdl(conv_tc_kernel<6, 128, 1, 0>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(6, 128, 1), st, p);
     return check_launch("conv_tc");
+}
+
+
+// fp32 training form of dd_conv_tc: fp32 NHWC activations, fp32 packed weights [rows][tap*Cin + c], TF32 tensor-core math
+// (10-bit mantissa operands, fp32 accumulate -- what torch's cudnn.allow_tf32 default gives the reference on a GPU).
+extern "C" int dd_conv_tc32(int kind, const float* x, const float* x2, int C1, int C2, const float* wp, int w_rows, const float* bias,
+                            const float* addend, float* y, int B, int H, int W, int Cout, void* stream) {
+    DD_REQUIRE(kind == DD_TC_CONV3x3 || kind == DD_TC_CONV1x1, "conv_tc32: 3x3 stride-1 and 1x1 only (kind %d)", kind);
+    DD_REQUIRE(C1 > 0 && C1 % 32 == 0 && C2 >= 0 && C2 % 32 == 0, "conv_tc32: channel counts (%d,%d) must be multiples of 32", C1, C2);
+    DD_REQUIRE((C2 == 0) == (x2 == nullptr), "conv_tc32: x2/C2 mismatch");
+    DD_REQUIRE(is_pow2(H) && is_pow2(W) && B > 0, "conv_tc32: H=%d, W=%d must be powers of two", H, W);
+    DD_REQUIRE(Cout >= 32 && Cout % 32 == 0 && w_rows >= Cout, "conv_tc32: Cout=%d must be a multiple of 32", Cout);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 1, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 1));
+        if (e != cudaSuccess) { set_error("conv_tc32: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
+        attr_done = true;
+    }
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.tw = W < 128 ? W : 128;
+    p.th = (128 / p.tw) < H ? (128 / p.tw) : H;
+    p.tn = 128 / (p.tw * p.th);
+    p.rows_valid = p.tw * p.th * p.tn;
+    while ((1 << p.tw_sh) < p.tw) ++p.tw_sh;
+    while ((1 << p.th_sh) < p.th) ++p.th_sh;
+    p.tiles_w = W / p.tw; p.tiles_h = H / p.th;
+    const int tiles_n = (B + p.tn - 1) / p.tn;
+    p.B = B; p.H = H; p.W = W;
+    p.chunks0 = C1 / 32; p.chunks1 = C2 / 32;
+    p.Cout = Cout; p.cout_valid = Cout;
+    p.bn = Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32);
+    p.out = y; p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(addend);
+    p.out_mul = 1;
+    if (kind == DD_TC_CONV3x3) {
+        p.ntaps = 9;
+        for (int t = 0; t < 9; ++t) { p.tap_dh[t] = (int8_t)(t / 3 - 1); p.tap_dw[t] = (int8_t)(t % 3 - 1); p.tap_plane[t] = 0; }
+    } else {
+        p.ntaps = 1;
+    }
+    const int Cin = C1 + C2, K = p.ntaps * Cin;
+    p.rows_per_phase = w_rows;
+    DD_REQUIRE(w_rows % p.bn == 0, "conv_tc32: packed weight rows %d must be a multiple of the %d-wide tile", w_rows, p.bn);
+    int rc = make_act_map(&p.tmA0, x, C1, C1, W, H, B, 1, p.tw, p.th, p.tn, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, true);
+    if (rc) return rc;
+    rc = make_act_map(&p.tmA1, x2 ? x2 : x, x2 ? C2 : C1, x2 ? C2 : C1, W, H, B, 1, p.tw, p.th, p.tn, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, true);
+    if (rc) return rc;
+    rc = make_w_map(&p.tmB, wp, K, w_rows, p.bn, 0, true);
+    if (rc) return rc;
+    p.splits = 1; p.kb_per_split = p.ntaps * (p.chunks0 + p.chunks1);
+    p.dbg = g_tc_dbg;
+    dim3 grid(p.tiles_w * p.tiles_h * tiles_n, Cout / p.bn, 1);
+    launch_pdl(conv_tc_kernel<3, 128, 1, 3, true>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), (cudaStream_t)stream, p);
+    return check_launch("conv_tc32");
+}
+
+// =============================================================================================
+// TF32 weight gradient on tcgen05:  dW[tap][ci][co] += sum_pixels Xa[pixel + tap][ci] * dY[pixel][co]
+// (autograd of blocks.py:78,103,123-124 / convblocks.py:29-67; Xa is the conv's input, already activated when the
+// block applies Mish first).  GEMM view with the PIXELS as the K dimension:
+//   M = 128 rows = four "units" (tap, 32-channel chunk) of the input, N = a tile of output channels, K = pixels.
+// kind::tf32 has no MN-major operand form (measured: any transpose bit in the instruction descriptor yields an all-zero
+// accumulator, profiles/README.md), so both operands are read K-major from CHANNEL-MAJOR (NCHW) fp32 copies of Xa and dY:
+// one operand row = one channel's 32 consecutive pixels (128 bytes), boxes (kw x kh pixels, 32 or N channels) land as the
+// canonical 128B-swizzled tiles.  A unit's tap shift is a shift of its TMA coordinates (zero fill outside the map = the
+// conv padding).  The pixel range is split over the grid; partial sums meet in dW through red.global.add.f32.
+// =============================================================================================
+namespace dd {
+
+struct WgParams {
+    CUtensorMap tmX0, tmX1, tmG;      // (Wp, H + 2, C, B) / (Wp, H, Cout, B) views of the padded channel-major copies
+    int8_t tap_dw[9], tap_dh[9];
+    int ntaps, chunks0, chunks1, units;
+    int cw, chn;                      // a K chunk = 32 consecutive pixels of one (padded) row; cw chunks per row, chn per image
+    int chunks_total, stages_per_cta; // 32-pixel chunks over the batch; pipeline stages (WG_KC chunks each) per CTA
+    int N, Cout, rows_total;
+    float* dw;
+};
+constexpr int WG_KC = 2;                          // 32-pixel chunks per pipeline stage
+constexpr int WG_A_BYTES = 128 * 128;             // 128 rows (4 units x 32 channels) x 32 pixels fp32
+constexpr int WG_STAGES = 3;
+constexpr int WG_STAGE_BYTES = WG_KC * (WG_A_BYTES + 128 * 128);      // + up to 128 dY channels
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 1024;
+constexpr int WG_THREADS = 192;                   // warps: TMA producer, MMA issuer + TMEM owner, 4 x epilogue
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+template <int TMEM_COLS>
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc32_kernel(const __grid_constant__ WgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + WG_STAGES * WG_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (WG_STAGES + s); };
+    const uint32_t tmem_full_bar = bars + 8u * (2 * WG_STAGES);
+    const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x, n_tile = blockIdx.y, split = blockIdx.z;
+    const int chunk0 = split * p.stages_per_cta * WG_KC;
+    const int nch = min(p.stages_per_cta * WG_KC, p.chunks_total - chunk0);      // chunks of this CTA (>= 1)
+    const int nst = (nch + WG_KC - 1) / WG_KC;
+    const uint32_t b_bytes = (uint32_t)p.N * 128u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmX0)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmG)) : "memory");
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+    pdl_sync();
+
+    if (warp == 0) {
+        // ===== producer: per 32-pixel chunk, the four input units of this group (each with its tap shift) + N dY channels =====
+        const int cpt = p.chunks0 + p.chunks1;
+        int u_tap[4], u_ch[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int u = g * 4 + j;
+            if (u >= p.units) u = 0;                        // padding unit of the last group: loaded, never written back
+            u_tap[j] = u / cpt; u_ch[j] = u % cpt;
+        }
+        int st = 0, round = 0;
+        for (int s = 0; s < nst; ++s) {
+            const int kcs = min(WG_KC, nch - s * WG_KC);
+            const uint32_t fb = full_bar(st), sS = base + st * WG_STAGE_BYTES;
+            if (round > 0) mbar_wait(empty_bar(st), (round - 1) & 1);
+            if (elect_one()) {
+                mbar_expect_tx(fb, (uint32_t)kcs * (WG_A_BYTES + b_bytes));
+                for (int kc = 0; kc < kcs; ++kc) {
+                    const int chunk = chunk0 + s * WG_KC + kc;
+                    const int n = chunk / p.chn, rc = chunk % p.chn;
+                    const int w0 = (rc % p.cw) * 32, h0 = rc / p.cw;
+                    const uint32_t sA = sS + kc * (WG_A_BYTES + b_bytes), sB = sA + WG_A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = u_ch[j], tp = u_tap[j];
+                        // row shift = coordinate (+1: one zero row above and below); column shift = which pre-shifted copy:
+                        // a TMA box origin must be 16-byte aligned, w0 - 1 in the innermost dimension is not (illegal instruction)
+                        const int sc = p.ntaps == 9 ? p.tap_dw[tp] + 1 : 0;
+                        if (c < p.chunks0) tma_load_5d(&p.tmX0, fb, sA + j * 4096, w0, h0 + p.tap_dh[tp] + 1, c * 32, n, sc);
+                        else tma_load_5d(&p.tmX1, fb, sA + j * 4096, w0, h0 + p.tap_dh[tp] + 1, (c - p.chunks0) * 32, n, sc);
+                    }
+                    tma_load_4d(&p.tmG, fb, sB, w0, h0, n_tile * p.N, n);
+                }
+            }
+            __syncwarp();
+            if (++st == WG_STAGES) { st = 0; ++round; }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: D[128 x N] += A[128 x 8 pixels] . B[N x 8 pixels]^T, K-major TF32, four K = 8 steps per chunk =====
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        int st = 0;
+        uint32_t par = 0;
+        for (int s = 0; s < nst; ++s) {
+            const int kcs = min(WG_KC, nch - s * WG_KC);
+            mbar_wait(full_bar(st), par);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sS = base + st * WG_STAGE_BYTES;
+                for (int kc = 0; kc < kcs; ++kc) {
+                    const uint64_t ad = umma_desc(sS + kc * (WG_A_BYTES + b_bytes)), bd = umma_desc(sS + kc * (WG_A_BYTES + b_bytes) + WG_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (s | kc | k) ? 1u : 0u);
+                }
+                umma_commit(empty_bar(st));
+            }
+            __syncwarp();
+            if (++st == WG_STAGES) { st = 0; par ^= 1u; }
+        }
+        if (elect_one()) umma_commit(tmem_full_bar);
+        __syncwarp();
+    } else {
+        // ===== epilogue: accumulate the partial tile into dW (rows = tap*Cin + ci, columns = co) =====
+        const int q = warp & 3, r = q * 32 + lane;
+        const int row = g * 128 + r;
+        const bool valid = row < p.rows_total;
+        float* dst = p.dw + (int64_t)row * p.Cout + n_tile * p.N;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c = 0; c < p.N; c += 32) {
+            uint32_t a[32];
+            tmem_ld32_issue(trow + (uint32_t)c, a);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    red_add_v4(dst + c + 4 * j, __uint_as_float(a[4 * j]), __uint_as_float(a[4 * j + 1]), __uint_as_float(a[4 * j + 2]),
+                               __uint_as_float(a[4 * j + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// (W, H, C, B) fp32 view of a channel-major tensor; box = (32, 1, rows channels, 1): `rows` operand rows of 32 pixels (128 bytes)
+static int make_nchw_map(CUtensorMap* tm, const void* ptr, int C, int W, int H, int B, int kw, int kh, int rows, int copies = 0) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
+    cuuint64_t dims[5] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B, (cuuint64_t)(copies > 0 ? copies : 1)};
+    cuuint64_t strides[4] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4, (cuuint64_t)B * C * H * W * 4};
+    cuuint32_t box[5] = {(cuuint32_t)kw, (cuuint32_t)kh, (cuuint32_t)rows, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, copies > 0 ? 5 : 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(NCHW C=%d W=%d H=%d B=%d box %d,%d,%d) failed: %d", C, W, H, B, kw, kh, rows, (int)r); return DD_ERR_CUDA; }
+    return DD_OK;
+}
+
+}  // namespace dd
+
+extern "C" int dd_conv_wgrad_tc32(int kind, const float* x_nchw, const float* x2_nchw, int C1, int C2, const float* dy_nchw, float* dw,
+                                  int B, int H, int W, int Wp, int Cout, void* stream) {
+    DD_REQUIRE(kind == DD_TC_CONV3x3 || kind == DD_TC_CONV1x1, "conv_wgrad_tc32: 3x3 stride-1 and 1x1 only (kind %d)", kind);
+    DD_REQUIRE(C1 > 0 && C1 % 32 == 0 && C2 >= 0 && C2 % 32 == 0 && Cout > 0 && Cout % 32 == 0,
+               "conv_wgrad_tc32: channel counts (%d,%d -> %d) must be multiples of 32", C1, C2, Cout);
+    DD_REQUIRE((C2 == 0) == (x2_nchw == nullptr), "conv_wgrad_tc32: x2/C2 mismatch");
+    DD_REQUIRE(H > 0 && W > 0 && B > 0 && Wp >= W && Wp % 32 == 0, "conv_wgrad_tc32: padded row width Wp=%d must be a multiple of 32 >= W=%d", Wp, W);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        if (e != cudaSuccess) { set_error("conv_wgrad_tc32: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
+        attr_done = true;
+    }
+    WgParams p;
+    memset(&p, 0, sizeof(p));
+    p.cw = Wp / 32;
+    p.chn = p.cw * H;
+    p.chunks_total = p.chn * B;
+    p.ntaps = kind == DD_TC_CONV3x3 ? 9 : 1;
+    for (int t = 0; t < p.ntaps; ++t) {
+        p.tap_dh[t] = (int8_t)(p.ntaps == 9 ? t / 3 - 1 : 0);
+        p.tap_dw[t] = (int8_t)(p.ntaps == 9 ? t % 3 - 1 : 0);
+    }
+    p.chunks0 = C1 / 32; p.chunks1 = C2 / 32;
+    p.units = p.ntaps * (p.chunks0 + p.chunks1);
+    p.N = Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32);
+    p.Cout = Cout; p.rows_total = p.ntaps * (C1 + C2); p.dw = dw;
+    const int groups = (p.units + 3) / 4, n_tiles = Cout / p.N;
+    const int stages_total = (p.chunks_total + WG_KC - 1) / WG_KC;
+    int S = (2 * num_sms()) / (groups * n_tiles);
+    if (S < 1) S = 1;
+    if (S > stages_total) S = stages_total;
+    p.stages_per_cta = (stages_total + S - 1) / S;
+    S = (stages_total + p.stages_per_cta - 1) / p.stages_per_cta;
+    const int copies = p.ntaps == 9 ? 3 : 1;
+    int rc = make_nchw_map(&p.tmX0, x_nchw, C1, Wp, H + 2, B, 32, 1, 32, copies);
+    if (rc) return rc;
+    rc = make_nchw_map(&p.tmX1, x2_nchw ? x2_nchw : x_nchw, x2_nchw ? C2 : C1, Wp, H + 2, B, 32, 1, 32, copies);
+    if (rc) return rc;
+    rc = make_nchw_map(&p.tmG, dy_nchw, Cout, Wp, H, B, 32, 1, p.N);
+    if (rc) return rc;
+    dim3 grid(groups, n_tiles, S);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.N == 32) launch_pdl(wgrad_tc32_kernel<32>, dim3(grid), dim3(WG_THREADS), WG_SMEM, st, p);
+    else if (p.N == 64) launch_pdl(wgrad_tc32_kernel<64>, dim3(grid), dim3(WG_THREADS), WG_SMEM, st, p);
+    else launch_pdl(wgrad_tc32_kernel<128>, dim3(grid), dim3(WG_THREADS), WG_SMEM, st, p);
+    return check_launch("conv_wgrad_tc32");
 }

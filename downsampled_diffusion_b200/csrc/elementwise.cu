@@ -202,31 +202,78 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
     for (int c = 0; c < C; ++c) yb[(int64_t)c * HW] = to_f(xb[c]);
 }
 
-// NCHW fp32 -> bf16 im2col rows (B*H*W, kpad), 3x3 pad 1.  One thread per (pixel, 8-column group).
-__global__ void im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                 int C, int H, int W, int kpad) {
+// NHWC fp32 -> channel-major fp32 with padding and column shifts:  y[s][b][c][h + hpad][w] = x[b][h][w + s - nshift/2][c]
+// (zero outside the map), rows Wp >= W wide, s < nshift (1 or 3).  This is the K-major operand layout of the TF32
+// weight-gradient GEMM (pixels = K): a row of 32 pixels is one 128-byte operand row.  TMA needs 16-byte aligned box
+// origins, so the +-1 column shift of a 3x3 tap cannot be a coordinate of the innermost (pixel) dimension -- it is baked
+// into three copies written from one read; the row shift stays a coordinate (one zero row above and below).
+// 32 x 32 (pixel x channel) tiles through shared memory: coalesced 128-byte reads along c, 128-byte writes along w.
+__global__ void __launch_bounds__(256) nhwc_to_chw_pad_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int H, int W,
+                                                              int Wp, int hpad, int nshift) {
     pdl_sync();
-    const int b = blockIdx.y;
-    const int groups = kpad >> 3;
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int HW = H * W;
-    if (idx >= (int64_t)HW * groups) return;
-    const int p = (int)(idx / groups), g = (int)(idx % groups);
-    const int h = p / W, w = p % W;
-    const float* xb = x + (int64_t)b * C * HW;
-    Vec<__nv_bfloat16> v;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int k = g * 8 + j;
-        float val = 0.f;
-        if (k < 9 * C) {
-            const int tap = k / C, c = k % C;
-            const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-            if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = xb[(int64_t)c * HW + hh * W + ww];
+    __shared__ float tile[34][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const int w0 = blockIdx.x * 32, hh = blockIdx.y, Hp = H + 2 * hpad;
+    const int cblocks = C >> 5, b = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 32;
+    const int h = hh - hpad;
+    const bool row_ok = h >= 0 && h < H;
+    if (row_ok) {
+        for (int i = ty; i < 34; i += 8) {                            // pixels w0 - 1 .. w0 + 32
+            const int w = w0 - 1 + i;
+            tile[i][tx] = (w >= 0 && w < W) ? x[(((int64_t)b * H + h) * W + w) * C + c0 + tx] : 0.f;
         }
-        v.v[j] = val;
     }
-    v.store(y + ((int64_t)b * HW + p) * kpad + g * 8);
+    __syncthreads();
+    const int64_t copy = (int64_t)B * C * Hp * Wp;
+    for (int s = 0; s < nshift; ++s) {
+        const int off = 1 + s - (nshift >> 1);                        // tile row of output column w0 + 0
+#pragma unroll
+        for (int i = ty; i < 32; i += 8)
+            y[s * copy + (((int64_t)b * C + c0 + i) * Hp + hh) * Wp + w0 + tx] = row_ok ? tile[tx + off][i] : 0.f;
+    }
+}
+
+// NCHW fp32 -> bf16 im2col rows (B*H*W, kpad), 3x3 pad 1.  One CTA per 32-pixel row segment: the 3 x 34 x C input
+// halo is read with coalesced loads into shared memory, the segment's 32 x kpad output block is contiguous in
+// memory and written with consecutive 16-byte stores (the first version read 8 strided floats per thread: 23 us
+// for 17 MB -- profiles/README.md).
+constexpr int IM2COL_TW = 32;
+template <int CT>          // CT > 0: compile-time channel count (no divisions in the fill loop); 0: run-time C
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                        int C_rt, int H, int W, int kpad) {
+    pdl_sync();
+    const int C = CT > 0 ? CT : C_rt;
+    extern __shared__ float s_halo[];                  // [C][3][IM2COL_TW + 2]
+    constexpr int HP = IM2COL_TW + 2;
+    const int b = blockIdx.y;
+    const int segs = (W + IM2COL_TW - 1) / IM2COL_TW;
+    const int h = blockIdx.x / segs, w0 = (blockIdx.x % segs) * IM2COL_TW;
+    const int HW = H * W;
+    const float* xb = x + (int64_t)b * C * HW;
+    for (int i = threadIdx.x; i < C * 3 * HP; i += 256) {
+        const int c = i / (3 * HP), rr = (i / HP) % 3, cc = i % HP;
+        const int hh = h + rr - 1, ww = w0 + cc - 1;
+        s_halo[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xb + (int64_t)c * HW + hh * W + ww) : 0.f;
+    }
+    __syncthreads();
+    const int groups = kpad >> 3;
+    const int npix = min(IM2COL_TW, W - w0);
+    __nv_bfloat16* yb = y + ((int64_t)b * HW + (int64_t)h * W + w0) * kpad;
+    for (int v = threadIdx.x; v < npix * groups; v += 256) {
+        const int pix = v / groups, g = v % groups;
+        Vec<__nv_bfloat16> o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = g * 8 + j;
+            float val = 0.f;
+            if (k < 9 * C) {
+                const int tap = k / C, c = k - tap * C;
+                val = s_halo[(c * 3 + tap / 3) * HP + pix + tap % 3];
+            }
+            o.v[j] = val;
+        }
+        o.store(yb + (int64_t)v * 8);
+    }
 }
 
 template <typename T>
@@ -375,11 +422,22 @@ int dd_nhwc_to_nchw(const void* x, int dtype, float* y, int B, int C, int H, int
     return check_launch("nhwc_to_nchw");
 }
 
+int dd_nhwc_to_chw_pad(const float* x, float* y, int B, int C, int H, int W, int Wp, int hpad, int nshift, void* stream) {
+    DD_REQUIRE(C % 32 == 0 && Wp % 32 == 0 && Wp >= W && hpad >= 0, "nhwc_to_chw_pad: C=%d must be a multiple of 32, Wp=%d a multiple of 32 >= W", C, Wp);
+    DD_REQUIRE(nshift == 1 || nshift == 3, "nhwc_to_chw_pad: nshift must be 1 or 3 (got %d)", nshift);
+    DD_REQUIRE((int64_t)B * (C / 32) <= 65535, "nhwc_to_chw_pad: B*C/32 exceeds the grid limit");
+    dim3 grid(Wp / 32, H + 2 * hpad, B * (C / 32));
+    launch_pdl(nhwc_to_chw_pad_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, y, B, C, H, W, Wp, hpad, nshift);
+    return check_launch("nhwc_to_chw_pad");
+}
+
 int dd_im2col3x3_nchw(const float* x, void* y, int B, int C, int H, int W, int kpad, void* stream) {
     DD_REQUIRE(kpad % 64 == 0 && kpad >= 9 * C, "im2col3x3: kpad=%d must be a multiple of 64 and >= 9*C", kpad);
-    int64_t n = (int64_t)H * W * (kpad / 8);
-    dim3 grid((unsigned)((n + 255) / 256), B);
-    launch_pdl(im2col3x3_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, C, H, W, kpad);
+    DD_REQUIRE(C > 0 && C <= 64, "im2col3x3: C=%d out of range (1..64)", C);
+    dim3 grid((unsigned)(H * ((W + IM2COL_TW - 1) / IM2COL_TW)), B);
+    const size_t smem = (size_t)C * 3 * (IM2COL_TW + 2) * sizeof(float);
+    if (C == 8) launch_pdl(im2col3x3_kernel<8>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, x, (__nv_bfloat16*)y, C, H, W, kpad);
+    else launch_pdl(im2col3x3_kernel<0>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, x, (__nv_bfloat16*)y, C, H, W, kpad);
     return check_launch("im2col3x3");
 }
 

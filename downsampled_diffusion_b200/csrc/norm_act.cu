@@ -62,7 +62,7 @@ template <int N> __device__ __forceinline__ FVec<N> ldg_f(const float* p) {
     return r;
 }
 
-constexpr int GN_UNR = 2;
+constexpr int GN_UNR = 4;
 // grid = (vector blocks within one image, B): no division to find the image, 32-bit index math only
 // (the first version spent ~25 of its 36 instructions per element on 64-bit index divisions -- profiles/README.md).
 template <typename T>
@@ -81,13 +81,13 @@ __global__ void __launch_bounds__(256, 4) gn_mish_kernel(const T* __restrict__ x
     const int c = (int)(i0 % cv) * VN;
     const int g = c / (int)cpg;
     const int64_t base = (int64_t)b * vec_per_img;
-    Vec<T> v[UNR], r[UNR];
+    uint4 xv[UNR], rv[UNR];                          // raw 16-byte vectors: 64 (+64) bytes in flight per thread
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
         const unsigned i = i0 + u * 256u;
         if (i < (unsigned)vec_per_img) {
-            v[u].load(x + (base + i) * VN);
-            if (residual) r[u].load(residual + (base + i) * VN);
+            xv[u] = *reinterpret_cast<const uint4*>(x + (base + i) * VN);
+            if (residual) rv[u] = *reinterpret_cast<const uint4*>(residual + (base + i) * VN);
         }
     }
     const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + (int64_t)b * G + g);
@@ -112,13 +112,88 @@ __global__ void __launch_bounds__(256, 4) gn_mish_kernel(const T* __restrict__ x
     for (int u = 0; u < UNR; ++u) {
         const unsigned i = i0 + u * 256u;
         if (i >= (unsigned)vec_per_img) break;
+        Vec<T> v, r;
+        v.from_raw(xv[u]);
+        if (residual) r.from_raw(rv[u]);
 #pragma unroll
         for (int j = 0; j < VN; ++j) {
-            float h = mish_t<T>(fmaf(v[u].v[j], sc.v[j], sh.v[j])) + tb.v[j];
-            if (residual) h += r[u].v[j];
-            v[u].v[j] = h;
+            float h = mish_t<T>(fmaf(v.v[j], sc.v[j], sh.v[j])) + tb.v[j];
+            if (residual) h += r.v[j];
+            v.v[j] = h;
         }
-        v[u].store(y + (base + i) * VN);
+        *reinterpret_cast<uint4*>(y + (base + i) * VN) = v.to_raw();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm + Mish over the partial sums of a split-K convolution (dd_conv_tc with DD_TC_SPLITK), for the
+// low-resolution maps (one CTA per image, HW*C <= 16384 values staged in shared memory):
+//   x = sum_s part[s] + bias -> {mean, rstd} per group (block reduction) -> mish(x_hat*gamma+beta) + tbias + residual.
+// Thread t owns channels 4*(t % (C/4)).. of the pixels t/(C/4), +256/(C/4), ...: one group per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_mish_sum_kernel(const float* __restrict__ part, int S, int64_t split_stride,
+                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                          int HW, int C, int G, float eps,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ tbias, int tb_stride,
+                                                          const int32_t* __restrict__ trow, int trow_stride,
+                                                          const __nv_bfloat16* __restrict__ residual) {
+    pdl_sync();
+    extern __shared__ float4 s_x[];                        // HW*C/4 summed vectors
+    __shared__ float s_stat[64][2];
+    const int b = blockIdx.x, cv = C >> 2, nvec = HW * cv;
+    const int c4 = threadIdx.x % cv, c = c4 * 4, cpg = C / G, g = c / cpg;
+    if (threadIdx.x < 2 * G) (&s_stat[0][0])[threadIdx.x] = 0.f;
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(part) + (int64_t)b * nvec;
+    const float4 bi = bias ? __ldg(reinterpret_cast<const float4*>(bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float sum = 0.f, sq = 0.f;
+    for (int v = threadIdx.x; v < nvec; v += 256) {
+        float4 a = bi;
+        for (int s = 0; s < S; ++s) {
+            const float4 t = __ldcg(src + s * (split_stride >> 2) + v);
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        s_x[v] = a;
+        sum += a.x + a.y + a.z + a.w;
+        sq += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    // lanes of one group are cpg/4 consecutive lanes (a power of two <= 32)
+    const int gl = cpg >> 2;
+    for (int o = 1; o < gl; o <<= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if ((threadIdx.x & (gl - 1)) == 0) { atomicAdd(&s_stat[g][0], sum); atomicAdd(&s_stat[g][1], sq); }
+    __syncthreads();
+    const float inv_n = 1.f / ((float)HW * (float)cpg);
+    const float mean = s_stat[g][0] * inv_n;
+    const float rstd = rsqrtf(fmaxf(s_stat[g][1] * inv_n - mean * mean, 0.f) + eps);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4), be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 tb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tbias) {
+        const int row = trow ? trow[(int64_t)b * trow_stride] : b;
+        tb = __ldg(reinterpret_cast<const float4*>(tbias + (int64_t)row * tb_stride) + c4);
+    }
+    const float sc[4] = {ga.x * rstd, ga.y * rstd, ga.z * rstd, ga.w * rstd};
+    const float sh[4] = {be.x - mean * sc[0], be.y - mean * sc[1], be.z - mean * sc[2], be.w - mean * sc[3]};
+    const float tbv[4] = {tb.x, tb.y, tb.z, tb.w};
+    for (int v = threadIdx.x; v < nvec; v += 256) {
+        const float4 a = s_x[v];
+        const float xin[4] = {a.x, a.y, a.z, a.w};
+        float h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = mish_fast(fmaf(xin[j], sc[j], sh[j])) + tbv[j];
+        const int64_t off = ((int64_t)b * nvec + v) * 4;
+        if (residual) {
+            const uint2 rr = *reinterpret_cast<const uint2*>(residual + off);
+            h[0] += __uint_as_float(rr.x << 16); h[1] += __uint_as_float(rr.x & 0xffff0000u);
+            h[2] += __uint_as_float(rr.y << 16); h[3] += __uint_as_float(rr.y & 0xffff0000u);
+        }
+        uint2 o;
+        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(h[0], h[1]);
+        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(h[2], h[3]);
+        *reinterpret_cast<uint2*>(y + off) = o;
     }
 }
 
@@ -429,6 +504,25 @@ int dd_gn_mish(const void* x, void* y, int dtype, int B, int HW, int C, int G, c
             (const T*)residual, vpi);
     });
     return check_launch("gn_mish");
+}
+
+int dd_gn_mish_sum(const float* part, int S, const float* bias, void* y_bf16, int B, int HW, int C, int G, float eps,
+                   const float* gamma, const float* beta, const float* tbias, int tb_stride, const int32_t* trow,
+                   int trow_stride, const void* residual_bf16, void* stream) {
+    DD_REQUIRE(S >= 1 && B > 0 && HW > 0 && G > 0 && G <= 64 && C % G == 0, "gn_mish_sum: bad sizes S=%d B=%d HW=%d C=%d G=%d", S, B, HW, C, G);
+    const int cv = C / 4, cpg = C / G;
+    DD_REQUIRE(C % 4 == 0 && 256 % cv == 0 && cpg % 4 == 0 && cpg / 4 <= 32 && ((cpg / 4) & (cpg / 4 - 1)) == 0,
+               "gn_mish_sum: unsupported channel layout C=%d G=%d", C, G);
+    DD_REQUIRE((int64_t)HW * C <= 16384, "gn_mish_sum: HW*C=%lld exceeds the shared-memory stage (16384)", (long long)HW * C);
+    DD_REQUIRE(tb_stride % 4 == 0, "gn_mish_sum: time-bias row stride must be a multiple of 4 floats");
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gn_mish_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4);
+        attr_done = true;
+    }
+    launch_pdl(gn_mish_sum_kernel, dim3(B), dim3(256), (size_t)HW * C * 4, (cudaStream_t)stream, part, S, (int64_t)B * HW * C, bias,
+               (__nv_bfloat16*)y_bf16, HW, C, G, eps, gamma, beta, tbias, tb_stride, trow, trow_stride, (const __nv_bfloat16*)residual_bf16);
+    return check_launch("gn_mish_sum");
 }
 
 int dd_layernorm_c(const void* x, void* y, int dtype, int64_t P, int C, const float* g, const float* b, float eps,

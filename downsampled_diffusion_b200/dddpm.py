@@ -30,6 +30,9 @@ class DownsampleDDPM(DDPM):
             f"Input channels to DDPM-Unet {unet_in} should be equal or larger to data color channels {self.in_channels}."
         self.downsample = get_downsampling(config, self.x_shape)
         self.upsample = get_upsampling(config, self.x_shape)
+        for net in (self.downsample, self.upsample):         # 'fp32' = validation mode for the resampling nets as well
+            if isinstance(net, _ResampleNet) and "precision" in config:
+                net.precision = config["precision"]
 
     # ---- latent <-> image ----------------------------------------------------------------------
     def _resample(self, net, x: torch.Tensor) -> torch.Tensor:

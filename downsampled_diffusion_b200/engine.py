@@ -194,17 +194,24 @@ class Program:
                 src = planes
             G = 0
             st_ptr = None
+            flags = 0
             if gn is not None:
                 G = gn.num_groups
-                stats = (self._new_stats_slot(B, G), 1)
-                st_ptr = stats[0]
+                # low-resolution layers: split-K partials, summed by the GroupNorm kernel (dd_gn_mish_sum)
+                S = int(L.lib().dd_conv_tc_splits(kcode, B, gh, gw, Cin, Cout_p)) if (residual is None and Cout_p == Cout) else 1
+                if S > 1 and gh * gw * Cout <= 16384 and S * B * gh * gw * Cout <= self.SPLITK_WS_FLOATS:
+                    flags = L.TC_SPLITK
+                    stats = (("split", S, b_t), 2)
+                else:
+                    stats = (self._new_stats_slot(B, G), 1)
+                    st_ptr = stats[0]
             taps = {"3x3": 9, "down": 9, "1x1": 1, "up": 4}[kind]
             self.conv_tc_flops.append(2.0 * B * Ho * Wo * Cout * taps * Cin)
             self.add("dd_conv_tc", kcode, L.ptr(src), 0, L.ptr(src2) if src2 is not None else None, x.C,
                      x2.C if x2 is not None else 0, L.ptr(wp), wp.shape[0], L.ptr(b_t) if b_t is not None else None,
                      L.ptr(residual.t) if residual is not None else None,
                      L.ptr(out_nchw) if out_nchw is not None else L.ptr(y.t), 1 if out_nchw is not None else 0,
-                     Cout if out_nchw is not None else 0, st_ptr, G, B, gh, gw, Cout_p, 0, *self.splitk_args())
+                     Cout if out_nchw is not None else 0, st_ptr, G, B, gh, gw, Cout_p, flags, *self.splitk_args())
             if y is not None and Cout_p != Cout:
                 raise ValueError("padded Cout is only supported with NCHW fp32 output")
         else:
@@ -258,6 +265,14 @@ class Program:
         y = self.act(x.H, x.W, x.C, x.B)
         st, mode = stats
         gamma, beta = self.f32(gn.weight), self.f32(gn.bias)
+        if mode == 2:       # x was never written: the conv left S fp32 partials in the shared split-K workspace
+            _, S, b_t = st
+            self.add("dd_gn_mish_sum", self.splitk_args()[0], S, L.ptr(b_t) if b_t is not None else None, L.ptr(y.t), x.B, x.H * x.W,
+                     x.C, gn.num_groups, GN_EPS, L.ptr(gamma), L.ptr(beta),
+                     _TbPtr(self, tb_col) if tb_col is not None else None, tb[0] if tb else 0,
+                     _TrowPtr(self) if tb_col is not None else None, _TrowStride(self) if tb_col is not None else 0,
+                     L.ptr(residual.t) if residual is not None else None)
+            return y
         self.add("dd_gn_mish", L.ptr(x.t), L.ptr(y.t), self.dcode, x.B, x.H * x.W, x.C, gn.num_groups,
                  st if isinstance(st, _ArenaPtr) else L.ptr(st), mode, GN_EPS, L.ptr(gamma), L.ptr(beta),
                  _TbPtr(self, tb_col) if tb_col is not None else None, tb[0] if tb else 0,

@@ -117,6 +117,14 @@ int dd_gn_mish(const void* x, void* y, int dtype, int B, int HW, int C, int G,
                const float* tbias, int tb_stride, const int32_t* trow, int trow_stride,
                const void* residual, void* stream);
 
+/* dd_gn_mish for a split-K convolution: x = sum_s part[s] + bias (part: (S, B, HW, C) fp32 from dd_conv_tc with
+ * DD_TC_SPLITK), GroupNorm statistics computed in the same launch (one CTA per image, HW*C <= 16384), then
+ * y = mish(gn(x)*gamma+beta) [+ tbias] [+ residual] as above.  y / residual: bf16 NHWC. */
+int dd_gn_mish_sum(const float* part, int S, const float* bias, void* y_bf16, int B, int HW, int C, int G, float eps,
+                   const float* gamma, const float* beta,
+                   const float* tbias, int tb_stride, const int32_t* trow, int trow_stride,
+                   const void* residual_bf16, void* stream);
+
 /* Channel LayerNorm of blocks.py:50-60: (x-mean_c)/(sqrt(var_c)+eps)*g+b, per pixel. x,y NHWC (P, C). */
 int dd_layernorm_c(const void* x, void* y, int dtype, int64_t P, int C, const float* g, const float* b,
                    float eps, void* stream);
@@ -188,12 +196,40 @@ int dd_space_to_depth2(const void* x, void* y, int B, int H, int W, int C, void*
 /* flags: DD_TC_W_PER_SAMPLE (1x1 only): wp is (B, w_rows, K), image b multiplies its own matrix -- the fused
  * LinearAttention output GEMM  out = q . (ctx_b . W_out^T)  (blocks.py:132-134). */
 #define DD_TC_W_PER_SAMPLE 1
+/* DD_TC_SPLITK (3x3 only, where dd_conv_tc_splits() > 1): the K range is split over S = dd_conv_tc_splits(...)
+ * CTAs per tile; every split writes its raw fp32 partial sums (no bias) to
+ *   splitk_ws[split][b][h][w][Cout]            (S * B*H*W*Cout floats),
+ * y, gn_stats and residual are ignored, and dd_gn_mish_sum consumes the partials (sum + bias + GroupNorm + Mish). */
+#define DD_TC_SPLITK 2
+int dd_conv_tc_splits(int kind, int B, int H, int W, int Cin, int Cout);
 int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2,
                const void* wp, int w_rows, const float* bias, const void* residual,
                void* y, int out_nchw_f32, int cout_valid,
                float* gn_stats, int G,
                int B, int H, int W, int Cout, int flags,
                float* splitk_ws, int64_t splitk_ws_floats, int32_t* splitk_cnt, int splitk_cnt_n, void* stream);
+
+/* fp32 training form of the tensor-core convolution (forward AND input gradient of the 3x3 stride-1 / 1x1 convolutions
+ * of blocks.py:78,103,123-124 and convblocks.py:29-67): x, x2, y, addend fp32 NHWC; wp fp32 (w_rows, taps*(C1+C2)) K-major;
+ * TF32 operands (tcgen05.mma.kind::tf32), fp32 accumulate.  y = conv(x|x2) + bias [+ addend]; addend may alias y
+ * (gradient accumulation).  Channel counts multiples of 32, power-of-two maps; anything else stays on dd_conv_direct. */
+int dd_conv_tc32(int kind, const float* x, const float* x2, int C1, int C2, const float* wp, int w_rows, const float* bias,
+                 const float* addend, float* y, int B, int H, int W, int Cout, void* stream);
+
+/* Channel-major padded copies for the weight-gradient GEMM:  y[s][b][c][h + hpad][w] = x[b][h][w + s - nshift/2][c],
+ * fp32, rows Wp (multiple of 32, >= W) wide, zeros outside the map; nshift = 3 bakes the column shifts of a 3x3 filter
+ * into three copies (a TMA box origin must be 16-byte aligned), nshift = 1 is the plain copy. */
+int dd_nhwc_to_chw_pad(const float* x, float* y, int B, int C, int H, int W, int Wp, int hpad, int nshift, void* stream);
+
+/* Weight gradient of the same convolutions on the tensor cores (TF32, pixels as the GEMM K dimension):
+ *   dw[tap][ci][co] += sum_pixels x[pixel+tap][ci] * dy[pixel][co].
+ * kind::tf32 reads K-major operands only, so the operands are channel-major copies made by dd_nhwc_to_chw_pad:
+ *   x_cm (, x2_cm): (nshift, B, C, H+2, Wp), hpad = 1, nshift = 3 for 3x3 and 1 for 1x1 -- the conv's input
+ *                   (the activated copy when the block applies Mish first);
+ *   dy_cm: (B, Cout, H, Wp), hpad = 0, nshift = 1.
+ * dw: fp32 (taps, C1+C2, Cout), ACCUMULATED with red.global.add (zero it first). */
+int dd_conv_wgrad_tc32(int kind, const float* x_cm, const float* x2_cm, int C1, int C2, const float* dy_cm, float* dw,
+                       int B, int H, int W, int Wp, int Cout, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Backward of the training denoising step (fp32 programs): autograd of ddpm.py:290-315 / dddpm.py:122-177.

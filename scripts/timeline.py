@@ -11,7 +11,7 @@ eng = plan.eng
 idx = [i for i, n in enumerate(eng.op_names) if n == "dd_conv_tc"]
 buf = torch.zeros(4096 * 16, dtype=torch.int64, device=dev)
 names = ["start", "prologue", "pdl_wait", "first_data", "last_mma", "acc_ready", "epi_done"]
-for which in (2, 24, 17):          # 3x3@32 (halo), 3x3@16 (halo), 3x3@8, 3x3@4
+for which in [int(a) for a in sys.argv[1:]] or (2, 16, 23):          # 3x3@32 (halo), 3x3@8 (8x8 halo form), 3x3@4 (split-K)
     op = eng.ops[idx[which]]
     for _ in range(3): op()
     torch.cuda.synchronize()
@@ -27,7 +27,6 @@ for which in (2, 24, 17):          # 3x3@32 (halo), 3x3@16 (halo), 3x3@8, 3x3@4
     print(f"conv #{which}: {len(t)} CTAs; kernel span {int(t[:, 6].max() - t0)} clk")
     print("   median per-CTA offsets from its own start:", {n: int(np.median(rel[:, i])) for i, n in enumerate(names)})
     print("   CTA start offsets (from first CTA): p50 %d p90 %d max %d" % tuple(np.percentile(t[:, 0] - t0, [50, 90, 100])))
-    print("   MMA-thread wait-on-data total: median %d clk; producer wait-on-empty total: median %d clk; producer last issue at %d" % (np.median(t[:, 7]), np.median(t[:, 8]), np.median(t[:, 9] - t[:, 0])))
     print("   epilogue split: drain+stage %d, stats %d, write-out %d" % (np.median(t[:, 10] - t[:, 5]), np.median(t[:, 11] - t[:, 10]), np.median(t[:, 6] - t[:, 11])))
     d = rel[:, 4] - rel[:, 3]
     print("   mainloop (first_data -> last_mma): median %d clk, epilogue (acc_ready -> done): median %d clk" % (np.median(d), np.median(rel[:, 6] - rel[:, 5])))

@@ -204,11 +204,14 @@ CONV_CASES = [
     ("3x3", 256, 256, 128, 16, 16, 3),    # halo kernel, two sources (skip concat), odd batch
     ("3x3", 256, 0, 256, 16, 16, 2),      # halo kernel, 2 n-tiles
     ("3x3", 64, 0, 64, 16, 8, 1),         # halo kernel, exactly one tile, bn = 64
-    ("3x3", 256, 256, 256, 8, 8, 3),      # concat-free two-source, 2 images per M tile (+ a ragged tile)
+    ("3x3", 256, 256, 256, 8, 8, 3),      # 8x8 halo form: (h, image, w) halo rows, two sources, ragged last tile
+    ("3x3", 64, 0, 128, 8, 8, 2),         # 8x8 halo form, one chunk, bn = 64
     ("3x3", 64, 0, 64, 4, 4, 5),          # 8 images per tile, ragged batch, 8 channels per GN group
-    ("3x3", 256, 0, 256, 4, 4, 64),       # split-K (16 tiles x 12 splits) with the GroupNorm epilogue in the finisher
-    ("3x3", 256, 256, 256, 8, 8, 64),     # split-K, two sources
-    ("down", 256, 0, 256, 4, 4, 64),      # split-K on the strided conv
+    ("3x3", 256, 0, 256, 4, 4, 64),       # split-K partials (32 tiles x 4 splits) + dd_gn_mish_sum
+    ("3x3", 256, 256, 256, 4, 4, 64),     # split-K, two sources (72 k-blocks)
+    ("3x3", 256, 0, 256, 2, 2, 7),        # split-K on a single ragged tile
+    ("3x3", 256, 256, 256, 8, 8, 64),     # 8x8 halo form at the benchmark batch, two sources
+    ("down", 256, 0, 256, 4, 4, 64),      # strided conv on the single-wave path
     ("1x1", 256, 0, 384, 16, 16, 2),
     ("1x1", 128, 0, 256, 2, 2, 3),
     ("down", 128, 0, 128, 32, 32, 2),
@@ -250,13 +253,25 @@ def test_conv_paths(cuda, kind, C1, C2, Cout, H, W, B, precision):
     prog.finalize_arena()
     prog.refresh_weights()
     prog.run_ops()
-    if precision == "bf16":            # twice: the split-K scratch and counters must come back zeroed
+    split = gn is not None and stats[1] == 2      # split-K: raw fp32 partials in the workspace, summed by dd_gn_mish_sum
+    if split:
+        S = stats[0][1]
+        ws = next(t for t in prog.keep if t.dtype == torch.float32 and t.numel() == prog.SPLITK_WS_FLOATS)
+        part = ws[:S * B * H * W * Cout].reshape(S, B, H, W, Cout)
+        y.t.copy_((part.sum(0) + conv.bias.detach()).to(y.t.dtype))
+        # the consumer: GroupNorm + Mish + time bias + residual over the partials == the same on the summed tensor
+        res2 = Act(nhwc(tc.randn(5, B, Cout, H, W), dt).to(cuda), B, H, W, Cout)
+        z = prog.gn_mish(y, stats, gn, residual=res2)
+        prog.weights_version = None                  # gamma / beta were packed after the first refresh
+        prog.refresh_weights()
+        prog.ops[-1]()
+        zr = F.mish(F.group_norm(from_nhwc((part.sum(0) + conv.bias.detach()).cpu()), 8, gn.weight.detach().cpu(), gn.bias.detach().cpu()))
+        assert tc.rel_l2(from_nhwc(z.t.cpu()), zr + from_nhwc(res2.t.cpu())) < 6e-3
+    elif precision == "bf16":          # twice: nothing may depend on state left behind by the first run
         first = y.t.clone()
         prog.stats_arena.zero_() if prog.stats_arena is not None else None
         prog.run_ops()
         assert tc.rel_l2(from_nhwc(y.t.cpu()), from_nhwc(first.cpu())) < 1e-3
-        ws_ptr = prog.splitk_args()
-        assert all(float(t.abs().max()) == 0.0 for t in prog.keep if t.dtype in (torch.float32, torch.int32) and t.numel() in (prog.SPLITK_WS_FLOATS, prog.SPLITK_COUNTERS))
     torch.cuda.synchronize()
     # reference on the operands the kernel really consumed
     xin = from_nhwc(xa.t.cpu())
@@ -277,7 +292,9 @@ def test_conv_paths(cuda, kind, C1, C2, Cout, H, W, B, precision):
     assert tc.rel_l2(from_nhwc(y.t.cpu()), ref) < tol
     if gn is not None:
         st, mode = stats
-        if mode == 1:        # {sum, sumsq} of the fp32 accumulator (+bias)
+        if mode == 2:
+            pass             # statistics are computed by dd_gn_mish_sum (checked above)
+        elif mode == 1:      # {sum, sumsq} of the fp32 accumulator (+bias)
             arena = prog.stats_arena.cpu().reshape(B, 8, 2)
             g = pre.reshape(B, 8, -1).double()
             assert tc.rel_l2(arena[..., 0], g.sum(-1)) < 1e-3 + 1e-2 * (precision == "bf16")

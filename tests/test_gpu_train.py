@@ -218,3 +218,67 @@ def test_conv_weight_and_input_gradients(cuda, kind):
     assert tc.rel_l2(prog.grad(xa).permute(0, 3, 1, 2), x.grad[:, :C1]) < 1e-5
     if C2:
         assert tc.rel_l2(prog.grad(x2a).permute(0, 3, 1, 2), x.grad[:, C1:]) < 1e-5
+
+
+# ---- TF32 tensor-core training form (dd_conv_tc32) ----------------------------------------------------
+
+@pytest.mark.parametrize("kind,C1,C2,Cout,H,W,B,pre_mish", [
+    ("3x3", 32, 0, 32, 16, 16, 3, True),        # ConvResBlock c2/c3 shape (convblocks.py:103-104), pre-activation
+    ("3x3", 64, 64, 128, 8, 8, 5, False),       # two sources (skip concat), 2 images per tile, ragged batch
+    ("1x1", 64, 0, 32, 32, 32, 2, True),        # ConvResBlock c1
+    ("3x3", 128, 0, 256, 4, 4, 9, False),       # 8 images per tile, 2 n-tiles
+])
+def test_tf32_conv_forward_and_gradients(cuda, kind, C1, C2, Cout, H, W, B, pre_mish):
+    """dd_conv_tc32 forward, input gradient (same kernel, flipped weights) and the fp32 weight gradient of a conv
+    lowered by TrainProgram(tf32=True), against torch autograd on CPU.  TF32 operands: tolerance 2e-3 relative."""
+    from downsampled_diffusion_b200.autograd import TrainProgram
+    from downsampled_diffusion_b200.engine import Act
+    torch.manual_seed(2)
+    Cin = C1 + C2
+    conv = torch.nn.Conv2d(Cin, Cout, 3, 1, 1) if kind == "3x3" else torch.nn.Conv2d(Cin, Cout, 1)
+    x = torch.randn(B, Cin, H, W, requires_grad=True)
+    y = conv(F.mish(x) if pre_mish else x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    holder = torch.nn.ModuleList([conv]).to(cuda)
+    prog = TrainProgram(holder, B, tf32=True)
+    nh = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().to(cuda)
+    xa = Act(nh(x[:, :C1]), B, H, W, C1)
+    x2a = Act(nh(x[:, C1:]), B, H, W, C2) if C2 else None
+    ya = prog.t_conv(xa, holder[0], x2=x2a, kind=kind, pre_mish=pre_mish)
+    assert "dd_conv_tc32" in prog.op_names
+    prog.gwritten.add(id(ya.t))
+    prog.build_backward()
+    prog.refresh_weights()
+    prog.run_ops()
+    assert tc.rel_l2(ya.t.permute(0, 3, 1, 2), y) < 2e-3
+    prog.grad(ya).copy_(nh(dy))
+    prog.run_backward()
+    pg = prog.param_grads()
+    assert tc.rel_l2(pg[id(holder[0].weight)], conv.weight.grad) < 2e-3
+    assert tc.rel_l2(pg[id(holder[0].bias)], conv.bias.grad) < 1e-5
+    assert tc.rel_l2(prog.grad(xa).permute(0, 3, 1, 2), x.grad[:, :C1]) < 2e-3
+    if C2:
+        assert tc.rel_l2(prog.grad(x2a).permute(0, 3, 1, 2), x.grad[:, C1:]) < 2e-3
+
+
+def test_tf32_training_objective_and_gradients(cuda, golden):
+    """The default (precision='bf16' sampling) model trains with TF32 tensor-core convolutions: objective within 1e-3,
+    gradient norms within 2e-2 of the reference's fp32 CPU autograd (golden vectors)."""
+    kind = "dddpm_ae"
+    m = tc.build_model(dict(tc.CS, precision="bf16"), dd, kind, device="cuda").to(cuda)
+    m.train()
+    x = tc.rand_pm1(51, 4, 3, 32, 32).to(cuda)
+    t = torch.tensor([3, 50, 99, 700], device=cuda)
+    torch.manual_seed(7)
+    eps = torch.randn(4, 8, 8, 8).to(cuda)
+    obj, d = m.losses(x, t, eps=eps)
+    obj.backward()
+    ref = float(golden[f"loss.{kind}.obj"])
+    assert abs(float(obj) - ref) <= 1e-3 * abs(ref)
+    norms = np.asarray(golden[f"loss.{kind}.grad_norms"])
+    for (n, p), r in zip(m.named_parameters(), norms):
+        got = 0.0 if p.grad is None else float(p.grad.double().norm())
+        assert abs(got - r) <= 2e-2 * max(r, 1e-6) + 1e-5, f"{n}: |grad| {got} vs reference {r}"
+    g = m.latent_model.final_conv[1].weight.grad
+    assert tc.rel_l2(g, G(golden, f"loss.{kind}.grad.latent_model.final_conv.1.weight")) < 1e-2
