@@ -152,8 +152,13 @@ def conv_roofline(model, plan, pk):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     tf = sum(flops) / (ms * 1e-3) / 1e12
+    traffic, tsrc = None, None        # DRAM bytes per launch from the committed ncu capture of the same launches (profiles/)
+    tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic, tsrc = tj.get("avg_dram_bytes_per_launch"), tj.get("source")
     return {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
-            "traffic": None, "kernel": "conv_tc_kernel", "launches_per_unet_step": len(idx),
+            "traffic": traffic, "traffic_source": tsrc, "kernel": "conv_tc_kernel", "launches_per_unet_step": len(idx),
             "avg_launch_us": 1000.0 * ms / len(idx), "conv_ms_per_unet_step": ms,
             "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)"}
 

@@ -132,8 +132,11 @@ class TrainProgram(Program):
     # ---- differentiable building blocks --------------------------------------------------------
     def t_conv(self, x: Optional[Act], conv: torch.nn.Module, *, x2: Act = None, kind: str = "3x3", residual: Act = None,
                pre_mish: bool = False, tanh: bool = False, out_nchw: torch.Tensor = None, in_nchw: torch.Tensor = None,
-               in_shape: Tuple[int, int, int] = None, bias: bool = True, need_dx: bool = True) -> Act:
+               in_shape: Tuple[int, int, int] = None, bias: bool = True, need_dx: bool = True, emit_mish: bool = False) -> Act:
         """conv / transposed conv with optional pre-Mish, residual add, tanh, NCHW input / output (fp32)."""
+        if (self.tf32 and kind in ("down", "up") and x is not None and x2 is None and residual is None and not pre_mish and not tanh
+                and out_nchw is None and in_nchw is None and self._strided_tc_ok(x, conv, kind)):
+            return self.t_conv_strided(x, conv, kind)
         w = conv.weight
         transposed = kind == "up"
         if in_nchw is not None:
@@ -172,12 +175,17 @@ class TrainProgram(Program):
             wp = self.packed((Cout, K), torch.float32, lambda buf: buf.copy_(w.detach().permute(0, 2, 3, 1).reshape(Cout, K)))
             xin = x
             if pre_mish:       # the activated copy feeds the tensor-core forward (TMA -> UMMA has no place for a pre-activation)
-                xm = self.act(H, W, C1, B)
-                self.add("dd_ew", 0, L.ptr(x.t), None, L.ptr(xm.t), x.t.numel(), 1.0, 0)
+                xm = getattr(x, "mish", None)          # written by the producer's epilogue when it was asked to (emit_mish)
+                if xm is None:
+                    xm = self.act(H, W, C1, B)
+                    self.add("dd_ew", 0, L.ptr(x.t), None, L.ptr(xm.t), x.t.numel(), 1.0, 0)
                 xin = xm
+            ym = self.act(Ho, Wo, Cout, B) if emit_mish else None
             self.add("dd_conv_tc32", kcode, L.ptr(xin.t), L.ptr(x2.t) if x2 is not None else None, C1, C2, L.ptr(wp), Cout,
                      L.ptr(b_t) if b_t is not None else None, L.ptr(residual.t) if residual is not None else None, L.ptr(y.t),
-                     B, H, W, Cout)
+                     L.ptr(ym.t) if ym is not None else None, None, B, H, W, Cout)
+            if ym is not None:
+                y.mish = ym
         else:
             self.add("dd_conv_direct", src, L.ptr(x2.t) if x2 is not None else None, C1, C2, L.DD_F32, L.ptr(wd),
                      L.ptr(b_t) if b_t is not None else None, L.ptr(residual.t) if residual is not None else None,
@@ -245,15 +253,10 @@ class TrainProgram(Program):
             if residual is not None:
                 self.add_into(residual, g)
             for (a, c_lo, c_n), wt in zip(srcs, wts):
-                if use_tc:
-                    if pre_mish:
-                        dst = self.empty(*a.t.shape, dtype=torch.float32)
-                        self.add("dd_conv_tc32", kcode, L.ptr(g), None, Cout, 0, L.ptr(wt), c_n, None, None, L.ptr(dst), B, Ho, Wo, c_n)
-                        self.add("dd_ew", 1, L.ptr(a.t), L.ptr(dst), L.ptr(self.grad(a)), dst.numel(), 1.0, self.acc(a))
-                    else:       # accumulate in the epilogue when the gradient already has a writer
-                        ga = self.grad(a)
-                        self.add("dd_conv_tc32", kcode, L.ptr(g), None, Cout, 0, L.ptr(wt), c_n, None, L.ptr(ga) if self.acc(a) else None,
-                                 L.ptr(ga), B, Ho, Wo, c_n)
+                if use_tc:      # epilogue fusions: * mish'(a) for a pre-activated conv, += the gradient's earlier writers
+                    ga = self.grad(a)
+                    self.add("dd_conv_tc32", kcode, L.ptr(g), None, Cout, 0, L.ptr(wt), c_n, None, L.ptr(ga) if self.acc(a) else None,
+                             L.ptr(ga), None, L.ptr(a.t) if pre_mish else None, B, Ho, Wo, c_n)
                     continue
                 direct = (not pre_mish) and not self.has_grad(a)
                 dst = self.grad(a) if direct else self.empty(*a.t.shape, dtype=torch.float32)
@@ -274,6 +277,47 @@ class TrainProgram(Program):
                 else:
                     self.add_into(a, dst)
         self.on_backward(backward)
+        return y
+
+    # ---- stride-2 / transposed convolutions as dense 3x3 convolutions on the tensor cores ------------------
+    @staticmethod
+    def _strided_tc_ok(x: Act, conv, kind: str) -> bool:
+        pow2 = lambda v: v > 0 and (v & (v - 1)) == 0
+        w = conv.weight
+        cin, cout = (w.shape[0], w.shape[1]) if kind == "up" else (w.shape[1], w.shape[0])
+        h, wd = (x.H, x.W) if kind == "up" else (x.H // 2, x.W // 2)
+        return cin % 32 == 0 and cout % 32 == 0 and pow2(x.H) and pow2(x.W) and h * wd >= 16
+
+    def t_conv_strided(self, x: Act, conv, kind: str) -> Act:
+        """Downsample (Conv2d 3x3 s2 p1, blocks.py:44) = a 3x3 s1 conv on the space-to-depth input (4*Cin channels);
+        Upsample (ConvTranspose2d 4x4 s2 p1, blocks.py:35) = a 3x3 s1 conv to 4*Cout sub-pixel channels + depth-to-space.
+        Weight blocks of (tap, plane) pairs that do not occur are zero; forward, input and weight gradient then run on
+        dd_conv_tc32 / dd_conv_wgrad_tc32 like every other 3x3 convolution."""
+        B, H, W, C = x.B, x.H, x.W, x.C
+        if kind == "down":
+            h, wd = H // 2, W // 2
+            x4 = self.act(h, wd, 4 * C, B)
+            self.add("dd_s2d_f32", L.ptr(x.t), L.ptr(x4.t), B, h, wd, C, 1)
+
+            def back_in():          # runs after the conv's backward wrote grad(x4)
+                if self.has_grad(x):
+                    tmp = self.empty(*x.t.shape, dtype=torch.float32)
+                    self.add("dd_s2d_f32", L.ptr(self.gy(x4)), L.ptr(tmp), B, h, wd, C, 0)
+                    self.add_into(x, tmp)
+                else:
+                    self.add("dd_s2d_f32", L.ptr(self.gy(x4)), L.ptr(self.grad(x)), B, h, wd, C, 0)
+                    self.acc(x)
+            self.on_backward(back_in)
+            return self.t_conv(x4, _DownAsConv3(conv), kind="3x3")
+        y4 = self.t_conv(x, _UpAsConv3(conv), kind="3x3")
+        cout = conv.weight.shape[1]
+        y = self.act(2 * H, 2 * W, cout, B)
+        self.add("dd_s2d_f32", L.ptr(y4.t), L.ptr(y.t), B, H, W, cout, 0)
+
+        def back_out():             # runs before the conv's backward: packed gradient of the sub-pixel channels
+            self.add("dd_s2d_f32", L.ptr(self.gy(y)), L.ptr(self.grad(y4)), B, H, W, cout, 1)
+            self.acc(y4)
+        self.on_backward(back_out)
         return y
 
     def t_gn_mish(self, x: Act, gn: torch.nn.GroupNorm, *, tb: torch.Tensor = None, tb_col: int = None, dtb: torch.Tensor = None,
@@ -548,7 +592,77 @@ class _W4:
         return self.p.detach().view(*self.shape)
 
 
-# make pgrad accept the _W4 wrapper: gradients are registered against the real parameter
+class _Virt:
+    """A parameter seen through a linear re-layout: `build` maps the real tensor to the virtual one (what the kernels
+    consume), `to_real` maps a gradient of the virtual tensor back onto the real parameter."""
+
+    def __init__(self, real, shape, build, to_real):
+        self.real, self.shape, self._build, self.to_real = real, tuple(shape), build, to_real
+
+    def detach(self):
+        return self._build(self.real.detach())
+
+    def numel(self):
+        n = 1
+        for s_ in self.shape:
+            n *= s_
+        return n
+
+
+_KH_OF = {(0, 0): 1, (0, -1): 3, (1, 0): 2, (1, 1): 0}          # ConvTranspose2d(4,2,1): (sub-pixel phase, input offset) -> kernel index
+_DOWN_OF = {0: (-1, 1), 1: (0, 0), 2: (0, 1)}                    # Conv2d(3,2,1): kernel index -> (packed offset, plane parity)
+
+
+class _UpAsConv3:
+    """ConvTranspose2d(Cin, Cout, 4, 2, 1) as Conv2d(Cin, 4*Cout, 3, 1, 1) on the input grid (+ depth-to-space):
+    out[2a+py][2b+px][co] = sum_{dh,dw,ci} x[a+dh][b+dw][ci] * w[ci][co][py+1-2dh][px+1-2dw]."""
+
+    def __init__(self, conv):
+        w, cin, cout = conv.weight, conv.weight.shape[0], conv.weight.shape[1]
+
+        def build(wr):
+            v = wr.new_zeros(4, cout, cin, 3, 3)
+            for (py, dh), kh in _KH_OF.items():
+                for (px, dw), kw in _KH_OF.items():
+                    v[py * 2 + px, :, :, dh + 1, dw + 1] = wr[:, :, kh, kw].t()
+            return v.view(4 * cout, cin, 3, 3)
+
+        def to_real(g):
+            g = g.reshape(4, cout, cin, 3, 3)
+            r = g.new_zeros(cin, cout, 4, 4)
+            for (py, dh), kh in _KH_OF.items():
+                for (px, dw), kw in _KH_OF.items():
+                    r[:, :, kh, kw] = g[py * 2 + px, :, :, dh + 1, dw + 1].t()
+            return r
+        self.weight = _Virt(w, (4 * cout, cin, 3, 3), build, to_real)
+        self.bias = None if conv.bias is None else _Virt(conv.bias, (4 * cout,), lambda b: b.repeat(4), lambda g: g.reshape(4, cout).sum(0))
+
+
+class _DownAsConv3:
+    """Conv2d(Cin, Cout, 3, 2, 1) as Conv2d(4*Cin, Cout, 3, 1, 1) on the space-to-depth input (channel = plane*Cin + ci)."""
+
+    def __init__(self, conv):
+        w, cout, cin = conv.weight, conv.weight.shape[0], conv.weight.shape[1]
+
+        def build(wr):
+            v = wr.new_zeros(cout, 4, cin, 3, 3)
+            for kh, (dh, py) in _DOWN_OF.items():
+                for kw, (dw, px) in _DOWN_OF.items():
+                    v[:, py * 2 + px, :, dh + 1, dw + 1] = wr[:, :, kh, kw]
+            return v.view(cout, 4 * cin, 3, 3)
+
+        def to_real(g):
+            g = g.reshape(cout, 4, cin, 3, 3)
+            r = g.new_zeros(cout, cin, 3, 3)
+            for kh, (dh, py) in _DOWN_OF.items():
+                for kw, (dw, px) in _DOWN_OF.items():
+                    r[:, :, kh, kw] = g[:, py * 2 + px, :, dh + 1, dw + 1]
+            return r
+        self.weight = _Virt(w, (cout, 4 * cin, 3, 3), build, to_real)
+        self.bias = conv.bias
+
+
+# make pgrad accept the wrappers: gradients are registered against the real parameter
 _orig_pgrad = TrainProgram.pgrad
 
 
@@ -556,6 +670,8 @@ def _pgrad(self, param, shape, to_param):
     if isinstance(param, _W4):
         real = param.p
         return _orig_pgrad(self, real, shape, lambda g, f=to_param, r=real: f(g).reshape(r.shape))
+    if isinstance(param, _Virt):
+        return _orig_pgrad(self, param.real, shape, lambda g, f=to_param, v=param: v.to_real(f(g)))
     return _orig_pgrad(self, param, shape, to_param)
 
 
@@ -581,10 +697,11 @@ class ResampleTrainProgram(TrainProgram):
             if isinstance(m, ConvResBlock):
                 if m.drop.p > 0 and net.training:
                     raise RuntimeError("Dropout2d in the resampling nets is only supported with p=0 (reference default)")
-                h = self.t_conv(x, m.c1, kind="1x1", pre_mish=True)
-                h = self.t_conv(h, m.c2, kind="3x3", pre_mish=True)
-                h = self.t_conv(h, m.c3, kind="3x3", pre_mish=True)
-                x = self.t_conv(h, m.c4, kind="1x1", pre_mish=True, residual=x if m.residual else None)
+                nxt_block = (i + 1 < len(layers) and isinstance(layers[i + 1], ConvResBlock) and not (m.upsample or m.downsample))
+                h = self.t_conv(x, m.c1, kind="1x1", pre_mish=True, emit_mish=True)       # c1..c3 outputs are only read through Mish
+                h = self.t_conv(h, m.c2, kind="3x3", pre_mish=True, emit_mish=True)
+                h = self.t_conv(h, m.c3, kind="3x3", pre_mish=True, emit_mish=True)
+                x = self.t_conv(h, m.c4, kind="1x1", pre_mish=True, residual=x if m.residual else None, emit_mish=nxt_block)
                 if m.upsample:
                     x = self.t_resample(x, up=True)
                 elif m.downsample:

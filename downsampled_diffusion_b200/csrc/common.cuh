@@ -49,6 +49,15 @@ __device__ __forceinline__ float mish_grad_f(float x) {
     return th + x * sg * (1.f - th * th);
 }
 
+// fast form for fused epilogues (ex2 / rcp approximations, ~1e-6 relative)
+__device__ __forceinline__ float mish_grad_fast(float x) {
+    const float e = __expf(fminf(x, 20.f));
+    const float n = e * (e + 2.f);
+    const float th = __fdividef(n, n + 2.f);
+    const float sg = __fdividef(e, 1.f + e);
+    return th + x * sg * (1.f - th * th);
+}
+
 template <typename T> struct Vec;   // 16-byte vector of activations
 template <> struct Vec<float> {
     static constexpr int N = 4;

@@ -56,6 +56,8 @@ struct TcParams {
     float* gn_stats;
     float* splitk_ws;           // (tiles, bn/4, 128, 4) fp32, all zero between launches (self-cleaning)
     int32_t* splitk_cnt;        // per-tile arrival counters, all zero between launches
+    float* out2;                // dd_conv_tc32: optional second output mish(y) (the next conv's activated input)
+    const float* mgrad;         // dd_conv_tc32: optional z, the result is multiplied by mish'(z) (input gradient through a pre-activation)
     long long* dbg;             // optional per-CTA timeline (8 clock64 stamps per CTA), NULL in production
 };
 
@@ -1155,10 +1157,211 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
 }
 
 
+// =============================================================================================
+// Persistent TF32 convolution for the fp32 training programs (dd_conv_tc32).
+// The resampling nets run 3x3 32->32 / 1x1 32<->64 convolutions over 2 M pixels: 16 384 tiles of 128 pixels with nine
+// (or one, two) k-blocks each.  One CTA per tile spends ~4.6 of its 6 us in launch, TMEM allocation, barrier setup and
+// the first load's latency (launch list: 340 us per conv against an 84 us HBM floor), so here a CTA walks tiles
+// t = blockIdx.x, += gridDim.x with the operand ring running across tile boundaries and TWO accumulator buffers in TMEM:
+// the epilogue of tile i (TMEM -> registers -> fp32 NHWC, bias / addend fused) overlaps the loads and MMAs of tile i+1.
+// Warps: 0 = A-operand TMA, 6 = weight TMA, 1 = MMA issuer + TMEM owner, 2..5 = epilogue.
+// =============================================================================================
+namespace dd {
+
+constexpr int P32_STAGES = 3;
+constexpr int P32_STAGE_BYTES = TC_A_BYTES + 128 * 128;        // 128 pixels + up to 128 weight rows, 32 fp32 channels each
+constexpr int P32_SMEM = P32_STAGES * P32_STAGE_BYTES + 1024 + 2048;
+constexpr int P32_TMEM_COLS = 256;                              // two 128-column accumulators
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc32_persist_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + P32_STAGES * P32_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (P32_STAGES + s); };
+    auto tfull_bar = [&](int b) { return bars + 8u * (2 * P32_STAGES + b); };
+    auto tempty_bar = [&](int b) { return bars + 8u * (2 * P32_STAGES + 2 + b); };
+    const uint32_t tmem_ptr_addr = bars + 8u * (2 * P32_STAGES + 4);
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 1024u - smem_u32(smem_raw)));      // [2][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cpt = p.chunks0 + p.chunks1;                  // 32-channel chunks per tap
+    const int num_kb = p.ntaps * cpt;
+    const int n_tiles = p.Cout / p.bn;
+    const int tiles_mn = p.tiles_w * p.tiles_h * ((p.B + p.tn - 1) / p.tn) * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA0)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB)) : "memory");
+        for (int s = 0; s < P32_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(P32_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+    pdl_sync();
+
+    if (warp == 0) {
+        // ===== A-operand producer =====
+        const uint32_t tx = (uint32_t)p.rows_valid * 128u;
+        const int chunks0 = p.chunks0;
+        int st = 0, round = 0;
+        for (int t = blockIdx.x; t < tiles_mn; t += gridDim.x) {
+            const int m_tile = t / n_tiles;
+            const int w0 = (m_tile % p.tiles_w) * p.tw, h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+            const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn;
+            int rem = 0, ti = 0;
+            for (int i = 0; i < num_kb; ++i) {
+                const uint32_t fb = full_bar(st);
+                if (round > 0) mbar_wait(empty_bar(st), (round - 1) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(fb, tx);
+                    const int cx = w0 + p.tap_dw[ti], cy = h0 + p.tap_dh[ti];
+                    if (rem < chunks0) tma_load_5d(&p.tmA0, fb, base + st * P32_STAGE_BYTES, rem * 32, cx, cy, n0, 0);
+                    else tma_load_5d(&p.tmA1, fb, base + st * P32_STAGE_BYTES, (rem - chunks0) * 32, cx, cy, n0, 0);
+                }
+                __syncwarp();
+                if (++st == P32_STAGES) { st = 0; ++round; }
+                if (++rem == cpt) { rem = 0; ++ti; }
+            }
+        }
+    } else if (warp == 6) {
+        // ===== weight producer =====
+        const uint32_t tx = (uint32_t)p.bn * 128u;
+        int st = 0, round = 0;
+        for (int t = blockIdx.x; t < tiles_mn; t += gridDim.x) {
+            const int brow = (t % n_tiles) * p.bn;
+            for (int i = 0; i < num_kb; ++i) {
+                const uint32_t fb = full_bar(st);
+                if (round > 0) mbar_wait(empty_bar(st), (round - 1) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(fb, tx);
+                    tma_load_2d(&p.tmB, fb, base + st * P32_STAGE_BYTES + TC_A_BYTES, i * 32, brow);
+                }
+                __syncwarp();
+                if (++st == P32_STAGES) { st = 0; ++round; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: accumulator buffer (it & 1), released by the epilogue through tempty =====
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        int st = 0, it = 0;
+        uint32_t par = 0;
+        for (int t = blockIdx.x; t < tiles_mn; t += gridDim.x, ++it) {
+            const int ab = it & 1;
+            if (it >= 2) mbar_wait(tempty_bar(ab), ((it >> 1) - 1) & 1);
+            tc_fence_after();
+            const uint32_t dcol = tmem_base + (uint32_t)(ab * 128);
+            for (int i = 0; i < num_kb; ++i) {
+                mbar_wait(full_bar(st), par);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t ad = umma_desc(base + st * P32_STAGE_BYTES), bd = umma_desc(base + st * P32_STAGE_BYTES + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_tf32(dcol, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+                    umma_commit(empty_bar(st));
+                }
+                __syncwarp();
+                if (++st == P32_STAGES) { st = 0; par ^= 1u; }
+            }
+            if (elect_one()) umma_commit(tfull_bar(ab));
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: y[pixel][c] = (acc + bias) [* mish'(z)] [+ addend];  optionally y2 = mish(y) =====
+        const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 64;
+        const int bn = p.bn;
+        float* yout = reinterpret_cast<float*>(p.out);
+        float* yout2 = p.out2;
+        const float* addp = reinterpret_cast<const float*>(p.residual);
+        const float* mgp = p.mgrad;
+        int it = 0;
+        for (int t = blockIdx.x; t < tiles_mn; t += gridDim.x, ++it) {
+            const int ab = it & 1;
+            const int m_tile = t / n_tiles, cbase = (t % n_tiles) * bn;
+            const int w0 = (m_tile % p.tiles_w) * p.tw, h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+            const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn;
+            float* sb = s_bias + ab * 128;
+            if (et < bn) sb[et] = p.bias ? p.bias[cbase + et] : 0.f;
+            const int ww = r & (p.tw - 1), hh = (r >> p.tw_sh) & (p.th - 1), n = n0 + (r >> (p.tw_sh + p.th_sh));
+            const bool valid = n < p.B && r < p.rows_valid;
+            const int64_t off = (((int64_t)n * p.H + (h0 + hh)) * p.W + (w0 + ww)) * p.Cout + cbase;
+            epi_bar();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 128);
+            // operands of the fused epilogue do not depend on the accumulator: the first 32-column group is requested
+            // BEFORE the wait on the MMAs (each lane reads its own pixel row: a latency-bound gather), later groups one ahead
+            float4 ad[8], zg[8];
+            auto fetch = [&](int c) {
+                if (!valid) return;
+                if (addp) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ad[j] = reinterpret_cast<const float4*>(addp + off + c)[j];
+                }
+                if (mgp) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) zg[j] = reinterpret_cast<const float4*>(mgp + off + c)[j];
+                }
+            };
+            fetch(0);
+            mbar_wait(tfull_bar(ab), (it >> 1) & 1);
+            tc_fence_after();
+            for (int c = 0; c < bn; c += 32) {
+                uint32_t acc[32];
+                tmem_ld32_issue(trow + (uint32_t)c, acc);
+                tmem_ld_wait();
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    v[j] = make_float4(__uint_as_float(acc[4 * j]) + sb[c + 4 * j], __uint_as_float(acc[4 * j + 1]) + sb[c + 4 * j + 1],
+                                       __uint_as_float(acc[4 * j + 2]) + sb[c + 4 * j + 2], __uint_as_float(acc[4 * j + 3]) + sb[c + 4 * j + 3]);
+                    if (mgp) {
+                        v[j].x *= mish_grad_fast(zg[j].x); v[j].y *= mish_grad_fast(zg[j].y);
+                        v[j].z *= mish_grad_fast(zg[j].z); v[j].w *= mish_grad_fast(zg[j].w);
+                    }
+                    if (addp) { v[j].x += ad[j].x; v[j].y += ad[j].y; v[j].z += ad[j].z; v[j].w += ad[j].w; }
+                }
+                if (c + 32 < bn) fetch(c + 32);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        reinterpret_cast<float4*>(yout + off + c)[j] = v[j];
+                        if (yout2)
+                            reinterpret_cast<float4*>(yout2 + off + c)[j] =
+                                make_float4(mish_fast(v[j].x), mish_fast(v[j].y), mish_fast(v[j].z), mish_fast(v[j].w));
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(ab));            // 128 arrivals release the accumulator buffer
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(P32_TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace dd
+
 // fp32 training form of dd_conv_tc: fp32 NHWC activations, fp32 packed weights [rows][tap*Cin + c], TF32 tensor-core math
 // (10-bit mantissa operands, fp32 accumulate -- what torch's cudnn.allow_tf32 default gives the reference on a GPU).
 extern "C" int dd_conv_tc32(int kind, const float* x, const float* x2, int C1, int C2, const float* wp, int w_rows, const float* bias,
-                            const float* addend, float* y, int B, int H, int W, int Cout, void* stream) {
+                            const float* addend, float* y, float* y_mish, const float* mish_grad_of, int B, int H, int W, int Cout,
+                            void* stream) {
     DD_REQUIRE(kind == DD_TC_CONV3x3 || kind == DD_TC_CONV1x1, "conv_tc32: 3x3 stride-1 and 1x1 only (kind %d)", kind);
     DD_REQUIRE(C1 > 0 && C1 % 32 == 0 && C2 >= 0 && C2 % 32 == 0, "conv_tc32: channel counts (%d,%d) must be multiples of 32", C1, C2);
     DD_REQUIRE((C2 == 0) == (x2 == nullptr), "conv_tc32: x2/C2 mismatch");
@@ -1166,7 +1369,7 @@ extern "C" int dd_conv_tc32(int kind, const float* x, const float* x2, int C1, i
     DD_REQUIRE(Cout >= 32 && Cout % 32 == 0 && w_rows >= Cout, "conv_tc32: Cout=%d must be a multiple of 32", Cout);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 1, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 1));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc32_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P32_SMEM);
         if (e != cudaSuccess) { set_error("conv_tc32: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
         attr_done = true;
     }
@@ -1185,6 +1388,7 @@ extern "C" int dd_conv_tc32(int kind, const float* x, const float* x2, int C1, i
     p.Cout = Cout; p.cout_valid = Cout;
     p.bn = Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32);
     p.out = y; p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(addend);
+    p.out2 = y_mish; p.mgrad = mish_grad_of;
     p.out_mul = 1;
     if (kind == DD_TC_CONV3x3) {
         p.ntaps = 9;
@@ -1203,8 +1407,9 @@ extern "C" int dd_conv_tc32(int kind, const float* x, const float* x2, int C1, i
     if (rc) return rc;
     p.splits = 1; p.kb_per_split = p.ntaps * (p.chunks0 + p.chunks1);
     p.dbg = g_tc_dbg;
-    dim3 grid(p.tiles_w * p.tiles_h * tiles_n, Cout / p.bn, 1);
-    launch_pdl(conv_tc_kernel<3, 128, 1, 3, true>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), (cudaStream_t)stream, p);
+    const int tiles = p.tiles_w * p.tiles_h * tiles_n * (Cout / p.bn);
+    const int ctas = tiles < 2 * num_sms() ? tiles : 2 * num_sms();            // persistent: two CTAs per SM walk the tiles
+    launch_pdl(conv_tc32_persist_kernel, dim3(ctas), dim3(TC_THREADS), P32_SMEM, (cudaStream_t)stream, p);
     return check_launch("conv_tc32");
 }
 

@@ -202,34 +202,63 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
     for (int c = 0; c < C; ++c) yb[(int64_t)c * HW] = to_f(xb[c]);
 }
 
+// fp32 space-to-depth / depth-to-space, NHWC: full (B, 2h, 2w, C) <-> packed (B, h, w, 4C) with packed channel
+// (py*2 + px)*C + c = full[2i + py][2j + px][c].  Lets the stride-2 and the transposed convolutions of the U-Net
+// (blocks.py:35,44) run as dense 3x3 stride-1 convolutions on the tensor cores (autograd.py).
+__global__ void s2d_f32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int h, int w, int cv, int to_packed,
+                               int64_t total) {
+    pdl_sync();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        // i indexes the PACKED tensor: (b, i_, j_, plane, c4)
+        const int c4 = (int)(i % cv);
+        int64_t r = i / cv;
+        const int pl = (int)(r & 3); r >>= 2;
+        const int j = (int)(r % w); r /= w;
+        const int ii = (int)(r % h);
+        const int64_t b = r / h;
+        const int64_t full = (((b * (2 * h) + 2 * ii + (pl >> 1)) * (2 * w)) + 2 * j + (pl & 1)) * cv + c4;
+        if (to_packed) dst[i] = src[full];
+        else dst[full] = src[i];
+    }
+}
+
 // NHWC fp32 -> channel-major fp32 with padding and column shifts:  y[s][b][c][h + hpad][w] = x[b][h][w + s - nshift/2][c]
 // (zero outside the map), rows Wp >= W wide, s < nshift (1 or 3).  This is the K-major operand layout of the TF32
 // weight-gradient GEMM (pixels = K): a row of 32 pixels is one 128-byte operand row.  TMA needs 16-byte aligned box
 // origins, so the +-1 column shift of a 3x3 tap cannot be a coordinate of the innermost (pixel) dimension -- it is baked
 // into three copies written from one read; the row shift stays a coordinate (one zero row above and below).
 // 32 x 32 (pixel x channel) tiles through shared memory: coalesced 128-byte reads along c, 128-byte writes along w.
+constexpr int CHWP_ROWS = 4;          // image rows per CTA: one CTA per row spent its time in launch overhead (264 k CTAs, 2.5 TB/s)
 __global__ void __launch_bounds__(256) nhwc_to_chw_pad_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int H, int W,
                                                               int Wp, int hpad, int nshift) {
     pdl_sync();
-    __shared__ float tile[34][33];
+    __shared__ float tile[CHWP_ROWS][34][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
-    const int w0 = blockIdx.x * 32, hh = blockIdx.y, Hp = H + 2 * hpad;
+    const int w0 = blockIdx.x * 32, hh0 = blockIdx.y * CHWP_ROWS, Hp = H + 2 * hpad;
     const int cblocks = C >> 5, b = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 32;
-    const int h = hh - hpad;
-    const bool row_ok = h >= 0 && h < H;
-    if (row_ok) {
-        for (int i = ty; i < 34; i += 8) {                            // pixels w0 - 1 .. w0 + 32
-            const int w = w0 - 1 + i;
-            tile[i][tx] = (w >= 0 && w < W) ? x[(((int64_t)b * H + h) * W + w) * C + c0 + tx] : 0.f;
+#pragma unroll
+    for (int r = 0; r < CHWP_ROWS; ++r) {
+        const int h = hh0 + r - hpad;
+        if (h >= 0 && h < H) {
+            for (int i = ty; i < 34; i += 8) {                        // pixels w0 - 1 .. w0 + 32
+                const int w = w0 - 1 + i;
+                tile[r][i][tx] = (w >= 0 && w < W) ? x[(((int64_t)b * H + h) * W + w) * C + c0 + tx] : 0.f;
+            }
         }
     }
     __syncthreads();
     const int64_t copy = (int64_t)B * C * Hp * Wp;
-    for (int s = 0; s < nshift; ++s) {
-        const int off = 1 + s - (nshift >> 1);                        // tile row of output column w0 + 0
 #pragma unroll
-        for (int i = ty; i < 32; i += 8)
-            y[s * copy + (((int64_t)b * C + c0 + i) * Hp + hh) * Wp + w0 + tx] = row_ok ? tile[tx + off][i] : 0.f;
+    for (int r = 0; r < CHWP_ROWS; ++r) {
+        const int hh = hh0 + r, h = hh - hpad;
+        if (hh >= Hp) break;
+        const bool row_ok = h >= 0 && h < H;
+        for (int s = 0; s < nshift; ++s) {
+            const int off = 1 + s - (nshift >> 1);                    // tile row of output column w0 + 0
+#pragma unroll
+            for (int i = ty; i < 32; i += 8)
+                y[s * copy + (((int64_t)b * C + c0 + i) * Hp + hh) * Wp + w0 + tx] = row_ok ? tile[r][tx + off][i] : 0.f;
+        }
     }
 }
 
@@ -422,11 +451,19 @@ int dd_nhwc_to_nchw(const void* x, int dtype, float* y, int B, int C, int H, int
     return check_launch("nhwc_to_nchw");
 }
 
+int dd_s2d_f32(const float* src, float* dst, int B, int h, int w, int C, int to_packed, void* stream) {
+    DD_REQUIRE(C % 4 == 0 && B > 0 && h > 0 && w > 0, "s2d_f32: C=%d must be a multiple of 4", C);
+    const int64_t total = (int64_t)B * h * w * 4 * (C / 4);
+    launch_pdl(s2d_f32_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)src, (float4*)dst, h, w, C / 4,
+               to_packed, total);
+    return check_launch("s2d_f32");
+}
+
 int dd_nhwc_to_chw_pad(const float* x, float* y, int B, int C, int H, int W, int Wp, int hpad, int nshift, void* stream) {
     DD_REQUIRE(C % 32 == 0 && Wp % 32 == 0 && Wp >= W && hpad >= 0, "nhwc_to_chw_pad: C=%d must be a multiple of 32, Wp=%d a multiple of 32 >= W", C, Wp);
     DD_REQUIRE(nshift == 1 || nshift == 3, "nhwc_to_chw_pad: nshift must be 1 or 3 (got %d)", nshift);
     DD_REQUIRE((int64_t)B * (C / 32) <= 65535, "nhwc_to_chw_pad: B*C/32 exceeds the grid limit");
-    dim3 grid(Wp / 32, H + 2 * hpad, B * (C / 32));
+    dim3 grid(Wp / 32, (H + 2 * hpad + CHWP_ROWS - 1) / CHWP_ROWS, B * (C / 32));
     launch_pdl(nhwc_to_chw_pad_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, y, B, C, H, W, Wp, hpad, nshift);
     return check_launch("nhwc_to_chw_pad");
 }

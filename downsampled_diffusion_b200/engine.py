@@ -32,10 +32,11 @@ class EngineCache(dict):
 
 class Act:
     """An NHWC activation tensor of a program."""
-    __slots__ = ("t", "B", "H", "W", "C")
+    __slots__ = ("t", "B", "H", "W", "C", "mish")
 
     def __init__(self, t: torch.Tensor, B: int, H: int, W: int, C: int):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+        self.mish = None        # training programs: Act holding mish(t) when the producing conv's epilogue wrote it
 
 
 def _is_pow2(v: int) -> bool:

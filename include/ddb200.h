@@ -211,10 +211,20 @@ int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int
 
 /* fp32 training form of the tensor-core convolution (forward AND input gradient of the 3x3 stride-1 / 1x1 convolutions
  * of blocks.py:78,103,123-124 and convblocks.py:29-67): x, x2, y, addend fp32 NHWC; wp fp32 (w_rows, taps*(C1+C2)) K-major;
- * TF32 operands (tcgen05.mma.kind::tf32), fp32 accumulate.  y = conv(x|x2) + bias [+ addend]; addend may alias y
- * (gradient accumulation).  Channel counts multiples of 32, power-of-two maps; anything else stays on dd_conv_direct. */
+ * TF32 operands (tcgen05.mma.kind::tf32), fp32 accumulate, persistent CTAs with two TMEM accumulators.
+ *   y = (conv(x|x2) + bias) [* mish'(mish_grad_of)] [+ addend];   y_mish = mish(y) when y_mish != NULL
+ * addend may alias y (gradient accumulation); mish_grad_of (same shape as y) makes the launch the input gradient of a
+ * conv that applies Mish first (convblocks.py:112-118); y_mish is the activated copy the next such conv consumes.
+ * Channel counts multiples of 32, power-of-two maps; anything else stays on dd_conv_direct. */
 int dd_conv_tc32(int kind, const float* x, const float* x2, int C1, int C2, const float* wp, int w_rows, const float* bias,
-                 const float* addend, float* y, int B, int H, int W, int Cout, void* stream);
+                 const float* addend, float* y, float* y_mish, const float* mish_grad_of,
+                 int B, int H, int W, int Cout, void* stream);
+
+/* fp32 NHWC space-to-depth (to_packed != 0): src (B, 2h, 2w, C) -> dst (B, h, w, 4C), packed channel (py*2+px)*C + c =
+ * src[2i+py][2j+px][c]; depth-to-space (to_packed == 0): src packed -> dst full.  With it the stride-2 conv and the
+ * transposed conv of the U-Net (blocks.py:35,44) are dense 3x3 stride-1 convolutions for dd_conv_tc32 (zero weight blocks
+ * where a (tap, plane) pair does not occur). */
+int dd_s2d_f32(const float* src, float* dst, int B, int h, int w, int C, int to_packed, void* stream);
 
 /* Channel-major padded copies for the weight-gradient GEMM:  y[s][b][c][h + hpad][w] = x[b][h][w + s - nshift/2][c],
  * fp32, rows Wp (multiple of 32, >= W) wide, zeros outside the map; nshift = 3 bakes the column shifts of a 3x3 filter

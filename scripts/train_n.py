@@ -6,7 +6,8 @@ from tests import common as tc
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 dev = torch.device("cuda:0")
-m = tc.build_model(dict(tc.C3, unet_dropout=0.1, precision="fp32"), dd, "dddpm_ae", device="cuda:0").to(dev).train()
+prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"          # "bf16" -> TF32 tensor-core training, "fp32" -> CUDA-core validation mode
+m = tc.build_model(dict(tc.C3, unet_dropout=0.1, precision=prec), dd, "dddpm_ae", device="cuda:0").to(dev).train()
 opt = torch.optim.Adam(m.parameters(), lr=2e-4)
 ema = dd.EMA(m, decay=0.995)
 x = tc.rand_pm1(1, B, 3, 256, 256).to(dev)

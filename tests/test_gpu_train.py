@@ -227,6 +227,8 @@ def test_conv_weight_and_input_gradients(cuda, kind):
     ("3x3", 64, 64, 128, 8, 8, 5, False),       # two sources (skip concat), 2 images per tile, ragged batch
     ("1x1", 64, 0, 32, 32, 32, 2, True),        # ConvResBlock c1
     ("3x3", 128, 0, 256, 4, 4, 9, False),       # 8 images per tile, 2 n-tiles
+    ("down", 64, 0, 96, 16, 16, 2, False),      # Downsample (blocks.py:44) as a 3x3 conv on the space-to-depth input
+    ("up", 64, 0, 32, 8, 8, 3, False),          # Upsample (blocks.py:35) as a 3x3 conv to 4*Cout sub-pixel channels
 ])
 def test_tf32_conv_forward_and_gradients(cuda, kind, C1, C2, Cout, H, W, B, pre_mish):
     """dd_conv_tc32 forward, input gradient (same kernel, flipped weights) and the fp32 weight gradient of a conv
@@ -235,7 +237,8 @@ def test_tf32_conv_forward_and_gradients(cuda, kind, C1, C2, Cout, H, W, B, pre_
     from downsampled_diffusion_b200.engine import Act
     torch.manual_seed(2)
     Cin = C1 + C2
-    conv = torch.nn.Conv2d(Cin, Cout, 3, 1, 1) if kind == "3x3" else torch.nn.Conv2d(Cin, Cout, 1)
+    conv = {"3x3": lambda: torch.nn.Conv2d(Cin, Cout, 3, 1, 1), "1x1": lambda: torch.nn.Conv2d(Cin, Cout, 1),
+            "down": lambda: torch.nn.Conv2d(Cin, Cout, 3, 2, 1), "up": lambda: torch.nn.ConvTranspose2d(Cin, Cout, 4, 2, 1)}[kind]()
     x = torch.randn(B, Cin, H, W, requires_grad=True)
     y = conv(F.mish(x) if pre_mish else x)
     dy = torch.randn_like(y)
