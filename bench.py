@@ -367,7 +367,7 @@ def run_train(args):
         parallel.allreduce_gradients(params)
         torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad()
         ema.update(model)
         return obj
 

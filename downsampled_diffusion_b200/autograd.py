@@ -120,7 +120,9 @@ class TrainProgram(Program):
             n = 1
             for s in shape:
                 n *= s
-            g = to_param(self.pg_arena[off:off + n].view(shape)).reshape(param.shape).clone()
+            g = to_param(self.pg_arena[off:off + n].view(shape)).reshape(param.shape)
+            if g.untyped_storage().data_ptr() == self.pg_arena.untyped_storage().data_ptr():
+                g = g.clone()                       # still a view of the arena (no permutation happened): detach it
             out[id(param)] = out[id(param)] + g if id(param) in out else g
         return out
 

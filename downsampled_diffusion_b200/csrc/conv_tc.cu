@@ -486,63 +486,15 @@ __device__ __forceinline__ void tc_epilogue_partial(const TcParams& p, uint32_t 
     }
 }
 
-// ---- fp32 NHWC epilogue (training form) -----------------------------------------------------------------
-// y[pixel][c] = acc + bias [+ addend[pixel][c]] (addend may alias y: gradient accumulation).  Each thread owns one
-// output row; 16-byte stores of a row are completed to full sectors by the next column group.
-__device__ __forceinline__ void tc_epilogue_f32(const TcParams& p, uint32_t tmem_base, uint32_t tmem_full_bar, float* s_bias, int n_tile,
-                                                int w0, int h0, int n0, int warp, int lane) {
-    const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 64;
-    const int bn = p.bn, cbase = n_tile * bn;
-    if (et < bn) s_bias[et] = (p.bias && cbase + et < p.Cout) ? p.bias[cbase + et] : 0.f;
-    const int ww = r & (p.tw - 1), hh = (r >> p.tw_sh) & (p.th - 1), n = n0 + (r >> (p.tw_sh + p.th_sh));
-    const bool valid = n < p.B && r < p.rows_valid;
-    const int64_t off = (((int64_t)n * p.H + (h0 + hh)) * p.W + (w0 + ww)) * p.Cout + cbase;
-    float* dst = reinterpret_cast<float*>(p.out) + off;
-    const float* add = p.residual ? reinterpret_cast<const float*>(p.residual) + off : nullptr;
-    epi_bar();
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t a0[32], a1[32];
-    auto emit = [&](int c, uint32_t (&acc)[32]) {
-        if (!valid) return;
-        float4 ad[8];
-        if (add) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ad[j] = reinterpret_cast<const float4*>(add + c)[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float4 v = make_float4(__uint_as_float(acc[4 * j]) + s_bias[c + 4 * j], __uint_as_float(acc[4 * j + 1]) + s_bias[c + 4 * j + 1],
-                                   __uint_as_float(acc[4 * j + 2]) + s_bias[c + 4 * j + 2], __uint_as_float(acc[4 * j + 3]) + s_bias[c + 4 * j + 3]);
-            if (add) { v.x += ad[j].x; v.y += ad[j].y; v.z += ad[j].z; v.w += ad[j].w; }
-            reinterpret_cast<float4*>(dst + c)[j] = v;
-        }
-    };
-    tmem_ld32_issue(trow, a0);
-    for (int c = 0; c < bn; c += 64) {
-        tmem_ld_wait();
-        if (c + 32 < bn) tmem_ld32_issue(trow + (uint32_t)(c + 32), a1);
-        emit(c, a0);
-        if (c + 32 < bn) {
-            tmem_ld_wait();
-            if (c + 64 < bn) tmem_ld32_issue(trow + (uint32_t)(c + 64), a0);
-            emit(c + 32, a1);
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Generic pipeline.  <STAGES, BROWS, KCH>: KCH 64-channel chunks per stage (KCH = 2 halves the per-k-block
 // barrier / issue overhead, which -- not bandwidth -- bounds small tiles: one warp needs ~400 clk to issue a
 // stage, see profiles/README.md).  Warp roles: 0 = A-operand TMA producer, 6 = B-operand TMA producer,
 // 1 = MMA issuer + TMEM owner, 2..5 = epilogue.
 // ---------------------------------------------------------------------------------------------
-// TF32 = the fp32 training form: operands are fp32 NHWC / fp32 packed weights, a pipeline chunk is 32 channels (the same
-// 128-byte rows), tcgen05.mma.kind::tf32 consumes 8 channels per instruction, EPI = 3 writes fp32 NHWC.
-template <int TC_STAGES, int BROWS, int KCH, int EPI, bool TF32 = false>      // EPI: 0 staged bf16, 1 legacy (fp32 NCHW / narrow), 2 split-K partial, 3 fp32 NHWC
+template <int TC_STAGES, int BROWS, int KCH, int EPI>      // EPI: 0 staged bf16, 1 legacy (fp32 NCHW / narrow), 2 split-K partial
 __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ TcParams p) {
-    constexpr int CH = TF32 ? 32 : 64;                   // channels per 128-byte operand row
+    constexpr int CH = 64;                               // channels per 128-byte operand row (bf16)
     constexpr int B_SLOT = BROWS * TC_BK * 2;
     constexpr int TC_STAGE_BYTES = KCH * (TC_A_BYTES + B_SLOT);
     extern __shared__ uint8_t smem_raw[];
@@ -642,8 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
     } else if (warp == 1) {
         // ===== MMA issuer: whole warp loops, one elected lane issues tcgen05.mma / commit =====
         // instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128
-        const uint32_t fmt = TF32 ? 2u : 1u;             // operand format field: 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32)
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
         uint32_t sA = base;
         int st = 0;
         uint32_t par = 0;
@@ -658,8 +609,7 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
                     const uint64_t bd = umma_desc(sA + KCH * TC_A_BYTES + j * B_SLOT);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k)
-                        if (TF32) umma_tf32(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | j | k) ? 1u : 0u);
-                        else umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | j | k) ? 1u : 0u);
+                        umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | j | k) ? 1u : 0u);
                 }
                 umma_commit(empty_bar(st));          // frees this smem stage when the MMAs retire
             }
@@ -675,8 +625,6 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
             tc_epilogue(p, tmem_base, tmem_full_bar, s_bias, m_tile, n_tile, phase, w0, h0, n0, warp, lane);
         else if constexpr (EPI == 2)
             tc_epilogue_partial(p, tmem_base, tmem_full_bar, n_tile, split, w0, h0, n0, warp, lane);
-        else if constexpr (EPI == 3)
-            tc_epilogue_f32(p, tmem_base, tmem_full_bar, s_bias, n_tile, w0, h0, n0, warp, lane);
         else
             tc_epilogue_staged(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, phase, w0, h0, n0,
                                warp, lane);

@@ -228,37 +228,33 @@ __global__ void s2d_f32_kernel(const float4* __restrict__ src, float4* __restric
 // origins, so the +-1 column shift of a 3x3 tap cannot be a coordinate of the innermost (pixel) dimension -- it is baked
 // into three copies written from one read; the row shift stays a coordinate (one zero row above and below).
 // 32 x 32 (pixel x channel) tiles through shared memory: coalesced 128-byte reads along c, 128-byte writes along w.
-constexpr int CHWP_ROWS = 4;          // image rows per CTA: one CTA per row spent its time in launch overhead (264 k CTAs, 2.5 TB/s)
+constexpr int CHWP_ROWS = 4;          // image rows per CTA
 __global__ void __launch_bounds__(256) nhwc_to_chw_pad_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int H, int W,
                                                               int Wp, int hpad, int nshift) {
     pdl_sync();
-    __shared__ float tile[CHWP_ROWS][34][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    __shared__ float tile[CHWP_ROWS][34][33];                         // [row][pixel w0 - 1 .. w0 + 32][channel]
     const int w0 = blockIdx.x * 32, hh0 = blockIdx.y * CHWP_ROWS, Hp = H + 2 * hpad;
     const int cblocks = C >> 5, b = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 32;
-#pragma unroll
-    for (int r = 0; r < CHWP_ROWS; ++r) {
-        const int h = hh0 + r - hpad;
-        if (h >= 0 && h < H) {
-            for (int i = ty; i < 34; i += 8) {                        // pixels w0 - 1 .. w0 + 32
-                const int w = w0 - 1 + i;
-                tile[r][i][tx] = (w >= 0 && w < W) ? x[(((int64_t)b * H + h) * W + w) * C + c0 + tx] : 0.f;
-            }
-        }
+    // ---- reads: 16 bytes (4 channels) per thread, 8 threads per pixel: 34 pixels x CHWP_ROWS rows
+    for (int i = threadIdx.x; i < CHWP_ROWS * 34 * 8; i += 256) {
+        const int c4 = i & 7, pix = (i >> 3) % 34, r = i / (34 * 8);
+        const int h = hh0 + r - hpad, w = w0 - 1 + pix;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h >= 0 && h < H && w >= 0 && w < W) v = *reinterpret_cast<const float4*>(x + (((int64_t)b * H + h) * W + w) * C + c0 + c4 * 4);
+        float* t = &tile[r][pix][c4 * 4];
+        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
     }
     __syncthreads();
+    // ---- writes: 16 bytes (4 pixels of one channel) per thread; the column shift is the pixel offset into the tile
     const int64_t copy = (int64_t)B * C * Hp * Wp;
-#pragma unroll
-    for (int r = 0; r < CHWP_ROWS; ++r) {
-        const int hh = hh0 + r, h = hh - hpad;
-        if (hh >= Hp) break;
-        const bool row_ok = h >= 0 && h < H;
-        for (int s = 0; s < nshift; ++s) {
-            const int off = 1 + s - (nshift >> 1);                    // tile row of output column w0 + 0
-#pragma unroll
-            for (int i = ty; i < 32; i += 8)
-                y[s * copy + (((int64_t)b * C + c0 + i) * Hp + hh) * Wp + w0 + tx] = row_ok ? tile[r][tx + off][i] : 0.f;
-        }
+    const int per_copy = CHWP_ROWS * 32 * 8;
+    for (int i = threadIdx.x; i < nshift * per_copy; i += 256) {
+        const int w4 = i & 7, c = (i >> 3) & 31, r = (i >> 8) % CHWP_ROWS, s = i / per_copy;
+        const int hh = hh0 + r;
+        if (hh >= Hp) continue;
+        const int p0 = w4 * 4 + 1 + s - (nshift >> 1);                // tile pixel of output column w0 + 4*w4
+        const float4 v = make_float4(tile[r][p0][c], tile[r][p0 + 1][c], tile[r][p0 + 2][c], tile[r][p0 + 3][c]);
+        *reinterpret_cast<float4*>(y + s * copy + (((int64_t)b * C + c0 + c) * Hp + hh) * Wp + w0 + w4 * 4) = v;
     }
 }
 

@@ -18,7 +18,7 @@ for i in range(N):
     obj, _ = m(x)
     obj.backward()
     torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
-    opt.step(); opt.zero_grad(set_to_none=False)
+    opt.step(); opt.zero_grad()
     ema.update(m)
 e1.record(); torch.cuda.synchronize()
 print("last step ms", e0.elapsed_time(e1), "loss", float(obj.detach()))
