@@ -234,7 +234,7 @@ class TrainProgram(Program):
                 g = self.gy(y)
                 gflags = 0
             M = B * Ho * Wo
-            if db is not None:
+            if db is not None and not use_tc:         # tensor-core path: fused into the dY operand copy below
                 self.add("dd_colsum", L.ptr(g), db, M, Cout, 1 if out_nchw is not None else 0, Ho * Wo)
             if use_tc:
                 # tensor-core weight gradient: K-major TF32 operands = padded channel-major copies of the input and of dY
@@ -242,12 +242,12 @@ class TrainProgram(Program):
                 Wp = max(32, W)
                 ns = 3 if ks == 3 else 1                  # column shifts are baked into copies (TMA origin alignment)
                 xT, gT = self.scratch("wg_x", ns * B * C1 * (H + 2) * Wp), self.scratch("wg_g", B * Cout * H * Wp)
-                self.add("dd_nhwc_to_chw_pad", L.ptr(xin.t), xT, B, C1, H, W, Wp, 1, ns)
+                self.add("dd_nhwc_to_chw_pad", L.ptr(xin.t), xT, B, C1, H, W, Wp, 1, ns, None)
                 x2T = None
                 if x2 is not None:
                     x2T = self.scratch("wg_x2", ns * B * C2 * (H + 2) * Wp)
-                    self.add("dd_nhwc_to_chw_pad", L.ptr(x2.t), x2T, B, C2, H, W, Wp, 1, ns)
-                self.add("dd_nhwc_to_chw_pad", L.ptr(g), gT, B, Cout, H, W, Wp, 0, 1)
+                    self.add("dd_nhwc_to_chw_pad", L.ptr(x2.t), x2T, B, C2, H, W, Wp, 1, ns, None)
+                self.add("dd_nhwc_to_chw_pad", L.ptr(g), gT, B, Cout, H, W, Wp, 0, 1, db)        # + bias gradient
                 self.add("dd_conv_wgrad_tc32", kcode, xT, x2T, C1, C2, gT, dw, B, H, W, Wp, Cout)
             else:
                 self.add("dd_conv_wgrad", src, L.ptr(x2.t) if x2 is not None else None, C1, C2, L.DD_F32, L.ptr(g), dw, B, H, W, Cout,

@@ -892,14 +892,15 @@ static int make_w_map(CUtensorMap* tm, const void* ptr, int K, int rows, int bn,
 }
 
 // (c, row, tap) view of the packed [row][tap*Cin + c] 3x3 weights: box (64, bn, 3) = the three taps of one filter row
-static int make_w_map_taps(CUtensorMap* tm, const void* ptr, int Cin, int rows, int bn) {
+static int make_w_map_taps(CUtensorMap* tm, const void* ptr, int Cin, int rows, int bn, bool f32 = false) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
+    const cuuint64_t es = f32 ? 4 : 2;
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)rows, 9};
-    cuuint64_t strides[2] = {(cuuint64_t)9 * Cin * 2, (cuuint64_t)Cin * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)bn, 3};
+    cuuint64_t strides[2] = {(cuuint64_t)9 * Cin * es, (cuuint64_t)Cin * es};
+    cuuint32_t box[3] = {f32 ? 32u : 64u, (cuuint32_t)bn, f32 ? 9u : 3u};          // fp32: all nine taps of a 32-channel chunk
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weight taps Cin=%d rows=%d bn=%d) failed: %d", Cin, rows, bn, (int)r); return DD_ERR_CUDA; }
@@ -1303,6 +1304,166 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc32_persist_kernel(const 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Halo form of the persistent TF32 convolution for the narrow 3x3 layers of the resampling nets (32 -> 32 channels on up to
+// 256x256 maps, convblocks.py:103-104).  Loading nine tap-shifted operand tiles per 128 pixels makes these layers
+// L2 -> SM bound (180 KB per tile, 2.95 GB per launch against ~12 TB/s: 350 us).  Here the CTA keeps ALL filter taps
+// resident in shared memory (9 * Cin * 32 * 4 bytes <= 72 KB, one TMA box at start) and loads one (18 x 10)-pixel halo per
+// 16 x 8 tile and 32-channel chunk (23 KB); the nine taps are nine shifted UMMA descriptors into it (row-group stride of
+// 10 halo rows), as in the bf16 halo kernel.  Per tile 23 KB arrive instead of 180 KB.
+// ---------------------------------------------------------------------------------------------
+constexpr int H32_RING = 4;
+constexpr int H32_W_MAX = 9 * 64 * 32 * 4;                                  // resident weights: Cin <= 64, 32 output channels
+constexpr int H32_SMEM = H32_W_MAX + H32_RING * HALO_SLOT + 1024 + 2048;
+constexpr int H32_BN = 32;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc32_halo_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t hbase = base + H32_W_MAX;
+    const uint32_t bars = hbase + H32_RING * HALO_SLOT;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (H32_RING + s); };
+    auto tfull_bar = [&](int b) { return bars + 8u * (2 * H32_RING + b); };
+    auto tempty_bar = [&](int b) { return bars + 8u * (2 * H32_RING + 2 + b); };
+    const uint32_t wfull_bar = bars + 8u * (2 * H32_RING + 4);
+    const uint32_t tmem_ptr_addr = bars + 8u * (2 * H32_RING + 5);
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 1024u - smem_u32(smem_raw)));      // [2][32]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = p.chunks0;                           // 32-channel chunks (single source)
+    const int n_tiles = p.Cout / H32_BN;
+    const int n_tile = blockIdx.x % n_tiles;                // fixed per CTA: its weights stay resident
+    const int m_tiles = p.tiles_w * p.tiles_h * p.B;
+    const int m_first = blockIdx.x / n_tiles, m_step = gridDim.x / n_tiles;
+    const uint32_t w_tap_bytes = H32_BN * 128u, w_chunk_bytes = 9u * w_tap_bytes;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmH0)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB3)) : "memory");
+        for (int s = 0; s < H32_RING; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+        mbar_init(wfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+    pdl_sync();
+
+    if (warp == 0) {
+        // ===== producer: the resident weights once, then one halo per (tile, chunk) =====
+        if (elect_one()) {
+            mbar_expect_tx(wfull_bar, (uint32_t)chunks * w_chunk_bytes);
+            for (int c = 0; c < chunks; ++c) tma_load_3d(&p.tmB3, wfull_bar, base + c * w_chunk_bytes, c * 32, n_tile * H32_BN, 0);
+        }
+        __syncwarp();
+        int st = 0, round = 0;
+        for (int m = m_first; m < m_tiles; m += m_step) {
+            const int w0 = (m % p.tiles_w) * HALO_TW, h0 = ((m / p.tiles_w) % p.tiles_h) * HALO_TH, n0 = m / (p.tiles_w * p.tiles_h);
+            for (int c = 0; c < chunks; ++c) {
+                if (round > 0) mbar_wait(empty_bar(st), (round - 1) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(full_bar(st), HALO_TX);
+                    tma_load_5d(&p.tmH0, full_bar(st), hbase + st * HALO_SLOT, c * 32, w0 - 1, h0 - 1, n0, 0);
+                }
+                __syncwarp();
+                if (++st == H32_RING) { st = 0; ++round; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H32_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        const uint64_t a_hi = ((uint64_t)(((HALO_TW + 2) * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        mbar_wait(wfull_bar, 0);
+        int st = 0, it = 0;
+        uint32_t par = 0;
+        for (int m = m_first; m < m_tiles; m += m_step, ++it) {
+            const int ab = it & 1;
+            if (it >= 2) mbar_wait(tempty_bar(ab), ((it >> 1) - 1) & 1);
+            tc_fence_after();
+            const uint32_t dcol = tmem_base + (uint32_t)(ab * H32_BN);
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(full_bar(st), par);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t halo = hbase + st * HALO_SLOT, wch = base + c * w_chunk_bytes;
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t rowA = halo + (uint32_t)((tap / 3) * (HALO_TW + 2) + tap % 3) * 128u;
+                        const uint64_t ad = (uint64_t)((rowA & 0x3FFFFu) >> 4) | a_hi;
+                        const uint64_t bd = umma_desc(wch + tap * w_tap_bytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_tf32(dcol, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (c | tap | k) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(st));
+                }
+                __syncwarp();
+                if (++st == H32_RING) { st = 0; par ^= 1u; }
+            }
+            if (elect_one()) umma_commit(tfull_bar(ab));
+            __syncwarp();
+        }
+    } else if (warp < 6) {
+        // ===== epilogue (as in conv_tc32_persist_kernel, 16 x 8 tile geometry) =====
+        const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 64;
+        float* yout = reinterpret_cast<float*>(p.out);
+        float* yout2 = p.out2;
+        const float* addp = reinterpret_cast<const float*>(p.residual);
+        const float* mgp = p.mgrad;
+        const int cbase = n_tile * H32_BN;
+        if (et < H32_BN) { s_bias[et] = p.bias ? p.bias[cbase + et] : 0.f; }
+        epi_bar();
+        int it = 0;
+        for (int m = m_first; m < m_tiles; m += m_step, ++it) {
+            const int ab = it & 1;
+            const int w0 = (m % p.tiles_w) * HALO_TW, h0 = ((m / p.tiles_w) % p.tiles_h) * HALO_TH, n0 = m / (p.tiles_w * p.tiles_h);
+            const int64_t off = (((int64_t)n0 * p.H + (h0 + (r >> 3))) * p.W + (w0 + (r & 7))) * p.Cout + cbase;
+            float4 ad[8], zg[8];
+            if (addp) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ad[j] = reinterpret_cast<const float4*>(addp + off)[j];
+            }
+            if (mgp) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) zg[j] = reinterpret_cast<const float4*>(mgp + off)[j];
+            }
+            mbar_wait(tfull_bar(ab), (it >> 1) & 1);
+            tc_fence_after();
+            uint32_t acc[32];
+            tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * H32_BN), acc);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(tempty_bar(ab));            // the accumulator is in registers: release the buffer before the stores
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 v = make_float4(__uint_as_float(acc[4 * j]) + s_bias[4 * j], __uint_as_float(acc[4 * j + 1]) + s_bias[4 * j + 1],
+                                       __uint_as_float(acc[4 * j + 2]) + s_bias[4 * j + 2], __uint_as_float(acc[4 * j + 3]) + s_bias[4 * j + 3]);
+                if (mgp) {
+                    v.x *= mish_grad_fast(zg[j].x); v.y *= mish_grad_fast(zg[j].y); v.z *= mish_grad_fast(zg[j].z); v.w *= mish_grad_fast(zg[j].w);
+                }
+                if (addp) { v.x += ad[j].x; v.y += ad[j].y; v.z += ad[j].z; v.w += ad[j].w; }
+                reinterpret_cast<float4*>(yout + off)[j] = v;
+                if (yout2) reinterpret_cast<float4*>(yout2 + off)[j] = make_float4(mish_fast(v.x), mish_fast(v.y), mish_fast(v.z), mish_fast(v.w));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(64) : "memory");
+    }
+}
+
 }  // namespace dd
 
 // fp32 training form of dd_conv_tc: fp32 NHWC activations, fp32 packed weights [rows][tap*Cin + c], TF32 tensor-core math
@@ -1318,6 +1479,7 @@ extern "C" int dd_conv_tc32(int kind, const float* x, const float* x2, int C1, i
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc32_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P32_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc32_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H32_SMEM);
         if (e != cudaSuccess) { set_error("conv_tc32: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
         attr_done = true;
     }
@@ -1355,6 +1517,21 @@ extern "C" int dd_conv_tc32(int kind, const float* x, const float* x2, int C1, i
     if (rc) return rc;
     p.splits = 1; p.kb_per_split = p.ntaps * (p.chunks0 + p.chunks1);
     p.dbg = g_tc_dbg;
+    static const bool halo32_off = getenv("DD_NO_HALO32") != nullptr;
+    if (!halo32_off && kind == DD_TC_CONV3x3 && C2 == 0 && C1 <= 64 && H >= HALO_TH && W >= HALO_TW && Cout <= 64) {
+        // narrow 3x3 layers: resident weights + one halo per tile
+        p.tw = HALO_TW; p.th = HALO_TH; p.tn = 1; p.rows_valid = 128; p.tw_sh = 3; p.th_sh = 4;
+        p.tiles_w = W / HALO_TW; p.tiles_h = H / HALO_TH; p.bn = H32_BN;
+        rc = make_act_map(&p.tmH0, x, C1, C1, W, H, B, 1, HALO_TW + 2, HALO_TH + 2, 1, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, true);
+        if (rc) return rc;
+        rc = make_w_map_taps(&p.tmB3, wp, C1, w_rows, H32_BN, true);
+        if (rc) return rc;
+        const int n_t = Cout / H32_BN, m_t = p.tiles_w * p.tiles_h * B;
+        int per = num_sms() / n_t;                      // CTAs per output-channel tile: one CTA per SM
+        if (per > m_t) per = m_t;
+        launch_pdl(conv_tc32_halo_kernel, dim3(per * n_t), dim3(TC_THREADS), H32_SMEM, (cudaStream_t)stream, p);
+        return check_launch("conv_tc32");
+    }
     const int tiles = p.tiles_w * p.tiles_h * tiles_n * (Cout / p.bn);
     const int ctas = tiles < 2 * num_sms() ? tiles : 2 * num_sms();            // persistent: two CTAs per SM walk the tiles
     launch_pdl(conv_tc32_persist_kernel, dim3(ctas), dim3(TC_THREADS), P32_SMEM, (cudaStream_t)stream, p);

@@ -230,9 +230,10 @@ __global__ void s2d_f32_kernel(const float4* __restrict__ src, float4* __restric
 // 32 x 32 (pixel x channel) tiles through shared memory: coalesced 128-byte reads along c, 128-byte writes along w.
 constexpr int CHWP_ROWS = 4;          // image rows per CTA
 __global__ void __launch_bounds__(256) nhwc_to_chw_pad_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int H, int W,
-                                                              int Wp, int hpad, int nshift) {
+                                                              int Wp, int hpad, int nshift, float* __restrict__ colsum) {
     pdl_sync();
     __shared__ float tile[CHWP_ROWS][34][33];                         // [row][pixel w0 - 1 .. w0 + 32][channel]
+    __shared__ float s_red[8][32];
     const int w0 = blockIdx.x * 32, hh0 = blockIdx.y * CHWP_ROWS, Hp = H + 2 * hpad;
     const int cblocks = C >> 5, b = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 32;
     // ---- reads: 16 bytes (4 channels) per thread, 8 threads per pixel: 34 pixels x CHWP_ROWS rows
@@ -245,6 +246,27 @@ __global__ void __launch_bounds__(256) nhwc_to_chw_pad_kernel(const float* __res
         t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
     }
     __syncthreads();
+    if (colsum) {
+        // per-channel sum of this tile's own pixels (the bias gradient when x is an output gradient: ddpm autograd of
+        // conv + bias), fused here because this kernel reads every element of dY anyway
+        const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+        float a = 0.f;
+#pragma unroll
+        for (int r = 0; r < CHWP_ROWS; ++r) {
+            const int h = hh0 + r - hpad;
+            if (h < 0 || h >= H) continue;
+            for (int pix = 1 + wrp; pix <= 32; pix += 8)
+                if (w0 - 1 + pix < W) a += tile[r][pix][lane];
+        }
+        s_red[wrp][lane] = a;
+        __syncthreads();
+        if (wrp == 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += s_red[k][lane];
+            atomicAdd(colsum + c0 + lane, t);
+        }
+    }
     // ---- writes: 16 bytes (4 pixels of one channel) per thread; the column shift is the pixel offset into the tile
     const int64_t copy = (int64_t)B * C * Hp * Wp;
     const int per_copy = CHWP_ROWS * 32 * 8;
@@ -455,12 +477,12 @@ int dd_s2d_f32(const float* src, float* dst, int B, int h, int w, int C, int to_
     return check_launch("s2d_f32");
 }
 
-int dd_nhwc_to_chw_pad(const float* x, float* y, int B, int C, int H, int W, int Wp, int hpad, int nshift, void* stream) {
+int dd_nhwc_to_chw_pad(const float* x, float* y, int B, int C, int H, int W, int Wp, int hpad, int nshift, float* colsum, void* stream) {
     DD_REQUIRE(C % 32 == 0 && Wp % 32 == 0 && Wp >= W && hpad >= 0, "nhwc_to_chw_pad: C=%d must be a multiple of 32, Wp=%d a multiple of 32 >= W", C, Wp);
     DD_REQUIRE(nshift == 1 || nshift == 3, "nhwc_to_chw_pad: nshift must be 1 or 3 (got %d)", nshift);
     DD_REQUIRE((int64_t)B * (C / 32) <= 65535, "nhwc_to_chw_pad: B*C/32 exceeds the grid limit");
     dim3 grid(Wp / 32, (H + 2 * hpad + CHWP_ROWS - 1) / CHWP_ROWS, B * (C / 32));
-    launch_pdl(nhwc_to_chw_pad_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, y, B, C, H, W, Wp, hpad, nshift);
+    launch_pdl(nhwc_to_chw_pad_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, y, B, C, H, W, Wp, hpad, nshift, colsum);
     return check_launch("nhwc_to_chw_pad");
 }
 

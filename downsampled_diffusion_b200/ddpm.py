@@ -19,6 +19,7 @@ from .schedule import diffusion_buffers, posterior_coef_table
 
 OBJECTIVE_NAMES = ("simple", "vlb", "hybrid")
 NOISE_RING_BYTES = 4 << 30      # pre-drawn chain noise is held in a ring of at most this many bytes
+HOST_NOISE_BLOCK = 50           # steps per host-to-device block of pre-drawn noise (copied on a side stream)
 
 
 class SamplingPlan:
@@ -39,6 +40,7 @@ class SamplingPlan:
         self.period = max(1, min(self.T, NOISE_RING_BYTES // per_step))
         self.noise = torch.empty(self.period, B, C, H, W, dtype=torch.float32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.copy_stream = torch.cuda.Stream(device=dev)          # host noise blocks are uploaded here (p_sample_loop)
         self.table_version = None
         self.clip = ddpm.clip_denoised
 
@@ -204,6 +206,30 @@ class DDPM(nn.Module):
             if noise is None:
                 for j in range(chunk):
                     plan.noise[base + j].copy_(torch.randn(shape, device=dev))
+            elif isinstance(noise, torch.Tensor) and not noise.is_cuda and chunk > HOST_NOISE_BLOCK:
+                # host noise: blocks of HOST_NOISE_BLOCK steps go up on a side stream while earlier blocks are consumed
+                # (2.1 GB per C3 chain = ~40 ms of PCIe time that would otherwise sit in front of the first step)
+                main = torch.cuda.current_stream(dev)
+                side = plan.copy_stream
+                side.wait_stream(main)                  # the ring slots being overwritten were consumed by earlier replays
+                events = []
+                for b0 in range(0, chunk, HOST_NOISE_BLOCK):
+                    b1 = min(chunk, b0 + HOST_NOISE_BLOCK)
+                    with torch.cuda.stream(side):
+                        plan.noise[base + b0:base + b1].copy_(noise[1 + done + b0:1 + done + b1], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                    events.append((b0, b1, ev))
+                for b0, b1, ev in events:
+                    main.wait_event(ev)
+                    for _ in range(b1 - b0):
+                        if self.use_graph:
+                            plan.graph.replay()
+                        else:
+                            plan.step_eager()
+                L._Counter.n += chunk * plan.launches_per_step if self.use_graph else 0
+                done += chunk
+                continue
             elif isinstance(noise, torch.Tensor):
                 plan.noise[base:base + chunk].copy_(noise[1 + done:1 + done + chunk], non_blocking=True)
             else:

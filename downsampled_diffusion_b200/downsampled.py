@@ -15,7 +15,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib as L
-from .engine import Act, EngineCache, Program, ensure_lazy
+from .engine import Act, EngineCache, Program, _is_pow2, ensure_lazy
 
 
 class ConvResBlock(nn.Module):
@@ -37,7 +37,10 @@ class _ResampleProgram(Program):
     """Launch list of a ConvResNet / SimpleDownConv / SimpleUpConv for a fixed (B, H, W)."""
 
     def __init__(self, net: nn.Module, B: int, C: int, H: int, W: int, precision: str, tanh: bool):
-        super().__init__(net, B, precision)
+        # 'bf16' (the sampling default) runs the 32/64-channel block convolutions on the tensor cores in TF32 over fp32
+        # activations (dd_conv_tc32, Mish copies written by the producing epilogue); 'fp32' is the CUDA-core validation mode.
+        self.tc = precision != "fp32"
+        super().__init__(net, B, "fp32")
         ensure_lazy()
         self.x_in = self.empty(B, C, H, W, dtype=torch.float32)
         layers = list(net.conv)
@@ -48,10 +51,17 @@ class _ResampleProgram(Program):
             if isinstance(m, ConvResBlock):
                 if m.drop.p > 0 and net.training:
                     raise RuntimeError("Dropout2d in the resampling nets is only supported with p=0 (reference default)")
-                h, _ = self.conv(x, m.c1, kind="1x1", pre_mish=True)
-                h, _ = self.conv(h, m.c2, kind="3x3", pre_mish=True)
-                h, _ = self.conv(h, m.c3, kind="3x3", pre_mish=True)
-                x, _ = self.conv(h, m.c4, kind="1x1", pre_mish=True, residual=x if m.residual else None)
+                if self.tc and self._tc_ok(x, m):
+                    nxt = (i + 1 < len(layers) and isinstance(layers[i + 1], ConvResBlock) and not (m.upsample or m.downsample))
+                    h = self.tc_conv(x, m.c1, "1x1")
+                    h = self.tc_conv(h, m.c2, "3x3")
+                    h = self.tc_conv(h, m.c3, "3x3")
+                    x = self.tc_conv(h, m.c4, "1x1", residual=x if m.residual else None, emit_mish=nxt)
+                else:
+                    h, _ = self.conv(x, m.c1, kind="1x1", pre_mish=True)
+                    h, _ = self.conv(h, m.c2, kind="3x3", pre_mish=True)
+                    h, _ = self.conv(h, m.c3, kind="3x3", pre_mish=True)
+                    x, _ = self.conv(h, m.c4, kind="1x1", pre_mish=True, residual=x if m.residual else None)
                 if m.upsample:
                     y = self.act(x.H * 2, x.W * 2, x.C, B)
                     self.add("dd_upsample_nearest2", L.ptr(x.t), L.ptr(y.t), self.dcode, B, x.H, x.W, x.C)
@@ -100,6 +110,29 @@ class _ResampleProgram(Program):
         if self.out is None:
             raise ValueError("resampling net must end in a plain convolution")
         self.refresh_weights()
+
+    # ---- TF32 tensor-core form of a ConvResBlock convolution (convblocks.py:112-118: conv(mish(x))) ----------------
+    @staticmethod
+    def _tc_ok(x, m) -> bool:
+        chans = (m.c1.in_channels, m.c1.out_channels, m.c4.out_channels)
+        return all(c % 32 == 0 for c in chans) and _is_pow2(x.H) and _is_pow2(x.W) and x.H * x.W >= 16
+
+    def tc_conv(self, x, conv: nn.Conv2d, kind: str, residual=None, emit_mish: bool = True):
+        Cin, Cout, ks = conv.in_channels, conv.out_channels, conv.kernel_size[0]
+        xm = x.mish
+        if xm is None:                      # block input that no epilogue activated (first block, after a resampling step)
+            xm = self.act(x.H, x.W, x.C, x.B)
+            self.add("dd_ew", 0, L.ptr(x.t), None, L.ptr(xm.t), x.t.numel(), 1.0, 0)
+        K = ks * ks * Cin
+        wp = self.packed((Cout, K), torch.float32, lambda buf: buf.copy_(conv.weight.detach().permute(0, 2, 3, 1).reshape(Cout, K)))
+        b_t = self.f32(conv.bias) if conv.bias is not None else None
+        y = self.act(x.H, x.W, Cout, x.B)
+        ym = self.act(x.H, x.W, Cout, x.B) if emit_mish else None
+        self.add("dd_conv_tc32", L.TC_CONV3x3 if ks == 3 else L.TC_CONV1x1, L.ptr(xm.t), None, Cin, 0, L.ptr(wp), Cout,
+                 L.ptr(b_t) if b_t is not None else None, L.ptr(residual.t) if residual is not None else None, L.ptr(y.t),
+                 L.ptr(ym.t) if ym is not None else None, None, x.B, x.H, x.W, Cout)
+        y.mish = ym
+        return y
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self.refresh_weights()

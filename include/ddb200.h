@@ -228,8 +228,10 @@ int dd_s2d_f32(const float* src, float* dst, int B, int h, int w, int C, int to_
 
 /* Channel-major padded copies for the weight-gradient GEMM:  y[s][b][c][h + hpad][w] = x[b][h][w + s - nshift/2][c],
  * fp32, rows Wp (multiple of 32, >= W) wide, zeros outside the map; nshift = 3 bakes the column shifts of a 3x3 filter
- * into three copies (a TMA box origin must be 16-byte aligned), nshift = 1 is the plain copy. */
-int dd_nhwc_to_chw_pad(const float* x, float* y, int B, int C, int H, int W, int Wp, int hpad, int nshift, void* stream);
+ * into three copies (a TMA box origin must be 16-byte aligned), nshift = 1 is the plain copy.
+ * colsum (optional, C floats): += sum over all pixels of x[..][c] -- the bias gradient when x is an output gradient. */
+int dd_nhwc_to_chw_pad(const float* x, float* y, int B, int C, int H, int W, int Wp, int hpad, int nshift, float* colsum,
+                       void* stream);
 
 /* Weight gradient of the same convolutions on the tensor cores (TF32, pixels as the GEMM K dimension):
  *   dw[tap][ci][co] += sum_pixels x[pixel+tap][ci] * dy[pixel][co].

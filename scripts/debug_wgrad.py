@@ -19,8 +19,8 @@ def run(kind, B, C, Cout, H, W, mode):
     xs, dys = x.to(dev), dy.to(dev)
     ns = 3 if taps == 9 else 1
     xd = torch.full((ns, B, C, H + 2, Wp), float("nan"), device=dev); dyd = torch.full((B, Cout, H, Wp), float("nan"), device=dev)
-    L.call("dd_nhwc_to_chw_pad", L.ptr(xs), L.ptr(xd), B, C, H, W, Wp, 1, ns, L.stream())
-    L.call("dd_nhwc_to_chw_pad", L.ptr(dys), L.ptr(dyd), B, Cout, H, W, Wp, 0, 1, L.stream())
+    L.call("dd_nhwc_to_chw_pad", L.ptr(xs), L.ptr(xd), B, C, H, W, Wp, 1, ns, None, L.stream())
+    L.call("dd_nhwc_to_chw_pad", L.ptr(dys), L.ptr(dyd), B, Cout, H, W, Wp, 0, 1, None, L.stream())
     dw = torch.zeros(taps, C, Cout, device=dev)
     L.call("dd_conv_wgrad_tc32", kind, L.ptr(xd), None, C, 0, L.ptr(dyd), L.ptr(dw), B, H, W, Wp, Cout, L.stream())
     torch.cuda.synchronize()
