@@ -60,6 +60,9 @@ SIGNATURES = {
     "dd_unpool2": [_p, _p, _i, _i, _i, _i, _f, _p],
     "dd_conv_tc32": [_i, _p, _p, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "dd_conv_wgrad_tc32": [_i, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p],
+    "dd_conv1x1_thin_in": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "dd_conv1x1_thin_out": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "dd_conv1x1_thin_wgrad": [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p],
     "dd_s2d_f32": [_p, _p, _i, _i, _i, _i, _i, _p],
     "dd_nhwc_to_chw_pad": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "dd_conv_tc": [_i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i64, _p, _i, _p],

@@ -172,7 +172,18 @@ class TrainProgram(Program):
                   and C2 % 32 == 0 and Cout % 32 == 0 and pow2(H) and pow2(W) and H * W >= 16)
         kcode = L.TC_CONV3x3 if ks == 3 else L.TC_CONV1x1
         xm = None
-        if use_tc:
+        thin_w = lambda c: c % 4 == 0 and 4 <= c <= 128 and (c & (c - 1)) == 0
+        plain1x1 = ks == 1 and not transposed and stride == 1 and x2 is None and residual is None and not pre_mish
+        thin_in = plain1x1 and in_nchw is not None and out_nchw is None and not tanh and C1 <= 8 and thin_w(Cout)
+        thin_out = plain1x1 and out_nchw is not None and in_nchw is None and Cout <= 8 and thin_w(C1) and Cout <= C1 // 4
+        if thin_in:        # 3 -> 64 input layer: HBM streaming kernel (K = 3 leaves nothing for a tensor core)
+            thin_wt = self.packed((C1, Cout), torch.float32, lambda buf: buf.copy_(w.detach().reshape(Cout, C1).t()))
+            self.add("dd_conv1x1_thin_in", src, L.ptr(thin_wt), L.ptr(b_t) if b_t is not None else None, L.ptr(y.t), B, H * W, C1, Cout, 0)
+        elif thin_out:     # 64 -> 3 (+tanh) output layer
+            thin_wt = self.packed((Cout, C1), torch.float32, lambda buf: buf.copy_(w.detach().reshape(Cout, C1)))
+            self.add("dd_conv1x1_thin_out", L.ptr(x.t), L.ptr(thin_wt), L.ptr(b_t) if b_t is not None else None, L.ptr(out_nchw), B, H * W,
+                     C1, Cout, 1 if tanh else 0)
+        elif use_tc:
             K = ks * ks * Cin
             wp = self.packed((Cout, K), torch.float32, lambda buf: buf.copy_(w.detach().permute(0, 2, 3, 1).reshape(Cout, K)))
             xin = x
@@ -234,6 +245,16 @@ class TrainProgram(Program):
                 g = self.gy(y)
                 gflags = 0
             M = B * Ho * Wo
+            if thin_in:         # dW (1, Cin, Cout) and the bias gradient from one pass over dY
+                self.add("dd_conv1x1_thin_wgrad", src, L.ptr(g), dw, 1, db, B, H * W, C1, Cout)
+                return
+            if thin_out:        # g is the (tanh-corrected) NCHW output gradient
+                if db is not None:
+                    self.add("dd_colsum", L.ptr(g), db, M, Cout, 1, Ho * Wo)
+                self.add("dd_conv1x1_thin_wgrad", L.ptr(g), L.ptr(x.t), dw, 0, None, B, H * W, Cout, C1)
+                if need_dx:
+                    self.add("dd_conv1x1_thin_in", L.ptr(g), L.ptr(thin_wt), None, L.ptr(self.grad(x)), B, H * W, Cout, C1, self.acc(x))
+                return
             if db is not None and not use_tc:         # tensor-core path: fused into the dY operand copy below
                 self.add("dd_colsum", L.ptr(g), db, M, Cout, 1 if out_nchw is not None else 0, Ho * Wo)
             if use_tc:

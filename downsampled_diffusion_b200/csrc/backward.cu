@@ -398,33 +398,39 @@ __global__ void sincos_emb_kernel(const float* __restrict__ t, const float* __re
     out[(int64_t)r * dim + half + k] = cosf(a);
 }
 
-// nearest x2 backward / avg-pool forward share one kernel shape: y[b,ho,wo,c] = scale * sum of the 2x2 block of x
-__global__ void pool2_sum_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int C, float scale,
+// nearest x2 backward / avg-pool forward share one kernel shape: y[b,ho,wo,c] = scale * sum of the 2x2 block of x.
+// 16-byte vectors along c, 64-bit divisions only once per vector (the scalar form ran at 1.4 TB/s on the 1 GB maps).
+__global__ void pool2_sum_kernel(const float4* __restrict__ x, float4* __restrict__ y, int H, int W, int cv, float scale,
                                  int64_t total) {
     pdl_sync();
     const int Ho = H >> 1, Wo = W >> 1;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        int64_t r = i / C;
+        const int c = (int)(i % cv);
+        int64_t r = i / cv;
         const int wo = (int)(r % Wo); r /= Wo;
         const int ho = (int)(r % Ho);
         const int64_t b = r / Ho;
-        const float* p = x + (((b * H + 2 * ho) * W + 2 * wo) * (int64_t)C) + c;
-        y[i] = scale * (p[0] + p[C] + p[(int64_t)W * C] + p[(int64_t)W * C + C]);
+        const float4* p = x + (((b * H + 2 * ho) * W + 2 * wo) * (int64_t)cv) + c;
+        const float4 a = p[0], bq = p[cv], cq = p[(int64_t)W * cv], d = p[(int64_t)W * cv + cv];
+        y[i] = make_float4(scale * (a.x + bq.x + cq.x + d.x), scale * (a.y + bq.y + cq.y + d.y), scale * (a.z + bq.z + cq.z + d.z),
+                           scale * (a.w + bq.w + cq.w + d.w));
     }
 }
 
-// avg-pool backward / nearest x2 forward: y[b,h,w,c] = scale * x[b,h/2,w/2,c]
-__global__ void unpool2_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int C, float scale, int64_t total) {
+// avg-pool backward / nearest x2 forward: y[b,h,w,c] = scale * x[b,h/2,w/2,c]; one thread per INPUT vector writes its 2x2 block
+__global__ void unpool2_kernel(const float4* __restrict__ x, float4* __restrict__ y, int H, int W, int cv, float scale, int64_t total) {
     pdl_sync();
-    const int Ho = H * 2, Wo = W * 2;
+    const int Wo = W * 2;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        int64_t r = i / C;
-        const int wo = (int)(r % Wo); r /= Wo;
-        const int ho = (int)(r % Ho);
-        const int64_t b = r / Ho;
-        y[i] = scale * x[(((b * H + (ho >> 1)) * W + (wo >> 1)) * (int64_t)C) + c];
+        const int c = (int)(i % cv);
+        int64_t r = i / cv;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int64_t b = r / H;
+        float4 v = x[i];
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        float4* q = y + (((b * (2 * H) + 2 * h) * Wo + 2 * w) * (int64_t)cv) + c;
+        q[0] = v; q[cv] = v; q[(int64_t)Wo * cv] = v; q[(int64_t)Wo * cv + cv] = v;
     }
 }
 
@@ -546,14 +552,16 @@ int dd_sincos_emb(const float* t, const float* freq, float* out, int R, int dim,
 
 int dd_pool2_sum(const float* x, float* y, int B, int H, int W, int C, float scale, void* stream) {
     DD_REQUIRE(H % 2 == 0 && W % 2 == 0, "pool2_sum: odd size");
-    const int64_t total = (int64_t)B * (H / 2) * (W / 2) * C;
-    launch_pdl(pool2_sum_kernel, dim3(grid_cap(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, H, W, C, scale, total);
+    DD_REQUIRE(C % 4 == 0, "pool2_sum: C=%d must be a multiple of 4", C);
+    const int64_t total = (int64_t)B * (H / 2) * (W / 2) * (C / 4);
+    launch_pdl(pool2_sum_kernel, dim3(grid_cap(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)x, (float4*)y, H, W, C / 4, scale, total);
     return check_launch("pool2_sum");
 }
 
 int dd_unpool2(const float* x, float* y, int B, int H, int W, int C, float scale, void* stream) {
-    const int64_t total = (int64_t)B * (H * 2) * (W * 2) * C;
-    launch_pdl(unpool2_kernel, dim3(grid_cap(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, H, W, C, scale, total);
+    DD_REQUIRE(C % 4 == 0, "unpool2: C=%d must be a multiple of 4", C);
+    const int64_t total = (int64_t)B * H * W * (C / 4);
+    launch_pdl(unpool2_kernel, dim3(grid_cap(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)x, (float4*)y, H, W, C / 4, scale, total);
     return check_launch("unpool2");
 }
 

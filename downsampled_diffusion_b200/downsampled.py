@@ -103,9 +103,20 @@ class _ResampleProgram(Program):
             else:
                 y = self.act(Ho, Wo, Cout, B)
                 dst = y.t
-            self.add("dd_conv_direct", L.ptr(self.x_in) if first else L.ptr(x.t), None, Cin, 0,
-                     L.DD_F32 if first else self.dcode, L.ptr(wd), L.ptr(b_t) if b_t is not None else None, None,
-                     L.ptr(dst), self.dcode, B, Hi, Wi, Cout, ks, stride, pad, mode, flags)
+            thin_w = lambda c: c % 4 == 0 and 4 <= c <= 128 and (c & (c - 1)) == 0
+            plain1x1 = ks == 1 and stride == 1 and not transposed
+            if plain1x1 and first and not last and Cin <= 8 and thin_w(Cout):            # 3 -> 64 input layer: HBM streaming kernel
+                wt = self.packed((Cin, Cout), torch.float32, lambda buf, m=m, Cin=Cin, Cout=Cout: buf.copy_(m.weight.detach().reshape(Cout, Cin).t()))
+                self.add("dd_conv1x1_thin_in", L.ptr(self.x_in), L.ptr(wt), L.ptr(b_t) if b_t is not None else None, L.ptr(dst), B, Hi * Wi,
+                         Cin, Cout, 0)
+            elif plain1x1 and last and not first and Cout <= 8 and thin_w(Cin) and Cout <= Cin // 4:     # 64 -> 3 (+tanh) output layer
+                wt = self.packed((Cout, Cin), torch.float32, lambda buf, m=m, Cin=Cin, Cout=Cout: buf.copy_(m.weight.detach().reshape(Cout, Cin)))
+                self.add("dd_conv1x1_thin_out", L.ptr(x.t), L.ptr(wt), L.ptr(b_t) if b_t is not None else None, L.ptr(dst), B, Hi * Wi,
+                         Cin, Cout, 1 if tanh else 0)
+            else:
+                self.add("dd_conv_direct", L.ptr(self.x_in) if first else L.ptr(x.t), None, Cin, 0,
+                         L.DD_F32 if first else self.dcode, L.ptr(wd), L.ptr(b_t) if b_t is not None else None, None,
+                         L.ptr(dst), self.dcode, B, Hi, Wi, Cout, ks, stride, pad, mode, flags)
             x = y
         if self.out is None:
             raise ValueError("resampling net must end in a plain convolution")

@@ -220,6 +220,20 @@ int dd_conv_tc32(int kind, const float* x, const float* x2, int C1, int C2, cons
                  const float* addend, float* y, float* y_mish, const float* mish_grad_of,
                  int B, int H, int W, int Cout, void* stream);
 
+/* 1x1 convolutions with a narrow side (<= 8 channels) -- the 3 -> 64 input layer and the 64 -> 3 (+tanh) output layer of the
+ * resampling nets (convblocks.py:143-156, dddpm.py:92-112) and their gradients: HBM streaming kernels, the narrow operand in the
+ * NCHW fp32 layout of the Python API, the wide one NHWC fp32 (a power-of-two multiple of 4 channels, <= 128).
+ *   thin_in :  y[b][p][c] (+)= sum_s x[b][s][p] * w[s][c] + bias[c]            w: (Cs, Cout)   (forward 3->64; input gradient of 64->3)
+ *   thin_out:  y[b][s][p] = act(sum_c x[b][p][c] * w[s][c] + bias[s])          w: (Cs, Cin)    (forward 64->3, optional tanh)
+ *   thin_wgrad: dw[s][c] += sum_{b,p} narrow[b][s][p] * wide[b][p][c]  ((Cs, Cw) when narrow_major, else (Cw, Cs));
+ *               dbias_wide[c] += sum wide (optional). */
+int dd_conv1x1_thin_in(const float* x_nchw, const float* w, const float* bias, float* y_nhwc, int B, int HW, int Cs, int Cout,
+                       int accumulate, void* stream);
+int dd_conv1x1_thin_out(const float* x_nhwc, const float* w, const float* bias, float* y_nchw, int B, int HW, int Cin, int Cs,
+                        int do_tanh, void* stream);
+int dd_conv1x1_thin_wgrad(const float* narrow_nchw, const float* wide_nhwc, float* dw, int narrow_major, float* dbias_wide,
+                          int B, int HW, int Cs, int Cw, void* stream);
+
 /* fp32 NHWC space-to-depth (to_packed != 0): src (B, 2h, 2w, C) -> dst (B, h, w, 4C), packed channel (py*2+px)*C + c =
  * src[2i+py][2j+px][c]; depth-to-space (to_packed == 0): src packed -> dst full.  With it the stride-2 conv and the
  * transposed conv of the U-Net (blocks.py:35,44) are dense 3x3 stride-1 convolutions for dd_conv_tc32 (zero weight blocks
