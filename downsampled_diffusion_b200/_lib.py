@@ -47,6 +47,7 @@ SIGNATURES = {
     "dd_space_to_depth2": [_p, _p, _i, _i, _i, _i, _p],
     "dd_zero": [_p, _i64, _p],
     "dd_debug_set_timeline": [_p],
+    "dd_debug_set_attn_timeline": [_p],
     "dd_conv_wgrad": [_p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "dd_colsum": [_p, _p, _i64, _i, _i, _i64, _p],
     "dd_dropout": [_p, _p, _i64, C.c_uint32, _f, _p],

@@ -45,26 +45,44 @@ __device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+#ifndef DD_ATTN_TIMELINE
+#define DD_ATTN_TIMELINE 0          // -DDD_ATTN_TIMELINE=1: per-CTA clock64 stamps (scripts/timeline_attn.py)
+#endif
+__device__ long long* g_attn_dbg = nullptr;
+__device__ __forceinline__ void astamp(int slot) {
+    if (DD_ATTN_TIMELINE && g_attn_dbg && threadIdx.x == 0) g_attn_dbg[(blockIdx.x + gridDim.x * blockIdx.y) * 8 + slot] = clock64();
+}
+
 __global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws,
                                                              int* __restrict__ tickets, int n, int heads, int chunk,
                                                              const __nv_bfloat16* __restrict__ Wout, int C,
                                                              __nv_bfloat16* __restrict__ Mb) {
+    astamp(0);
     constexpr int DH = 32;
     const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
     const int S = gridDim.y, sp = blockIdx.y;
     const int HD = heads * DH, C3 = 3 * HD;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    // the projection weights do not depend on the previous kernel: pull this warp's rows of the head's (C x 32) slice
-    // towards the SM while the grid dependency is still pending (the fold at the end is otherwise two exposed L2 trips)
-    for (int c0 = warp * 16; c0 < C; c0 += 128)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(Wout + (int64_t)(c0 + (lane & 15)) * HD + hd * DH + (lane >> 4) * 16));
+    // the projection weights do not depend on the previous kernel: this head's (C x 32) slice is copied to shared memory
+    // (cp.async, 80-byte rows) while the grid dependency is still pending -- in the fold at the end these loads were two
+    // exposed L2 round trips (4600 of the 12 400 clk a CTA lives on the 4x4 maps, scripts/timeline_attn.py)
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __nv_bfloat16* s_w = reinterpret_cast<__nv_bfloat16*>(s_dyn);                  // [C][LM_PITCH]
+    for (int i = threadIdx.x; i < C * 4; i += 256) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_w + (i >> 2) * LM_PITCH + (i & 3) * 8);
+        const __nv_bfloat16* src = Wout + (int64_t)(i >> 2) * HD + hd * DH + (i & 3) * 8;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     pdl_sync();
+    astamp(1);
 
     __shared__ __align__(16) __nv_bfloat16 s_kv[8][2][LM_SLAB][LM_PITCH];     // 40 KB, later reused (fold stage)
     __shared__ float s_ctx[DH][DH + 1];
     __shared__ float s_mw[8][DH];
     __shared__ float s_s[DH], s_M[DH];
+    __shared__ float s_sw[8][DH];                                            // per-warp softmax denominators for the merge
     __shared__ int s_last;
 
     const __nv_bfloat16* kb = qkv + (int64_t)b * n * C3 + HD + hd * DH;      // v = k + HD
@@ -165,7 +183,23 @@ __global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloa
         s_run[i] += __shfl_xor_sync(0xffffffffu, s_run[i], 1);
         s_run[i] += __shfl_xor_sync(0xffffffffu, s_run[i], 2);
     }
-    // ---- merge the 8 warps: CTA max, rescale, shared-memory accumulation
+    astamp(2);
+    __nv_bfloat16 (*s_cb)[LM_PITCH] = reinterpret_cast<__nv_bfloat16 (*)[LM_PITCH]>(&s_kv[0][0][0][0]);      // bf16 [d][e] for the fold
+    const bool single = (S == 1) && (n_hi - n_lo <= LM_SLAB);         // only warp 0 had rows (4x4 maps): nothing to merge
+    if (single) {
+        if (warp == 0) {
+            __syncwarp();                                               // the slab's ldmatrix reads are done: s_cb aliases it
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float i0 = 1.f / s_run[mt * 2], i1 = 1.f / s_run[mt * 2 + 1];
+                    *reinterpret_cast<uint32_t*>(&s_cb[mt * 16 + g][nt * 8 + 2 * t]) = pack_bf2(acc[mt][nt][0] * i0, acc[mt][nt][1] * i0);
+                    *reinterpret_cast<uint32_t*>(&s_cb[mt * 16 + g + 8][nt * 8 + 2 * t]) = pack_bf2(acc[mt][nt][2] * i1, acc[mt][nt][3] * i1);
+                }
+        }
+    } else {
+    // ---- merge the 8 warps: CTA max, rescale, per-warp partials parked in shared memory, summed by all threads
     if (t == 0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) s_mw[warp][g + 8 * i] = m_run[i];
@@ -180,20 +214,23 @@ __global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloa
         f_own[i] = (m_run[i] == -INFINITY) ? 0.f : __expf(m_run[i] - M);       // a warp without rows contributes nothing
         if (warp == 0 && t == 0) s_M[g + 8 * i] = M;
     }
-    // each warp parks its rescaled partial in its own (now idle) slab: [32][33] context + 32 sums, then a tree-free
-    // sum over the 8 warps (shared-memory float atomics would be CAS loops under 8-way contention)
-    float* my = reinterpret_cast<float*>(&s_kv[warp][0][0][0]);          // 5120 B per warp >= (32*33 + 32) * 4
+    // each warp parks its rescaled partial in its own (now idle) slab as [32][40] floats, 8-byte stores (conflict free per
+    // half warp; the first version's scalar stores at pitch 33 were 4-way conflicted), then a tree-free sum over the 8 warps
+    // (shared-memory float atomics would be CAS loops under 8-way contention)
+    float* my = reinterpret_cast<float*>(&s_kv[warp][0][0][0]);          // 5120 B per warp = 32 * 40 * 4
     __syncwarp();
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                my[(mt * 16 + g + 8 * (j >> 1)) * 33 + nt * 8 + 2 * t + (j & 1)] = acc[mt][nt][j] * f_own[mt * 2 + (j >> 1)];
+        for (int nt = 0; nt < 4; ++nt) {
+            *reinterpret_cast<float2*>(&my[(mt * 16 + g) * 40 + nt * 8 + 2 * t]) =
+                make_float2(acc[mt][nt][0] * f_own[mt * 2], acc[mt][nt][1] * f_own[mt * 2]);
+            *reinterpret_cast<float2*>(&my[(mt * 16 + g + 8) * 40 + nt * 8 + 2 * t]) =
+                make_float2(acc[mt][nt][2] * f_own[mt * 2 + 1], acc[mt][nt][3] * f_own[mt * 2 + 1]);
+        }
     if (t == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) my[32 * 33 + g + 8 * i] = s_run[i] * f_own[i];
+        for (int i = 0; i < 4; ++i) s_sw[warp][g + 8 * i] = s_run[i] * f_own[i];
     }
     __syncthreads();
     {
@@ -205,12 +242,12 @@ __global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloa
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int i = threadIdx.x + 256 * k;
-                part[k] += w0[w * WSTRIDE + (i >> 5) * 33 + (i & 31)];
+                part[k] += w0[w * WSTRIDE + (i >> 5) * 40 + (i & 31)];
             }
         float ssum = 0.f;
         if (threadIdx.x < DH) {
 #pragma unroll
-            for (int w = 0; w < 8; ++w) ssum += w0[w * WSTRIDE + 32 * 33 + threadIdx.x];
+            for (int w = 0; w < 8; ++w) ssum += s_sw[w][threadIdx.x];
         }
         __syncthreads();                                                 // slab memory is reused below
 #pragma unroll
@@ -222,8 +259,8 @@ __global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloa
     }
     __syncthreads();
 
+    astamp(3);
     // normalised context as bf16 [d][e] (pitch 40) for the fold; reuses the slab memory
-    __nv_bfloat16 (*s_cb)[LM_PITCH] = reinterpret_cast<__nv_bfloat16 (*)[LM_PITCH]>(&s_kv[0][0][0][0]);
     float* s_fac = reinterpret_cast<float*>(&s_kv[1][0][0][0]);              // [S][32] split factors, then 1/total at [16][32]
     if (S == 1) {
         for (int i = threadIdx.x; i < DH * DH; i += 256) {
@@ -243,7 +280,10 @@ __global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloa
             __threadfence();                              // acquire side for the reads below
         }
         __syncthreads();
-        if (!s_last) return;
+        if (!s_last) {
+            asm volatile("cp.async.wait_all;" ::: "memory");        // no copy may be in flight when the CTA retires
+            return;
+        }
         const float* w0 = ws + (int64_t)bh * S * LA_WS;
         if (threadIdx.x < DH) {
             const int d = threadIdx.x;
@@ -265,8 +305,11 @@ __global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloa
             s_cb[d][e] = __float2bfloat16_rn(o * s_fac[16 * DH + d]);
         }
     }
+    }   // !single
+    asm volatile("cp.async.wait_group 0;" ::: "memory");       // this thread's share of the weight slice has landed
     __syncthreads();
 
+    astamp(4);
     // ---- projection fold: Mb[c][hd*32 + d] = sum_e Wout[c][hd*32 + e] * ctx[d][e]   (M = c, N = d, K = e)
     uint32_t bf[2][4][2];
 #pragma unroll
@@ -276,18 +319,17 @@ __global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloa
             bf[ks][nt][0] = *reinterpret_cast<const uint32_t*>(&s_cb[nt * 8 + g][ks * 16 + 2 * t]);
             bf[ks][nt][1] = *reinterpret_cast<const uint32_t*>(&s_cb[nt * 8 + g][ks * 16 + 2 * t + 8]);
         }
-    const __nv_bfloat16* wh = Wout + hd * DH;
     __nv_bfloat16* mb = Mb + (int64_t)b * C * HD + hd * DH;
     for (int c0 = warp * 16; c0 < C; c0 += 128) {
         uint32_t aw[2][4];
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            const __nv_bfloat16* p0 = wh + (int64_t)(c0 + g) * HD + ks * 16 + 2 * t;
-            const __nv_bfloat16* p1 = p0 + 8 * HD;
-            aw[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(p0));
-            aw[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(p1));
-            aw[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 8));
-            aw[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(p1 + 8));
+            const __nv_bfloat16* p0 = s_w + (c0 + g) * LM_PITCH + ks * 16 + 2 * t;
+            const __nv_bfloat16* p1 = p0 + 8 * LM_PITCH;
+            aw[ks][0] = *reinterpret_cast<const uint32_t*>(p0);
+            aw[ks][1] = *reinterpret_cast<const uint32_t*>(p1);
+            aw[ks][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+            aw[ks][3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
@@ -298,6 +340,7 @@ __global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloa
             *reinterpret_cast<uint32_t*>(mb + (int64_t)(c0 + g + 8) * HD + nt * 8 + 2 * t) = pack_bf2(o[2], o[3]);
         }
     }
+    astamp(5);
 }
 
 }  // namespace dd
@@ -305,6 +348,11 @@ __global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloa
 using namespace dd;
 
 extern "C" {
+
+int dd_debug_set_attn_timeline(long long* buf) {
+    cudaError_t e = cudaMemcpyToSymbol(g_attn_dbg, &buf, sizeof(buf));
+    return e == cudaSuccess ? DD_OK : DD_ERR_CUDA;
+}
 
 int64_t dd_linattn_mix_ws_floats(int B, int n, int heads) {
     const int chunk = lm_chunk(n);
@@ -320,7 +368,15 @@ int dd_linattn_mix(const void* qkv, int dtype, int B, int n, int heads, int dh, 
     const int S = (n + chunk - 1) / chunk;
     DD_REQUIRE(ws != nullptr && ws_floats >= dd_linattn_mix_ws_floats(B, n, heads), "linattn_mix: workspace too small");
     int* tickets = reinterpret_cast<int*>(ws + (int64_t)B * heads * S * LA_WS);
-    launch_pdl(linattn_ctxmix_kernel, dim3(B * heads, S), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)qkv, ws,
+    const size_t dyn = (size_t)C * LM_PITCH * sizeof(__nv_bfloat16);          // this head's (C x 32) projection slice, 80-byte rows
+    DD_REQUIRE(dyn <= 96 * 1024, "linattn_mix: C=%d too large for the shared-memory weight slice", C);
+    static size_t dyn_set = 0;
+    if (dyn > dyn_set) {
+        cudaError_t e = cudaFuncSetAttribute(linattn_ctxmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) { set_error("linattn_mix: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
+        dyn_set = dyn;
+    }
+    launch_pdl(linattn_ctxmix_kernel, dim3(B * heads, S), dim3(256), dyn, (cudaStream_t)stream, (const __nv_bfloat16*)qkv, ws,
                tickets, n, heads, chunk, (const __nv_bfloat16*)Wout_bf16, C, (__nv_bfloat16*)Mb_bf16);
     return check_launch("linattn_mix");
 }

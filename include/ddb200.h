@@ -296,6 +296,9 @@ int dd_unpool2(const float* x, float* y, int B, int H, int W, int C, float scale
 /* Debug only: when buf != NULL every dd_conv_tc CTA writes 8 clock64() stamps (start, prologue done, dependency
  * wait done, first operands landed, last MMA issued, accumulator visible, epilogue done) to buf[cta*8 + i]. */
 int dd_debug_set_timeline(long long* buf);
+/* Same for dd_linattn_mix (6 stamps per CTA: start, dependency resolved, context done, warps merged, context normalised, end);
+ * only instrumented builds (-DDD_ATTN_TIMELINE=1) write them. */
+int dd_debug_set_attn_timeline(long long* buf);
 
 /* cudaMemsetAsync(ptr, 0, bytes): clears the GroupNorm {sum,sumsq} arena once per U-Net step. */
 int dd_zero(void* ptr, int64_t bytes, void* stream);

@@ -285,3 +285,87 @@ def test_tf32_training_objective_and_gradients(cuda, golden):
         assert abs(got - r) <= 2e-2 * max(r, 1e-6) + 1e-5, f"{n}: |grad| {got} vs reference {r}"
     g = m.latent_model.final_conv[1].weight.grad
     assert tc.rel_l2(g, G(golden, f"loss.{kind}.grad.latent_model.final_conv.1.weight")) < 1e-2
+
+
+# ---- kernel-level checks of the training-path entry points added with the tensor-core path ---------------------
+
+def test_conv_tc32_fused_epilogue(cuda):
+    """dd_conv_tc32: y = (conv + bias) * mish'(z) + addend and y_mish = mish(y), on both TF32 kernels (halo form: 3x3 32->32
+    on a 16x16 map; generic persistent form: 1x1 64->32 and a two-n-tile 3x3)."""
+    from downsampled_diffusion_b200 import _lib as L
+    for (ks, Cin, Cout, H, W, B) in ((3, 32, 32, 16, 16, 3), (1, 64, 32, 32, 32, 2), (3, 64, 256, 8, 8, 5)):
+        x, w, b = tc.randn(1, B, Cin, H, W), tc.randn(2, Cout, Cin, ks, ks) * 0.1, tc.randn(3, Cout)
+        z, add = tc.randn(4, B, Cout, H, W), tc.randn(5, B, Cout, H, W)
+        ref = F.conv2d(x, w, b, padding=ks // 2)
+        zz = z.clone().requires_grad_(True)
+        F.mish(zz).sum().backward()                                  # mish'(z)
+        ref = ref * zz.grad + add
+        nh = lambda t: t.permute(0, 2, 3, 1).contiguous().to(cuda)
+        xd, zd, ad = nh(x), nh(z), nh(add)
+        wp = w.permute(0, 2, 3, 1).reshape(Cout, ks * ks * Cin).contiguous().to(cuda)
+        bd = b.to(cuda)
+        y = torch.empty(B, H, W, Cout, device=cuda)
+        ym = torch.empty_like(y)
+        L.call("dd_conv_tc32", L.TC_CONV3x3 if ks == 3 else L.TC_CONV1x1, L.ptr(xd), None, Cin, 0, L.ptr(wp), Cout, L.ptr(bd), L.ptr(ad),
+               L.ptr(y), L.ptr(ym), L.ptr(zd), B, H, W, Cout, L.stream())
+        assert tc.rel_l2(y.permute(0, 3, 1, 2), ref) < 2e-3, (ks, Cin, Cout)
+        assert tc.rel_l2(ym.permute(0, 3, 1, 2), F.mish(y.permute(0, 3, 1, 2).cpu())) < 1e-5
+
+
+def test_thin_conv_kernels(cuda):
+    """3 -> 64 / 64 -> 3 layers of the resampling nets: forward, tanh, weight gradient (both layouts), bias gradient."""
+    from downsampled_diffusion_b200 import _lib as L
+    B, H, W, Cs, Cw = 3, 16, 32, 3, 64
+    xn, w, b = tc.randn(1, B, Cs, H, W), tc.randn(2, Cw, Cs) * 0.3, tc.randn(3, Cw)
+    y = torch.empty(B, H, W, Cw, device=cuda)
+    xnd, wtd, bd = xn.to(cuda), w.t().contiguous().to(cuda), b.to(cuda)          # named: raw pointers do not keep temporaries alive
+    L.call("dd_conv1x1_thin_in", L.ptr(xnd), L.ptr(wtd), L.ptr(bd), L.ptr(y), B, H * W, Cs, Cw, 0, L.stream())
+    ref = F.conv2d(xn, w.view(Cw, Cs, 1, 1), b)
+    assert tc.rel_l2(y.permute(0, 3, 1, 2), ref) < 1e-6
+    L.call("dd_conv1x1_thin_in", L.ptr(xnd), L.ptr(wtd), None, L.ptr(y), B, H * W, Cs, Cw, 1, L.stream())
+    assert tc.rel_l2(y.permute(0, 3, 1, 2), 2 * ref - b.view(1, -1, 1, 1)) < 1e-6            # accumulate, no bias
+    xw, w2, b2 = tc.randn(4, B, Cw, H, W), tc.randn(5, Cs, Cw) * 0.2, tc.randn(6, Cs)
+    xwd = xw.permute(0, 2, 3, 1).contiguous().to(cuda)
+    w2d, b2d = w2.to(cuda), b2.to(cuda)
+    for do_tanh in (0, 1):
+        yo = torch.empty(B, Cs, H, W, device=cuda)
+        L.call("dd_conv1x1_thin_out", L.ptr(xwd), L.ptr(w2d), L.ptr(b2d), L.ptr(yo), B, H * W, Cw, Cs, do_tanh, L.stream())
+        r = F.conv2d(xw, w2.view(Cs, Cw, 1, 1), b2)
+        assert tc.rel_l2(yo, torch.tanh(r) if do_tanh else r) < 1e-5
+    g = tc.randn(7, B, Cs, H, W)                                            # narrow operand (NCHW), wide operand xw (NHWC)
+    want = torch.einsum("bshw,bchw->sc", g.double(), xw.double()).float()
+    gd = g.to(cuda)
+    for narrow_major in (1, 0):
+        dw = torch.zeros(Cs, Cw, device=cuda) if narrow_major else torch.zeros(Cw, Cs, device=cuda)
+        db = torch.zeros(Cw, device=cuda)
+        L.call("dd_conv1x1_thin_wgrad", L.ptr(gd), L.ptr(xwd), L.ptr(dw), narrow_major, L.ptr(db), B, H * W, Cs, Cw, L.stream())
+        assert tc.rel_l2(dw if narrow_major else dw.t(), want) < 1e-5
+        assert tc.rel_l2(db, xw.sum((0, 2, 3))) < 1e-5
+
+
+def test_operand_copies_and_space_to_depth(cuda):
+    from downsampled_diffusion_b200 import _lib as L
+    B, H, W, C = 2, 8, 16, 32
+    x = tc.randn(1, B, H, W, C)
+    xd = x.to(cuda)
+    Wp = 32
+    y = torch.full((3, B, C, H + 2, Wp), float("nan"), device=cuda)
+    cs = torch.zeros(C, device=cuda)
+    L.call("dd_nhwc_to_chw_pad", L.ptr(xd), L.ptr(y), B, C, H, W, Wp, 1, 3, L.ptr(cs), L.stream())
+    ref = torch.zeros(3, B, C, H + 2, Wp)
+    xc = x.permute(0, 3, 1, 2)
+    for s in range(3):
+        for wcol in range(Wp):                  # a shifted copy may carry x[W-1] into the first padding column: it meets a zero of dY
+            src = wcol + s - 1
+            if 0 <= src < W:
+                ref[s, :, :, 1:H + 1, wcol] = xc[:, :, :, src]
+    assert torch.equal(y.cpu(), ref)
+    assert tc.rel_l2(cs, x.sum((0, 1, 2))) < 1e-5
+    full = tc.randn(2, B, 2 * H, 2 * W, C).to(cuda)
+    packed = torch.empty(B, H, W, 4 * C, device=cuda)
+    L.call("dd_s2d_f32", L.ptr(full), L.ptr(packed), B, H, W, C, 1, L.stream())
+    want = torch.stack([full[:, py::2, px::2, :] for py in (0, 1) for px in (0, 1)], dim=3).reshape(B, H, W, 4 * C)
+    assert torch.equal(packed, want)
+    back = torch.empty_like(full)
+    L.call("dd_s2d_f32", L.ptr(packed), L.ptr(back), B, H, W, C, 0, L.stream())
+    assert torch.equal(back, full)
