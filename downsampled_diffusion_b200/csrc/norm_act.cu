@@ -139,22 +139,25 @@ __global__ void __launch_bounds__(256) gn_mish_sum_kernel(const float* __restric
                                                           const int32_t* __restrict__ trow, int trow_stride,
                                                           const __nv_bfloat16* __restrict__ residual) {
     pdl_sync();
-    extern __shared__ float4 s_x[];                        // HW*C/4 summed vectors
+    extern __shared__ float4 s_x[];                        // this CTA's summed vectors: HW * (C/4) / gridDim.y
     __shared__ float s_stat[64][2];
-    const int b = blockIdx.x, cv = C >> 2, nvec = HW * cv;
-    const int c4 = threadIdx.x % cv, c = c4 * 4, cpg = C / G, g = c / cpg;
+    // grid (B, parts): a CTA owns C/parts channels (whole groups) of one image -- one CTA per image left the 4x4 layers with
+    // 64 CTAs on 148 SMs and every load latency exposed
+    const int b = blockIdx.x, cv = C >> 2, cvp = cv / gridDim.y, nloc = HW * cvp;
+    const int c4 = blockIdx.y * cvp + threadIdx.x % cvp, c = c4 * 4, cpg = C / G, g = c / cpg;
     if (threadIdx.x < 2 * G) (&s_stat[0][0])[threadIdx.x] = 0.f;
     __syncthreads();
-    const float4* src = reinterpret_cast<const float4*>(part) + (int64_t)b * nvec;
+    const float4* src = reinterpret_cast<const float4*>(part) + (int64_t)b * HW * cv;
     const float4 bi = bias ? __ldg(reinterpret_cast<const float4*>(bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     float sum = 0.f, sq = 0.f;
-    for (int v = threadIdx.x; v < nvec; v += 256) {
+    for (int vl = threadIdx.x; vl < nloc; vl += 256) {
+        const int v = (vl / cvp) * cv + c4;                 // vector index inside the image
         float4 a = bi;
         for (int s = 0; s < S; ++s) {
             const float4 t = __ldcg(src + s * (split_stride >> 2) + v);
             a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
         }
-        s_x[v] = a;
+        s_x[vl] = a;
         sum += a.x + a.y + a.z + a.w;
         sq += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
     }
@@ -178,13 +181,14 @@ __global__ void __launch_bounds__(256) gn_mish_sum_kernel(const float* __restric
     const float sc[4] = {ga.x * rstd, ga.y * rstd, ga.z * rstd, ga.w * rstd};
     const float sh[4] = {be.x - mean * sc[0], be.y - mean * sc[1], be.z - mean * sc[2], be.w - mean * sc[3]};
     const float tbv[4] = {tb.x, tb.y, tb.z, tb.w};
-    for (int v = threadIdx.x; v < nvec; v += 256) {
-        const float4 a = s_x[v];
+    for (int vl = threadIdx.x; vl < nloc; vl += 256) {
+        const int v = (vl / cvp) * cv + c4;
+        const float4 a = s_x[vl];
         const float xin[4] = {a.x, a.y, a.z, a.w};
         float h[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) h[j] = mish_fast(fmaf(xin[j], sc[j], sh[j])) + tbv[j];
-        const int64_t off = ((int64_t)b * nvec + v) * 4;
+        const int64_t off = ((int64_t)b * HW * cv + v) * 4;
         if (residual) {
             const uint2 rr = *reinterpret_cast<const uint2*>(residual + off);
             h[0] += __uint_as_float(rr.x << 16); h[1] += __uint_as_float(rr.x & 0xffff0000u);
@@ -520,7 +524,10 @@ int dd_gn_mish_sum(const float* part, int S, const float* bias, void* y_bf16, in
         cudaFuncSetAttribute(gn_mish_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4);
         attr_done = true;
     }
-    launch_pdl(gn_mish_sum_kernel, dim3(B), dim3(256), (size_t)HW * C * 4, (cudaStream_t)stream, part, S, (int64_t)B * HW * C, bias,
+    int parts = 1;
+    for (int pt = 4; pt > 1; pt >>= 1)
+        if (G % pt == 0 && cv % pt == 0 && 256 % (cv / pt) == 0) { parts = pt; break; }
+    launch_pdl(gn_mish_sum_kernel, dim3(B, parts), dim3(256), (size_t)HW * C * 4 / parts, (cudaStream_t)stream, part, S, (int64_t)B * HW * C, bias,
                (__nv_bfloat16*)y_bf16, HW, C, G, eps, gamma, beta, tbias, tb_stride, trow, trow_stride, (const __nv_bfloat16*)residual_bf16);
     return check_launch("gn_mish_sum");
 }
