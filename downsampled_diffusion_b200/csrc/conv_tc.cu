@@ -1315,7 +1315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc32_persist_kernel(const 
 // ---------------------------------------------------------------------------------------------
 constexpr int H32_RING = 4;
 constexpr int H32_W_MAX = 9 * 64 * 32 * 4;                                  // resident weights: Cin <= 64, 32 output channels
-constexpr int H32_SMEM = H32_W_MAX + H32_RING * HALO_SLOT + 1024 + 2048;
+constexpr int H32_SMEM = H32_W_MAX + H32_RING * HALO_SLOT + 1024 + 2048 + 4 * 32 * 36 * 4;
 constexpr int H32_BN = 32;
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc32_halo_kernel(const __grid_constant__ TcParams p) {
@@ -1331,6 +1331,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc32_halo_kernel(const __g
     const uint32_t tmem_ptr_addr = bars + 8u * (2 * H32_RING + 5);
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
     float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 1024u - smem_u32(smem_raw)));      // [2][32]
+    float* s_stage = reinterpret_cast<float*>(smem_raw + (bars + 2048u - smem_u32(smem_raw)));     // [4 warps][32][36] epilogue transpose
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunks = p.chunks0;                           // 32-channel chunks (single source)
@@ -1413,28 +1414,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc32_halo_kernel(const __g
             __syncwarp();
         }
     } else if (warp < 6) {
-        // ===== epilogue (as in conv_tc32_persist_kernel, 16 x 8 tile geometry) =====
-        const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 64;
+        // ===== epilogue: TMEM row per lane -> warp-private shared-memory transpose -> coalesced fp32 NHWC I/O =====
+        // A lane owns one pixel's 32 channels after the TMEM load; written that way every 16-byte store of a warp lands in a
+        // different 128-byte row (and the fused operands are gathered the same way).  Through a [32][36]-float staging tile the
+        // warp instead moves (4 pixels x 128 bytes) per instruction: lanes 8k..8k+7 cover one pixel's row.
+        const int q = warp & 3, et = threadIdx.x - 64;
         float* yout = reinterpret_cast<float*>(p.out);
         float* yout2 = p.out2;
         const float* addp = reinterpret_cast<const float*>(p.residual);
         const float* mgp = p.mgrad;
         const int cbase = n_tile * H32_BN;
+        float* stg = s_stage + q * (32 * 36);
         if (et < H32_BN) { s_bias[et] = p.bias ? p.bias[cbase + et] : 0.f; }
         epi_bar();
+        const int c4 = lane & 7, prow = lane >> 3;          // transposed view: this lane's 4 channels, its pixel within a group of 4
+        const float4 bv = *reinterpret_cast<const float4*>(s_bias + 4 * c4);
         int it = 0;
         for (int m = m_first; m < m_tiles; m += m_step, ++it) {
             const int ab = it & 1;
             const int w0 = (m % p.tiles_w) * HALO_TW, h0 = ((m / p.tiles_w) % p.tiles_h) * HALO_TH, n0 = m / (p.tiles_w * p.tiles_h);
-            const int64_t off = (((int64_t)n0 * p.H + (h0 + (r >> 3))) * p.W + (w0 + (r & 7))) * p.Cout + cbase;
+            // tile rows q*32 + 4i + prow, i = 0..7: image row h0 + 4q + (4i + prow) / 8, column w0 + (4i + prow) % 8
+            int64_t off[8];
             float4 ad[8], zg[8];
-            if (addp) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) ad[j] = reinterpret_cast<const float4*>(addp + off)[j];
-            }
-            if (mgp) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) zg[j] = reinterpret_cast<const float4*>(mgp + off)[j];
+            for (int i = 0; i < 8; ++i) {
+                const int rr = 4 * i + prow;
+                off[i] = (((int64_t)n0 * p.H + (h0 + 4 * q + (rr >> 3))) * p.W + (w0 + (rr & 7))) * p.Cout + cbase + 4 * c4;
+                if (addp) ad[i] = *reinterpret_cast<const float4*>(addp + off[i]);
+                if (mgp) zg[i] = *reinterpret_cast<const float4*>(mgp + off[i]);
             }
             mbar_wait(tfull_bar(ab), (it >> 1) & 1);
             tc_fence_after();
@@ -1443,16 +1450,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc32_halo_kernel(const __g
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(tempty_bar(ab));            // the accumulator is in registers: release the buffer before the stores
+            __syncwarp();                           // the previous tile's transposed reads of the staging tile are done
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 v = make_float4(__uint_as_float(acc[4 * j]) + s_bias[4 * j], __uint_as_float(acc[4 * j + 1]) + s_bias[4 * j + 1],
-                                       __uint_as_float(acc[4 * j + 2]) + s_bias[4 * j + 2], __uint_as_float(acc[4 * j + 3]) + s_bias[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(stg + lane * 36 + 4 * j) = make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + prow) * 36 + 4 * c4);
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                 if (mgp) {
-                    v.x *= mish_grad_fast(zg[j].x); v.y *= mish_grad_fast(zg[j].y); v.z *= mish_grad_fast(zg[j].z); v.w *= mish_grad_fast(zg[j].w);
+                    v.x *= mish_grad_fast(zg[i].x); v.y *= mish_grad_fast(zg[i].y); v.z *= mish_grad_fast(zg[i].z); v.w *= mish_grad_fast(zg[i].w);
                 }
-                if (addp) { v.x += ad[j].x; v.y += ad[j].y; v.z += ad[j].z; v.w += ad[j].w; }
-                reinterpret_cast<float4*>(yout + off)[j] = v;
-                if (yout2) reinterpret_cast<float4*>(yout2 + off)[j] = make_float4(mish_fast(v.x), mish_fast(v.y), mish_fast(v.z), mish_fast(v.w));
+                if (addp) { v.x += ad[i].x; v.y += ad[i].y; v.z += ad[i].z; v.w += ad[i].w; }
+                *reinterpret_cast<float4*>(yout + off[i]) = v;
+                if (yout2) *reinterpret_cast<float4*>(yout2 + off[i]) = make_float4(mish_fast(v.x), mish_fast(v.y), mish_fast(v.z), mish_fast(v.w));
             }
         }
     }
