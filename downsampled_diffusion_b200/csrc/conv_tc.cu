@@ -33,7 +33,7 @@ constexpr int TC_TMEM_COLS = 128;
 
 struct TcParams {
     CUtensorMap tmA0, tmA1, tmB;
-    CUtensorMap tmB3;            // weights as (c, row, tap): one box = a filter row of three taps (8x8 halo form)
+    CUtensorMap tmB3;            // fp32 weights as (c, row, tap): one box = all nine taps of a 32-channel chunk (conv_tc32_halo_kernel)
     CUtensorMap tmH0, tmH1;      // halo boxes (64 ch, tw+2, th+2, 1, 1) of source 0 / 1 (halo kernel only)
     int8_t tap_dw[16], tap_dh[16], tap_plane[16];
     int ntaps;              // taps per phase
@@ -46,9 +46,7 @@ struct TcParams {
     int G, cpg_mask, cpg_shift;
     int tw_sh, th_sh;           // log2(tw), log2(th): tile geometry is all powers of two
     int rows_valid;             // tw*th*tn (< 128 when one image has fewer than 128 pixels and tn is forced to 1)
-    int interleave;             // 8x8 halo variant: GEMM row r = (h = r >> 4, image = (r >> 3) & 1, w = r & 7)
     int w_per_sample;           // weights are (B, rows, K): every image multiplies its own matrix (fused attention output)
-    int exp_shift, exp_bo;      // experiment: A tile placed exp_shift rows (128 B) past the 1024-B aligned slot; base_offset on/off
     int splits, kb_per_split;   // split-K over the (tap, chunk) loop; partial sums meet in splitk_ws
     void* out;
     const float* bias;
@@ -211,7 +209,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
             const int c0 = cbase + ch;
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += s_bias[ch + j];
-            if (p.gn_stats && !(p.exp_bo & 4)) {
+            if (p.gn_stats) {
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     float s8 = 0.f, q8 = 0.f;
@@ -235,7 +233,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
                     }
                 }
             }
-            if (valid && !(p.exp_bo & 2)) {
+            if (valid) {
                 if (p.out_nchw_f32) {
                     float* o = reinterpret_cast<float*>(p.out);
                     const int64_t hw = (int64_t)Ho * Wo;
@@ -304,8 +302,7 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
     const int rps = p.tw * p.th;                       // rows of this tile that belong to one image
     const int pitch = bn * 2 + 16;                     // bytes; +16 keeps 16-byte row accesses conflict free
     if (et < bn) s_bias[et] = (p.bias && cbase + et < p.Cout) ? p.bias[cbase + et] : 0.f;
-    const bool il = p.interleave != 0;
-    const bool valid = (n0 + (il ? ((r >> 3) & 1) : (r >> (p.tw_sh + p.th_sh)))) < p.B && r < p.rows_valid;
+    const bool valid = (n0 + (r >> (p.tw_sh + p.th_sh))) < p.B && r < p.rows_valid;
     const bool do_stats = p.gn_stats != nullptr;
     epi_bar();
     mbar_wait(tmem_full_bar, 0);
@@ -374,10 +371,8 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
             const int gl = o & ((1 << ng_sh) - 1), sl = o >> ng_sh;
             float sa0 = 0.f, qa0 = 0.f, sa1 = 0.f, qa1 = 0.f;
             if (act) {
-                // rows of sample sl: contiguous, or (interleaved) 8-row groups alternating between the two images
-                const int rbase = il ? (8 * sl + (l16 & 7) + 16 * (l16 >> 3)) : ((sl << rps_sh2) + l16);
-                const int rs = il ? 32 : 16;                                // row stride between a lane's rows
-                const float* ps = s_part + (2 * (gl * spg)) * TC_BM + rbase;
+                constexpr int rs = 16;                                      // row stride between a lane's rows
+                const float* ps = s_part + (2 * (gl * spg)) * TC_BM + (sl << rps_sh2) + l16;
                 const int cnt = rps >> 4;                                   // rows per lane (0 when rps < 16)
                 for (int k = 0; k < spg; ++k, ps += 2 * TC_BM) {
                     if (cnt == 0) { if (l16 < rps) { sa0 += ps[0]; qa0 += ps[TC_BM]; } continue; }
@@ -422,9 +417,9 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int row = row0 + u * row_step;
-            const int n = n0 + (il ? ((row >> 3) & 1) : (row >> rps_sh));
+            const int n = n0 + (row >> rps_sh);
             ok[u] = row < TC_BM && row < rows_valid && n < Bn;
-            const int ww = row & (p.tw - 1), hh = il ? (row >> 4) : ((row >> p.tw_sh) & (p.th - 1));
+            const int ww = row & (p.tw - 1), hh = (row >> p.tw_sh) & (p.th - 1);
             const int oh = (h0 + hh) * mul + py, ow = (w0 + ww) * mul + px;
             off[u] = (((int64_t)n * Ho + oh) * Wo + ow) * Cout + cbase + pc * 8;
             if (ok[u]) {
@@ -654,39 +649,14 @@ constexpr int HALO_SLOT = (HALO_TX + 1023) / 1024 * 1024;           // 23552
 constexpr int HALO_NH = 2, HALO_NB = 4;
 constexpr int HALO_B_BYTES = 128 * TC_BK * 2;
 constexpr int HALO_SMEM = HALO_NH * HALO_SLOT + HALO_NB * HALO_B_BYTES + 1024 + 1024;
-constexpr int HALO8_TX = 2 * 10 * 10 * TC_BK * 2;                   // 8x8 maps: (10 x 2 images x 10) halo rows, 25600 bytes
-constexpr int HALO8_SLOT = (HALO8_TX + 1023) / 1024 * 1024;         // 26624
-constexpr int HALO8_B_RING = 160 * 1024;                            // weight ring of the 8x8 form (1 CTA per SM)
-constexpr int HALO8_SMEM = HALO_NH * HALO8_SLOT + HALO8_B_RING + 1024 + 1024;
-
-// NT = output tiles per CTA.  NT = 2 ("dual tile"): the two halo slots hold the halos of two consecutive tiles of the
-// SAME 64-channel chunk (single-buffered), every weight tile is loaded once and multiplied into two TMEM accumulators:
-// weight traffic per output pixel halves.  These layers sit on the L2 -> SM throughput cap (~6.3 KB/clk chip-wide),
-// 85 % of their operand bytes being weight re-reads (profiles/README.md), and the grid becomes a single wave.
-// PERM = the 8x8-map form: a tile is all 64 pixels of TWO images.  The halo box is taken from a (C, W, N, H) view of
-// the activation, i.e. it lands as rows (h, image, w) -- 10 x 2 x 10 -- so that the 8-pixel row groups of the tile
-// (row h of image 0, row h of image 1, row h+1 of image 0, ...) are a uniform 10 smem rows apart and ONE M=128 UMMA
-// descriptor covers both images; a filter row further down is 20 smem rows on.
-template <int NT, bool PERM>
-__global__ void __launch_bounds__(TC_THREADS, PERM ? 1 : 2) conv_tc_halo_kernel(const __grid_constant__ TcParams p) {
-    static_assert(!(PERM && NT != 1), "the 8x8 form has one tile per CTA");
-    constexpr int NSTG = HALO_NH / NT;                  // halo pipeline depth: 2 (one tile) or 1 (two tiles)
-    constexpr uint32_t HALO_SLOT = PERM ? HALO8_SLOT : dd::HALO_SLOT;
-    constexpr uint32_t HALO_TX = PERM ? HALO8_TX : dd::HALO_TX;
-    constexpr uint32_t DY_BYTES = (PERM ? 2 : 1) * (HALO_TW + 2) * 128u;      // smem bytes between filter rows
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __grid_constant__ TcParams p) {
+    constexpr int NT = 1;                               // output tiles per CTA (a two-tile form was measured and dropped, profiles/README.md)
+    constexpr int NSTG = HALO_NH;                       // halo pipeline depth
+    constexpr uint32_t DY_BYTES = (HALO_TW + 2) * 128u;                       // smem bytes between filter rows
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    // weight ring: 4 x 16 KB next to two resident CTAs; the 8x8 form owns the SM and runs 160 KB of bn-row slots (10 or
-    // 20 stages) -- with 4 stages it had ~80 KB in flight per ~2300-clk L2 round trip and was latency-bound (11.5 us
-    // against 10.1 us for the generic path, profiles/README.md)
-    // One weight TMA per TAPS_PER_LOAD taps: a producer iteration (wait, expect_tx, issue) costs ~400 clk, more than the
-    // four N=64 MMAs of a tap, so the 8x8 form loads a whole filter row (3 taps, 3-D box of the (c, row, tap) view).
-    constexpr int TAPS_PER_LOAD = PERM ? 3 : 1;
-    const uint32_t B_TAP_BYTES = PERM ? (uint32_t)(p.bn * TC_BK * 2) : (uint32_t)dd::HALO_B_BYTES;
-    const uint32_t HALO_B_BYTES = TAPS_PER_LOAD * B_TAP_BYTES;
-    const int HALO_NB = PERM ? (int)(HALO8_B_RING / HALO_B_BYTES) : dd::HALO_NB;
     const uint32_t bbase = base + HALO_NH * HALO_SLOT;
-    const uint32_t bars = bbase + (PERM ? (uint32_t)HALO8_B_RING : (uint32_t)(dd::HALO_NB * dd::HALO_B_BYTES));
+    const uint32_t bars = bbase + HALO_NB * HALO_B_BYTES;
     auto hfull = [&](int s) { return bars + 8u * s; };
     auto hempty = [&](int s) { return bars + 8u * (HALO_NH + s); };
     auto bfull = [&](int s) { return bars + 8u * (2 * HALO_NH + s); };
@@ -705,7 +675,7 @@ __global__ void __launch_bounds__(TC_THREADS, PERM ? 1 : 2) conv_tc_halo_kernel(
         const int m_tile = blockIdx.x * NT + s;
         w0[s] = (m_tile % p.tiles_w) * p.tw;
         h0[s] = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
-        n0[s] = (m_tile / (p.tiles_w * p.tiles_h)) * (PERM ? 2 : 1);
+        n0[s] = m_tile / (p.tiles_w * p.tiles_h);
     }
     const int nchunks = p.chunks0 + p.chunks1;
     const int cin = nchunks * 64;
@@ -732,7 +702,7 @@ __global__ void __launch_bounds__(TC_THREADS, PERM ? 1 : 2) conv_tc_halo_kernel(
     if (threadIdx.x == 0) tstamp(p, 2);
 
     if (warp == 0) {
-        const uint32_t b_tx = (uint32_t)p.bn * TC_BK * 2 * TAPS_PER_LOAD;
+        const uint32_t b_tx = (uint32_t)p.bn * TC_BK * 2;
         const int brow = n_tile * p.bn, chunks0 = p.chunks0;
         int bs = 0, bround = 0, hs = 0, hround = 0;
         uint32_t sB = bbase;
@@ -745,21 +715,19 @@ __global__ void __launch_bounds__(TC_THREADS, PERM ? 1 : 2) conv_tc_halo_kernel(
                     const uint32_t dst = base + (hs * NT + s) * HALO_SLOT;
                     const CUtensorMap* tm = c < chunks0 ? &p.tmH0 : &p.tmH1;
                     const int cc = (c < chunks0 ? c : c - chunks0) * 64;
-                    if (PERM) tma_load_5d(tm, hfull(hs), dst, cc, w0[s] - 1, n0[s], h0[s] - 1, 0);     // (C, W, N, H, P) view
-                    else tma_load_5d(tm, hfull(hs), dst, cc, w0[s] - 1, h0[s] - 1, n0[s], 0);
+                    tma_load_5d(tm, hfull(hs), dst, cc, w0[s] - 1, h0[s] - 1, n0[s], 0);
                 }
             }
             __syncwarp();
             if (++hs == NSTG) { hs = 0; ++hround; }
             int kcoord = c * 64;
 #pragma unroll 1
-            for (int tap = 0; tap < 9; tap += TAPS_PER_LOAD) {
+            for (int tap = 0; tap < 9; ++tap) {
                 const uint32_t fb = bfull(bs);
                 if (bround > 0) mbar_wait(bempty(bs), (bround - 1) & 1);
                 if (elect_one()) {
                     mbar_expect_tx(fb, b_tx);
-                    if (PERM) tma_load_3d(&p.tmB3, fb, sB, c * 64, brow, tap);
-                    else tma_load_2d(&p.tmB, fb, sB, kcoord, brow);
+                    tma_load_2d(&p.tmB, fb, sB, kcoord, brow);
                 }
                 __syncwarp();
                 kcoord += cin;
@@ -781,11 +749,11 @@ __global__ void __launch_bounds__(TC_THREADS, PERM ? 1 : 2) conv_tc_halo_kernel(
             for (int r = 0; r < 3; ++r) {
 #pragma unroll 1
                 for (int sx = 0; sx < 3; ++sx) {
-                    if (!PERM || sx == 0) mbar_wait(bfull(bs), bpar);
+                    mbar_wait(bfull(bs), bpar);
                     if (acc == 0 && lane == 0) tstamp(p, 3);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t bd = umma_desc(sB + (PERM ? sx * B_TAP_BYTES : 0u));
+                        const uint64_t bd = umma_desc(sB);
 #pragma unroll
                         for (int s = 0; s < NT; ++s) {
                             const uint64_t ad = (uint64_t)(((rowA + s * HALO_SLOT + 128u * sx) & 0x3FFFFu) >> 4) | a_hi;
@@ -794,14 +762,12 @@ __global__ void __launch_bounds__(TC_THREADS, PERM ? 1 : 2) conv_tc_halo_kernel(
                                 umma_f16(tmem_base + (uint32_t)(s * TC_TMEM_COLS), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
                                          (acc | k) ? 1u : 0u);
                         }
-                        if (!PERM || sx == 2) umma_commit(bempty(bs));
+                        umma_commit(bempty(bs));
                     }
                     __syncwarp();
                     acc = 1u;
-                    if (!PERM || sx == 2) {
-                        sB += HALO_B_BYTES;
-                        if (++bs == HALO_NB) { bs = 0; bpar ^= 1u; sB = bbase; }
-                    }
+                    sB += HALO_B_BYTES;
+                    if (++bs == HALO_NB) { bs = 0; bpar ^= 1u; sB = bbase; }
                 }
                 rowA += DY_BYTES;
             }
@@ -860,22 +826,6 @@ static int make_act_map(CUtensorMap* tm, const void* ptr, int C, int pitch, int 
     return DD_OK;
 }
 
-// (C, W, N, H, 1) view of an NHWC activation for the 8x8 halo form: box (64, W + 2, 2, H + 2, 1)
-static int make_act_map_perm(CUtensorMap* tm, const void* ptr, int C, int pitch, int W, int H, int N) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
-    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)N, (cuuint64_t)H, 1};
-    cuuint64_t strides[4] = {(cuuint64_t)pitch * 2, (cuuint64_t)H * W * pitch * 2, (cuuint64_t)W * pitch * 2,
-                             (cuuint64_t)N * H * W * pitch * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)(W + 2), 2, (cuuint32_t)(H + 2), 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(permuted activation C=%d W=%d H=%d N=%d) failed: %d", C, W, H, N, (int)r); return DD_ERR_CUDA; }
-    return DD_OK;
-}
-
 static int make_w_map(CUtensorMap* tm, const void* ptr, int K, int rows, int bn, int batch, bool f32 = false) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
@@ -891,8 +841,8 @@ static int make_w_map(CUtensorMap* tm, const void* ptr, int K, int rows, int bn,
     return DD_OK;
 }
 
-// (c, row, tap) view of the packed [row][tap*Cin + c] 3x3 weights: box (64, bn, 3) = the three taps of one filter row
-static int make_w_map_taps(CUtensorMap* tm, const void* ptr, int Cin, int rows, int bn, bool f32 = false) {
+// (c, row, tap) view of the packed fp32 [row][tap*Cin + c] 3x3 weights: box (32, bn, 9) = all nine taps of a 32-channel chunk
+static int make_w_map_taps(CUtensorMap* tm, const void* ptr, int Cin, int rows, int bn, bool f32 = true) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
     const cuuint64_t es = f32 ? 4 : 2;
@@ -957,9 +907,7 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, 64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(4, 64, 2));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 1));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64, 1));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO8_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM);
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
         attr_done = true;
     }
@@ -974,13 +922,6 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     p.tw = W < 128 ? W : 128;
     p.th = (128 / p.tw) < H ? (128 / p.tw) : H;
     if (halo) { p.tw = HALO_TW; p.th = HALO_TH; }
-    // The 8x8 halo form is an opt-in experiment too: it cuts the A-operand L2 traffic 9x and batches three taps per weight
-    // load, yet measures 12.0 us against 10.1 us for the generic path (profiles/README.md): with bn = 64 every MMA takes
-    // ~100 clk whatever feeds it -- cta_group::1 reads its shared-memory operands at ~64 B/clk, which caps M128 x N64 x K16 at
-    // 25 % and N128 at 50 % of the tensor pipe.  The lever that is left is cta_group::2 (half of B per SM), not less traffic.
-    static const bool halo8_on = getenv("DD_HALO8") != nullptr;
-    const bool halo8 = halo8_on && !halo_off && kind == DD_TC_CONV3x3 && H == 8 && W == 8 && Cout >= 64 && !out_nchw_f32 && !wps;
-    p.interleave = halo8 ? 1 : 0;
     p.tn = wps ? 1 : 128 / (p.tw * p.th);      // per-sample weights: one image per tile (rows beyond it are ignored)
     p.rows_valid = p.tw * p.th * p.tn;
     p.tw_sh = 0; while ((1 << p.tw_sh) < p.tw) ++p.tw_sh;
@@ -1042,14 +983,6 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     if (rc) return rc;
     rc = make_w_map(&p.tmB, wp, K, w_rows, p.bn, wps ? B : 0);
     if (rc) return rc;
-    if (halo8) {
-        rc = make_w_map_taps(&p.tmB3, wp, Cin, w_rows, p.bn);
-        if (rc) return rc;
-        rc = make_act_map_perm(&p.tmH0, x, C1, x_pitch, W, H, B);
-        if (rc) return rc;
-        rc = make_act_map_perm(&p.tmH1, x2 ? x2 : x, x2 ? C2 : C1, x2 ? C2 : x_pitch, W, H, B);
-        if (rc) return rc;
-    }
     if (halo) {
         rc = make_act_map(&p.tmH0, x, C1, x_pitch, W, H, B, 1, HALO_TW + 2, HALO_TH + 2, 1, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
@@ -1059,7 +992,7 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     }
 
     p.splits = 1; p.kb_per_split = p.ntaps * (p.chunks0 + p.chunks1);
-    p.splitk_ws = nullptr; p.splitk_cnt = nullptr; p.exp_shift = 0; p.exp_bo = 0;
+    p.splitk_ws = nullptr; p.splitk_cnt = nullptr;
     p.dbg = g_tc_dbg;
     (void)splitk_cnt; (void)splitk_cnt_n;
     if (flags & DD_TC_SPLITK) {
@@ -1075,23 +1008,14 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
         fprintf(stderr, "conv_tc kind=%d B=%d H=%d W=%d C=%d+%d Cout=%d grid=(%u,%u,%u) bn=%d num_kb=%d splits=%d kb_per=%d\n", kind, B, H, W,
                 C1, C2, Cout, grid.x, grid.y, grid.z, p.bn, p.kb_per_split, p.splits, p.kb_per_split);
     const int ctas = (int)(grid.x * grid.y * grid.z);
-    // dual-tile halo CTAs (two accumulators per weight load) are an opt-in experiment: measured on B200 they do not
-    // help (3x3 128->128 @32x32: 22.2 -> 22.7 us, 256->256 @16x16: 17.5 -> 24.0 us; profiles/README.md) -- these layers
-    // are bound by tensor-pipe occupancy per wave, not by weight re-reads, and the single-buffered halo costs more.
-    static const bool dual_on = getenv("DD_HALO_DUAL") != nullptr;
-    const bool halo_dual = halo && dual_on && grid.x % 2 == 0 && 2 * ctas >= 3 * num_sms();
     const bool pair = ((p.chunks0 + p.chunks1) % 2 == 0) && (p.chunks0 % 2 == 0);     // two chunks per stage never straddle the sources
     cudaStream_t st = (cudaStream_t)stream;
     if (p.splits > 1)
         launch_pdl(conv_tc_kernel<8, 64, 1, 2>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
     else if (out_nchw_f32 || p.bn < 32)
         launch_pdl(conv_tc_kernel<3, 128, 1, 1>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
-    else if (halo8)
-        launch_pdl(conv_tc_halo_kernel<1, true>, dim3(grid), dim3(TC_THREADS), HALO8_SMEM, st, p);
-    else if (halo && halo_dual)
-        launch_pdl(conv_tc_halo_kernel<2, false>, dim3(grid.x / 2, grid.y, 1), dim3(TC_THREADS), HALO_SMEM, st, p);
     else if (halo)
-        launch_pdl(conv_tc_halo_kernel<1, false>, dim3(grid), dim3(TC_THREADS), HALO_SMEM, st, p);
+        launch_pdl(conv_tc_halo_kernel, dim3(grid), dim3(TC_THREADS), HALO_SMEM, st, p);
     else if (ctas > num_sms())      // more than one wave: two CTAs per SM so epilogues overlap main loops
         launch_pdl(conv_tc_kernel<3, 128, 1, 0>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
     else if (p.bn <= 64 && pair)

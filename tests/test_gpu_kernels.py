@@ -204,13 +204,13 @@ CONV_CASES = [
     ("3x3", 256, 256, 128, 16, 16, 3),    # halo kernel, two sources (skip concat), odd batch
     ("3x3", 256, 0, 256, 16, 16, 2),      # halo kernel, 2 n-tiles
     ("3x3", 64, 0, 64, 16, 8, 1),         # halo kernel, exactly one tile, bn = 64
-    ("3x3", 256, 256, 256, 8, 8, 3),      # 8x8 halo form: (h, image, w) halo rows, two sources, ragged last tile
-    ("3x3", 64, 0, 128, 8, 8, 2),         # 8x8 halo form, one chunk, bn = 64
+    ("3x3", 256, 256, 256, 8, 8, 3),      # 8x8 maps: two images per tile, two sources, ragged last tile
+    ("3x3", 64, 0, 128, 8, 8, 2),         # 8x8 maps, one chunk, bn = 64
     ("3x3", 64, 0, 64, 4, 4, 5),          # 8 images per tile, ragged batch, 8 channels per GN group
     ("3x3", 256, 0, 256, 4, 4, 64),       # split-K partials (32 tiles x 4 splits) + dd_gn_mish_sum
     ("3x3", 256, 256, 256, 4, 4, 64),     # split-K, two sources (72 k-blocks)
     ("3x3", 256, 0, 256, 2, 2, 7),        # split-K on a single ragged tile
-    ("3x3", 256, 256, 256, 8, 8, 64),     # 8x8 halo form at the benchmark batch, two sources
+    ("3x3", 256, 256, 256, 8, 8, 64),     # 8x8 maps at the benchmark batch, two sources
     ("down", 256, 0, 256, 4, 4, 64),      # strided conv on the single-wave path
     ("1x1", 256, 0, 384, 16, 16, 2),
     ("1x1", 128, 0, 256, 2, 2, 3),
