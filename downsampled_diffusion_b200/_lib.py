@@ -19,6 +19,7 @@ CONV_PRE_MISH, CONV_TANH, CONV_OUT_NCHW, CONV_IN_NCHW = 1, 2, 4, 8
 TC_CONV3x3, TC_CONV1x1, TC_DOWN, TC_UPT = 0, 1, 2, 3
 TC_W_PER_SAMPLE = 1
 TC_SPLITK = 2
+TC_PAIR = 4
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 

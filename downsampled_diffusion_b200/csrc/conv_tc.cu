@@ -46,6 +46,7 @@ struct TcParams {
     int G, cpg_mask, cpg_shift;
     int tw_sh, th_sh;           // log2(tw), log2(th): tile geometry is all powers of two
     int rows_valid;             // tw*th*tn (< 128 when one image has fewer than 128 pixels and tn is forced to 1)
+    int pair_nt;                // CTA-pair halo kernel: 128-column accumulator blocks per CTA (N of the pair's MMA = bn * pair_nt)
     int w_per_sample;           // weights are (B, rows, K): every image multiplies its own matrix (fused attention output)
     int splits, kb_per_split;   // split-K over the (tap, chunk) loop; partial sums meet in splitk_ws
     void* out;
@@ -135,6 +136,43 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA pair (cta_group::2): the exact instruction forms are those of CUTLASS' cute/arch/{copy_sm100_tma,mma_sm100_umma}.hpp
+//      and cutlass/arch/barrier.h (the pair's shared-memory windows differ in bit 24 of the shared::cluster address)
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion is signalled on the LEADER CTA's mbarrier (same offset, peer bit cleared)
+__device__ __forceinline__ void tma_load_5d_2sm(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+// arrive on the same barrier offset in both CTAs of the pair when the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -792,6 +830,142 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __gri
     }
 }
 
+// =============================================================================================
+// CTA-pair form of the halo kernel (tcgen05 cta_group::2).
+// With both operands in shared memory a cta_group::1 MMA is paced by its operand reads (~64 B/clk: M128 x N128 x K16 takes
+// ~128 clk, half the tensor-pipe rate -- profiles/README.md).  Two CTAs of a cluster (one SM pair) compute a 256-pixel x N tile
+// together: each loads the halo of ITS 128 pixels and HALF of the weight rows, the leader issues one M = 256 MMA per k-step,
+// each SM reads 128 A rows + N/2 B rows and the accumulator rows land in each CTA's own TMEM.  For N = 256 an SM reads the
+// same bytes as before for twice the math.
+//   * full barriers live in the leader; both CTAs' TMA loads signal them (cta_group::2 loads, peer bit of the barrier address
+//     cleared), the leader's producer arms them with the pair's byte count;
+//   * empty / accumulator-ready barriers exist in both CTAs; the leader's tcgen05.commit multicasts to both;
+//   * TMEM is allocated with cta_group::2 by warp 1 of both CTAs; a cluster barrier brackets setup and teardown.
+// =============================================================================================
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo2_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bbase = base + HALO_NH * HALO_SLOT;
+    const uint32_t bars = bbase + HALO_NB * HALO_B_BYTES;
+    auto hfull = [&](int s) { return bars + 8u * s; };
+    auto hempty = [&](int s) { return bars + 8u * (HALO_NH + s); };
+    auto bfull = [&](int s) { return bars + 8u * (2 * HALO_NH + s); };
+    auto bempty = [&](int s) { return bars + 8u * (2 * HALO_NH + HALO_NB + s); };
+    const uint32_t tmem_full_bar = bars + 8u * (2 * HALO_NH + 2 * HALO_NB);
+    const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 512u - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool leader = cluster_ctarank() == 0;
+    const int m_tile = blockIdx.x, n_pair = blockIdx.y;           // blockIdx.x pairs (2k, 2k+1) form a cluster
+    const int w0 = (m_tile % p.tiles_w) * p.tw, h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th, n0 = m_tile / (p.tiles_w * p.tiles_h);
+    const int nchunks = p.chunks0 + p.chunks1;
+    const int cin = nchunks * 64;
+    const int N2 = p.bn * p.pair_nt;                                // N of the pair's MMA: 128 or 256
+    const int half_rows = N2 >> 1;                                  // weight rows each CTA loads per tap
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmH0)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB)) : "memory");
+        for (int s = 0; s < HALO_NH; ++s) { mbar_init(hfull(s), 1); mbar_init(hempty(s), 1); }
+        for (int s = 0; s < HALO_NB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        if (N2 == 256) asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(256) : "memory");
+        else asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                     // barriers of both CTAs are initialised before any remote signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+    pdl_sync();
+
+    if (warp == 0) {
+        // ===== producer (both CTAs): own halo, own half of the weight rows; completion goes to the leader's barriers =====
+        const uint32_t b_tx = (uint32_t)half_rows * TC_BK * 2;
+        const int brow = n_pair * N2 + (leader ? 0 : half_rows), chunks0 = p.chunks0;
+        int bs = 0, bround = 0, hs = 0, hround = 0;
+        uint32_t sB = bbase;
+        for (int c = 0; c < nchunks; ++c) {
+            if (hround > 0) mbar_wait(hempty(hs), (hround - 1) & 1);
+            if (elect_one()) {
+                if (leader) mbar_expect_tx(hfull(hs), 2 * HALO_TX);
+                const CUtensorMap* tm = c < chunks0 ? &p.tmH0 : &p.tmH1;
+                tma_load_5d_2sm(tm, hfull(hs), base + hs * HALO_SLOT, (c < chunks0 ? c : c - chunks0) * 64, w0 - 1, h0 - 1, n0, 0);
+            }
+            __syncwarp();
+            if (++hs == HALO_NH) { hs = 0; ++hround; }
+            int kcoord = c * 64;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+                if (bround > 0) mbar_wait(bempty(bs), (bround - 1) & 1);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(bfull(bs), 2 * b_tx);
+                    tma_load_2d_2sm(&p.tmB, bfull(bs), sB, kcoord, brow);
+                }
+                __syncwarp();
+                kcoord += cin;
+                sB += HALO_B_BYTES;
+                if (++bs == HALO_NB) { bs = 0; ++bround; sB = bbase; }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        // ===== MMA issuer (leader only): M = 256 over the pair, N = N2 =====
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        const uint64_t a_hi = ((uint64_t)(((HALO_TW + 2) * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        int bs = 0, hs = 0;
+        uint32_t bpar = 0, hpar = 0, acc = 0;
+        uint32_t sB = bbase;
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(hfull(hs), hpar);
+            uint32_t rowA = base + hs * HALO_SLOT;
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll 1
+                for (int sx = 0; sx < 3; ++sx) {
+                    mbar_wait(bfull(bs), bpar);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t ad = (uint64_t)(((rowA + 128u * sx) & 0x3FFFFu) >> 4) | a_hi;
+                        const uint64_t bd = umma_desc(sB);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k)
+                            umma_f16_2sm(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (acc | k) ? 1u : 0u);
+                        umma_commit_2sm(bempty(bs));
+                    }
+                    __syncwarp();
+                    acc = 1u;
+                    sB += HALO_B_BYTES;
+                    if (++bs == HALO_NB) { bs = 0; bpar ^= 1u; sB = bbase; }
+                }
+                rowA += (HALO_TW + 2) * 128u;
+            }
+            if (elect_one()) umma_commit_2sm(hempty(hs));
+            __syncwarp();
+            if (++hs == HALO_NH) { hs = 0; hpar ^= 1u; }
+        }
+        if (elect_one()) umma_commit_2sm(tmem_full_bar);
+        __syncwarp();
+    } else if (warp >= 2 && warp < 6) {
+        // ===== epilogue (both CTAs): own 128 rows, N2 columns in 128-wide passes =====
+        for (int s = 0; s < p.pair_nt; ++s)
+            tc_epilogue_staged(p, tmem_base + (uint32_t)(s * TC_TMEM_COLS), tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)),
+                               n_pair * p.pair_nt + s, 0, w0, h0, n0, warp, lane);
+    }
+    tc_fence_before();
+    cluster_sync_all();                     // the peer's shared memory and TMEM stay alive until both CTAs are done
+    if (warp == 1) {
+        tc_fence_after();
+        if (N2 == 256) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128) : "memory");
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -858,6 +1032,20 @@ static int make_w_map_taps(CUtensorMap* tm, const void* ptr, int Cin, int rows, 
 }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// launch with a (2,1,1) thread-block cluster + programmatic dependent launch
+template <typename... KArgs, typename... Args>
+static void launch_pair_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace dd
 
@@ -1009,11 +1197,30 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
                 C1, C2, Cout, grid.x, grid.y, grid.z, p.bn, p.kb_per_split, p.splits, p.kb_per_split);
     const int ctas = (int)(grid.x * grid.y * grid.z);
     const bool pair = ((p.chunks0 + p.chunks1) % 2 == 0) && (p.chunks0 % 2 == 0);     // two chunks per stage never straddle the sources
+    // CTA-pair (cta_group::2) form of the halo kernel: two consecutive pixel tiles per cluster, N = 128 or 256 per MMA.
+    // Opt-in (DD_TC_PAIR): parity-green, but as a one-tile-per-CTA kernel it loses to the single-CTA form on this network
+    // (3x3 128->128 @32x32 22.2 -> 25.0 us, 256->256 @16x16 17.5 -> 20.5 us, 512->128 @16x16 21.5 -> 18.8 us; profiles/README.md):
+    // the 256-column epilogue is exposed and clusters schedule in pairs.  It is the base for a persistent pair kernel.
+    const bool cta_pair = halo && (flags & DD_TC_PAIR) && p.bn == 128 && grid.x % 2 == 0 && grid.z == 1;
+    p.pair_nt = (cta_pair && Cout % 256 == 0) ? 2 : 1;
+    if (cta_pair) {
+        static bool pattr = false;
+        if (!pattr) {
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+            if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
+            pattr = true;
+        }
+        rc = make_w_map(&p.tmB, wp, K, w_rows, 64 * p.pair_nt, 0);         // each CTA loads half of the pair's weight rows
+        if (rc) return rc;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (p.splits > 1)
         launch_pdl(conv_tc_kernel<8, 64, 1, 2>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
     else if (out_nchw_f32 || p.bn < 32)
         launch_pdl(conv_tc_kernel<3, 128, 1, 1>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
+    else if (cta_pair)
+        launch_pair_pdl(conv_tc_halo2_kernel, dim3(grid.x, Cout / (p.bn * p.pair_nt), 1), dim3(TC_THREADS), HALO_SMEM, st, p);
     else if (halo)
         launch_pdl(conv_tc_halo_kernel, dim3(grid), dim3(TC_THREADS), HALO_SMEM, st, p);
     else if (ctas > num_sms())      // more than one wave: two CTAs per SM so epilogues overlap main loops

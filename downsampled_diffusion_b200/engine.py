@@ -70,6 +70,7 @@ class Program:
         self.packers: List[Callable[[], None]] = [] # re-run when the module's parameters change
         self.weights_version = None
         self.n_gn = 0
+        self.tc_flags = 0                           # extra dd_conv_tc flags for every conv of the program (tests: L.TC_PAIR)
         self.gn_slots: List[Tuple[int, int]] = []   # (B*G*2 offset, G) per GroupNorm of a bf16 program
         self.stats_arena: Optional[torch.Tensor] = None
 
@@ -195,13 +196,13 @@ class Program:
                 src = planes
             G = 0
             st_ptr = None
-            flags = 0
+            flags = self.tc_flags
             if gn is not None:
                 G = gn.num_groups
                 # low-resolution layers: split-K partials, summed by the GroupNorm kernel (dd_gn_mish_sum)
                 S = int(L.lib().dd_conv_tc_splits(kcode, B, gh, gw, Cin, Cout_p)) if (residual is None and Cout_p == Cout) else 1
                 if S > 1 and gh * gw * Cout <= 16384 and S * B * gh * gw * Cout <= self.SPLITK_WS_FLOATS:
-                    flags = L.TC_SPLITK
+                    flags |= L.TC_SPLITK
                     stats = (("split", S, b_t), 2)
                 else:
                     stats = (self._new_stats_slot(B, G), 1)

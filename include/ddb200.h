@@ -201,6 +201,9 @@ int dd_space_to_depth2(const void* x, void* y, int B, int H, int W, int C, void*
  *   splitk_ws[split][b][h][w][Cout]            (S * B*H*W*Cout floats),
  * y, gn_stats and residual are ignored, and dd_gn_mish_sum consumes the partials (sum + bias + GroupNorm + Mish). */
 #define DD_TC_SPLITK 2
+/* DD_TC_PAIR (3x3 on maps >= 16x8, Cout a multiple of 128, an even number of pixel tiles): run the halo kernel as thread-block
+ * clusters of two CTAs with tcgen05 cta_group::2 (M = 256 per MMA, each CTA loads half of the weight rows).  Opt-in. */
+#define DD_TC_PAIR 4
 int dd_conv_tc_splits(int kind, int B, int H, int W, int Cin, int Cout);
 int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2,
                const void* wp, int w_rows, const float* bias, const void* residual,

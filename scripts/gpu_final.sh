@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end evidence pass: parity suite, both bench arms, launch list + DRAM traffic + one full capture, training bench.
 cd "$(dirname "$0")/.."
-tag=${1:-r01_e}
+tag=${1:-r01_f}
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest_$tag.log 2>&1; tail -2 gpurun_out/pytest_$tag.log
 timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference_$tag.json 2> gpurun_out/bench_reference_$tag.err; echo "ref exit $?"

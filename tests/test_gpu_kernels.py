@@ -221,9 +221,16 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize("kind,C1,C2,Cout,H,W,B", [("3x3", 128, 0, 128, 32, 32, 2), ("3x3", 256, 256, 128, 16, 16, 4),
+                                                    ("3x3", 256, 0, 256, 16, 16, 2)])
+def test_conv_cta_pair(cuda, kind, C1, C2, Cout, H, W, B):
+    """The cta_group::2 form of the halo kernel (opt-in flag DD_TC_PAIR): N = 128 and N = 256 per pair, two sources."""
+    test_conv_paths(cuda, kind, C1, C2, Cout, H, W, B, "bf16", tc_flags=L().TC_PAIR)
+
+
 @pytest.mark.parametrize("kind,C1,C2,Cout,H,W,B", CONV_CASES)
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_conv_paths(cuda, kind, C1, C2, Cout, H, W, B, precision):
+def test_conv_paths(cuda, kind, C1, C2, Cout, H, W, B, precision, tc_flags=0):
     """dd_conv_direct (fp32) and dd_conv_tc (tcgen05, bf16) against F.conv2d / F.conv_transpose2d on CPU,
     including bias, residual add and the GroupNorm {sum,sumsq} epilogue."""
     from downsampled_diffusion_b200.engine import Act, Program, ensure_lazy
@@ -241,6 +248,7 @@ def test_conv_paths(cuda, kind, C1, C2, Cout, H, W, B, precision):
     holder = torch.nn.ModuleList([conv] + ([gn] if gn else [])).to(cuda)
     ensure_lazy()
     prog = Program(holder, B, precision)
+    prog.tc_flags = tc_flags
     dt = prog.adt
     x = tc.randn(1, B, C1, H, W)
     x2 = tc.randn(2, B, C2, H, W) if C2 else None
