@@ -51,7 +51,7 @@ SIGNATURES = {
     "dd_debug_set_attn_timeline": [_p],
     "dd_conv_wgrad": [_p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "dd_colsum": [_p, _p, _i64, _i, _i, _i64, _p],
-    "dd_dropout": [_p, _p, _i64, C.c_uint32, _f, _p],
+    "dd_dropout": [_p, _p, _i64, C.c_uint32, _p, _f, _p],
     "dd_gn_mish_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p],
     "dd_layernorm_c_bwd": [_p, _p, _p, _f, _i64, _i, _p, _i, _p, _p, _p],
     "dd_linattn_save": [_p, _i, _i, _i, _p, _p],

@@ -12,6 +12,7 @@ tensor-core backward is the next step.
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -39,6 +40,11 @@ class TrainProgram(Program):
         self.pg_total = 0
         self.pg_arena: Optional[torch.Tensor] = None
         self._emit_bwd = False
+        # dropout: one seed per forward call, drawn on the device (torch's CUDA generator) and read by the kernels from
+        # device memory, so the launch lists hold no per-call host values and can be replayed as CUDA graphs
+        self.seed_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.n_dropout = 0
+        self.graphs = None                                # (forward graph, launches, backward graph, launches)
 
     # ---- launch recording -------------------------------------------------------------------
     def add(self, name: str, *args) -> None:
@@ -126,10 +132,49 @@ class TrainProgram(Program):
             out[id(param)] = out[id(param)] + g if id(param) in out else g
         return out
 
-    def run_backward(self) -> None:
+    def pre_backward(self) -> None:
+        """device-side resets at the head of the backward list (subclasses add theirs)"""
         L.call("dd_zero", self.pg_arena.data_ptr(), self.pg_arena.numel() * 4, L.stream())
+
+    def _backward_list(self) -> None:
+        self.pre_backward()
         for op in self.bops:
             op()
+
+    # Both launch lists are static (fixed buffers, weights repacked in place, the dropout seed in device memory), so after
+    # one eager pass each -- lazy CUDA initialisation and cudaFuncSetAttribute calls must not happen inside a capture --
+    # they are captured once and replayed: a training step issues two graph launches per network instead of ~1000 kernel
+    # launches, which is what keeps the GPU fed when the host has to wait for a loss value every step.
+    def _capture_graphs(self) -> None:
+        self.run_ops()
+        self._backward_list()          # gradient inputs hold whatever they hold: the results are overwritten by the real pass
+        torch.cuda.synchronize()
+        out = []
+        for fn in (self.run_ops, self._backward_list):
+            g = torch.cuda.CUDAGraph()
+            n0 = L._Counter.n
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                fn()
+            out += [g, L._Counter.n - n0]
+        self.graphs = tuple(out)
+
+    @staticmethod
+    def _graphs_enabled() -> bool:
+        return os.environ.get("DD_TRAIN_GRAPH", "1") != "0" and not os.environ.get("DD_DEBUG")
+
+    def run_forward(self) -> None:
+        if not self._graphs_enabled():
+            return self.run_ops()
+        if self.graphs is None:
+            self._capture_graphs()
+        self.graphs[0].replay()
+        L._Counter.n += self.graphs[1]
+
+    def run_backward(self) -> None:
+        if not self._graphs_enabled() or self.graphs is None:
+            return self._backward_list()
+        self.graphs[2].replay()
+        L._Counter.n += self.graphs[3]
 
     # ---- differentiable building blocks --------------------------------------------------------
     def t_conv(self, x: Optional[Act], conv: torch.nn.Module, *, x2: Act = None, kind: str = "3x3", residual: Act = None,
@@ -355,11 +400,11 @@ class TrainProgram(Program):
                  (tb.data_ptr() + 4 * tb_col) if tb is not None else None, J, None, 0,
                  L.ptr(residual.t) if residual is not None else None)
         out = y
-        seed_box = None
         if dropout > 0:
             out = self.act(x.H, x.W, C, B)
-            seed_box = _SeedArg(self)
-            self.add("dd_dropout", L.ptr(y.t), L.ptr(out.t), y.t.numel(), seed_box, float(dropout))
+            self.n_dropout += 1
+            salt = self.n_dropout                      # one mask stream per dropout layer, one seed per forward call
+            self.add("dd_dropout", L.ptr(y.t), L.ptr(out.t), y.t.numel(), salt, L.ptr(self.seed_dev), float(dropout))
         s1, s2, s3 = (self.empty(B, C, dtype=torch.float32) for _ in range(3))
         dgam = self.pgrad(gn.weight, (C,), lambda g: g)
         dbet = self.pgrad(gn.bias, (C,), lambda g: g)
@@ -368,7 +413,7 @@ class TrainProgram(Program):
             g = self.gy(out)
             if dropout > 0:
                 gm = self.grad(y)
-                self.add("dd_dropout", L.ptr(g), L.ptr(gm), g.numel(), seed_box, float(dropout))
+                self.add("dd_dropout", L.ptr(g), L.ptr(gm), g.numel(), salt, L.ptr(self.seed_dev), float(dropout))
                 self.gwritten.add(id(y.t))
                 g = gm
             if residual is not None:
@@ -413,19 +458,8 @@ class _PgPtr:
         return int(self.prog.pg_arena.data_ptr() + 4 * self.off)
 
 
-class _SeedArg:
-    """dropout seed drawn per forward call (torch RNG on the host), reused by the backward launch."""
-
-    def __init__(self, prog):
-        self.prog = prog
-
-    @property
-    def _as_parameter_(self):
-        return int(self.prog.dropout_seed & 0xFFFFFFFF)
-
-
 def _ensure_types():
-    """ctypes resolves `_as_parameter_` at call time, so _PgPtr / _SeedArg need no special argtypes."""
+    """ctypes resolves `_as_parameter_` at call time, so _PgPtr / _ScratchPtr need no special argtypes."""
     ensure_lazy()
 
 
@@ -441,7 +475,6 @@ class UnetTrainEngine(TrainProgram):
         if H % (1 << (n_levels - 1)) or W % (1 << (n_levels - 1)):
             raise ValueError(f"input {H}x{W} must be divisible by 2^{n_levels - 1}")
         dim, cin = unet.dim, unet.in_channels
-        self.dropout_seed = 0
         self.x_in = self.empty(B, cin, H, W, dtype=torch.float32)
         self.eps_out = self.empty(B, cin, H, W, dtype=torch.float32)
         self.out_grad = self.empty(B, cin, H, W, dtype=torch.float32)
@@ -581,13 +614,17 @@ class UnetTrainEngine(TrainProgram):
         self.refresh_weights()
         self.x_in.copy_(x)
         self.t_float.copy_(time.to(torch.float32))
-        self.dropout_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
-        self.run_ops()
+        if self.n_dropout:
+            self.seed_dev.random_()
+        self.run_forward()
         return self.eps_out.clone()
+
+    def pre_backward(self) -> None:
+        super().pre_backward()
+        self.dtb.zero_()
 
     def backward(self, grad_out: torch.Tensor):
         self.out_grad.copy_(grad_out)
-        self.dtb.zero_()
         self.run_backward()
         return self.dx_in.clone() if self.need_input_grad else None
 
@@ -793,7 +830,7 @@ class ResampleTrainProgram(TrainProgram):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self.refresh_weights()
         self.x_in.copy_(x)
-        self.run_ops()
+        self.run_forward()
         return self.out.clone()
 
     def backward(self, grad_out: torch.Tensor):

@@ -139,9 +139,12 @@ __device__ __forceinline__ float dropout_scale(uint32_t seed, uint64_t idx, uint
     return ((uint32_t)z >= thresh) ? keep_inv : 0.f;      // P(drop) = thresh / 2^32
 }
 
-__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, uint32_t seed, uint32_t thresh,
-                               float keep_inv) {
+// The per-call seed lives in device memory (seed_dev, may be null) so that a launch recorded in a CUDA graph draws a fresh
+// mask on every replay; `salt` separates the dropout layers of one network.
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, uint32_t salt,
+                               const uint32_t* __restrict__ seed_dev, uint32_t thresh, float keep_inv) {
     pdl_sync();
+    const uint32_t seed = (salt * 0x9E3779B9u) ^ (seed_dev ? *seed_dev : 0u);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         y[i] = x[i] * dropout_scale(seed, (uint64_t)i, thresh, keep_inv);
 }
@@ -484,10 +487,11 @@ int dd_colsum(const float* x, float* out, int64_t M, int C, int nchw, int64_t HW
     return check_launch("colsum");
 }
 
-int dd_dropout(const float* x, float* y, int64_t n, uint32_t seed, float p, void* stream) {
+int dd_dropout(const float* x, float* y, int64_t n, uint32_t salt, const uint32_t* seed_dev, float p, void* stream) {
     DD_REQUIRE(p >= 0.f && p < 1.f, "dropout: p must be in [0,1)");
     const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
-    launch_pdl(dropout_kernel, dim3(grid_cap(n, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, n, seed, thresh, 1.f / (1.f - p));
+    launch_pdl(dropout_kernel, dim3(grid_cap(n, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, n, salt, seed_dev, thresh,
+               1.f / (1.f - p));
     return check_launch("dropout");
 }
 

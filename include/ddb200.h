@@ -271,8 +271,10 @@ int dd_conv_wgrad(const void* x, const void* x2, int C1, int C2, int in_dtype, c
 /* out[c] += sum_m x[m][c]  (x: (M, C) fp32, or NCHW with M = B*HW when nchw != 0): bias gradients. */
 int dd_colsum(const float* x, float* out, int64_t M, int C, int nchw, int64_t HW, void* stream);
 /* y = x * mask / (1-p), mask from a counter-based hash of (seed, index): nn.Dropout of blocks.py:111 (the same
- * call with the same seed masks the gradient in the backward pass). */
-int dd_dropout(const float* x, float* y, int64_t n, uint32_t seed, float p, void* stream);
+ * call with the same seed masks the gradient in the backward pass).  seed = hash(salt) ^ *seed_dev: the per-step seed
+ * is read from device memory (seed_dev may be NULL) so that the launch can sit in a replayed CUDA graph; salt separates
+ * the dropout layers of one network. */
+int dd_dropout(const float* x, float* y, int64_t n, uint32_t salt, const uint32_t* seed_dev, float p, void* stream);
 /* GroupNorm+Mish backward (blocks.py:79-84): x pre-norm conv output, stats {mean,rstd}; writes per-(b,c) sums
  * s_dhxh, s_dh, s_dy ((B, C) fp32: reduce over b for dgamma, dbeta; s_dy is the time-bias gradient) and dx. */
 int dd_gn_mish_bwd(const float* x, const float* dy, const float* stats, const float* gamma, const float* beta,

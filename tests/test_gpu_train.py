@@ -100,6 +100,48 @@ def test_dropout_training_mode_runs_and_masks(cuda):
         assert torch.equal(m.latent_model(x, t), m.latent_model(x, t))
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graph_replay_matches_eager_launch_lists(cuda, monkeypatch, precision):
+    """The captured forward / backward graphs of the three networks give the gradients of the eager launch lists, on the
+    capturing call and on later replays (with new inputs and repacked weights)."""
+    def run(m, seed):
+        x = tc.rand_pm1(seed, 4, 3, 32, 32).to(cuda)
+        t = torch.tensor([3, 50, 99, 700], device=cuda)
+        torch.manual_seed(seed)
+        eps = torch.randn(4, 8, 8, 8).to(cuda)
+        m.zero_grad()
+        obj, _ = m.losses(x, t, eps=eps)
+        obj.backward()
+        return float(obj), [p.grad.detach().clone() for p in m.parameters()]
+
+    def fresh():
+        m = tc.build_model(dict(tc.CS, precision=precision), dd, "dddpm_ae", device="cuda").to(cuda)
+        m.train()
+        return m
+
+    tol = 1e-5 if precision == "fp32" else 1e-4         # weight-gradient atomics reorder; TF32 tiles are deterministic otherwise
+    monkeypatch.setenv("DD_TRAIN_GRAPH", "0")
+    m = fresh()
+    ref = [run(m, s) for s in (61, 62, 63)]
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(1.01)                                # bumps the parameter version: weights are repacked outside the graphs
+    ref.append(run(m, 64))
+    monkeypatch.setenv("DD_TRAIN_GRAPH", "1")
+    m = fresh()
+    got = [run(m, s) for s in (61, 62, 63)]
+    progs = [p for net in (m.latent_model, m.downsample, m.upsample) for p in net._train_programs.values()]
+    assert len(progs) == 3 and all(p.graphs is not None for p in progs)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(1.01)
+    got.append(run(m, 64))
+    for (lo, go), (lr, gr) in zip(got, ref):
+        assert abs(lo - lr) <= tol * abs(lr)
+        for a, b in zip(go, gr):
+            assert tc.rel_l2(a, b) < tol
+
+
 def test_training_step_with_ema_and_grad_accumulation(cuda):
     """Two micro-batches (gradient_accumulate_every=2, trainer_ddpm.py:35,219-229), Adam step, EMA update."""
     cfg = dict(tc.CS, precision="fp32")
