@@ -11,6 +11,7 @@ from .dddpm import DownsampleDDPM, DownsampleDDPMAutoencoder
 from .downsampled import ConvResNet, SimpleDownConv, SimpleUpConv, get_downsampling, get_upsampling
 from .ema import EMA
 from .schedule import make_beta_schedule
+from .evalfmt import fix_samples
 
 __all__ = ["Unet", "DDPM", "DownsampleDDPM", "DownsampleDDPMAutoencoder", "ConvResNet", "SimpleDownConv",
-           "SimpleUpConv", "get_downsampling", "get_upsampling", "EMA", "make_beta_schedule"]
+           "SimpleUpConv", "get_downsampling", "get_upsampling", "EMA", "make_beta_schedule", "fix_samples"]

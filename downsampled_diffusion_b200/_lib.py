@@ -32,6 +32,10 @@ SIGNATURES = {
     "dd_mse_rowsum": [_p, _p, _p, _i, _i64, _f, _p],
     "dd_mse_rowsum_bwd": [_p, _p, _p, _p, _i, _i64, _f, _p],
     "dd_ema_update": [_p, _p, _i, _i, _f, _f, _p],
+    "dd_q_sample_step": [_p, _p, _i64, _i, _p, _p, _i, _p, _i, _i64, _p],
+    "dd_vlb_terms": [_p, _p, _p, _p, _i64, _i, _p, _p, _i, _i, _p, _p, _i64, _i, _i, _i64, _p],
+    "dd_prior_kl": [_p, _f, _f, _p, _i, _i64, _p],
+    "dd_fix_samples": [_p, _p, _i, _i, _i, _i, _p],
     "dd_nchw_to_nhwc": [_p, _p, _i, _i, _i, _i, _i, _p],
     "dd_nhwc_to_nchw": [_p, _i, _p, _i, _i, _i, _i, _p],
     "dd_im2col3x3_nchw": [_p, _p, _i, _i, _i, _i, _i, _p],

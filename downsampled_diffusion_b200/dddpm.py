@@ -78,6 +78,11 @@ class DownsampleDDPM(DDPM):
         assert list(x_recon.shape)[1:] == self.x_shape
         return x_recon, z_recon
 
+    @torch.no_grad()
+    def test_losses(self, x: torch.Tensor, noise=None) -> dict:
+        """dddpm.py:145-148: the variational bound of the latent chain, evaluated on z = downsample(x)."""
+        return self.test_losses_(self.rescaled_downsample(x), noise=noise)
+
     # ---- training objective ------------------------------------------------------------------------
     def loss_recon(self, x: torch.Tensor, z_hat: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         """dddpm.py:114-120: per-sample reconstruction error, zeroed for t >= t_rec_max."""

@@ -15,7 +15,7 @@ from torch import nn
 from . import _lib as L
 from . import ops
 from .engine import EngineCache
-from .schedule import diffusion_buffers, posterior_coef_table
+from .schedule import diffusion_buffers, eval_coef_table, posterior_coef_table
 
 OBJECTIVE_NAMES = ("simple", "vlb", "hybrid")
 NOISE_RING_BYTES = 4 << 30      # pre-drawn chain noise is held in a ring of at most this many bytes
@@ -75,6 +75,36 @@ class SamplingPlan:
                 self.step_eager()
             self.graph = g
             self.launches_per_step = len(e.ops) + 3
+
+
+EVAL_TABLE_KEYS = ("sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
+                   "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
+                   "posterior_log_variance_clipped")
+
+
+class EvalPlan(SamplingPlan):
+    """Captured step of the evaluation chain (DDPM.test_losses_, ddpm.py:391-442): q_sample at the device-side step
+    counter -> U-Net -> variational-bound term and squared-error row sums written to column T-1-t -> counter tick.
+    The reference runs the U-Net twice per step on identical inputs (ddpm.py:199 and :418); here it runs once."""
+
+    def __init__(self, ddpm: "DDPM", shape: Sequence[int]):
+        super().__init__(ddpm, shape)
+        dev = self.t_dev.device
+        B = shape[0]
+        self.tab = eval_coef_table({k: getattr(ddpm, k) for k in EVAL_TABLE_KEYS}).to(dev)
+        self.x0 = torch.zeros(*shape, dtype=torch.float32, device=dev)
+        self.vlb = torch.zeros(B, self.T, dtype=torch.float32, device=dev)
+        self.sq = torch.zeros(B, self.T, dtype=torch.float32, device=dev)
+
+    def step_eager(self) -> None:
+        e = self.eng
+        B, n = self.shape[0], self.shape[0] * self.chw
+        L.call("dd_q_sample_step", L.ptr(self.x0), L.ptr(self.noise), n, self.period, L.ptr(self.tab), L.ptr(self.t_dev), self.T,
+               L.ptr(e.x_in), B, self.chw, L.stream())
+        e.run()
+        L.call("dd_vlb_terms", L.ptr(self.x0), L.ptr(e.x_in), L.ptr(e.eps_out), L.ptr(self.noise), n, self.period, L.ptr(self.tab),
+               L.ptr(self.t_dev), 0, self.T, L.ptr(self.vlb), L.ptr(self.sq), self.T, 1, B, self.chw, L.stream())
+        L.call("dd_tick", L.ptr(self.t_dev), 1, L.stream())
 
 
 class DDPM(nn.Module):
@@ -259,6 +289,76 @@ class DDPM(nn.Module):
         x_0 = self.q_sample(x, t, eps)
         eps_hat = self.latent_model(x_0, t)
         return self.predict_x_from_eps(x_0, t, eps_hat, clip=False)
+
+    # ---- evaluation-side chain ----------------------------------------------------
+    def _eval_tab(self) -> torch.Tensor:
+        c = getattr(self, "_eval_tab_cache", None)
+        if c is None or c.device != self.betas.device:
+            c = eval_coef_table({k: getattr(self, k) for k in EVAL_TABLE_KEYS}).to(self.betas.device)
+            self._eval_tab_cache = c
+        return c
+
+    @torch.no_grad()
+    def vlb_terms(self, x: torch.Tensor, x_t: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """ddpm.py:317-365: L_t = KL(q(x_{t-1}|x_t,x) || p(x_{t-1}|x_t)) for t > 0, L_0 = -log p(x|x_1) (discretised
+        Gaussian); (N,) in bits/dim.  U-Net, then one fused kernel (evaluation only: no gradient, like its one caller)."""
+        assert x.shape == x_t.shape
+        eps_hat = self.latent_model(x_t, t)
+        return ops.vlb_terms_raw(x, x_t, eps_hat, self._eval_tab(), t.to(torch.int32).contiguous(), self.timesteps)
+
+    @torch.no_grad()
+    def calc_prior(self, x: torch.Tensor) -> torch.Tensor:
+        """ddpm.py:367-389: the prior term L_T, (N,) in bits/dim."""
+        return ops.prior_kl(x, float(self.sqrt_alphas_cumprod[-1]), float(self.log_one_minus_alphas_cumprod[-1]))
+
+    def eval_plan(self, shape) -> EvalPlan:
+        key = ("eval", tuple(shape), getattr(self.latent_model, "precision", None))
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = EvalPlan(self, shape)
+            self._plans[key] = plan
+        return plan
+
+    @torch.no_grad()
+    def test_losses_(self, x: torch.Tensor, noise: Union[torch.Tensor, Sequence[torch.Tensor], None] = None) -> dict:
+        """ddpm.py:391-442: every term of the variational bound and of L_simple for t = T-1 .. 0, one graph replay per
+        step.  noise: optional pre-drawn (T, N, C, H, W) eps, entry k belonging to t = T-1-k; when None the draws are
+        made on the device in the reference's order (one randn_like(x) per step)."""
+        x = x.contiguous().float()
+        shape, T = tuple(x.shape), self.timesteps
+        plan = self.eval_plan(shape)
+        plan.prepare()
+        dev = plan.eng.device
+        plan.x0.copy_(x)
+        plan.t_dev.fill_(T - 1)
+        done = 0
+        while done < T:
+            base = done % plan.period
+            chunk = min(plan.period - base, T - done)
+            if noise is None:
+                for j in range(chunk):
+                    plan.noise[base + j].copy_(torch.randn(shape, device=dev))
+            elif isinstance(noise, torch.Tensor):
+                plan.noise[base:base + chunk].copy_(noise[done:done + chunk], non_blocking=True)
+            else:
+                for j in range(chunk):
+                    plan.noise[base + j].copy_(noise[done + j], non_blocking=True)
+            for _ in range(chunk):
+                if self.use_graph:
+                    plan.graph.replay()
+                else:
+                    plan.step_eager()
+            L._Counter.n += chunk * plan.launches_per_step if self.use_graph else 0
+            done += chunk
+        vlb_t = plan.vlb.clone()
+        L_simple_t = plan.sq.sum(dim=0) / float(x.numel())           # get_loss(eps, eps_hat).mean() per step (ddpm.py:419)
+        prior = self.calc_prior(x)
+        return {"vlb_t": vlb_t, "prior": prior, "vlb": vlb_t.sum(dim=1) + prior, "L_simple_t": L_simple_t,
+                "L_simple": L_simple_t.sum()}
+
+    def test_losses(self, x: torch.Tensor, noise=None) -> dict:
+        """ddpm.py:444-446."""
+        return self.test_losses_(x, noise=noise)
 
     # ---- training objective --------------------------------------------------------------------
     def loss_ddpm(self, eps: torch.Tensor, eps_hat: torch.Tensor, t: torch.Tensor) -> torch.Tensor:

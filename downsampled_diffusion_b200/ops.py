@@ -143,3 +143,32 @@ def posterior_step_raw(x_t, eps_hat, noise, coef, t_idx, t_stride: int, noise_st
     L.call("dd_posterior_step", L.ptr(x_t), L.ptr(eps_hat), L.ptr(noise), L.ptr(coef), L.ptr(t_idx), t_stride,
            noise_step_stride, T, noise_period, 1 if clip else 0, L.ptr(out), B, chw, L.stream())
     return out
+
+
+# ---- evaluation-side chain and output formatting (8(f).2) --------------------------------------
+def vlb_terms_raw(x, x_t, eps_hat, tab, t32, T: int) -> torch.Tensor:
+    """DDPM.vlb_terms (ddpm.py:317-365) given the U-Net output, per-sample int32 t: (B,) bits/dim."""
+    x, x_t, eps_hat = _f32c(x), _f32c(x_t), _f32c(eps_hat)
+    B, chw = _flat(x)
+    out = torch.empty(B, dtype=torch.float32, device=x.device)
+    L.call("dd_vlb_terms", L.ptr(x), L.ptr(x_t), L.ptr(eps_hat), None, 0, 0, L.ptr(tab), L.ptr(t32), 1, T, L.ptr(out), None, 1, 0,
+           B, chw, L.stream())
+    return out
+
+
+def prior_kl(x, sqrt_ac_last: float, log_1mac_last: float) -> torch.Tensor:
+    """DDPM.calc_prior (ddpm.py:367-389): (B,) bits/dim."""
+    x = _f32c(x)
+    B, chw = _flat(x)
+    out = torch.empty(B, dtype=torch.float32, device=x.device)
+    L.call("dd_prior_kl", L.ptr(x), float(sqrt_ac_last), float(log_1mac_last), L.ptr(out), B, chw, L.stream())
+    return out
+
+
+def fix_samples_raw(samples: torch.Tensor) -> torch.Tensor:
+    """Per-image min-max normalisation, x255, NCHW -> NHWC (device tensor); utils/eval_helpers.py:37-41."""
+    x = _f32c(samples)
+    B, C, H, W = x.shape
+    out = torch.empty(B, H, W, C, dtype=torch.float32, device=x.device)
+    L.call("dd_fix_samples", L.ptr(x), L.ptr(out), B, C, H, W, L.stream())
+    return out

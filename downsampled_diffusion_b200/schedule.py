@@ -71,3 +71,13 @@ def posterior_coef_table(buf) -> torch.Tensor:
             buf["posterior_mean_coef1"], buf["posterior_mean_coef2"]]
     cols = [c.detach().float().cpu() for c in cols] + [sig]
     return torch.stack(cols, dim=1).contiguous()
+
+
+def eval_coef_table(buf) -> torch.Tensor:
+    """(T, 8) fp32 rows consumed by dd_q_sample_step / dd_vlb_terms: {sqrt_ac, sqrt_1mac, sqrt_recip_ac,
+    sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2, post_logvar_clipped, 0} -- the scalars DDPM.vlb_terms
+    (ddpm.py:339-342) gathers with extract()."""
+    cols = [buf[k].detach().float().cpu() for k in (
+        "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+        "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped")]
+    return torch.stack(cols + [torch.zeros_like(cols[0])], dim=1).contiguous()

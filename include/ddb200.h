@@ -84,6 +84,33 @@ int dd_ema_update(const uint64_t* table, const int32_t* chunks, int n_chunks, in
                   float decay, float one_minus_decay, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Evaluation-side chain and sampler output formatting
+ * tab: (T, 8) fp32 rows {sqrt_ac, sqrt_1mac, sqrt_recip_ac, sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2,
+ * post_logvar_clipped, 0} -- the scalars ddpm.py gathers with extract() (helpers.py:31-34).
+ * ---------------------------------------------------------------------------------------- */
+
+/* q_sample (ddpm.py:256-273) for ONE step shared by the batch, read from the device-side step counter t_idx[0]
+ * (test_losses_, ddpm.py:409-411); eps = noise + ((T-1-t) mod noise_period) * noise_step_stride (no mod when 0). */
+int dd_q_sample_step(const float* x, const float* noise, int64_t noise_step_stride, int noise_period, const float* tab,
+                     const int32_t* t_idx, int T, float* out, int B, int64_t chw, void* stream);
+
+/* DDPM.vlb_terms (ddpm.py:317-365) given eps_hat = UNet(x_t, t): predict_x_from_eps(clip) -> q_posterior of both
+ * means -> normal_kl (losses.py:17-52) for t > 0, minus discretized_gaussian_log_likelihood (losses.py:66-109) for
+ * t == 0 -> flat_bits (utils/utils.py:43-48).  Sample b uses t_idx[b*t_stride].  vlb[b*out_stride + col], col = T-1-t
+ * when col_from_t (the stacking order of ddpm.py:423) else 0.  When sq != NULL also sq[...] = sum_chw (eps - eps_hat)^2
+ * (the L_simple term, ddpm.py:418-419), eps addressed like dd_q_sample_step's noise (eps_step_stride 0 = plain (B, chw)). */
+int dd_vlb_terms(const float* x, const float* x_t, const float* eps_hat, const float* eps, int64_t eps_step_stride, int eps_period,
+                 const float* tab, const int32_t* t_idx, int t_stride, int T, float* vlb, float* sq, int64_t out_stride,
+                 int col_from_t, int B, int64_t chw, void* stream);
+
+/* DDPM.calc_prior (ddpm.py:367-389): out[b] = flat_bits(normal_kl(sqrt_ac[T-1] x, log(1-ac[T-1]), 0, 0)). */
+int dd_prior_kl(const float* x, float sqrt_ac_last, float log_1mac_last, float* out, int B, int64_t chw, void* stream);
+
+/* fix_samples (utils/eval_helpers.py:37-41; min_max_norm_image, utils/utils.py:16-24): per-image
+ * (x - min) / (max - min) * 255, NCHW fp32 -> NHWC fp32 (the np.moveaxis of the reference). */
+int dd_fix_samples(const float* x, float* y, int B, int C, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * U-Net pieces (models/unet/unet.py, models/unet/blocks.py)
  * ---------------------------------------------------------------------------------------- */
 

@@ -356,6 +356,87 @@ def dddpm_sample(sd: SD, cfg: dict, buf: Dict[str, Tensor], noises: Sequence[Ten
 
 
 # --------------------------------------------------------------------------------------
+# evaluation-side chain  (models/diffusion/ddpm.py:317-446, models/utils/losses.py:17-109)
+# --------------------------------------------------------------------------------------
+def flat_bits(x: Tensor) -> Tensor:
+    """utils/utils.py:43-48: mean over the non-batch dimensions, in bits."""
+    return flatten_loss(x, "mean") / np.log(2.0)
+
+
+def normal_kl(mean1, logvar1, mean2, logvar2) -> Tensor:
+    """losses.py:17-52: KL(N(mean1, e^logvar1) || N(mean2, e^logvar2)), python scalars allowed for the second Gaussian."""
+    ref = next(v for v in (mean1, logvar1, mean2, logvar2) if isinstance(v, Tensor))
+    logvar1, logvar2 = (v if isinstance(v, Tensor) else torch.tensor(v).to(ref) for v in (logvar1, logvar2))
+    return 0.5 * (logvar2 - logvar1 - 1.0 + torch.exp(logvar1 - logvar2) + ((mean1 - mean2) ** 2) * torch.exp(-logvar2))
+
+
+def approx_standard_normal_cdf(x: Tensor) -> Tensor:
+    """losses.py:55-63 (tanh approximation of the normal CDF)."""
+    return 0.5 * (1.0 + torch.tanh(np.sqrt(2.0 / np.pi) * (x + 0.044715 * torch.pow(x, 3))))
+
+
+def discretized_gaussian_log_likelihood(x: Tensor, means: Tensor, log_scales: Tensor) -> Tensor:
+    """losses.py:66-109: log-probability of the 1/255-wide bin around x under N(means, e^{2 log_scales}); open bins at +-0.999."""
+    if list(log_scales.shape) == [x.shape[0], 1, 1, 1]:
+        log_scales = log_scales * torch.ones_like(x)
+    centered = x - means
+    inv_stdv = torch.exp(-log_scales)
+    cdf_plus = approx_standard_normal_cdf(inv_stdv * (centered + 1.0 / 255.0))
+    cdf_min = approx_standard_normal_cdf(inv_stdv * (centered - 1.0 / 255.0))
+    log_cdf_plus = torch.log(cdf_plus.clamp(min=1e-12))
+    log_one_minus_cdf_min = torch.log((1.0 - cdf_min).clamp(min=1e-12))
+    mid = torch.log((cdf_plus - cdf_min).clamp(min=1e-12))
+    return torch.where(x < -0.999, log_cdf_plus, torch.where(x > 0.999, log_one_minus_cdf_min, mid))
+
+
+def vlb_terms(buf: Dict[str, Tensor], x: Tensor, x_t: Tensor, t: Tensor, eps_hat: Tensor) -> Tensor:
+    """ddpm.py:317-365 with the U-Net output of p_mean_variance (ddpm.py:199) passed in."""
+    true_mean, _, true_logvar = q_posterior(buf, x, x_t, t)
+    pred_mean, _, pred_logvar = q_posterior(buf, predict_x_from_eps(buf, x_t, t, eps_hat, clip=True), x_t, t)
+    kl = flat_bits(normal_kl(true_mean, true_logvar, pred_mean, pred_logvar))
+    nll = flat_bits(-discretized_gaussian_log_likelihood(x, pred_mean, 0.5 * pred_logvar))
+    return torch.where(t == 0, nll, kl)
+
+
+def calc_prior(buf: Dict[str, Tensor], x: Tensor, T: int) -> Tensor:
+    """ddpm.py:367-389: KL(q(x_T | x) || N(0, I)) in bits/dim."""
+    t = torch.full((x.shape[0],), T - 1, dtype=torch.long)
+    mean = extract(buf["sqrt_alphas_cumprod"], t, x.dim()) * x
+    logvar = extract(buf["log_one_minus_alphas_cumprod"], t, x.dim())
+    return flat_bits(normal_kl(mean, logvar, 0.0, 0.0))
+
+
+def test_losses(sd: SD, cfg: dict, buf: Dict[str, Tensor], x: Tensor, noises: Sequence[Tensor],
+                pre: str = "latent_model.") -> Dict[str, Tensor]:
+    """DDPM.test_losses_ (ddpm.py:391-442) with the per-step draws passed in: noises[k] is the eps of step t = T-1-k.
+    The reference evaluates the U-Net twice per step on identical inputs (ddpm.py:199 and :418); once is enough."""
+    T = cfg["T"]
+    vlb_t, ls_t = [], []
+    for k, i in enumerate(reversed(range(T))):
+        t = torch.full((x.shape[0],), i, dtype=torch.long)
+        eps = noises[k]
+        x_t = q_sample(buf, x, t, eps)
+        eps_hat = unet_forward(sd, cfg, x_t, t, pre)
+        vlb_t.append(vlb_terms(buf, x, x_t, t, eps_hat))
+        ls_t.append(F.mse_loss(eps, eps_hat, reduction="none").mean())
+    vlb_t = torch.stack(vlb_t, dim=1)
+    ls_t = torch.stack(ls_t, dim=0)
+    prior = calc_prior(buf, x, T)
+    return {"vlb_t": vlb_t, "prior": prior, "vlb": vlb_t.sum(dim=1) + prior, "L_simple_t": ls_t, "L_simple": ls_t.sum()}
+
+
+test_losses.__test__ = False        # not a pytest test
+
+
+def fix_samples(samples: Tensor) -> np.ndarray:
+    """utils/eval_helpers.py:37-41 with min_max_norm_image (utils/utils.py:16-24): per-image min-max -> x255 -> NHWC numpy."""
+    b = samples.shape[0]
+    lo = samples.reshape(b, -1).min(dim=1).values[:, None, None, None]
+    hi = samples.reshape(b, -1).max(dim=1).values[:, None, None, None]
+    return np.moveaxis(((samples - lo) / (hi - lo) * 255.0).cpu().numpy(), 1, -1)
+
+
+# --------------------------------------------------------------------------------------
 # EMA  (trainers/ema.py:36-44)
 # --------------------------------------------------------------------------------------
 def ema_update(shadow: Sequence[Tensor], params: Sequence[Tensor], decay: float) -> List[Tensor]:

@@ -54,6 +54,13 @@ def rand_pm1(seed: int, *shape) -> torch.Tensor:
     return torch.rand(*shape, generator=torch.Generator().manual_seed(seed)) * 2 - 1
 
 
+def eval_images(seed: int, *shape) -> torch.Tensor:
+    """Evaluation inputs: values on the uint8 grid rescaled to [-1, 1] (what losses.py:66-109 assumes), so that the
+    open bins beyond +-0.999 of the discretised likelihood occur."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, shape, generator=g).float() / 127.5 - 1.0
+
+
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))

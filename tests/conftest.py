@@ -15,8 +15,11 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np
-    path = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
-    return np.load(path)
+    out = {}
+    for name in ("golden_v1.npz", "golden_v2.npz"):     # v1: oracle/make_golden.py, v2: oracle/make_golden_eval.py
+        with np.load(os.path.join(ROOT, "tests", "golden", name)) as z:
+            out.update({k: z[k] for k in z.files})
+    return out
 
 
 @pytest.fixture(scope="session")

@@ -146,3 +146,42 @@ def test_ema(golden):
     got = dict(zip(names, shadow))
     for n in ("final_conv.1.weight", "downs.0.0.block1.block.0.bias", "mid_attn.fn.norm.g", "time_mlp.3.weight"):
         assert torch.equal(got[n], T(golden[f"ema.{n}"])), n
+
+
+# ---- evaluation-side chain, output formatting (golden_v2 from oracle/make_golden_eval.py) ----------
+def eval_noise(seed, x, n):
+    torch.manual_seed(seed)
+    return [torch.randn_like(x) for _ in range(n)]
+
+
+def test_vlb_terms_and_prior(golden):
+    sd = sd_of(tc.C1, "ddpm")
+    buf = O.schedule_buffers("linear", 1000)
+    x = tc.eval_images(71, 4, 1, 28, 28)
+    eps = tc.randn(72, 4, 1, 28, 28)
+    for key, t in (("eval.c1.vlb_terms", torch.tensor([0, 1, 500, 999])), ("eval.c1.vlb_terms_t0", torch.zeros(4, dtype=torch.long))):
+        x_t = O.q_sample(buf, x, t, eps)
+        with torch.no_grad():
+            eps_hat = O.unet_forward(sd, tc.C1, x_t, t, "latent_model.")
+        got = O.vlb_terms(buf, x, x_t, t, eps_hat)
+        np.testing.assert_allclose(got.numpy(), golden[key], rtol=2e-5)
+    assert torch.equal(O.calc_prior(buf, x, 1000), T(golden["eval.c1.prior"]))
+
+
+@pytest.mark.parametrize("tag,cfg,kind,shape,seed,xseed", [("c1", tc.C1, "ddpm", (2, 1, 28, 28), 9, 73),
+                                                          ("cs", tc.CS, "dddpm_ae", (2, 3, 32, 32), 10, 74)])
+def test_evaluation_chain(golden, tag, cfg, kind, shape, seed, xseed):
+    cfg = dict(cfg, T=50)
+    sd = sd_of(cfg, kind)
+    buf = O.schedule_buffers("linear", 50)
+    x = tc.eval_images(xseed, *shape)
+    with torch.no_grad():
+        z = O.rescaled_downsample(sd, cfg, x) if kind != "ddpm" else x          # dddpm.py:146-148
+        got = O.test_losses(sd, cfg, buf, z, eval_noise(seed, z, 50))
+    for k, v in got.items():
+        np.testing.assert_allclose(v.numpy(), golden[f"eval.{tag}.test_losses.{k}"], rtol=3e-5, err_msg=k)
+
+
+def test_fix_samples(golden):
+    out = O.fix_samples(tc.randn(75, 3, 3, 32, 32))
+    assert out.shape == (3, 32, 32, 3) and np.array_equal(out, golden["fix_samples.out"])
