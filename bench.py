@@ -355,7 +355,9 @@ def run_train(args):
     model = tc.build_model(cfg, dd, "dddpm_ae", device=str(dev)).to(dev).train()
     model.downsample.precision = model.upsample.precision = cfg["precision"]
     ema = dd.EMA(model, decay=0.995)
-    opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    # the trainer's clip_grad_norm_(1.0) -> Adam.step -> EMA.update (trainer_ddpm.py:243-254) as the package's fused optimizer
+    opt = dd.Adam(model.parameters(), lr=2e-4, max_grad_norm=1.0)
+    opt.attach_ema(ema, model)
     params = [p for p in model.parameters()]
     x_host = torch.empty(B, *IMAGE, dtype=torch.float32, pin_memory=True)
     x_host.copy_(tc.rand_pm1(100 + rank, B, *IMAGE))
@@ -365,10 +367,8 @@ def run_train(args):
         obj, _ = model(x)
         obj.backward()
         parallel.allreduce_gradients(params)
-        torch.nn.utils.clip_grad_norm_(params, 1.0)
-        opt.step()
+        opt.step(ema="update")
         opt.zero_grad()
-        ema.update(model)
         return obj
 
     def barrier():

@@ -12,6 +12,7 @@ from .downsampled import ConvResNet, SimpleDownConv, SimpleUpConv, get_downsampl
 from .ema import EMA
 from .schedule import make_beta_schedule
 from .evalfmt import fix_samples
+from .optim import Adam
 
 __all__ = ["Unet", "DDPM", "DownsampleDDPM", "DownsampleDDPMAutoencoder", "ConvResNet", "SimpleDownConv",
-           "SimpleUpConv", "get_downsampling", "get_upsampling", "EMA", "make_beta_schedule", "fix_samples"]
+           "SimpleUpConv", "get_downsampling", "get_upsampling", "EMA", "make_beta_schedule", "fix_samples", "Adam"]

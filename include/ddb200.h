@@ -84,6 +84,27 @@ int dd_ema_update(const uint64_t* table, const int32_t* chunks, int n_chunks, in
                   float decay, float one_minus_decay, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Optimizer step of the training loop: trainer_ddpm.py:128-135 / :243-250 = clip_grad_norm_(1.0),
+ * Adam.step (trainers/trainer.py:69), zero_grad, EMA.update.  table: device array of n_tensors*6 uint64
+ * {param, grad, exp_avg, exp_avg_sq, shadow (0 = none), numel}, all fp32; chunks as in dd_ema_update.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Total gradient L2 norm over every tensor and the clip coefficient, left on the device:
+ * norm_out[0] = ||g||_2, norm_out[1] = min(max_norm / (||g||_2 + 1e-6), 1) (1 when max_norm <= 0).
+ * partial: n_chunks floats of scratch.  torch.nn.utils.clip_grad_norm_ without its host synchronisation. */
+int dd_grad_norm(const uint64_t* table, const int32_t* chunks, int n_chunks, int chunk_elems, float max_norm, float* partial,
+                 float* norm_out, void* stream);
+
+/* One pass over all parameters: g *= norm_out[1] (skipped when norm_out == NULL); torch.optim.Adam's update
+ * (exp_avg.lerp_(g, 1-beta1); exp_avg_sq = beta2*exp_avg_sq + (1-beta2)*g*g; p += neg_step_size * exp_avg /
+ * (sqrt(exp_avg_sq)/bias_correction2_sqrt + eps), neg_step_size = -lr/(1-beta1^step)); then the EMA of trainers/ema.py:36-44
+ * on the fresh parameter (ema_mode 1), a plain copy (2: EMA.reset during warm-up, trainer_ddpm.py:107-109) or nothing (0);
+ * zero_grad != 0 clears the gradient in place. */
+int dd_adam_ema_step(const uint64_t* table, const int32_t* chunks, int n_chunks, int chunk_elems, const float* norm_out,
+                     float one_minus_beta1, float beta2, float one_minus_beta2, float bias_correction2_sqrt, float eps,
+                     float neg_step_size, int ema_mode, float decay, float one_minus_decay, int zero_grad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Evaluation-side chain and sampler output formatting
  * tab: (T, 8) fp32 rows {sqrt_ac, sqrt_1mac, sqrt_recip_ac, sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2,
  * post_logvar_clipped, 0} -- the scalars ddpm.py gathers with extract() (helpers.py:31-34).

@@ -442,3 +442,26 @@ def fix_samples(samples: Tensor) -> np.ndarray:
 def ema_update(shadow: Sequence[Tensor], params: Sequence[Tensor], decay: float) -> List[Tensor]:
     """p_ema <- p_ema*decay + (1-decay)*p, parameter by parameter, buffers untouched."""
     return [s * decay + (1 - decay) * p for s, p in zip(shadow, params)]
+
+
+# --------------------------------------------------------------------------------------
+# optimizer step of the trainer  (trainers/trainer.py:69 Adam(lr); trainers/trainer_ddpm.py:128-135: clip_grad_norm_(1.0),
+# opt.step()).  Both are torch library code (pinned torch==1.9.0, README.md:17); restated from their published algorithm:
+# Kingma & Ba 2015, Algorithm 1 in the eps-outside-sqrt, bias-corrected form torch.optim.Adam implements; clipping by the
+# global L2 norm with torch's 1e-6 guard.
+# --------------------------------------------------------------------------------------
+def clip_grad_norm(grads: Sequence[Tensor], max_norm: float) -> Tuple[Tensor, List[Tensor]]:
+    """total norm = || (||g_i||_2)_i ||_2 ; g_i *= min(max_norm / (total + 1e-6), 1)."""
+    total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g, 2) for g in grads]), 2)
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return total, [g * coef for g in grads]
+
+
+def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, beta1: float = 0.9, beta2: float = 0.999,
+              eps: float = 1e-8) -> Tuple[Tensor, Tensor, Tensor]:
+    """One Adam update of one tensor; returns (p, m, v).  step counts from 1."""
+    m = m + (g - m) * (1 - beta1)
+    v = v * beta2 + (1 - beta2) * g * g
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    denom = v.sqrt() / math.sqrt(bc2) + eps
+    return p - (lr / bc1) * m / denom, m, v

@@ -29,7 +29,8 @@ def main():
     out = {}
 
     def put(name, t):
-        out[name] = t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+        # a copy: .numpy() of a CPU parameter aliases it, and the optimizer below keeps writing to the parameters
+        out[name] = t.detach().cpu().numpy().copy() if isinstance(t, torch.Tensor) else np.array(t, copy=True)
 
     def ref_model(cfg, kind, seed=0):
         mine = tc.build_model(cfg, ours, kind, seed)

@@ -54,9 +54,10 @@ def test_vlb_terms_kernel_vs_oracle_and_golden(cuda, golden):
     close(m.calc_prior(x.to(cuda)), golden["eval.c1.prior"], 2e-6)
 
 
-@pytest.mark.parametrize("tag,cfg,kind,shape,seed,xseed", [("c1", tc.C1, "ddpm", (2, 1, 28, 28), 9, 73),
-                                                          ("cs", tc.CS, "dddpm_ae", (2, 3, 32, 32), 10, 74)])
-@pytest.mark.parametrize("precision,rtol", [("fp32", 2e-4), ("bf16", 6e-2)])
+@pytest.mark.parametrize("tag,cfg,kind,shape,seed,xseed,precision,rtol", [
+    ("c1", tc.C1, "ddpm", (2, 1, 28, 28), 9, 73, "fp32", 2e-4),          # 28x28 maps have no bf16 tensor-core tiling (fp32 mode only)
+    ("cs", tc.CS, "dddpm_ae", (2, 3, 32, 32), 10, 74, "fp32", 2e-4),
+    ("cs", tc.CS, "dddpm_ae", (2, 3, 32, 32), 10, 74, "bf16", 6e-2)])
 def test_evaluation_chain_vs_reference(cuda, golden, tag, cfg, kind, shape, seed, xseed, precision, rtol):
     cfg = dict(cfg, T=50, precision=precision)
     m = tc.build_model(cfg, dd, kind, device="cuda").to(cuda).eval()

@@ -411,3 +411,86 @@ def test_operand_copies_and_space_to_depth(cuda):
     back = torch.empty_like(full)
     L.call("dd_s2d_f32", L.ptr(packed), L.ptr(back), B, H, W, C, 0, L.stream())
     assert torch.equal(back, full)
+
+
+# ---- optimizer step of the trainer: clip_grad_norm_ + Adam + EMA in three launches -------------------
+OPT_NAMES = ("final_conv.1.weight", "downs.0.0.block1.block.0.bias", "mid_attn.fn.norm.g", "time_mlp.3.weight")
+
+
+def _set_grads(net, step):
+    g = torch.Generator().manual_seed(80 + step)
+    for p in net.parameters():          # the gradients oracle/make_golden_eval.py fed the reference's optimizer
+        p.grad = ((0.05 if step == 0 else 0.0005) * torch.randn(p.shape, generator=g)).to(p.device)
+
+
+def test_fused_adam_matches_torch_adam_of_the_reference_trainer(cuda, golden):
+    net = tc.build_model(tc.CS, dd, "unet").to(cuda)
+    twin = tc.build_model(tc.CS, dd, "unet").to(cuda)               # torch's own CUDA implementation, same gradients
+    opt = dd.Adam(net.parameters(), lr=2e-4, max_grad_norm=1.0)
+    topt = torch.optim.Adam(twin.parameters(), lr=2e-4)
+    for step in range(2):
+        _set_grads(net, step)
+        _set_grads(twin, step)
+        opt.step()
+        tnorm = torch.nn.utils.clip_grad_norm_(twin.parameters(), 1.0)
+        topt.step()
+        ref_norm = float(golden[f"optim.norm{step}"])
+        assert abs(float(opt.grad_norm) - ref_norm) <= 2e-6 * ref_norm and abs(float(tnorm) - ref_norm) <= 1e-5 * ref_norm
+        sd, tsd = net.state_dict(), twin.state_dict()
+        for n in OPT_NAMES:                                          # against the reference's CPU run: within 2 ulp of the weights
+            ref = G(golden, f"optim.step{step}.{n}").to(cuda)
+            assert (sd[n] - ref).abs().max() <= 2.4e-7 * max(1.0, float(ref.abs().max())), n
+        for n in sd:
+            assert (sd[n] - tsd[n]).abs().max() <= 2.4e-7 * max(1.0, float(tsd[n].abs().max())), n
+    # optimizer state has torch's layout: a torch.optim.Adam continues from it and vice versa
+    state = opt.state_dict()
+    assert set(state["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(state["state"][0]["step"]) == 2.0
+    topt2 = torch.optim.Adam(net.parameters(), lr=2e-4)
+    topt2.load_state_dict(state)
+    opt2 = dd.Adam(twin.parameters(), lr=2e-4, max_grad_norm=1.0)
+    opt2.load_state_dict(topt.state_dict())
+    _set_grads(net, 2)
+    _set_grads(twin, 2)
+    torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+    topt2.step()
+    opt2.step()
+    for a, b in zip(net.parameters(), twin.parameters()):
+        assert (a - b).abs().max() <= 2.4e-7 * max(1.0, float(a.abs().max()))
+
+
+def test_fused_adam_ema_and_weight_refresh(cuda):
+    m = tc.build_model(dict(tc.CS, precision="fp32"), dd, "dddpm_ae", device="cuda").to(cuda).train()
+    twin = tc.build_model(dict(tc.CS, precision="fp32"), dd, "dddpm_ae", device="cuda").to(cuda).train()
+    ema, tema = dd.EMA(m, decay=0.9), dd.EMA(twin, decay=0.9)
+    opt = dd.Adam(m.parameters(), lr=1e-3, max_grad_norm=1.0)
+    opt.attach_ema(ema, m)
+    topt = dd.Adam(twin.parameters(), lr=1e-3, max_grad_norm=1.0)
+    x = tc.rand_pm1(90, 4, 3, 32, 32).to(cuda)
+    t = torch.tensor([3, 50, 99, 700], device=cuda)
+    eps = tc.randn(91, 4, 8, 8, 8).to(cuda)
+    losses = []
+    for step, mode in enumerate(("reset", "update", "update")):
+        for mod, o in ((m, opt), (twin, topt)):
+            obj, _ = mod.losses(x, t, eps=eps)
+            obj.backward()
+        losses.append(float(obj))
+        opt.step(ema=mode, zero_grad=(step == 1))                   # fused: clip + Adam + EMA (+ gradient reset)
+        topt.step()                                                 # unfused: the same optimizer, then the EMA calls of the trainer
+        (tema.reset if mode == "reset" else tema.update)(twin)
+        if step == 1:
+            assert all(p.grad is not None and not p.grad.any() for p in m.parameters())
+        else:
+            opt.zero_grad()
+        topt.zero_grad()
+        # (weight-gradient atomics make the two models' gradients differ in the last bits, hence not torch.equal)
+        for a, b in zip(m.parameters(), twin.parameters()):
+            assert torch.allclose(a, b, rtol=0, atol=2e-6)
+        for a, b in zip(ema.ema_model.parameters(), tema.ema_model.parameters()):
+            assert torch.allclose(a, b, rtol=0, atol=2e-6)
+    assert losses[0] != losses[1] != losses[2]                      # the training programs saw the updated weights (version bump)
+    with torch.no_grad():                                           # and so does the shadow model's sampling engine
+        a = ema.ema_model.latent_model(eps, t)
+        b = tema.ema_model.latent_model(eps, t)
+    assert tc.rel_l2(a, b) < 1e-4
+    with pytest.raises(RuntimeError):
+        dd.Adam(twin.parameters(), lr=1e-3).step(ema="update")

@@ -185,3 +185,22 @@ def test_evaluation_chain(golden, tag, cfg, kind, shape, seed, xseed):
 def test_fix_samples(golden):
     out = O.fix_samples(tc.randn(75, 3, 3, 32, 32))
     assert out.shape == (3, 32, 32, 3) and np.array_equal(out, golden["fix_samples.out"])
+
+
+def test_trainer_optimizer_step(golden):
+    """clip_grad_norm_(1.0) + Adam(lr=2e-4) of the reference's trainer, two steps on synthetic gradients (golden_v2)."""
+    net = tc.build_model(tc.CS, ours, "unet")
+    names = [n for n, _ in net.named_parameters()]
+    ps = [p.detach().clone() for p in net.parameters()]
+    ms, vs = [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps]
+    for step in range(2):
+        g = torch.Generator().manual_seed(80 + step)
+        grads = [(0.05 if step == 0 else 0.0005) * torch.randn(p.shape, generator=g) for p in ps]
+        total, grads = O.clip_grad_norm(grads, 1.0)
+        np.testing.assert_allclose(float(total), float(golden[f"optim.norm{step}"]), rtol=1e-6)
+        for i in range(len(ps)):
+            ps[i], ms[i], vs[i] = O.adam_step(ps[i], grads[i], ms[i], vs[i], step + 1, 2e-4)
+        for n in ("final_conv.1.weight", "downs.0.0.block1.block.0.bias", "mid_attn.fn.norm.g", "time_mlp.3.weight"):
+            ref = T(golden[f"optim.step{step}.{n}"])
+            assert (ps[names.index(n)] - ref).abs().max() <= 2.4e-7 * max(1.0, float(ref.abs().max())), n
+    assert float(golden["optim.norm0"]) > 1.0 > float(golden["optim.norm1"])      # step 0 was clipped, step 1 was not
