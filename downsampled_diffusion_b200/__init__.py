@@ -11,8 +11,8 @@ from .dddpm import DownsampleDDPM, DownsampleDDPMAutoencoder
 from .downsampled import ConvResNet, SimpleDownConv, SimpleUpConv, get_downsampling, get_upsampling
 from .ema import EMA
 from .schedule import make_beta_schedule
-from .evalfmt import fix_samples
+from .evalfmt import fix_samples, generate_samples
 from .optim import Adam
 
 __all__ = ["Unet", "DDPM", "DownsampleDDPM", "DownsampleDDPMAutoencoder", "ConvResNet", "SimpleDownConv",
-           "SimpleUpConv", "get_downsampling", "get_upsampling", "EMA", "make_beta_schedule", "fix_samples", "Adam"]
+           "SimpleUpConv", "get_downsampling", "get_upsampling", "EMA", "make_beta_schedule", "fix_samples", "generate_samples", "Adam"]

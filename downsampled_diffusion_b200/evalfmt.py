@@ -19,3 +19,34 @@ def fix_samples(samples: torch.Tensor, out: torch.Tensor = None, non_blocking: b
         out = torch.empty(dev.shape, dtype=torch.float32, pin_memory=True)
     out.copy_(dev, non_blocking=non_blocking)
     return out.numpy()
+
+
+@torch.no_grad()
+def generate_samples(model, n_samples: int, batch_size: int, every: int = 1):
+    """The sampling loop of generate_model_samples.py:41-51: ceil(n_samples / batch_size) calls of `model.sample`, each
+    batch passed through `fix_samples`.  Returns (sample_list, latent_list) -- lists of (B, H, W, C) float32 arrays, the
+    objects the reference hands to np.save (:61, :67); latent_list is empty for a plain DDPM.
+
+    The formatted batch goes to pinned host memory with a non-blocking copy that overlaps the next batch's chain; the host
+    waits on one event per batch only when it collects the arrays at the end."""
+    n_batches = -(-n_samples // batch_size)
+    pending = []
+    for _ in range(n_batches):
+        out = model.sample(batch_size, every)
+        parts = out if isinstance(out, tuple) else (out,)
+        host = []
+        for t in parts:
+            dev = ops.fix_samples_raw(t)
+            buf = torch.empty(dev.shape, dtype=torch.float32, pin_memory=True)
+            buf.copy_(dev, non_blocking=True)
+            host.append(buf)
+        ev = torch.cuda.Event()
+        ev.record()
+        pending.append((ev, host))
+    sample_list, latent_list = [], []
+    for ev, host in pending:
+        ev.synchronize()
+        sample_list.append(host[0].numpy())
+        if len(host) > 1:
+            latent_list.append(host[1].numpy())
+    return sample_list, latent_list

@@ -38,6 +38,7 @@ class Adam(torch.optim.Optimizer):
         self.grad_norm: Optional[torch.Tensor] = None      # device scalar: total gradient norm of the last step (before clipping)
         self._ema = None
         self._plans = {}
+        self._steps = {}                                    # group index -> number of steps taken
 
     # ---- EMA fusion -------------------------------------------------------------------------------
     def attach_ema(self, ema, model: torch.nn.Module) -> None:
@@ -53,10 +54,43 @@ class Adam(torch.optim.Optimizer):
         return {id(p): s for p, s in zip(model.parameters(), ema.ema_model.parameters())}
 
     # ---- launch plan per parameter group ---------------------------------------------------------------
+    # torch keeps one CPU `step` tensor per parameter and increments each of them every step (~380 host operations); here
+    # the count lives in one Python number per group and is written into the per-parameter tensors when a state_dict is taken.
+    def _sync_steps(self) -> None:
+        for gi, group in enumerate(self.param_groups):
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st:
+                    st["step"] = torch.tensor(float(self._steps.get(gi, 0)), dtype=torch.float32)
+
+    def state_dict(self):
+        self._sync_steps()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict) -> None:
+        super().load_state_dict(state_dict)
+        self._plans.clear()                                 # exp_avg / exp_avg_sq were replaced
+        self._steps = {}
+        for gi, group in enumerate(self.param_groups):
+            steps = [float(self.state[p]["step"]) for p in group["params"] if self.state.get(p)]
+            if steps:
+                if min(steps) != max(steps):
+                    raise RuntimeError("parameters of one group carry different step counts")
+                self._steps[gi] = int(steps[0])
+
     def _plan(self, gi: int, group, with_shadow: bool):
-        shadow = self._shadow_of() if with_shadow else {}
-        rows, chunks, key = [], [], []
+        """Pointer table + chunk list of the group.  Parameters, moments and shadows stay where they are between steps
+        (load_state_dict / attach_ema / a replaced ema_model rebuild the plan); gradients re-created by autograd after
+        zero_grad(set_to_none=True) may move, so their pointers -- and the parameters' -- are re-read every step and the
+        table goes up again only when one changed, from pinned memory on the current stream (the host never waits)."""
         params = [p for p in group["params"] if p.grad is not None]
+        ema_id = id(self._ema[0].ema_model) if (with_shadow and self._ema is not None) else 0
+        key = (ema_id, tuple(p.data_ptr() for p in params), tuple(p.grad.data_ptr() for p in params))
+        plan = self._plans.get((gi, with_shadow))
+        if plan is not None and plan["key"] == key:
+            return plan
+        shadow = self._shadow_of() if with_shadow else {}
+        rows, chunks = [], []
         for i, p in enumerate(params):
             st = self.state[p]
             if len(st) == 0:
@@ -70,21 +104,17 @@ class Adam(torch.optim.Optimizer):
                     raise RuntimeError("downsampled_diffusion_b200.Adam needs contiguous fp32 CUDA tensors (no CPU fallback)")
             rows += [p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), s.data_ptr() if s is not None else 0, p.numel()]
             chunks += [[i, c] for c in range((p.numel() + CHUNK - 1) // CHUNK)]
-        key = tuple(rows)
-        plan = self._plans.get((gi, with_shadow))
-        if plan is None or plan["key"] != key:
-            dev = params[0].device
-            # gradients re-created by autograd after zero_grad(set_to_none=True) may move: the pointer table then goes up
-            # again, from pinned memory on the current stream, so the host never waits for the device here
-            table = torch.tensor(rows, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)     # uint64 bit patterns
-            if plan is not None and plan["numels"] == key[5::6]:
-                plan.update(key=key, params=params, table=table)
-            else:
-                plan = dict(key=key, params=params, table=table, numels=key[5::6],
-                            chunks=torch.tensor(chunks, dtype=torch.int32, device=dev), n=len(chunks),
-                            partial=torch.empty(len(chunks), dtype=torch.float32, device=dev),
-                            norm=torch.zeros(2, dtype=torch.float32, device=dev))
-            self._plans[(gi, with_shadow)] = plan
+        dev = params[0].device
+        table = torch.tensor(rows, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)     # uint64 bit patterns
+        numels = tuple(rows[5::6])
+        if plan is not None and plan["numels"] == numels:
+            plan.update(key=key, params=params, table=table)
+        else:
+            plan = dict(key=key, params=params, table=table, numels=numels,
+                        chunks=torch.tensor(chunks, dtype=torch.int32, device=dev), n=len(chunks),
+                        partial=torch.empty(len(chunks), dtype=torch.float32, device=dev),
+                        norm=torch.zeros(2, dtype=torch.float32, device=dev))
+        self._plans[(gi, with_shadow)] = plan
         return plan
 
     @torch.no_grad()
@@ -110,12 +140,8 @@ class Adam(torch.optim.Optimizer):
                 raise NotImplementedError("weight_decay / amsgrad / maximize are not part of the reference's optimizer")
             plan = self._plan(gi, group, ema_mode != 0)
             params = plan["params"]
-            step_t = self.state[params[0]]["step"]          # host-side counter (a CPU scalar tensor, as torch keeps it) ...
-            if self.state[params[-1]]["step"] is not step_t:
-                for p in params:                            # ... shared by the group's parameters: one increment per step
-                    self.state[p]["step"] = step_t
-            step_t += 1
-            step = float(step_t)
+            self._steps[gi] = self._steps.get(gi, 0) + 1
+            step = float(self._steps[gi])
             beta1, beta2 = group["betas"]
             bc1 = 1.0 - beta1 ** step
             bc2 = 1.0 - beta2 ** step
@@ -132,12 +158,16 @@ class Adam(torch.optim.Optimizer):
             # the kernel wrote through raw pointers: tell autograd / the packed-weight caches that the parameters changed
             torch.autograd.graph.increment_version(params)
         if ema_mode and self._ema is not None:
-            _invalidate(self._ema[0].ema_model)
+            # the shadow's weights changed under its packed caches: same bookkeeping as EMA.update, through the version counters
+            em = self._ema[0].ema_model
+            if getattr(self, "_shadow_params", (None, None))[0] is not em:
+                self._shadow_params = (em, list(em.parameters()))
+            torch.autograd.graph.increment_version(self._shadow_params[1])
         return loss
 
 
 def _invalidate(model: torch.nn.Module) -> None:
-    """The shadow's weights changed under its packed caches (same bookkeeping as EMA.update)."""
+    """(kept for callers that write a model's weights through raw pointers)"""
     for m in model.modules():
         if hasattr(m, "invalidate"):
             m.invalidate()

@@ -133,3 +133,20 @@ def test_fix_samples_bit_exact(cuda, golden):
     assert np.array_equal(dd.fix_samples(big.to(cuda)), O.fix_samples(big))
     odd = tc.randn(77, 2, 1, 5, 7)
     assert np.array_equal(dd.fix_samples(odd.to(cuda)), O.fix_samples(odd))
+
+
+def test_generate_samples_loop(cuda):
+    """generate_model_samples.py:41-51: batches of `sample` -> `fix_samples`, with the host copies overlapped."""
+    cfg = dict(tc.CS, T=20, precision="fp32")
+    m = tc.build_model(cfg, dd, "dddpm_ae", device="cuda").to(cuda).eval()
+    torch.manual_seed(4)
+    xs, zs = dd.generate_samples(m, 5, 2)
+    assert len(xs) == len(zs) == 3 and xs[0].shape == (2, 32, 32, 3) and zs[0].shape == (2, 8, 8, 8)
+    torch.manual_seed(4)
+    for k in range(3):
+        x, z = m.sample(2)
+        assert np.array_equal(xs[k], O.fix_samples(x.cpu())) and np.array_equal(zs[k], O.fix_samples(z.cpu()))
+    assert all(a.min() == 0.0 and a.max() == 255.0 for a in xs + zs)
+    plain = tc.build_model(dict(tc.C1, T=20, precision="fp32"), dd, "ddpm", device="cuda").to(cuda).eval()
+    xs, zs = dd.generate_samples(plain, 3, 3)
+    assert len(xs) == 1 and zs == [] and xs[0].shape == (3, 28, 28, 1)
