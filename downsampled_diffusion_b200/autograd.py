@@ -18,7 +18,8 @@ from typing import Callable, Dict, List, Optional, Tuple
 import torch
 
 from . import _lib as L
-from .engine import Act, EngineCache, Program, ensure_lazy
+from .engine import Act, EngineCache, Program, ensure_lazy, params_version
+from .relayout import EXACT, GatherPlan, apply_codes, codes_from_probes
 
 GN_EPS = 1e-5
 
@@ -83,6 +84,109 @@ class TrainProgram(Program):
         self.pg_arena = torch.zeros(max(self.pg_total, 1), dtype=torch.float32, device=self.device)
         for key, n in self.scratch_need.items():
             self.scratch_buf[key] = torch.empty(n, dtype=torch.float32, device=self.device)
+        self.repack_plan = self.grad_plan = None
+        if not os.environ.get("DD_NO_RELAYOUT_PLAN"):
+            with torch.no_grad():
+                self._build_repack_plan()
+                self._build_grad_plan()
+
+    # ---- tabulated re-layouts (relayout.py): weights -> packed buffers, packed gradients -> parameter gradients --------
+    def _build_repack_plan(self) -> None:
+        params = list(self.module.parameters())
+        if not params or not self.packers or max(p.numel() for p in params) >= EXACT or len(params) >= EXACT:
+            return
+        dev = self.device
+        cand = [i for i, b in enumerate(self.packed_bufs) if b.dtype == torch.float32 and b.is_contiguous()]
+        saved = [p.data for p in params]
+        snaps = []
+        try:
+            for which in (0, 1):            # sources hold "tensor ordinal + 1", then "element index"
+                for i, p in enumerate(params):
+                    p.data = (torch.full(p.shape, float(i + 1), dtype=torch.float32, device=dev) if which == 0 else
+                              torch.arange(p.numel(), dtype=torch.float32, device=dev).view(p.shape))
+                for b in self.packed_bufs:
+                    b.zero_()
+                for pk in self.packers:
+                    pk()
+                snaps.append([self.packed_bufs[i].detach().clone() for i in cand])
+        finally:
+            for p, d in zip(params, saved):
+                p.data = d
+        for b in self.packed_bufs:
+            b.zero_()
+        for pk in self.packers:             # the real weights again: also the reference the tables are checked against
+            pk()
+        numels = torch.tensor([p.numel() for p in params], dtype=torch.int64, device=dev)
+        offsets = torch.cumsum(numels, 0) - numels
+        flat = torch.cat([p.detach().reshape(-1).float() for p in params])
+        dsts, codes, fast = [], [], set()
+        for j, i in enumerate(cand):
+            c = codes_from_probes(snaps[0][j], snaps[1][j], numels)
+            if c is not None and torch.equal(apply_codes(c, flat, offsets), self.packed_bufs[i].reshape(-1)):
+                dsts.append(self.packed_bufs[i])
+                codes.append(c)
+                fast.add(i)
+        if not dsts:
+            return
+        self.repack_plan = GatherPlan(dsts, codes)
+        self.repack_params = params
+        self.slow_packers = [pk for i, pk in enumerate(self.packers) if i not in fast]
+
+    def refresh_weights(self) -> None:
+        if getattr(self, "repack_plan", None) is None:
+            return super().refresh_weights()
+        v = params_version(self.module)
+        if v != self.weights_version:
+            self.repack_plan.run(tuple(p.data_ptr() for p in self.repack_params))
+            for pk in self.slow_packers:
+                pk()
+            self.weights_version = v
+
+    def _build_grad_plan(self) -> None:
+        total = self.pg_total
+        if total == 0 or total + 1 >= EXACT * 4096:
+            return
+        dev = self.device
+        count: Dict[int, int] = {}
+        for param, _, _, _ in self.pg_specs:
+            count[id(param)] = count.get(id(param), 0) + 1
+        cand = [k for k, (param, _, _, _) in enumerate(self.pg_specs) if count[id(param)] == 1]
+        pos1 = torch.arange(1, total + 1, dtype=torch.int64, device=dev)          # position + 1: zero stays "no source"
+        probes = ((pos1 >> 12).float(), (pos1 & 4095).float())
+        check = (pos1.float() * 0.6180339887).frac() - 0.5            # validation data (no RNG draw: callers seed around the build)
+
+        def through(arena, k):
+            param, off, shape, to_param = self.pg_specs[k]
+            n = 1
+            for s_ in shape:
+                n *= s_
+            return to_param(arena[off:off + n].view(shape)).reshape(-1)
+        codes, self.grad_fast, fast, start = [], [], set(), 0
+        for k in cand:
+            param, off, shape, _ = self.pg_specs[k]
+            hi, lo = through(probes[0], k), through(probes[1], k)
+            if hi.numel() != param.numel():
+                continue
+            hi_i, lo_i = hi.round().long(), lo.round().long()
+            if not (bool((hi == hi_i).all()) and bool((lo == lo_i).all())):
+                continue
+            pos = hi_i * 4096 + lo_i                                               # = source position + 1, 0 = constant zero
+            if not bool(((pos >= 0) & (pos <= total)).all()):
+                continue
+            c = torch.where(pos > 0, (1 << 32) | (pos - 1), torch.zeros_like(pos))
+            got = torch.where(pos > 0, check[(pos - 1).clamp(min=0)], torch.zeros((), device=dev))
+            if not torch.equal(got, through(check, k)):
+                continue
+            n = param.numel()
+            pad = (-n) % 4                                                          # every gradient starts 16-byte aligned
+            codes.append(torch.cat([c, torch.zeros(pad, dtype=torch.int64, device=dev)]) if pad else c)
+            self.grad_fast.append((param, start, n))
+            fast.add(k)
+            start += n + pad
+        if not codes:
+            return
+        self.grad_plan = GatherPlan([None], [torch.cat(codes)], first_dst_per_call=True)
+        self.slow_specs = [sp for k, sp in enumerate(self.pg_specs) if k not in fast]
 
     # ---- gradient buffers ---------------------------------------------------------------------
     def grad(self, a: Act) -> torch.Tensor:
@@ -122,7 +226,15 @@ class TrainProgram(Program):
 
     def param_grads(self) -> Dict[int, torch.Tensor]:
         out: Dict[int, torch.Tensor] = {}
-        for param, off, shape, to_param in self.pg_specs:
+        specs = self.pg_specs
+        if getattr(self, "grad_plan", None) is not None:
+            # one launch writes every tabulated gradient, in parameter layout, into one fresh buffer; the gradients are views
+            flat = torch.empty(self.grad_plan.total, dtype=torch.float32, device=self.device)
+            self.grad_plan.run((self.pg_arena.data_ptr(),), dst0=flat)
+            for param, o, n in self.grad_fast:
+                out[id(param)] = flat[o:o + n].view(param.shape)
+            specs = self.slow_specs
+        for param, off, shape, to_param in specs:
             n = 1
             for s in shape:
                 n *= s

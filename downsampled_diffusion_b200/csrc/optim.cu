@@ -125,6 +125,33 @@ __global__ void __launch_bounds__(256) adam_ema_kernel(const uint64_t* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-tensor re-layout: dst_seg[i] = code ? src[(code >> 32) - 1][code & 0xffffffff] : 0 for every element of every
+// segment, one launch.  The training programs derive ~600 packed weight buffers (K-major matrices, flipped / transposed
+// input-gradient forms, space-to-depth forms of the strided convs) from the fp32 master parameters after every optimizer
+// step, and map the packed weight gradients back to parameter layout; each re-layout is a fixed permutation, so it is
+// tabulated once (engine side, by pushing index codes through the packing functions) and replayed here instead of ~900
+// strided-copy launches per step.  16 B of traffic per element (8 code, 4 gathered read, 4 write).
+// segs: n_segs * 3 uint64 {dst pointer, first element in `codes`, element count}; blocks: n_blocks * 2 int32 {segment, chunk}.
+// ---------------------------------------------------------------------------------------------
+constexpr int GATHER_CHUNK = 4096;
+
+__global__ void __launch_bounds__(256) gather_f32_kernel(const uint64_t* __restrict__ segs, const int32_t* __restrict__ blocks,
+                                                         const unsigned long long* __restrict__ codes,
+                                                         const uint64_t* __restrict__ src_table, float* dst0) {
+    pdl_sync();
+    const int si = blocks[2 * blockIdx.x], ci = blocks[2 * blockIdx.x + 1];
+    float* __restrict__ dst = (si == 0 && dst0) ? dst0 : reinterpret_cast<float*>(segs[3 * si]);
+    const unsigned long long* __restrict__ code = codes + segs[3 * si + 1];
+    const int64_t n = (int64_t)segs[3 * si + 2];
+    const int64_t lo = (int64_t)ci * GATHER_CHUNK, hi = min(lo + (int64_t)GATHER_CHUNK, n);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const unsigned long long c = code[i];
+        const uint32_t ord = (uint32_t)(c >> 32);
+        dst[i] = ord ? reinterpret_cast<const float*>(src_table[ord - 1])[(uint32_t)c] : 0.f;
+    }
+}
+
 }  // namespace dd
 
 using namespace dd;
@@ -149,6 +176,14 @@ int dd_adam_ema_step(const uint64_t* table, const int32_t* chunks, int n_chunks,
                zero_grad};
     launch_pdl(adam_ema_kernel, dim3(n_chunks), dim3(256), 0, (cudaStream_t)stream, table, chunks, chunk_elems, norm_out, a);
     return check_launch("adam_ema_step");
+}
+
+int dd_gather_f32(const uint64_t* segs, const int32_t* blocks, int n_blocks, const uint64_t* codes, const uint64_t* src_table,
+                  float* dst0, void* stream) {
+    DD_REQUIRE(n_blocks > 0, "gather_f32: nothing to do");
+    launch_pdl(gather_f32_kernel, dim3(n_blocks), dim3(256), 0, (cudaStream_t)stream, segs, blocks,
+               reinterpret_cast<const unsigned long long*>(codes), src_table, dst0);
+    return check_launch("gather_f32");
 }
 
 }  // extern "C"

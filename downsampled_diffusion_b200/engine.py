@@ -68,6 +68,7 @@ class Program:
         self.conv_tc_flops: List[float] = []        # algorithmic 2*M*N*K of every dd_conv_tc launch, in order
         self.keep: List[torch.Tensor] = []          # packed weights etc. referenced by raw pointer
         self.packers: List[Callable[[], None]] = [] # re-run when the module's parameters change
+        self.packed_bufs: List[torch.Tensor] = []   # packers[i] fills packed_bufs[i]
         self.weights_version = None
         self.n_gn = 0
         self.tc_flags = 0                           # extra dd_conv_tc flags for every conv of the program (tests: L.TC_PAIR)
@@ -94,6 +95,7 @@ class Program:
             with torch.no_grad():
                 fill(buf)
         self.packers.append(pack)
+        self.packed_bufs.append(buf)
         return buf
 
     def f32(self, param: torch.Tensor, pad_to: int = None) -> torch.Tensor:

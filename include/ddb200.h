@@ -104,6 +104,14 @@ int dd_adam_ema_step(const uint64_t* table, const int32_t* chunks, int n_chunks,
                      float one_minus_beta1, float beta2, float one_minus_beta2, float bias_correction2_sqrt, float eps,
                      float neg_step_size, int ema_mode, float decay, float one_minus_decay, int zero_grad, void* stream);
 
+/* Multi-tensor re-layout (weight packing after an optimizer step, packed weight gradients back to parameter layout):
+ * for every element i of every segment, dst[i] = code ? ((const float*)src_table[(code >> 32) - 1])[code & 0xffffffff] : 0.
+ * segs: n_segs*3 uint64 {dst pointer, index of the segment's first code, element count}; blocks: n_blocks*2 int32
+ * {segment, chunk of 4096 elements}; codes: uint64 per destination element.  dst0 != NULL replaces segment 0's destination
+ * (a buffer allocated per call). */
+int dd_gather_f32(const uint64_t* segs, const int32_t* blocks, int n_blocks, const uint64_t* codes, const uint64_t* src_table,
+                  float* dst0, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Evaluation-side chain and sampler output formatting
  * tab: (T, 8) fp32 rows {sqrt_ac, sqrt_1mac, sqrt_recip_ac, sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2,

@@ -494,3 +494,41 @@ def test_fused_adam_ema_and_weight_refresh(cuda):
     assert tc.rel_l2(a, b) < 1e-4
     with pytest.raises(RuntimeError):
         dd.Adam(twin.parameters(), lr=1e-3).step(ema="update")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_tabulated_relayouts_match_the_packing_expressions(cuda, precision):
+    """relayout.py: weights -> packed buffers and packed gradients -> parameter gradients through one gather launch each,
+    bit for bit what the torch expressions they were tabulated from produce, before and after an optimizer step."""
+    m = tc.build_model(dict(tc.CS, precision=precision), dd, "dddpm_ae", device="cuda").to(cuda).train()
+    opt = torch.optim.SGD(m.parameters(), lr=0.01)
+    x = tc.rand_pm1(61, 4, 3, 32, 32).to(cuda)
+    t = torch.tensor([3, 50, 99, 700], device=cuda)
+    eps = tc.randn(61, 4, 8, 8, 8).to(cuda)
+    for step in range(2):
+        opt.zero_grad()
+        obj, _ = m.losses(x, t, eps=eps)
+        obj.backward()
+        for net in (m.latent_model, m.downsample, m.upsample):
+            (prog,) = net._train_programs.values()
+            assert prog.repack_plan is not None and prog.grad_plan is not None
+            # gradients: the gather launch against the per-parameter expressions, on the same arena
+            fast = prog.param_grads()
+            plan, prog.grad_plan = prog.grad_plan, None
+            slow = prog.param_grads()
+            prog.grad_plan = plan
+            assert fast.keys() == slow.keys() and all(torch.equal(fast[k], slow[k]) for k in fast)
+        opt.step()
+        for net in (m.latent_model, m.downsample, m.upsample):
+            (prog,) = net._train_programs.values()
+            # packed weights of the updated parameters: the gather launch against every packing expression
+            prog.refresh_weights()
+            got = [b.clone() for b in prog.packed_bufs]
+            for pk in prog.packers:
+                pk()
+            assert all(torch.equal(a, b) for a, b in zip(got, prog.packed_bufs))
+            n_fast = len(prog.packers) - len(prog.slow_packers)
+            if step == 0:
+                print(type(net).__name__, "packers tabulated:", n_fast, "of", len(prog.packers), "; gradients tabulated:",
+                      len(prog.grad_fast), "of", len(prog.pg_specs))
+            assert n_fast >= 0.9 * len(prog.packers) and len(prog.grad_fast) >= 0.8 * len(prog.pg_specs)
