@@ -67,6 +67,23 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int 
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return
     world = dist.get_world_size()
+    # The training programs hand out each network's parameter gradients as views of ONE flat buffer (autograd.py,
+    # param_grads): such a group is reduced in place, as it lies, with no gather / scatter copies around the collective.
+    by_storage = {}
+    for p in params:
+        if p.grad is not None:
+            by_storage.setdefault(p.grad.untyped_storage().data_ptr(), []).append(p.grad)
+    loose = []
+    for gs in by_storage.values():
+        lo = min(g.storage_offset() for g in gs)
+        hi = max(g.storage_offset() + g.numel() for g in gs)
+        dense = all(g.is_contiguous() and g.dtype == torch.float32 for g in gs) and 10 * sum(g.numel() for g in gs) >= 9 * (hi - lo)
+        if len(gs) > 1 and dense:
+            flat = torch.empty(0, dtype=torch.float32, device=gs[0].device).set_(gs[0].untyped_storage(), lo, (hi - lo,))
+            dist.all_reduce(flat)
+            flat.div_(world)
+        else:
+            loose += gs
     bucket, size = [], 0
 
     def flush():
@@ -82,11 +99,9 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int 
             off += g.numel()
         bucket, size = [], 0
 
-    for p in params:
-        if p.grad is None:
-            continue
-        bucket.append(p.grad)
-        size += p.grad.numel() * 4
+    for g in loose:
+        bucket.append(g)
+        size += g.numel() * 4
         if size >= bucket_bytes:
             flush()
     flush()

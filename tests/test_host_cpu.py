@@ -98,6 +98,16 @@ q = torch.nn.Parameter(torch.zeros(3, 3)); q.grad = torch.full((3, 3), float(10 
 allreduce_gradients([p, q], bucket_bytes=16)
 assert torch.allclose(p.grad, torch.full((10,), sum(range(1, world + 1)) / world))
 assert torch.allclose(q.grad, torch.full((3, 3), 10 * sum(range(1, world + 1)) / world))
+# gradients handed out as views of one flat buffer (what the training programs do) are reduced in place
+flat = torch.arange(44, dtype=torch.float32) * (rank + 1)
+a = torch.nn.Parameter(torch.zeros(2, 5)); a.grad = flat[0:10].view(2, 5)
+b = torch.nn.Parameter(torch.zeros(19)); b.grad = flat[12:31]                # 2 elements of alignment gap before it, 1 after
+c = torch.nn.Parameter(torch.zeros(12)); c.grad = flat[32:44]
+allreduce_gradients([a, b, c, p])
+mean = sum(range(1, world + 1)) / world
+assert torch.allclose(flat, torch.arange(44, dtype=torch.float32) * mean), "flat gradient buffer was not reduced in place"
+assert a.grad.data_ptr() == flat.data_ptr() and torch.allclose(b.grad, torch.arange(12, 31, dtype=torch.float32) * mean)
+assert torch.allclose(p.grad, torch.full((10,), mean))                      # p went through the bucket path again (already equal on all ranks)
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 """
