@@ -420,7 +420,7 @@ def run_train(args):
                 "gpu_launches": launches, "last_loss": loss,
                 "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 4},
                 "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
-                             "traffic": None, "kernel": "whole step; forward + input-gradient convolutions on tcgen05 kind::tf32, weight gradients on CUDA cores" if args.train_precision != "fp32" else "whole step (fp32 CUDA-core convolutions)",
+                             "traffic": None, "kernel": "whole step; forward, input-gradient and weight-gradient convolutions on tcgen05 kind::tf32" if args.train_precision != "fp32" else "whole step (fp32 CUDA-core convolutions)",
                              "peak_source": pk["src"] + " sustained bf16"},
                 "clocks": sampler.summary()}
         if world == 1 and not args.no_cpu:

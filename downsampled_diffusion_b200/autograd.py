@@ -168,15 +168,12 @@ class TrainProgram(Program):
             if hi.numel() != param.numel():
                 continue
             hi_i, lo_i = hi.round().long(), lo.round().long()
-            if not (bool((hi == hi_i).all()) and bool((lo == lo_i).all())):
-                continue
             pos = hi_i * 4096 + lo_i                                               # = source position + 1, 0 = constant zero
-            if not bool(((pos >= 0) & (pos <= total)).all()):
+            got = torch.where(pos > 0, check[(pos - 1).clamp(min=0, max=total - 1)], torch.zeros((), device=dev))
+            ok = (hi == hi_i) & (lo == lo_i) & (pos >= 0) & (pos <= total) & (got == through(check, k))
+            if not bool(ok.all()):                                                  # one host synchronisation per parameter
                 continue
             c = torch.where(pos > 0, (1 << 32) | (pos - 1), torch.zeros_like(pos))
-            got = torch.where(pos > 0, check[(pos - 1).clamp(min=0)], torch.zeros((), device=dev))
-            if not torch.equal(got, through(check, k)):
-                continue
             n = param.numel()
             pad = (-n) % 4                                                          # every gradient starts 16-byte aligned
             codes.append(torch.cat([c, torch.zeros(pad, dtype=torch.int64, device=dev)]) if pad else c)

@@ -59,12 +59,10 @@ def codes_from_probes(ord_probe: torch.Tensor, idx_probe: torch.Tensor, numels: 
     -- to int64 codes; None when the values are not a clean placement (non-integers, out of range)."""
     o, x = ord_probe.reshape(-1), idx_probe.reshape(-1)
     ordi, idx = o.round().long(), x.round().long()
-    if not (bool((o == ordi).all()) and bool((x == idx).all())):
-        return None
-    if not (bool((ordi >= 0).all()) and bool((ordi <= numels.numel()).all()) and bool((idx >= 0).all())):
-        return None
-    lim = numels[(ordi - 1).clamp(min=0)]
-    if not bool(((ordi > 0) & (idx < lim) | (ordi == 0) & (idx == 0)).all()):
+    lim = numels[(ordi - 1).clamp(min=0, max=numels.numel() - 1)]
+    ok = (o == ordi) & (x == idx) & (ordi >= 0) & (ordi <= numels.numel()) & (idx >= 0) & \
+         (((ordi > 0) & (idx < lim)) | ((ordi == 0) & (idx == 0)))
+    if not bool(ok.all()):                      # one host synchronisation per destination
         return None
     return (ordi << 32) | idx
 
