@@ -34,6 +34,8 @@ SIGNATURES = {
     "dd_ema_update": [_p, _p, _i, _i, _f, _f, _p],
     "dd_grad_norm": [_p, _p, _i, _i, _f, _p, _p, _p],
     "dd_adam_ema_step": [_p, _p, _i, _i, _p, _f, _f, _f, _f, _f, _f, _i, _f, _f, _i, _p],
+    "dd_bicubic2d": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "dd_bicubic2d_bwd": [_p, _p, _i, _i, _i, _i, _i, _p],
     "dd_gather_f32": [_p, _p, _i, _p, _p, _p, _p],
     "dd_q_sample_step": [_p, _p, _i64, _i, _p, _p, _i, _p, _i, _i64, _p],
     "dd_vlb_terms": [_p, _p, _p, _p, _i64, _i, _p, _p, _i, _i, _p, _p, _i64, _i, _i, _i64, _p],

@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256) linattn_save_kernel(const float* __restri
 // small elementwise pieces
 // ---------------------------------------------------------------------------------------------
 // mode 0: y = mish(x); 1: y = g * mish'(x) (+= if accumulate); 2: y = g * (1 - t^2), t = tanh output;
-// 3: y (+)= alpha * x ; 4: sinusoidal embedding handled separately
+// 3: y (+)= alpha * x ; 4: y = tanh(x)
 __global__ void ew_kernel(int mode, const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ y, int64_t n,
                           float alpha, int accumulate) {
     pdl_sync();
@@ -384,6 +384,7 @@ __global__ void ew_kernel(int mode, const float* __restrict__ x, const float* __
         if (mode == 0) v = mish_f(x[i]);
         else if (mode == 1) v = g[i] * mish_grad_f(x[i]);
         else if (mode == 2) v = g[i] * (1.f - x[i] * x[i]);
+        else if (mode == 4) v = tanhf(x[i]);
         else v = alpha * x[i];
         y[i] = accumulate ? y[i] + v : v;
     }
@@ -544,7 +545,7 @@ int dd_linattn_bwd(const float* qkv, const float* dout, const float* saved, floa
 }
 
 int dd_ew(int mode, const float* x, const float* g, float* y, int64_t n, float alpha, int accumulate, void* stream) {
-    DD_REQUIRE(mode >= 0 && mode <= 3 && n > 0, "ew: bad mode");
+    DD_REQUIRE(mode >= 0 && mode <= 4 && n > 0, "ew: bad mode");
     launch_pdl(ew_kernel, dim3(grid_cap(n, 256)), dim3(256), 0, (cudaStream_t)stream, mode, x, g, y, n, alpha, accumulate);
     return check_launch("ew");
 }

@@ -36,10 +36,8 @@ class DownsampleDDPM(DDPM):
 
     # ---- latent <-> image ----------------------------------------------------------------------
     def _resample(self, net, x: torch.Tensor) -> torch.Tensor:
-        if isinstance(net, _ResampleNet):
-            return net(x, tanh=bool(self.force_latent))      # tanh fused into the last 1x1 conv
-        y = net(x)                                            # 'deterministic' (bicubic) mode: library op
-        return torch.tanh(y) if self.force_latent else y
+        # tanh fused into the last 1x1 conv ('convolutional*' modes) / applied by the bicubic resampler ('deterministic')
+        return net(x, tanh=bool(self.force_latent))
 
     def rescaled_downsample(self, x: torch.Tensor) -> torch.Tensor:
         """dddpm.py:92-101."""

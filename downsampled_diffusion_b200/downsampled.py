@@ -7,11 +7,9 @@ runs a fixed list of libddb200 launches (engine.Program).
 """
 from __future__ import annotations
 
-from functools import partial
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from . import _lib as L
@@ -212,12 +210,52 @@ class SimpleUpConv(_ResampleNet):
         self.conv = nn.Sequential(*[nn.ConvTranspose2d(o, i, 4, stride=2, padding=1) for i, o in self.in_out[::-1]])
 
 
+class _BicubicFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size, tanh):
+        if not x.is_cuda:
+            raise RuntimeError("downsampled_diffusion_b200 runs on CUDA tensors only (no CPU fallback)")
+        x = x.contiguous().float()
+        B, C, H, W = x.shape
+        y = torch.empty(B, C, size[0], size[1], dtype=torch.float32, device=x.device)
+        L.call("dd_bicubic2d", L.ptr(x), L.ptr(y), B * C, H, W, size[0], size[1], L.stream())
+        if tanh:
+            L.call("dd_ew", 4, L.ptr(y), None, L.ptr(y), y.numel(), 1.0, 0, L.stream())
+            ctx.save_for_backward(y)
+        ctx.geom, ctx.tanh = (B, C, H, W, size[0], size[1]), tanh
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        B, C, H, W, Ho, Wo = ctx.geom
+        gy = gy.contiguous().float()
+        if ctx.tanh:
+            (y,) = ctx.saved_tensors
+            g2 = torch.empty_like(gy)
+            L.call("dd_ew", 2, L.ptr(y), L.ptr(gy), L.ptr(g2), gy.numel(), 1.0, 0, L.stream())
+            gy = g2
+        gx = torch.empty(B, C, H, W, dtype=torch.float32, device=gy.device)
+        L.call("dd_bicubic2d_bwd", L.ptr(gy), L.ptr(gx), B * C, H, W, Ho, Wo, L.stream())
+        return gx, None, None
+
+
+class Interpolate:
+    """convblocks.py:8-26 ('deterministic' mode): `F.interpolate(size, mode='bicubic', align_corners=True)` as the
+    libddb200 kernel `dd_bicubic2d` (+ its input gradient); callable like the partial the reference returns.  The
+    reference never asks for another mode (wrapper.py:24, 53 call get_interpolate(size) with the defaults)."""
+
+    def __init__(self, size: tuple):
+        self.size = (int(size[0]), int(size[1]))
+
+    def __call__(self, x: torch.Tensor, tanh: bool = False) -> torch.Tensor:
+        return _BicubicFn.apply(x, self.size, bool(tanh))
+
+
 def get_interpolate(size: tuple, mode: str = None, align: bool = True):
-    """convblocks.py:8-26 ('deterministic' mode): bicubic F.interpolate, a library call kept for API parity
-    only -- it is not part of the BASELINE configurations and has no kernel in libddb200."""
-    align = None if mode == "nearest" else align
-    mode = "bicubic" if mode is None else mode
-    return partial(F.interpolate, size=size, mode=mode, align_corners=align)
+    """convblocks.py:8-26."""
+    if mode not in (None, "bicubic") or not align:
+        raise NotImplementedError("only the reference's default (bicubic, align_corners=True) has a kernel in libddb200")
+    return Interpolate(size)
 
 
 def get_upsampling(config: dict, shape: tuple):

@@ -104,6 +104,12 @@ int dd_adam_ema_step(const uint64_t* table, const int32_t* chunks, int n_chunks,
                      float one_minus_beta1, float beta2, float one_minus_beta2, float bias_correction2_sqrt, float eps,
                      float neg_step_size, int ema_mode, float decay, float one_minus_decay, int zero_grad, void* stream);
 
+/* The 'deterministic' resampler (convblocks.py:8-26; wrapper.py:22-24, 49-53): F.interpolate(size=(Hout, Wout),
+ * mode='bicubic', align_corners=True) on `planes` = B*C contiguous fp32 planes, cubic convolution A = -0.75, taps clamped to
+ * the image; and its input gradient (gx is overwritten). */
+int dd_bicubic2d(const float* x, float* y, int planes, int Hin, int Win, int Hout, int Wout, void* stream);
+int dd_bicubic2d_bwd(const float* gy, float* gx, int planes, int Hin, int Win, int Hout, int Wout, void* stream);
+
 /* Multi-tensor re-layout (weight packing after an optimizer step, packed weight gradients back to parameter layout):
  * for every element i of every segment, dst[i] = code ? ((const float*)src_table[(code >> 32) - 1])[code & 0xffffffff] : 0.
  * segs: n_segs*3 uint64 {dst pointer, index of the segment's first code, element count}; blocks: n_blocks*2 int32
@@ -345,7 +351,7 @@ int dd_linattn_save(const float* ws, int B, int n, int heads, float* saved, void
 int dd_linattn_bwd(const float* qkv, const float* dout, const float* saved, float* dctx, float* dqkv,
                    int B, int n, int heads, int dh, void* stream);
 /* elementwise: mode 0 y=mish(x); 1 y=g*mish'(x); 2 y=g*(1-x^2) (tanh backward, x = tanh output); 3 y=alpha*x;
- * accumulate != 0 adds into y. */
+ * 4 y=tanh(x); accumulate != 0 adds into y. */
 int dd_ew(int mode, const float* x, const float* g, float* y, int64_t n, float alpha, int accumulate, void* stream);
 /* SinusoidalPosEmb (blocks.py:22-29): out (R, dim) = [sin(t*freq), cos(t*freq)]. */
 int dd_sincos_emb(const float* t, const float* freq, float* out, int R, int dim, void* stream);

@@ -231,15 +231,46 @@ def conv_resnet(sd: SD, pre: str, x: Tensor, n_down: int, n_blocks: int, upsampl
     return F.conv2d(x, sd[f"{pre}{idx}.weight"], sd[f"{pre}{idx}.bias"])
 
 
+def _cubic_matrix(n_in: int, n_out: int) -> Tensor:
+    """(n_out, n_in) interpolation matrix of one axis of bicubic resizing with align_corners=True: Keys' cubic convolution
+    kernel with A = -0.75, source position o * (n_in-1)/(n_out-1), four taps clamped to the axis -- the published
+    algorithm behind torch's upsample_bicubic2d (third-party to the reference, pinned torch==1.9.0), in float64."""
+    A = -0.75
+    near = lambda v: ((A + 2.0) * v - (A + 3.0)) * v * v + 1.0                  # |v| <= 1
+    far = lambda v: ((A * v - 5.0 * A) * v + 8.0 * A) * v - 4.0 * A             # 1 < |v| < 2
+    scale = (n_in - 1) / (n_out - 1) if n_out > 1 else 0.0
+    M = torch.zeros(n_out, n_in, dtype=torch.float64)
+    for o in range(n_out):
+        real = np.float32(scale) * np.float32(o)                                # the source index is formed in fp32
+        base = min(int(math.floor(real)), n_in - 1)
+        t = min(max(float(real) - base, 0.0), 1.0)
+        for j, w in enumerate((far(t + 1.0), near(t), near(1.0 - t), far(2.0 - t))):
+            M[o, min(max(base - 1 + j, 0), n_in - 1)] += w
+    return M
+
+
+def bicubic_resize(x: Tensor, size: Tuple[int, int]) -> Tensor:
+    """get_interpolate(size)(x), convblocks.py:8-26: F.interpolate(x, size, mode='bicubic', align_corners=True)."""
+    My, Mx = _cubic_matrix(x.shape[2], size[0]), _cubic_matrix(x.shape[3], size[1])
+    return torch.einsum("oh,bchw,pw->bcop", My, x.double(), Mx).to(x.dtype)
+
+
 def rescaled_downsample(sd: SD, cfg: dict, x: Tensor) -> Tensor:
-    """dddpm.py:92-101 (convolutional_res mode)."""
-    z = conv_resnet(sd, "downsample.conv.", x, cfg["n_downsamples"], cfg["d_n_blocks"], upsample=False)
+    """dddpm.py:92-101 (convolutional_res mode; 'deterministic' = bicubic, wrapper.py:49-53)."""
+    if cfg.get("d_mode") == "deterministic":
+        s = cfg["image_size"] // 2 ** cfg["n_downsamples"]
+        z = bicubic_resize(x, (s, s))
+    else:
+        z = conv_resnet(sd, "downsample.conv.", x, cfg["n_downsamples"], cfg["d_n_blocks"], upsample=False)
     return torch.tanh(z) if cfg["force_latent"] else z
 
 
 def rescaled_upsample(sd: SD, cfg: dict, z: Tensor) -> Tensor:
-    """dddpm.py:103-112 (convolutional_res mode)."""
-    x = conv_resnet(sd, "upsample.conv.", z, cfg["n_downsamples"], cfg["u_n_blocks"], upsample=True)
+    """dddpm.py:103-112 (convolutional_res mode; 'deterministic' = bicubic, wrapper.py:22-24)."""
+    if cfg.get("u_mode") == "deterministic":
+        x = bicubic_resize(z, (cfg["image_size"], cfg["image_size"]))
+    else:
+        x = conv_resnet(sd, "upsample.conv.", z, cfg["n_downsamples"], cfg["u_n_blocks"], upsample=True)
     return torch.tanh(x) if cfg["force_latent"] else x
 
 

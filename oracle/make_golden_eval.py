@@ -70,6 +70,25 @@ def main():
     s = tc.randn(75, 3, 3, 32, 32)
     put("fix_samples.out", fix_samples(s))
 
+    # ---- 'deterministic' (bicubic) resampler mode: wrapper.py:22-24, 49-53; loss + gradient through the up-sampler ----
+    cfg = dict(tc.CS, d_mode="deterministic", u_mode="deterministic", unet_in=3)
+    m = ref_model(cfg, "dddpm")
+    x = tc.rand_pm1(85, 4, 3, 32, 32)
+    with torch.no_grad():
+        z = m.rescaled_downsample(x)
+        put("det.z", z)
+        put("det.xhat", m.rescaled_upsample(z))
+    m.train()
+    t = torch.tensor([3, 50, 99, 700])
+    torch.manual_seed(12)
+    obj, d = m.losses(x, t)
+    obj.backward()
+    put("det.loss.obj", obj)
+    put("det.loss.latent", d["latent"])
+    put("det.loss.recon", d["recon"])
+    put("det.loss.grad_final", dict(m.named_parameters())["latent_model.final_conv.1.weight"].grad)
+    put("det.loss.grad_init", dict(m.named_parameters())["latent_model.downs.0.0.block1.block.0.weight"].grad)
+
     # ---- one trainer step: clip_grad_norm_(1.0) + Adam(lr=2e-4), twice (trainer_ddpm.py:118-144, trainer.py:69) ----
     net = ref_model(tc.CS, "unet")
     opt = torch.optim.Adam(net.parameters(), lr=2e-4)

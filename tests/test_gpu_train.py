@@ -532,3 +532,42 @@ def test_tabulated_relayouts_match_the_packing_expressions(cuda, precision):
                 print(type(net).__name__, "packers tabulated:", n_fast, "of", len(prog.packers), "; gradients tabulated:",
                       len(prog.grad_fast), "of", len(prog.pg_specs))
             assert n_fast >= 0.9 * len(prog.packers) and len(prog.grad_fast) >= 0.8 * len(prog.pg_specs)
+
+
+# ---- 'deterministic' resampler mode (convblocks.py:8-26, wrapper.py:22-24, 49-53): bicubic kernels -----------------------
+def test_deterministic_bicubic_mode_forward_and_gradient(cuda, golden):
+    cfg = dict(tc.CS, d_mode="deterministic", u_mode="deterministic", unet_in=3, precision="fp32")
+    m = tc.build_model(cfg, dd, "dddpm", device="cuda").to(cuda).train()
+    x = tc.rand_pm1(85, 4, 3, 32, 32).to(cuda)
+    with torch.no_grad():
+        z = m.rescaled_downsample(x)
+        xhat = m.rescaled_upsample(z)
+    assert (z.cpu() - G(golden, "det.z")).abs().max() < 5e-6 and (xhat.cpu() - G(golden, "det.xhat")).abs().max() < 5e-6
+    t = torch.tensor([3, 50, 99, 700], device=cuda)
+    torch.manual_seed(12)
+    eps = torch.randn(4, 3, 8, 8).to(cuda)
+    obj, d = m.losses(x, t, eps=eps)
+    obj.backward()
+    for key, val in (("obj", obj), ("latent", d["latent"]), ("recon", d["recon"])):
+        ref = float(golden[f"det.loss.{key}"])
+        assert abs(float(val.detach()) - ref) <= 1e-4 * abs(ref), key
+    params = dict(m.named_parameters())
+    assert tc.rel_l2(params["latent_model.final_conv.1.weight"].grad, G(golden, "det.loss.grad_final")) < 2e-4
+    assert tc.rel_l2(params["latent_model.downs.0.0.block1.block.0.weight"].grad, G(golden, "det.loss.grad_init")) < 2e-4
+    # the kernels alone: forward against the restatement, backward against its transpose, odd sizes, up and down
+    from downsampled_diffusion_b200.downsampled import Interpolate, get_interpolate
+    for (h, w), size in (((32, 32), (8, 8)), ((8, 8), (32, 32)), ((7, 13), (20, 9)), ((5, 5), (1, 1))):
+        a = tc.randn(86, 2, 3, h, w)
+        a_dev = a.to(cuda).requires_grad_(True)
+        y = Interpolate(size)(a_dev, tanh=True)
+        gy = tc.randn(87, *y.shape)
+        y.backward(gy.to(cuda))
+        a_ref = a.clone().requires_grad_(True)
+        y_ref = torch.tanh(O.bicubic_resize(a_ref, size))
+        y_ref.backward(gy)
+        assert (y.detach().cpu() - y_ref.detach()).abs().max() < 1e-5, (h, w, size)
+        assert (a_dev.grad.cpu() - a_ref.grad).abs().max() < 1e-5 * max(1.0, float(a_ref.grad.abs().max())), (h, w, size)
+    with pytest.raises(NotImplementedError):
+        get_interpolate((8, 8), mode="nearest")
+    with pytest.raises(RuntimeError):
+        Interpolate((8, 8))(torch.zeros(1, 3, 32, 32))

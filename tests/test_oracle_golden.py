@@ -204,3 +204,23 @@ def test_trainer_optimizer_step(golden):
             ref = T(golden[f"optim.step{step}.{n}"])
             assert (ps[names.index(n)] - ref).abs().max() <= 2.4e-7 * max(1.0, float(ref.abs().max())), n
     assert float(golden["optim.norm0"]) > 1.0 > float(golden["optim.norm1"])      # step 0 was clipped, step 1 was not
+
+
+def test_deterministic_bicubic_resampler(golden):
+    """'deterministic' mode (wrapper.py:22-24, 49-53): the bicubic restatement against the reference's F.interpolate."""
+    cfg = dict(tc.CS, d_mode="deterministic", u_mode="deterministic", unet_in=3)
+    x = tc.rand_pm1(85, 4, 3, 32, 32)
+    z = O.rescaled_downsample({}, cfg, x)
+    assert (z - T(golden["det.z"])).abs().max() < 2e-6
+    assert (O.rescaled_upsample({}, cfg, z) - T(golden["det.xhat"])).abs().max() < 2e-6
+    # the objective of the non-autoencoder dDDPM through the bicubic up-sampler, with autograd on the restatement
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd_of(cfg, "dddpm").items()}
+    buf = O.schedule_buffers("linear", 1000)
+    t = torch.tensor([3, 50, 99, 700])
+    torch.manual_seed(12)
+    eps = torch.randn(4, 3, 8, 8)
+    obj, d = O.dddpm_losses(sd, cfg, buf, x, t, eps, autoencoder=False)
+    obj.backward()
+    np.testing.assert_allclose(float(obj), float(golden["det.loss.obj"]), rtol=2e-5)
+    np.testing.assert_allclose(float(d["recon"]), float(golden["det.loss.recon"]), rtol=2e-5)
+    assert tc.rel_l2(sd["latent_model.final_conv.1.weight"].grad, T(golden["det.loss.grad_final"])) < 1e-4
