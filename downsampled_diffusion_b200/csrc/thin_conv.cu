@@ -18,22 +18,38 @@ __global__ void __launch_bounds__(256) thin_in_kernel(const float* __restrict__ 
 #pragma unroll
     for (int s = 0; s < THIN_MAX; ++s) wr[s] = s < Cs ? __ldg(reinterpret_cast<const float4*>(w + (int64_t)s * cv * 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const int ppb = blockDim.x / cv;                       // pixels per CTA pass
-    for (int64_t pix = (int64_t)blockIdx.x * ppb + threadIdx.x / cv; pix < total; pix += (int64_t)gridDim.x * ppb) {
-        const int64_t b = pix / HW;
-        const int p = (int)(pix - b * HW);
-        const float* xb = x + b * Cs * HW + p;
-        float4 a = bv;
+    const uint32_t ppb = blockDim.x / cv;                  // pixels per CTA pass
+    const uint32_t step = gridDim.x * ppb, n = (uint32_t)total, hw = (uint32_t)HW;      // total < 2^31 / cv (checked by the host)
+    // two pixels in flight per thread: the narrow loads of the second overlap the store of the first
+    for (uint32_t pix = blockIdx.x * ppb + threadIdx.x / cv; pix < n; pix += 2 * step) {
+        const uint32_t pix2 = pix + step;
+        const bool two = pix2 < n;
+        const uint32_t b = pix / hw, p = pix - b * hw;
+        const uint32_t b2 = two ? pix2 / hw : b, p2 = two ? pix2 - b2 * hw : p;
+        const float* xa = x + (int64_t)b * Cs * HW + p;
+        const float* xb = x + (int64_t)b2 * Cs * HW + p2;
+        float va[THIN_MAX], vb[THIN_MAX];
+#pragma unroll
+        for (int s = 0; s < THIN_MAX; ++s) {
+            va[s] = s < Cs ? __ldg(xa + (int64_t)s * HW) : 0.f;
+            vb[s] = s < Cs ? __ldg(xb + (int64_t)s * HW) : 0.f;
+        }
+        float4 a = bv, c = bv;
 #pragma unroll
         for (int s = 0; s < THIN_MAX; ++s) {
             if (s < Cs) {
-                const float v = __ldg(xb + (int64_t)s * HW);
-                a.x = fmaf(v, wr[s].x, a.x); a.y = fmaf(v, wr[s].y, a.y); a.z = fmaf(v, wr[s].z, a.z); a.w = fmaf(v, wr[s].w, a.w);
+                a.x = fmaf(va[s], wr[s].x, a.x); a.y = fmaf(va[s], wr[s].y, a.y); a.z = fmaf(va[s], wr[s].z, a.z); a.w = fmaf(va[s], wr[s].w, a.w);
+                c.x = fmaf(vb[s], wr[s].x, c.x); c.y = fmaf(vb[s], wr[s].y, c.y); c.z = fmaf(vb[s], wr[s].z, c.z); c.w = fmaf(vb[s], wr[s].w, c.w);
             }
         }
-        float4* dst = reinterpret_cast<float4*>(y) + pix * cv + c4;
-        if (accumulate) { const float4 o = *dst; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
-        *dst = a;
+        float4* da = reinterpret_cast<float4*>(y) + (int64_t)pix * cv + c4;
+        float4* dc = reinterpret_cast<float4*>(y) + (int64_t)pix2 * cv + c4;
+        if (accumulate) {
+            const float4 o = *da; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+            if (two) { const float4 q = *dc; c.x += q.x; c.y += q.y; c.z += q.z; c.w += q.w; }
+        }
+        *da = a;
+        if (two) *dc = c;
     }
 }
 
@@ -61,7 +77,7 @@ __global__ void __launch_bounds__(256) thin_out_kernel(const float* __restrict__
                 if (s < Cs) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
         }
         if (ok && c4 < Cs) {                                 // lane s of the pixel's group writes channel s
-            const int64_t b = pix / HW;
+            const int64_t b = (uint32_t)pix / (uint32_t)HW;  // total < 2^31 (checked by the host): 32-bit division
             const int p = (int)(pix - b * HW);
             float r = 0.f;
 #pragma unroll
@@ -82,7 +98,7 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float* __restrict
 #pragma unroll
     for (int s = 0; s < THIN_MAX; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t pix = (int64_t)blockIdx.x * ppb + pl; pix < total; pix += (int64_t)gridDim.x * ppb) {
-        const int64_t b = pix / HW;
+        const int64_t b = (uint32_t)pix / (uint32_t)HW;      // total < 2^31 (checked by the host): 32-bit division
         const int p = (int)(pix - b * HW);
         const float4 v = *(reinterpret_cast<const float4*>(wide) + pix * cv + c4);
         bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
@@ -137,6 +153,7 @@ extern "C" {
 int dd_conv1x1_thin_in(const float* x_nchw, const float* w, const float* bias, float* y_nhwc, int B, int HW, int Cs, int Cout,
                        int accumulate, void* stream) {
     DD_REQUIRE(thin_ok(Cs, Cout) && B > 0 && HW > 0, "conv1x1_thin_in: narrow side %d (1..8), wide side %d (4..128, power of two)", Cs, Cout);
+    DD_REQUIRE((int64_t)B * HW < (1LL << 31) / 32, "conv1x1_thin_in: %lld pixels exceed the 32-bit index range of the kernel", (long long)B * HW);
     const int cv = Cout / 4;
     const int64_t total = (int64_t)B * HW;
     launch_pdl(thin_in_kernel, dim3(thin_grid(total, 256 / cv)), dim3(256), 0, (cudaStream_t)stream, x_nchw, w, bias, y_nhwc, HW, Cs, cv, accumulate, total);
@@ -146,6 +163,7 @@ int dd_conv1x1_thin_in(const float* x_nchw, const float* w, const float* bias, f
 int dd_conv1x1_thin_out(const float* x_nhwc, const float* w, const float* bias, float* y_nchw, int B, int HW, int Cin, int Cs, int do_tanh,
                         void* stream) {
     DD_REQUIRE(thin_ok(Cs, Cin) && B > 0 && HW > 0, "conv1x1_thin_out: narrow side %d (1..8), wide side %d (4..128, power of two)", Cs, Cin);
+    DD_REQUIRE((int64_t)B * HW < (1LL << 31) / 32, "conv1x1_thin_out: %lld pixels exceed the 32-bit index range of the kernel", (long long)B * HW);
     const int cv = Cin / 4;
     const int64_t total = (int64_t)B * HW;
     launch_pdl(thin_out_kernel, dim3(thin_grid(total, 256 / cv)), dim3(256), 0, (cudaStream_t)stream, x_nhwc, w, bias, y_nchw, HW, Cs, cv, do_tanh, total);
@@ -155,6 +173,7 @@ int dd_conv1x1_thin_out(const float* x_nhwc, const float* w, const float* bias, 
 int dd_conv1x1_thin_wgrad(const float* narrow_nchw, const float* wide_nhwc, float* dw, int narrow_major, float* dbias_wide, int B, int HW,
                           int Cs, int Cw, void* stream) {
     DD_REQUIRE(thin_ok(Cs, Cw) && B > 0 && HW > 0, "conv1x1_thin_wgrad: narrow side %d (1..8), wide side %d (4..128, power of two)", Cs, Cw);
+    DD_REQUIRE((int64_t)B * HW < (1LL << 31) / 32, "conv1x1_thin_wgrad: %lld pixels exceed the 32-bit index range of the kernel", (long long)B * HW);
     const int cv = Cw / 4;
     const int64_t total = (int64_t)B * HW;
     const int ds = narrow_major ? Cw : 1, dc = narrow_major ? 1 : Cs;         // dw is (Cs, Cw) or (Cw, Cs)
