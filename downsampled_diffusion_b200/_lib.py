@@ -20,6 +20,7 @@ TC_CONV3x3, TC_CONV1x1, TC_DOWN, TC_UPT = 0, 1, 2, 3
 TC_W_PER_SAMPLE = 1
 TC_SPLITK = 2
 TC_PAIR = 4
+TC_STRIDED_IN = 8
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 

@@ -42,6 +42,7 @@ struct TcParams {
     int B, H, W;            // GEMM pixel grid
     int Cout, cout_valid, bn, rows_per_phase;
     int out_mul;            // 1, or 2 for the sub-pixel phases of the transposed conv
+    int in_mul;             // 1, or 2 when a stride-2 conv reads its input through a stride-2 tensor map (DD_TC_STRIDED_IN)
     int out_nchw_f32;
     int G, cpg_mask, cpg_shift;
     int tw_sh, th_sh;           // log2(tw), log2(th): tile geometry is all powers of two
@@ -576,7 +577,8 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
         const uint32_t tx = (uint32_t)KCH * p.rows_valid * TC_BK * 2;
         const int chunks0 = p.chunks0;
         int rem = kb0 % cpt, ti = phase * p.ntaps + kb0 / cpt;
-        int cx = w0 + p.tap_dw[ti], cy = h0 + p.tap_dh[ti], cp = p.tap_plane[ti];
+        const int wi0 = w0 * p.in_mul, hi0 = h0 * p.in_mul;      // tile origin in input pixels
+        int cx = wi0 + p.tap_dw[ti], cy = hi0 + p.tap_dh[ti], cp = p.tap_plane[ti];
         uint32_t sA = base;
         int st = 0, round = 0;
         for (int i = 0; i < num_st; ++i) {
@@ -597,7 +599,7 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
             rem += KCH;
             if (rem == cpt) {
                 rem = 0; ++ti;
-                if (i + 1 < num_st) { cx = w0 + p.tap_dw[ti]; cy = h0 + p.tap_dh[ti]; cp = p.tap_plane[ti]; }
+                if (i + 1 < num_st) { cx = wi0 + p.tap_dw[ti]; cy = hi0 + p.tap_dh[ti]; cp = p.tap_plane[ti]; }
             }
         }
     } else if (warp == 6) {
@@ -983,16 +985,17 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// stride 2: the map traverses every other pixel of a (2W x 2H) image (TMA elementStrides), so a box still lands as tw x th rows
 static int make_act_map(CUtensorMap* tm, const void* ptr, int C, int pitch, int W, int H, int N, int P, int tw, int th, int tn,
-                        CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B, bool f32 = false) {
+                        CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B, bool f32 = false, int stride = 1) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
     cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)P};
     const cuuint64_t es = f32 ? 4 : 2;
     cuuint64_t strides[4] = {(cuuint64_t)pitch * es, (cuuint64_t)W * pitch * es, (cuuint64_t)H * W * pitch * es,
                              (cuuint64_t)N * H * W * pitch * es};
-    cuuint32_t box[5] = {f32 ? 32u : 64u, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    cuuint32_t box[5] = {f32 ? 32u : 64u, (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), (cuuint32_t)tn, 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
     CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1136,12 +1139,16 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
         while ((1 << p.cpg_shift) < cpg) ++p.cpg_shift;
     }
     const int Cin = C1 + C2;
-    int planes = 1, phases = 1, K;
+    int planes = 1, phases = 1, K, in_stride = 1;
     if (kind == DD_TC_CONV3x3) {
         p.ntaps = 9;
         for (int t = 0; t < 9; ++t) { p.tap_dh[t] = (int8_t)(t / 3 - 1); p.tap_dw[t] = (int8_t)(t % 3 - 1); p.tap_plane[t] = 0; }
     } else if (kind == DD_TC_CONV1x1) {
         p.ntaps = 1;
+    } else if (kind == DD_TC_DOWN && (flags & DD_TC_STRIDED_IN)) {
+        // x is the plain (B, 2H, 2W, C) input: input pixel (2*ho + ky - 1, 2*wo + kx - 1) through a stride-2 tensor map
+        p.ntaps = 9; in_stride = 2;
+        for (int t = 0; t < 9; ++t) { p.tap_dh[t] = (int8_t)(t / 3 - 1); p.tap_dw[t] = (int8_t)(t % 3 - 1); p.tap_plane[t] = 0; }
     } else if (kind == DD_TC_DOWN) {
         // input row 2*ho + ky - 1: ky=0 -> odd plane, ho-1; ky=1 -> even plane, ho; ky=2 -> odd plane, ho
         p.ntaps = 9; planes = 4;
@@ -1165,9 +1172,13 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
 
     if (x_pitch <= 0) x_pitch = C1;
     DD_REQUIRE(x_pitch >= C1 && x_pitch % 8 == 0, "conv_tc: bad channel pitch %d", x_pitch);
-    int rc = make_act_map(&p.tmA0, x, C1, x_pitch, W, H, B, planes, p.tw, p.th, p.tn);
+    p.in_mul = in_stride;
+    DD_REQUIRE(in_stride == 1 || (x2 == nullptr && p.tw * in_stride <= 256 && p.th * in_stride <= 256), "conv_tc: strided input needs one source and tiles <= 128 wide");
+    int rc = make_act_map(&p.tmA0, x, C1, x_pitch, W * in_stride, H * in_stride, B, planes, p.tw, p.th, p.tn,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, false, in_stride);
     if (rc) return rc;
-    rc = make_act_map(&p.tmA1, x2 ? x2 : x, x2 ? C2 : C1, x2 ? C2 : x_pitch, W, H, B, planes, p.tw, p.th, p.tn);
+    rc = make_act_map(&p.tmA1, x2 ? x2 : x, x2 ? C2 : C1, x2 ? C2 : x_pitch, W * in_stride, H * in_stride, B, planes, p.tw, p.th, p.tn,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, false, in_stride);
     if (rc) return rc;
     rc = make_w_map(&p.tmB, wp, K, w_rows, p.bn, wps ? B : 0);
     if (rc) return rc;

@@ -192,13 +192,15 @@ class Program:
                 kcode = L.TC_UPT
             src, src2 = x.t, (x2.t if x2 is not None else None)
             gh, gw = (Ho, Wo) if kind == "down" else (H, W)
-            if kind == "down":
-                planes = self.empty(4, B, Ho, Wo, x.C)
-                self.add("dd_space_to_depth2", L.ptr(x.t), L.ptr(planes), B, H, W, x.C)
-                src = planes
             G = 0
             st_ptr = None
             flags = self.tc_flags
+            if kind == "down" and os.environ.get("DD_NO_STRIDED_TMA"):
+                planes = self.empty(4, B, Ho, Wo, x.C)           # the four parity planes of the input (space-to-depth copy)
+                self.add("dd_space_to_depth2", L.ptr(x.t), L.ptr(planes), B, H, W, x.C)
+                src = planes
+            elif kind == "down":
+                flags |= L.TC_STRIDED_IN                          # the kernel reads every other pixel through a stride-2 tensor map
             if gn is not None:
                 G = gn.num_groups
                 # low-resolution layers: split-K partials, summed by the GroupNorm kernel (dd_gn_mish_sum)

@@ -266,6 +266,9 @@ int dd_space_to_depth2(const void* x, void* y, int B, int H, int W, int C, void*
 /* DD_TC_PAIR (3x3 on maps >= 16x8, Cout a multiple of 128, an even number of pixel tiles): run the halo kernel as thread-block
  * clusters of two CTAs with tcgen05 cta_group::2 (M = 256 per MMA, each CTA loads half of the weight rows).  Opt-in. */
 #define DD_TC_PAIR 4
+/* DD_TC_STRIDED_IN (DD_TC_DOWN only): x is the plain NHWC input (B, 2H, 2W, C) instead of its four space-to-depth parity
+ * planes; the kernel reads every other pixel through a stride-2 tensor map (TMA elementStrides), no copy. */
+#define DD_TC_STRIDED_IN 8
 int dd_conv_tc_splits(int kind, int B, int H, int W, int Cin, int Cout);
 int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2,
                const void* wp, int w_rows, const float* bias, const void* residual,
