@@ -6,6 +6,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -122,3 +123,56 @@ def test_sharded_sampling_and_grad_allreduce_gloo(tmp_path):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_relayout_tables_from_probes():
+    """relayout.py: index codes pushed through a packing expression give the gather table of a pure placement and are
+    rejected for anything else (host-side logic; the launch itself is covered by the GPU tests)."""
+    from downsampled_diffusion_b200.relayout import apply_codes, codes_from_probes
+    shapes = [(4, 3, 3, 3), (5,), (2, 6)]
+    numels = torch.tensor([int(np.prod(s)) for s in shapes])
+    offsets = torch.cumsum(numels, 0) - numels
+
+    def probes(which):
+        return [torch.full(s, float(i + 1)) if which == 0 else torch.arange(int(np.prod(s)), dtype=torch.float32).view(s)
+                for i, s in enumerate(shapes)]
+
+    def pack(ws):          # a K-major flipped weight matrix with two zero rows of padding, and a padded bias
+        w, b, m = ws
+        a = torch.zeros(6, 27)
+        a[:4] = w.flip(2, 3).permute(0, 2, 3, 1).reshape(4, 27)
+        c = torch.zeros(8)
+        c[:5] = b
+        return a, c, m.t().contiguous()
+
+    real = [torch.randn(s) for s in shapes]
+    flat = torch.cat([r.reshape(-1) for r in real])
+    for o, x, want in zip(pack(probes(0)), pack(probes(1)), pack(real)):
+        codes = codes_from_probes(o, x, numels)
+        assert codes is not None and codes.dtype == torch.int64
+        assert torch.equal(apply_codes(codes, flat, offsets), want.reshape(-1))
+    # not placements: a sum of two elements, a scaled copy, an index beyond its tensor
+    w0, w1 = probes(0)[0], probes(1)[0]
+    summed = codes_from_probes(w0[:, 0] + w0[:, 1], w1[:, 0] + w1[:, 1], numels)      # may look like a placement by accident ...
+    assert summed is None or not torch.equal(apply_codes(summed, flat, offsets), (real[0][:, 0] + real[0][:, 1]).reshape(-1))
+    # ... which is why every table is also checked against its expression on the real data
+    assert codes_from_probes(w0 * 0.5, w1 * 0.5, numels) is None
+    assert codes_from_probes(torch.full((3,), 2.0), torch.tensor([0.0, 4.0, 5.0]), numels) is None     # tensor 2 has 5 elements
+
+
+def test_fused_adam_host_contract():
+    """optim.Adam: torch's param-group / state layout (state_dicts move both ways), loud failure on CPU tensors."""
+    w = torch.nn.Parameter(torch.zeros(3, 2))
+    ours, theirs = dd.Adam([w], lr=2e-4, max_grad_norm=1.0), torch.optim.Adam([w], lr=2e-4)
+    assert ours.param_groups[0].keys() == theirs.param_groups[0].keys()
+    theirs.load_state_dict(ours.state_dict())
+    ours.load_state_dict(theirs.state_dict())
+    w.grad = torch.ones_like(w)
+    with pytest.raises(RuntimeError):
+        ours.step()                                   # CPU tensors: no fallback
+    with pytest.raises(RuntimeError):
+        ours.step(ema="update")                       # no EMA attached
+    with pytest.raises(ValueError):
+        ours.step(ema="sometimes")
+    with pytest.raises(ValueError):
+        dd.Adam([w], lr=-1.0)
