@@ -176,3 +176,24 @@ def test_fused_adam_host_contract():
         ours.step(ema="sometimes")
     with pytest.raises(ValueError):
         dd.Adam([w], lr=-1.0)
+
+
+def test_resampler_factory_modes():
+    """wrapper.py:6-59: the three modes construct, unknown modes raise like the reference; the deterministic mode is the
+    bicubic kernel wrapper (CUDA only) and refuses the interpolation modes the reference never asks for."""
+    from downsampled_diffusion_b200.downsampled import Interpolate, get_interpolate
+    shape = (3, 32, 32)
+    for mode, kind in (("deterministic", Interpolate), ("convolutional", dd.SimpleDownConv), ("convolutional_res", dd.ConvResNet)):
+        cfg = dict(tc.CS, d_mode=mode, u_mode=mode, unet_in=3 if mode == "deterministic" else 8)
+        down, up = dd.get_downsampling(cfg, shape), dd.get_upsampling(cfg, shape)
+        assert isinstance(down, kind)
+        assert isinstance(up, Interpolate if mode == "deterministic" else (dd.SimpleUpConv if mode == "convolutional" else dd.ConvResNet))
+    assert dd.get_downsampling(dict(tc.CS, d_mode="deterministic"), shape).size == (8, 8)
+    assert dd.get_upsampling(dict(tc.CS, u_mode="deterministic"), shape).size == (32, 32)
+    for fn in (dd.get_downsampling, dd.get_upsampling):
+        with pytest.raises(NotImplementedError):
+            fn(dict(tc.CS, d_mode="wavelet", u_mode="wavelet"), shape)
+    with pytest.raises(NotImplementedError):
+        get_interpolate((8, 8), mode="bilinear")
+    with pytest.raises(RuntimeError):
+        Interpolate((8, 8))(torch.zeros(1, 3, 32, 32))          # CPU tensor: no fallback
