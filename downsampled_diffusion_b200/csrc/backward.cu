@@ -212,6 +212,51 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restri
     }
 }
 
+// The same, one image per blockIdx.y: the group sums S1 / S2, mean and rstd of the image's G groups are formed once per block in
+// shared memory (the kernel above recomputes them with 2 * cpg loads for every element), four channels per thread.
+// Needs C / G % 4 == 0 and G <= 64.
+__global__ void __launch_bounds__(256) gn_bwd_apply4_kernel(const float4* __restrict__ x, const float4* __restrict__ dy,
+                                                            const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int HW, int C, int G,
+                                                            const float* __restrict__ s_dhxh, const float* __restrict__ s_dh,
+                                                            float4* __restrict__ dx, int accumulate) {
+    pdl_sync();
+    __shared__ float sS1[64], sS2[64], sMean[64], sRstd[64];
+    const int b = blockIdx.y, cpg = C / G, C4 = C >> 2;
+    const float inv_n = 1.f / ((float)HW * (float)cpg);
+    if (threadIdx.x < G) {
+        const int g = threadIdx.x;
+        float S1 = 0.f, S2 = 0.f;
+        for (int k = 0; k < cpg; ++k) {
+            const int cc = g * cpg + k;
+            S1 += gamma[cc] * s_dh[(int64_t)b * C + cc];
+            S2 += gamma[cc] * s_dhxh[(int64_t)b * C + cc];
+        }
+        sS1[g] = S1; sS2[g] = S2;
+        sMean[g] = stats[((int64_t)b * G + g) * 2]; sRstd[g] = stats[((int64_t)b * G + g) * 2 + 1];
+    }
+    __syncthreads();
+    const int n4 = HW * C4;
+    const int64_t base = (int64_t)b * n4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const int c = (i % C4) * 4, g = c / cpg;
+        const float mean = sMean[g], rstd = sRstd[g], S1 = sS1[g], S2 = sS2[g];
+        const float4 xv = x[base + i], dv = dy[base + i];
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+        float4 v;
+#define GNB_ONE(F)                                                                \
+        {                                                                         \
+            const float xh = (xv.F - mean) * rstd;                                \
+            const float dh = dv.F * mish_grad_f(xh * ga.F + be.F);                \
+            v.F = rstd * (ga.F * dh - S1 * inv_n - xh * S2 * inv_n);              \
+        }
+        GNB_ONE(x) GNB_ONE(y) GNB_ONE(z) GNB_ONE(w)
+#undef GNB_ONE
+        if (accumulate) { const float4 o = dx[base + i]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        dx[base + i] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // channel LayerNorm backward (blocks.py:57-60; eps added to the std).  One warp per pixel.
 //   y = (x-mu)/(sigma+eps)*g + b ; u = dy*g ; s = sigma+eps
@@ -533,8 +578,18 @@ int dd_gn_mish_bwd(const float* x, const float* dy, const float* stats, const fl
     launch_pdl(gn_bwd_reduce_kernel, dim3(B * G), dim3(256), 0, (cudaStream_t)stream, x, dy, stats, gamma, beta, HW, C, G, s_dhxh,
                s_dh, s_dy);
     const int64_t total = (int64_t)B * HW * C;
-    launch_pdl(gn_bwd_apply_kernel, dim3(grid_cap(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, dy, stats, gamma, beta, HW, C,
-               G, (const float*)s_dhxh, (const float*)s_dh, dx, accumulate, total);
+    const uintptr_t align = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+                            reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta);
+    if ((C / G) % 4 == 0 && G <= 64 && B <= 65535 && (align & 15) == 0 && (int64_t)HW * C < (1LL << 31)) {
+        int gx = (HW * (C / 4) + 255) / 256;
+        const int cap = (8 * num_sms() + B - 1) / B;
+        if (gx > cap) gx = cap;
+        launch_pdl(gn_bwd_apply4_kernel, dim3(gx < 1 ? 1 : gx, B), dim3(256), 0, (cudaStream_t)stream, (const float4*)x, (const float4*)dy,
+                   stats, gamma, beta, HW, C, G, (const float*)s_dhxh, (const float*)s_dh, (float4*)dx, accumulate);
+    } else {
+        launch_pdl(gn_bwd_apply_kernel, dim3(grid_cap(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, dy, stats, gamma, beta, HW, C,
+                   G, (const float*)s_dhxh, (const float*)s_dh, dx, accumulate, total);
+    }
     return check_launch("gn_mish_bwd");
 }
 
