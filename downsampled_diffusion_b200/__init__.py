@@ -13,6 +13,7 @@ from .ema import EMA
 from .schedule import make_beta_schedule
 from .evalfmt import fix_samples, generate_samples
 from .optim import Adam
+from . import parallel
 
 __all__ = ["Unet", "DDPM", "DownsampleDDPM", "DownsampleDDPMAutoencoder", "ConvResNet", "SimpleDownConv",
            "SimpleUpConv", "get_downsampling", "get_upsampling", "EMA", "make_beta_schedule", "fix_samples", "generate_samples", "Adam"]

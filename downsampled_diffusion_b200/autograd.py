@@ -141,6 +141,7 @@ class TrainProgram(Program):
             for pk in self.slow_packers:
                 pk()
             self.weights_version = v
+            self.pack_epoch += 1
 
     def _build_grad_plan(self) -> None:
         total = self.pg_total
@@ -957,12 +958,20 @@ class _NetFn(torch.autograd.Function):
         ctx.prog = prog
         ctx.n_params = len(params)
         ctx.params = params
+        # the activations backward() needs live in the program's buffers, not on ctx: stamp the forward so that a
+        # second forward through the same program before this one's backward is an error, not a silent wrong gradient
+        prog.generation = getattr(prog, "generation", 0) + 1
+        ctx.generation = prog.generation
         with torch.no_grad():
             return prog.forward(x, extra) if extra is not None else prog.forward(x)
 
     @staticmethod
     def backward(ctx, grad_out):
         prog = ctx.prog
+        if ctx.generation != prog.generation:
+            raise RuntimeError("backward() of a forward whose saved activations were overwritten: the same network ran forward again "
+                               "(same batch shape) before this backward.  Run forward -> backward per micro-batch, or wrap the "
+                               "extra forward in torch.no_grad().")
         with torch.no_grad():
             dx = prog.backward(grad_out.contiguous().float())
             pg = prog.param_grads()

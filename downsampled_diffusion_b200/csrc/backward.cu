@@ -435,6 +435,7 @@ __device__ __forceinline__ float ew_one(int mode, float x, float g, float alpha)
     if (mode == 1) return g * mish_grad_f(x);
     if (mode == 2) return g * (1.f - x * x);
     if (mode == 4) return tanhf(x);
+    if (mode == 5) { const float d = __fsub_rn(x, g); return __fmul_rn(d, d); }      // F.mse_loss(x, g, reduction='none')
     return alpha * x;
 }
 
@@ -442,7 +443,7 @@ __device__ __forceinline__ float ew_one(int mode, float x, float g, float alpha)
 __global__ void __launch_bounds__(256) ew4_kernel(int mode, const float4* __restrict__ x, const float4* __restrict__ g,
                                                   float4* __restrict__ y, int64_t n4, float alpha, int accumulate) {
     pdl_sync();
-    const bool needs_g = (mode == 1 || mode == 2);
+    const bool needs_g = (mode == 1 || mode == 2 || mode == 5);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 a = x[i];
         const float4 b = needs_g ? g[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(256) ew4_kernel(int mode, const float4* __rest
 __global__ void ew_kernel(int mode, const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ y, int64_t n,
                           float alpha, int accumulate) {
     pdl_sync();
-    const bool needs_g = (mode == 1 || mode == 2);
+    const bool needs_g = (mode == 1 || mode == 2 || mode == 5);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float v = ew_one(mode, x[i], needs_g ? g[i] : 0.f, alpha);
         y[i] = accumulate ? y[i] + v : v;
@@ -631,7 +632,7 @@ int dd_linattn_bwd(const float* qkv, const float* dout, const float* saved, floa
 }
 
 int dd_ew(int mode, const float* x, const float* g, float* y, int64_t n, float alpha, int accumulate, void* stream) {
-    DD_REQUIRE(mode >= 0 && mode <= 4 && n > 0, "ew: bad mode");
+    DD_REQUIRE(mode >= 0 && mode <= 5 && n > 0, "ew: bad mode");
     const uintptr_t align = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(y);
     if ((align & 15) == 0 && n % 4 == 0) {
         launch_pdl(ew4_kernel, dim3(grid_cap(n / 4, 256)), dim3(256), 0, (cudaStream_t)stream, mode, (const float4*)x, (const float4*)g,

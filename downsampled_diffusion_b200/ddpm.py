@@ -41,7 +41,6 @@ class SamplingPlan:
         self.noise = torch.empty(self.period, B, C, H, W, dtype=torch.float32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.copy_stream = torch.cuda.Stream(device=dev)          # host noise blocks are uploaded here (p_sample_loop)
-        self.table_version = None
         self.clip = ddpm.clip_denoised
 
     def step_eager(self) -> None:
@@ -54,11 +53,7 @@ class SamplingPlan:
     def prepare(self) -> None:
         """(Re)build the time-bias table and the graph when the U-Net's weights changed."""
         e = self.eng
-        e.refresh_weights()
-        if self.table_version != e.weights_version or e.time_table is None:
-            e.build_time_table(self.T)
-            self.table_version = e.weights_version
-        e.bind_table(e.time_table, self.t_dev, 0)
+        e.bind_table(e.time_table(self.T), self.t_dev, 0)       # refreshes the packed weights, refills the table in place if stale
         if self.graph is None:
             # warm-up on a side stream (lazy CUDA initialisation must not happen inside capture)
             self.t_dev.fill_(self.T - 1)
@@ -130,9 +125,17 @@ class DDPM(nn.Module):
         self._plans = EngineCache()
         self.use_graph = config.get("cuda_graph", True)
 
-    # reference spelling of the flatten helpers (ddpm.py:45-52)
-    def flatten_loss(self, per_elem_or_pair):
-        raise NotImplementedError("use mse_rows(a, b); the flatten is fused with the squared error")
+    # reference spelling of the loss helpers (ddpm.py:45-52): `flatten_loss(get_loss(target, output))`
+    def get_loss(self, target: torch.Tensor, output: torch.Tensor) -> "ops.SquaredError":
+        """partial(l2_loss, reduction='none') of ddpm.py:46: the per-element squared error, held as the operand pair so
+        that `flatten_loss` / `.mean()` run the fused reduction kernel; `.tensor()` materialises it."""
+        return ops.SquaredError(target, output)
+
+    def flatten_loss(self, x) -> torch.Tensor:
+        """reduce_mean / reduce_sum over all non-batch dimensions (ddpm.py:47-50, utils/utils.py:27-40)."""
+        if isinstance(x, ops.SquaredError):
+            return ops.mse_rows(x.target, x.output, self.loss_flat == "mean")
+        return ops.reduce_rows(x, self.loss_flat == "mean")
 
     def mse_rows(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         """flatten_loss(get_loss(a, b)): per-sample sum/mean of squared error (ddpm.py:45-52, 279)."""

@@ -70,6 +70,7 @@ class Program:
         self.packers: List[Callable[[], None]] = [] # re-run when the module's parameters change
         self.packed_bufs: List[torch.Tensor] = []   # packers[i] fills packed_bufs[i]
         self.weights_version = None
+        self.pack_epoch = 0                         # bumped every time the packers re-run: consumers of derived data compare it
         self.n_gn = 0
         self.tc_flags = 0                           # extra dd_conv_tc flags for every conv of the program (tests: L.TC_PAIR)
         self.gn_slots: List[Tuple[int, int]] = []   # (B*G*2 offset, G) per GroupNorm of a bf16 program
@@ -109,6 +110,7 @@ class Program:
             for pk in self.packers:
                 pk()
             self.weights_version = v
+            self.pack_epoch += 1
 
     def add(self, name: str, *args) -> None:
         fn = getattr(L.lib(), name)
@@ -398,7 +400,7 @@ class UnetEngine(Program):
         self.trow: Optional[torch.Tensor] = None                # int32 row index per sample (None: row = b)
         self.trow_stride = 0
         self.tb = (J,)
-        self.time_table: Optional[torch.Tensor] = None
+        self._tables: Dict[int, list] = {}                      # T -> [(T, J) table, pack_epoch it was filled at]
         self._build(unet)
         self.finalize_arena()
         self.refresh_weights()
@@ -528,14 +530,21 @@ class UnetEngine(Program):
         L.call("dd_time_bias", L.ptr(t_float), t_float.numel(), self.module.dim, L.ptr(self.freq), L.ptr(w1), L.ptr(b1),
                L.ptr(w2), L.ptr(b2), L.ptr(wc), L.ptr(bc), self.J, L.ptr(out), L.stream())
 
-    def build_time_table(self, T: int) -> torch.Tensor:
+    def time_table(self, T: int) -> torch.Tensor:
         """(T, J) fp32: every ResnetBlock's time bias for every step -- they depend on t only, so the
-        sampling chain looks them up instead of running the 18 Linear layers per step."""
+        sampling chain looks them up instead of running the 18 Linear layers per step.
+
+        ONE buffer per T for the life of the engine, refilled in place whenever the packed weights were refreshed
+        since it was last filled: captured graphs hold its address, so it must neither move nor go stale."""
         self.refresh_weights()
-        tab = self.empty(T, self.J, dtype=torch.float32)
-        self.time_bias_rows(torch.arange(T, dtype=torch.float32, device=self.device), tab)
-        self.time_table = tab
-        return tab
+        ent = self._tables.get(T)
+        if ent is None:
+            ent = [self.empty(T, self.J, dtype=torch.float32), -1]
+            self._tables[T] = ent
+        if ent[1] != self.pack_epoch:
+            self.time_bias_rows(torch.arange(T, dtype=torch.float32, device=self.device), ent[0])
+            ent[1] = self.pack_epoch
+        return ent[0]
 
     def bind_table(self, table: torch.Tensor, trow: torch.Tensor, stride: int) -> None:
         self.tb_rows, self.trow, self.trow_stride = table, trow, stride

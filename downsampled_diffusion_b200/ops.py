@@ -136,6 +136,39 @@ def mse_rows(a, b, mean: bool) -> torch.Tensor:
     return mse_rowsum_raw(a, b, mean)
 
 
+class SquaredError:
+    """`l2_loss(target, output, reduction='none')` (models/utils/losses.py:12-14) kept as its operand pair: the reference
+    only ever reduces it (`flatten_loss(...)`, `.mean()`), which the fused row-sum kernel does without materialising it."""
+
+    def __init__(self, target: torch.Tensor, output: torch.Tensor):
+        assert target.shape == output.shape
+        self.target, self.output = target, output
+        self.shape = target.shape
+
+    def tensor(self) -> torch.Tensor:
+        a, b = _f32c(self.target), _f32c(self.output)
+        y = torch.empty_like(a)
+        L.call("dd_ew", 5, L.ptr(a), L.ptr(b), L.ptr(y), a.numel(), 1.0, 0, L.stream())
+        return y
+
+    def sum(self) -> torch.Tensor:
+        return mse_rows(self.target, self.output, False).sum()
+
+    def mean(self) -> torch.Tensor:
+        return mse_rows(self.target, self.output, False).sum() / float(self.target.numel())
+
+
+def reduce_rows(x: torch.Tensor, mean: bool) -> torch.Tensor:
+    """Sum (or mean) over all non-batch dimensions of a plain tensor (utils/utils.py:27-40); forward only."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        raise NotImplementedError("flatten_loss of a plain tensor is forward-only; pass get_loss(target, output) for the differentiable form")
+    x = _f32c(x)
+    B, chw = _flat(x)
+    out = torch.zeros(B, dtype=torch.float32, device=x.device)
+    L.call("dd_colsum", L.ptr(x), L.ptr(out), chw, B, 1, chw, L.stream())      # (1, B, chw) read as NCHW: channel sums = row sums
+    return out / float(chw) if mean else out
+
+
 def posterior_step_raw(x_t, eps_hat, noise, coef, t_idx, t_stride: int, noise_step_stride: int, T: int,
                        noise_period: int, clip: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     B, chw = _flat(x_t)

@@ -61,6 +61,16 @@ def sample_sharded(model, total_batch: int, noise: Optional[torch.Tensor] = None
     return gather_batch(out, total_batch)
 
 
+def _allreduce_mean(flat: torch.Tensor, world: int) -> None:
+    """In-place mean over the group: NCCL averages inside the collective (ReduceOp.AVG, no second pass over the
+    buffer); gloo (the CPU tests) has no AVG, so it sums and divides."""
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(flat)
+        flat.div_(world)
+
+
 def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int = 64 << 20) -> None:
     """DDP-style mean all-reduce of .grad over the default group, in flat fp32 buckets (NCCL over NVLink 5;
     NVSwitch makes the cost bandwidth-bound, so buckets are sized for launch latency, not link count)."""
@@ -80,8 +90,7 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int 
         dense = all(g.is_contiguous() and g.dtype == torch.float32 for g in gs) and 10 * sum(g.numel() for g in gs) >= 9 * (hi - lo)
         if len(gs) > 1 and dense:
             flat = torch.empty(0, dtype=torch.float32, device=gs[0].device).set_(gs[0].untyped_storage(), lo, (hi - lo,))
-            dist.all_reduce(flat)
-            flat.div_(world)
+            _allreduce_mean(flat, world)
         else:
             loose += gs
     bucket, size = [], 0
@@ -91,8 +100,7 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int 
         if not bucket:
             return
         flat = torch.cat([g.reshape(-1) for g in bucket])
-        dist.all_reduce(flat)
-        flat.div_(world)
+        _allreduce_mean(flat, world)
         off = 0
         for g in bucket:
             g.copy_(flat[off:off + g.numel()].view_as(g))

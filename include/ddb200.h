@@ -354,7 +354,7 @@ int dd_linattn_save(const float* ws, int B, int n, int heads, float* saved, void
 int dd_linattn_bwd(const float* qkv, const float* dout, const float* saved, float* dctx, float* dqkv,
                    int B, int n, int heads, int dh, void* stream);
 /* elementwise: mode 0 y=mish(x); 1 y=g*mish'(x); 2 y=g*(1-x^2) (tanh backward, x = tanh output); 3 y=alpha*x;
- * 4 y=tanh(x); accumulate != 0 adds into y. */
+ * 4 y=tanh(x); 5 y=(x-g)^2 (l2_loss(..., reduction='none'), models/utils/losses.py:12-14); accumulate != 0 adds into y. */
 int dd_ew(int mode, const float* x, const float* g, float* y, int64_t n, float alpha, int accumulate, void* stream);
 /* SinusoidalPosEmb (blocks.py:22-29): out (R, dim) = [sin(t*freq), cos(t*freq)]. */
 int dd_sincos_emb(const float* t, const float* freq, float* out, int R, int dim, void* stream);

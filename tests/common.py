@@ -68,3 +68,15 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
 
 def max_abs(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a.double().cpu() - b.double().cpu()).abs().max())
+
+
+# ---- full T-step chains at the BASELINE sizes (tests/test_gpu_chain_full.py, oracle/make_golden_chain.py) ----------
+CHAIN_ROWS = 3                                   # rows of the benchmarked batch that the CPU side follows
+CHAIN_SEEDS = {"c2": 7102, "c3": 7103}
+
+
+def chain_noise(tag: str, T: int, rows: int, C: int, H: int, W: int) -> torch.Tensor:
+    """Pre-drawn chain noise (T+1, rows, C, H, W) of the checked rows: entry 0 is the start image, entry 1+k the
+    k-th step's z.  CPU generator, so the GPU test, the oracle and the reference-side generator see the same bits."""
+    g = torch.Generator().manual_seed(CHAIN_SEEDS[tag])
+    return torch.randn(T + 1, rows, C, H, W, generator=g)

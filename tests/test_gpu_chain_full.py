@@ -1,0 +1,98 @@
+"""The benchmarked output itself: FULL T=1000 ancestral chains at the BASELINE sizes against the REAL reference.
+
+north_star's second correctness criterion ("the full chain's final samples within a stated per-pixel tolerance",
+reference models/diffusion/ddpm.py:229-249, dddpm.py:76-90).  tests/golden/golden_v3.npz holds what the unmodified
+reference's `sample()` returned for CHAIN_ROWS rows under the pre-drawn noise of tests/common.chain_noise
+(oracle/make_golden_chain.py).  Every sample's chain is independent, so the GPU runs the benchmarked
+batch (C3: 64, C2: 256) with those rows in front and device-drawn noise behind them, through the public
+`model.sample(B, noise=...)`, and the checked rows must land on the reference's:
+
+    bf16 tensor-core path:  latent max-abs <= 5e-2, image max-abs <= 2e-2     
+    fp32 validation mode:   both            <= 1e-3
+
+Also here: the C4-size (256x256) training objective and gradients against the reference's autograd.
+"""
+import numpy as np
+import pytest
+import torch
+
+import downsampled_diffusion_b200 as dd
+from tests import common as tc
+
+pytestmark = pytest.mark.gpu
+
+BF16_LATENT, BF16_IMAGE, FP32_BOTH = 5e-2, 2e-2, 1e-3
+
+
+def _full_chain(cuda, tag, cfg, hw, B, precision):
+    m = tc.build_model(dict(cfg, precision=precision), dd, "dddpm_ae", device="cuda").to(cuda).eval()
+    m.downsample.precision = m.upsample.precision = precision
+    T, rows = cfg["T"], tc.CHAIN_ROWS
+    g = torch.Generator(device=cuda).manual_seed(99)
+    noise = torch.randn(T + 1, B, cfg["unet_in"], hw, hw, generator=g, device=cuda)
+    noise[:, :rows] = tc.chain_noise(tag, T, rows, cfg["unet_in"], hw, hw).to(cuda)
+    with torch.no_grad():
+        x, z = m.sample(B, noise=noise)
+    assert z.shape == (B, cfg["unet_in"], hw, hw) and torch.isfinite(x).all()
+    return x[:rows].cpu(), z[:rows].cpu()
+
+
+def _check(golden, tag, x, z, lat_bar, img_bar, what):
+    zr = torch.from_numpy(np.asarray(golden[f"fullchain.{tag}.z"]))
+    xr = torch.from_numpy(np.asarray(golden[f"fullchain.{tag}.x"]))
+    if xr.shape[-1] != x.shape[-1]:
+        x = x[:, :, ::2, ::2]                    # the C3 fixture keeps every second pixel
+    ez, ex = tc.max_abs(z, zr), tc.max_abs(x, xr)
+    print(f"full chain {tag} {what}: latent max-abs {ez:.3e} (bar {lat_bar}), image max-abs {ex:.3e} (bar {img_bar}), "
+          f"latent rel-L2 {tc.rel_l2(z, zr):.3e}")
+    assert ez <= lat_bar, f"{tag} {what}: latent max-abs {ez} > {lat_bar}"
+    assert ex <= img_bar, f"{tag} {what}: image max-abs {ex} > {img_bar}"
+
+
+def test_c3_full_chain_batch64_bf16_vs_reference(cuda, golden):
+    x, z = _full_chain(cuda, "c3", tc.C3, 32, 64, "bf16")
+    _check(golden, "c3", x, z, BF16_LATENT, BF16_IMAGE, "bf16 B=64")
+
+
+def test_c2_full_chain_batch256_bf16_vs_reference(cuda, golden):
+    x, z = _full_chain(cuda, "c2", tc.C2, 16, 256, "bf16")
+    _check(golden, "c2", x, z, BF16_LATENT, BF16_IMAGE, "bf16 B=256")
+
+
+def test_c3_full_chain_fp32_mode_vs_reference(cuda, golden):
+    x, z = _full_chain(cuda, "c3", tc.C3, 32, tc.CHAIN_ROWS, "fp32")
+    _check(golden, "c3", x, z, FP32_BOTH, FP32_BOTH, "fp32 mode")
+
+
+def test_c2_full_chain_fp32_mode_vs_reference(cuda, golden):
+    x, z = _full_chain(cuda, "c2", tc.C2, 16, tc.CHAIN_ROWS, "fp32")
+    _check(golden, "c2", x, z, FP32_BOTH, FP32_BOTH, "fp32 mode")
+
+
+@pytest.mark.parametrize("precision,tol_obj,tol_norm,tol_grad", [("fp32", 1e-4, 2e-3, 5e-4), ("bf16", 2e-3, 3e-2, 2e-2)])
+def test_c4_size_training_step_vs_reference_autograd(cuda, golden, precision, tol_obj, tol_norm, tol_grad):
+    """256x256 training objective + all parameter-gradient norms + three gradients against the reference's autograd
+    (2 rows; `precision='bf16'` modules train with TF32 tensor-core convolutions, 'fp32' is the CUDA-core validation mode)."""
+    m = tc.build_model(dict(tc.C3, precision=precision), dd, "dddpm_ae", device="cuda").to(cuda).train()
+    m.downsample.precision = m.upsample.precision = precision
+    x = tc.rand_pm1(31, 2, 3, 256, 256).to(cuda)
+    t = torch.tensor([50, 700], device=cuda)
+    eps = tc.randn(32, 2, 8, 32, 32).to(cuda)
+    obj, d = m.losses(x, t, eps=eps)
+    obj.backward()
+    for key, val in (("obj", obj), ("latent", d["latent"]), ("recon", d["recon"])):
+        ref = float(golden[f"fulltrain.c4.{key}"])
+        assert abs(float(val) - ref) <= tol_obj * abs(ref) + 1e-6, (key, float(val), ref)
+    norms = np.asarray(golden["fulltrain.c4.grad_norms"])
+    worst = 0.0
+    for (n, p), ref in zip(m.named_parameters(), norms):
+        got = 0.0 if p.grad is None else float(p.grad.double().norm())
+        err = abs(got - ref) / max(ref, 1e-6)
+        worst = max(worst, err)
+        assert err <= tol_norm + 1e-5 / max(ref, 1e-6), f"{n}: |grad| {got} vs reference {ref}"
+    print(f"C4-size training ({precision}): worst relative gradient-norm error {worst:.2e}")
+    params = dict(m.named_parameters())
+    for n in ("upsample.conv.1.c2.weight", "downsample.conv.0.weight"):
+        assert tc.rel_l2(params[n].grad, torch.from_numpy(np.asarray(golden[f"fulltrain.c4.grad.{n}"]))) <= tol_grad, n
+    n = "latent_model.mid_block1.block1.block.0.weight"
+    assert tc.rel_l2(params[n].grad[:32, :32], torch.from_numpy(np.asarray(golden[f"fulltrain.c4.grad.{n}[:32,:32]"]))) <= tol_grad, n

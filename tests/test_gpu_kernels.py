@@ -187,7 +187,7 @@ def test_time_bias(cuda):
     sd = net.state_dict()
     eng_net = tc.build_model(tc.CS, dd, "unet").to(cuda)
     eng = eng_net.engine(2, 8, 8, "fp32")
-    tab = eng.build_time_table(1000).cpu()
+    tab = eng.time_table(1000).cpu()
     t = torch.tensor([0, 1, 37, 500, 999])
     temb = O.time_mlp(sd, "", t, tc.CS["unet_chan"])
     for rb_name in ("downs.0.0", "mid_block2", "ups.0.1"):

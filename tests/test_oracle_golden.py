@@ -224,3 +224,38 @@ def test_deterministic_bicubic_resampler(golden):
     np.testing.assert_allclose(float(obj), float(golden["det.loss.obj"]), rtol=2e-5)
     np.testing.assert_allclose(float(d["recon"]), float(golden["det.loss.recon"]), rtol=2e-5)
     assert tc.rel_l2(sd["latent_model.final_conv.1.weight"].grad, T(golden["det.loss.grad_final"])) < 1e-4
+
+
+# ---- full T=1000 chains at the BASELINE sizes (golden_v3.npz, oracle/make_golden_chain.py) -----------------------
+@pytest.mark.parametrize("tag,cfg,hw,rows", [("c2", tc.C2, 16, 2), ("c3", tc.C3, 32, 1)])
+def test_full_chain_oracle_vs_reference(golden, tag, cfg, hw, rows):
+    """The oracle's decomposed loop over all 1000 steps lands on what the unmodified reference's `sample()` returned
+    for the same pre-drawn noise (first `rows` rows: every row's chain is independent; bounded so the CPU suite stays short)."""
+    sd = sd_of(cfg, "dddpm_ae")
+    buf = O.schedule_buffers("linear", cfg["T"])
+    noise = tc.chain_noise(tag, cfg["T"], tc.CHAIN_ROWS, cfg["unet_in"], hw, hw)[:, :rows]
+    with torch.no_grad():
+        x, z = O.dddpm_sample(sd, cfg, buf, list(noise))
+    zr, xr = T(golden[f"fullchain.{tag}.z"])[:rows], T(golden[f"fullchain.{tag}.x"])[:rows]
+    if xr.shape[-1] != x.shape[-1]:
+        x = x[:, :, ::2, ::2]
+    assert tc.max_abs(z, zr) < 2e-4 and tc.max_abs(x, xr) < 2e-4
+
+
+def test_full_size_training_objective_oracle_vs_reference(golden):
+    cfg = tc.C3
+    model = tc.build_model(cfg, ours, "dddpm_ae")
+    names = [n for n, _ in model.named_parameters()]
+    sd = {k: v.detach().clone().requires_grad_(k in names) for k, v in model.state_dict().items()}
+    buf = O.schedule_buffers("linear", cfg["T"])
+    x, t, eps = tc.rand_pm1(31, 2, 3, 256, 256), torch.tensor([50, 700]), tc.randn(32, 2, 8, 32, 32)
+    obj, d = O.dddpm_losses(sd, cfg, buf, x, t, eps, autoencoder=True)
+    obj.backward()
+    for key, val in (("obj", obj), ("latent", d["latent"]), ("recon", d["recon"])):
+        ref = float(golden[f"fulltrain.c4.{key}"])
+        assert abs(float(val) - ref) <= 1e-5 * abs(ref) + 1e-7, key
+    norms = np.asarray(golden["fulltrain.c4.grad_norms"])
+    for n, ref in zip(names, norms):
+        g = sd[n].grad
+        got = 0.0 if g is None else float(g.double().norm())
+        assert abs(got - ref) <= 1e-4 * max(ref, 1e-6) + 1e-7, n
