@@ -74,14 +74,38 @@ class ClockSampler(threading.Thread):
 
 
 # -------------------------------------------------------------------------------------------------
+def cpu_kind() -> str:
+    from oracle import build_ref
+    return "reference" if build_ref.available() else "port"
+
+
 def cpu_reference_rate(n_steps: int, batch: int, threads: int):
-    """The reference algorithm (oracle port of ddpm.py:229-249 + dddpm.py:103-112) on the host cores:
-    `n_steps` ancestral steps on a batch of `batch` latents + one up-net pass, extrapolated to T=1000."""
-    from oracle import ddpm_oracle as O
+    """The reference's own CPU path on the host cores: `n_steps` ancestral steps on a batch of `batch` latents + one
+    up-net pass, extrapolated to T=1000.  With oracle/_ref present (oracle/build_ref.py) this is the UNMODIFIED reference
+    (`DownsampleDDPMAutoencoder.p_sample` / `rescaled_upsample`, models/diffusion/ddpm.py:203-227, dddpm.py:103-112);
+    otherwise the oracle port of the same algorithm."""
+    from oracle import build_ref
     from tests import common as tc
-    import downsampled_diffusion_b200 as dd
     torch.set_num_threads(threads)
     cfg = c3_config("fp32")
+    if build_ref.available():
+        ref = build_ref.load()
+        model = tc.build_model(cfg, ref, "dddpm_ae").eval()
+        g = torch.Generator().manual_seed(0)
+        img = torch.randn(batch, *LATENT, generator=g)
+        with torch.no_grad():
+            model.p_sample(img, torch.full((batch,), T_STEPS - 1, dtype=torch.long))      # warm-up step
+            t0 = time.perf_counter()
+            for i in range(n_steps):
+                img = model.p_sample(img, torch.full((batch,), T_STEPS - 1 - i, dtype=torch.long))
+            t1 = time.perf_counter()
+            model.rescaled_upsample(img[:max(1, batch // 4)])
+            t2 = time.perf_counter()
+        step_s = (t1 - t0) / n_steps
+        up_s = (t2 - t1) / max(1, batch // 4) * batch
+        return batch / (step_s * T_STEPS + up_s), step_s, up_s
+    from oracle import ddpm_oracle as O
+    import downsampled_diffusion_b200 as dd
     model = tc.build_model(cfg, dd, "dddpm_ae")
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     buf = O.schedule_buffers("linear", T_STEPS)
@@ -110,13 +134,15 @@ def run_reference(args):
         rate, step_s, up_s = cpu_reference_rate(args.cpu_steps, args.cpu_batch, threads)
         vals.append(rate)
     rate = sum(vals) / len(vals)
+    kind = cpu_kind()
     sample = (f"{args.cpu_steps} ancestral steps + up-net on a batch of {args.cpu_batch} latents per bench step, "
-              f"extrapolated x{T_STEPS}/{args.cpu_steps}; oracle port of the reference (pure-Python reference cannot travel to the GPU box)")
+              f"extrapolated x{T_STEPS}/{args.cpu_steps}; " + ("the unmodified reference from oracle/_ref (torch CPU)" if kind == "reference"
+                                                               else "oracle port of the reference (oracle/_ref absent)"))
     line = {"impl": "reference", "metric": "samples/sec, full T=1000 dDDPM x3 sampling", "value": rate, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.cpu_batch / rate,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C3: dDDPM x3, latent 8x32x32 -> 3x256x256, T=1000 (CPU sample)", "cpu_batch": args.cpu_batch},
-            "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -177,6 +203,21 @@ def step_time_ms(plan, reps=50):
     return e0.elapsed_time(e1) / reps
 
 
+def time_chains(chain, noise, n, barrier, final_gather, x_host=None):
+    """CUDA-event time of `n` full chains (ms), barrier + synchronize on both sides."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(n):
+        x, _ = chain(noise)
+        if x_host is not None:
+            x_host.copy_(x, non_blocking=True)
+        final_gather(x)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
 def run_ours(args):
     import torch.distributed as dist
     import downsampled_diffusion_b200 as dd
@@ -193,35 +234,43 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
     pk = peaks()
-    B = args.batch
+    # BASELINE configs[2] as written: ONE batch of `--batch` (64) samples, sharded over the N GPUs of the box (strong scaling:
+    # 64 / N per GPU, no communication during the chain, one gather of the images).  The saturating figure the survey also
+    # asks for (64 samples PER GPU, weak) is measured after it and reported under "weak_64_per_gpu".
+    G = args.batch
+    assert G % world == 0, f"global batch {G} must divide over {world} GPUs"
+    B = G // world
     cfg = c3_config(args.precision)
     model = tc.build_model(cfg, dd, "dddpm_ae", device=str(dev)).to(dev).eval()
     model.downsample.precision = model.upsample.precision = args.precision
-    shape = (B, *LATENT)
-
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    noise_dev = torch.randn(T_STEPS + 1, *shape, generator=gen, device=dev)        # 2.1 GB at B=64
-    noise_host = torch.empty(noise_dev.shape, dtype=torch.float32, pin_memory=True)
-    noise_host.copy_(noise_dev)
-    x_host = torch.empty(B, *IMAGE, dtype=torch.float32, pin_memory=True)
-    torch.cuda.synchronize()
-
-    @torch.no_grad()
-    def chain(noise):
-        z = model.p_sample_loop(shape, noise=noise)
-        x = model.rescaled_upsample(z)
-        return x, z
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    gathered = [torch.empty(B, *IMAGE, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    def make_case(Bc):
+        shape = (Bc, *LATENT)
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        noise_dev = torch.randn(T_STEPS + 1, *shape, generator=gen, device=dev)        # 2.1 GB at 64 per GPU
+        gathered = [torch.empty(Bc, *IMAGE, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
 
-    def final_gather(x):
-        if world > 1:
-            dist.gather(x, gathered, dst=0)
+        @torch.no_grad()
+        def chain(noise):
+            z = model.p_sample_loop(shape, noise=noise)
+            x = model.rescaled_upsample(z)
+            return x, z
+
+        def final_gather(x):
+            if world > 1:
+                dist.gather(x, gathered, dst=0)
+        return shape, noise_dev, chain, final_gather
+
+    shape, noise_dev, chain, final_gather = make_case(B)
+    noise_host = torch.empty(noise_dev.shape, dtype=torch.float32, pin_memory=True)
+    noise_host.copy_(noise_dev)
+    x_host = torch.empty(B, *IMAGE, dtype=torch.float32, pin_memory=True)
+    torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         x, _ = chain(noise_dev)
@@ -232,64 +281,80 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     n0 = _lib.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        x, _ = chain(noise_dev)
-        final_gather(x)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = time_chains(chain, noise_dev, args.steps, barrier, final_gather)
     launches = _lib.launches() - n0
     sampler.stop_flag.set()
     sampler.join(timeout=3)
 
     # ---- end to end: host noise in, host images out -------------------------------------------------
     chain(noise_host)            # one warm-up through the host path
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e2.record()
-    for _ in range(args.steps):
-        x, _ = chain(noise_host)
-        x_host.copy_(x, non_blocking=True)
-        final_gather(x)
-    e3.record()
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
+    ms_e2e = time_chains(chain, noise_host, args.steps, barrier, final_gather, x_host)
+
+    # ---- the default call: model.sample(B) with the noise drawn on the device (what a drop-in user runs) ----
+    @torch.no_grad()
+    def default_call(_):
+        x, z = model.sample(B)
+        return x, z
+    n_def = max(1, args.steps // 4)
+    default_call(None)
+    ms_def = time_chains(default_call, None, n_def, barrier, final_gather, x_host)
+
+    # ---- weak figure: 64 samples per GPU (only differs from the above for N > 1) --------------------
+    ms_weak, n_weak = None, max(2, args.steps // 4)
+    if world > 1:
+        del noise_dev, noise_host
+        shape_w, noise_w, chain_w, gather_w = make_case(G)
+        for _ in range(2):
+            chain_w(noise_w)
+        ms_weak = time_chains(chain_w, noise_w, n_weak, barrier, gather_w)
+        del noise_w
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev)
+        t = torch.tensor([ms, ms_e2e, ms_def, ms_weak], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_def, ms_weak = (float(v) for v in t)
+
+    train = None
+    if not args.no_train:
+        del chain
+        torch.cuda.empty_cache()
+        train = train_record(args, world, rank, dev, pk, sub=True)
 
     if rank == 0:
         plan = model.sampling_plan(shape)
         step_ms = step_time_ms(plan)
         roof = conv_roofline(model, plan, pk)
-        total = world * B * args.steps
+        total = G * args.steps
         value = total / (ms / 1000.0)
         e2e = total / (ms_e2e / 1000.0)
         unet_tf = UNET_GFLOP * B / step_ms            # GFLOP / ms = TFLOP/s
         line = {
             "metric": "samples/sec, full T=1000 dDDPM x3 sampling", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "C3 (BASELINE configs[2]): dDDPM x3, T=1000 ancestral chain on latent 8x32x32 + up-net to 3x256x256",
-                       "batch_per_gpu": B, "global_batch": world * B, "weights": "random init seed 0, 22.67M params",
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "C3 (BASELINE configs[2]): dDDPM x3, T=1000 ancestral chain on latent 8x32x32 + up-net to 3x256x256, "
+                                   "one batch of 64 sharded over the GPUs",
+                       "batch_per_gpu": B, "global_batch": G, "weights": "random init seed 0, 22.67M params",
                        "parallelism": f"batch-sharded x{world}, no comm in chain, final gather",
-                       "l2": "per-chain noise stream (2.1 GB) exceeds L2; weights (45 MB bf16) L2-resident by design",
+                       "l2": "per-chain noise stream (33 MB per sample) exceeds L2 at every batch size; weights (45 MB bf16) L2-resident by design",
                        "cuda_graph": "one graph per ancestral step, replayed 1000x"},
             "unet_step_ms": step_ms, "unet_step_tflops": unet_tf, "unet_step_frac_of_sustained_peak": unet_tf / pk["tf_sustained"],
             "gpu_launches": launches,
-            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(noise_host.numel() * 4),
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int((T_STEPS + 1) * B * 8192 * 4),
                     "d2h_bytes_per_step": int(x_host.numel() * 4)},
+            "default_call": {"value": G * n_def / (ms_def / 1000.0), "unit": "samples/s", "chains": n_def,
+                             "what": "model.sample(B) with noise=None: start image and per-step z drawn with torch.randn on the device, images read back"},
             "roofline": roof, "clocks": sampler.summary(),
         }
+        if ms_weak is not None:
+            line["weak_64_per_gpu"] = {"value": world * G * n_weak / (ms_weak / 1000.0), "unit": "samples/s", "batch_per_gpu": G,
+                                       "global_batch": world * G, "chains": n_weak, "scaling": "weak"}
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             rate, step_s, up_s = cpu_reference_rate(args.cpu_steps, args.cpu_batch, threads)
-            line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+            line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": threads, "kind": cpu_kind(),
                                     "sample": f"{args.cpu_steps} ancestral steps ({step_s * 1e3:.1f} ms/step) + up-net on {args.cpu_batch} latents, extrapolated to T=1000"}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -302,6 +367,11 @@ def run_ours(args):
 # all-reduce (N > 1), clip, Adam, EMA.  `python bench.py --workload train [--gpus N]`; the driver's default run
 # is the sampling workload above.
 TRAIN_GFLOP = 57.5          # per sample, forward + backward (torch flop counter on the reference)
+# Algorithmic HBM bytes per sample of a layer-per-kernel training step ("training roofline"): the conv /
+# norm / attention outputs of the three networks are 67.0 M fp32 elements per sample (down-net 26.2 M, up-net 36.7 M, U-Net
+# 4.1 M; activations fused into their producers); each is written and read once in forward, read once in backward, and its
+# gradient is written and read once: 5 passes x 4 B.
+TRAIN_GB_PER_SAMPLE = 67.0e6 * 4 * 5 / 1e9
 
 
 def cpu_train_rate(batch: int, threads: int):
@@ -323,11 +393,107 @@ def cpu_train_rate(batch: int, threads: int):
     return batch / (time.perf_counter() - t0)
 
 
-def run_train(args):
+def train_record(args, world, rank, dev, pk, sub=False):
+    """Times the C4 training step on every rank (process group already initialised for world > 1); returns the record on
+    rank 0, None elsewhere.  sub=True: the `train` sub-record of the sampling line (bounded: --train-steps steps)."""
     import torch.distributed as dist
     import downsampled_diffusion_b200 as dd
     from downsampled_diffusion_b200 import _lib, parallel
     from tests import common as tc
+
+    B = args.train_batch
+    steps = args.train_steps if sub else args.steps
+    warmup = min(args.warmup, 5) if sub else args.warmup
+    cfg = dict(tc.C3, unet_dropout=0.1, precision="fp32" if args.train_precision == "fp32" else "bf16")
+    model = tc.build_model(cfg, dd, "dddpm_ae", device=str(dev)).to(dev).train()
+    model.downsample.precision = model.upsample.precision = cfg["precision"]
+    ema = dd.EMA(model, decay=0.995)
+    # the trainer's clip_grad_norm_(1.0) -> Adam.step -> EMA.update (trainer_ddpm.py:243-254) as the package's fused optimizer
+    opt = dd.Adam(model.parameters(), lr=2e-4, max_grad_norm=1.0)
+    opt.attach_ema(ema, model)
+    params = [p for p in model.parameters()]
+    x_host = torch.empty(B, *IMAGE, dtype=torch.float32, pin_memory=True)
+    x_host.copy_(tc.rand_pm1(100 + rank, B, *IMAGE))
+    x_dev = x_host.to(dev)
+    reducer = parallel.GradReducer(model) if world > 1 else None
+
+    def step(x):
+        if reducer is not None:
+            reducer.arm()
+        obj, _ = model(x)
+        obj.backward()
+        if reducer is not None:
+            reducer.finish()
+        opt.step(ema="update")
+        opt.zero_grad()
+        return obj
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step(x_dev)
+    barrier()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    n0 = _lib.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        step(x_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launches() - n0
+    sampler.stop_flag.set()
+    sampler.join(timeout=3)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e2.record()
+    loss = 0.0
+    for _ in range(steps):
+        loss = float(step(x_host.to(dev, non_blocking=True)))        # H2D of the batch, D2H of the loss, every step
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    del model, ema, opt
+    if rank != 0:
+        return None
+    total = world * B * steps
+    value, e2e = total / (ms / 1e3), total / (ms_e2e / 1e3)
+    step_ms = ms / steps
+    tf = TRAIN_GFLOP * B / step_ms           # per GPU, GFLOP/ms = TFLOP/s
+    gbs = TRAIN_GB_PER_SAMPLE * B / (step_ms * 1e-3)
+    line = {"metric": "samples/sec, dDDPM x3 256x256 training step (p_losses fwd+bwd, clip, Adam, EMA)", "value": value,
+            "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.train_precision == "fp32" else "tf32",
+            "data": "synthetic",
+            "config": {"workload": "C4 (BASELINE configs[3]): dDDPM x3 256x256 training, x ~ U(-1,1), dropout 0.1",
+                       "batch_per_gpu": B, "global_batch": world * B,
+                       "parallelism": f"data-parallel x{world}, per-network NCCL gradient all-reduce (AVG) launched from the backward pass on a side stream",
+                       "l2": "activations of one step (tens of GB) exceed L2"},
+            "gpu_launches": launches, "last_loss": loss,
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 4},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+                         "algorithmic_bytes_per_sample": TRAIN_GB_PER_SAMPLE * 1e9,
+                         "kernel": "whole step (the resampling nets' 32/64-channel convolutions at 64^2..256^2 are HBM-bound, SURVEY.md 8(d)); "
+                                   "bytes = every activation written once and read once per consumer, forward + backward, fp32",
+                         "tensor_tflops": tf, "tensor_frac_of_sustained_bf16": tf / pk["tf_sustained"],
+                         "peak_source": pk["src"] + " HBM copy bandwidth"},
+            "clocks": sampler.summary()}
+    return line
+
+
+def run_train(args):
+    import torch.distributed as dist
+    from downsampled_diffusion_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -349,80 +515,8 @@ def run_train(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
-    pk = peaks()
-    B = args.train_batch
-    cfg = dict(tc.C3, unet_dropout=0.1, precision="fp32" if args.train_precision == "fp32" else "bf16")
-    model = tc.build_model(cfg, dd, "dddpm_ae", device=str(dev)).to(dev).train()
-    model.downsample.precision = model.upsample.precision = cfg["precision"]
-    ema = dd.EMA(model, decay=0.995)
-    # the trainer's clip_grad_norm_(1.0) -> Adam.step -> EMA.update (trainer_ddpm.py:243-254) as the package's fused optimizer
-    opt = dd.Adam(model.parameters(), lr=2e-4, max_grad_norm=1.0)
-    opt.attach_ema(ema, model)
-    params = [p for p in model.parameters()]
-    x_host = torch.empty(B, *IMAGE, dtype=torch.float32, pin_memory=True)
-    x_host.copy_(tc.rand_pm1(100 + rank, B, *IMAGE))
-    x_dev = x_host.to(dev)
-
-    def step(x):
-        obj, _ = model(x)
-        obj.backward()
-        parallel.allreduce_gradients(params)
-        opt.step(ema="update")
-        opt.zero_grad()
-        return obj
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step(x_dev)
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    n0 = _lib.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step(x_dev)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = _lib.launches() - n0
-    sampler.stop_flag.set()
-    sampler.join(timeout=3)
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e2.record()
-    loss = 0.0
-    for _ in range(args.steps):
-        loss = float(step(x_host.to(dev, non_blocking=True)))        # H2D of the batch, D2H of the loss, every step
-    e3.record()
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+    line = train_record(args, world, rank, dev, peaks())
     if rank == 0:
-        total = world * B * args.steps
-        value, e2e = total / (ms / 1e3), total / (ms_e2e / 1e3)
-        tf = TRAIN_GFLOP * B / (ms / args.steps)           # per GPU, GFLOP/ms = TFLOP/s
-        line = {"metric": "samples/sec, dDDPM x3 256x256 training step (p_losses fwd+bwd, clip, Adam, EMA)", "value": value,
-                "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.train_precision == "fp32" else "tf32",
-                "data": "synthetic",
-                "config": {"workload": "C4 (BASELINE configs[3]): dDDPM x3 256x256 training, x ~ U(-1,1), dropout 0.1",
-                           "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"data-parallel x{world}, bucketed NCCL gradient all-reduce",
-                           "l2": "activations of one step (tens of GB) exceed L2"},
-                "gpu_launches": launches, "last_loss": loss,
-                "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 4},
-                "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
-                             "traffic": None, "kernel": "whole step; forward, input-gradient and weight-gradient convolutions on tcgen05 kind::tf32" if args.train_precision != "fp32" else "whole step (fp32 CUDA-core convolutions)",
-                             "peak_source": pk["src"] + " sustained bf16"},
-                "clocks": sampler.summary()}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             rate = cpu_train_rate(args.cpu_batch_train, threads)
@@ -449,6 +543,8 @@ def main():
     ap.add_argument("--train-batch", type=int, default=32, help="images per GPU per training step")
     ap.add_argument("--train-precision", default="tf32", choices=["tf32", "fp32"], help="tf32: tcgen05 kind::tf32 convolutions; fp32: CUDA-core validation mode")
     ap.add_argument("--cpu-batch-train", type=int, default=2)
+    ap.add_argument("--train-steps", type=int, default=20, help="steps of the C4 training sub-record of the sampling line")
+    ap.add_argument("--no-train", action="store_true", help="skip the C4 training sub-record")
     args = ap.parse_args()
     if args.workload == "train":
         run_train(args)

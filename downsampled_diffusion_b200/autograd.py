@@ -229,6 +229,7 @@ class TrainProgram(Program):
             # one launch writes every tabulated gradient, in parameter layout, into one fresh buffer; the gradients are views
             flat = torch.empty(self.grad_plan.total, dtype=torch.float32, device=self.device)
             self.grad_plan.run((self.pg_arena.data_ptr(),), dst0=flat)
+            self.last_flat = flat                   # the data-parallel reducer all-reduces this buffer in place (parallel.GradReducer)
             for param, o, n in self.grad_fast:
                 out[id(param)] = flat[o:o + n].view(param.shape)
             specs = self.slow_specs
@@ -950,6 +951,16 @@ class ResampleTrainProgram(TrainProgram):
 
 
 # =====================================================================================================
+# Called as hook(flat) right after a network's parameter gradients were written into their flat buffer, i.e. in the middle of
+# loss.backward(): parallel.GradReducer uses it to start that network's all-reduce while the other networks still back-propagate.
+_grads_ready_hook = None
+
+
+def set_grads_ready_hook(fn) -> None:
+    global _grads_ready_hook
+    _grads_ready_hook = fn
+
+
 class _NetFn(torch.autograd.Function):
     """One autograd node per network: forward/backward are the program's two launch lists."""
 
@@ -974,7 +985,10 @@ class _NetFn(torch.autograd.Function):
                                "extra forward in torch.no_grad().")
         with torch.no_grad():
             dx = prog.backward(grad_out.contiguous().float())
+            prog.last_flat = None
             pg = prog.param_grads()
+            if _grads_ready_hook is not None and prog.last_flat is not None:
+                _grads_ready_hook(prog.last_flat)
         grads = tuple(pg.get(id(p)) if ctx.needs_input_grad[3 + i] else None for i, p in enumerate(ctx.params))
         return (None, dx if ctx.needs_input_grad[1] else None, None) + grads
 

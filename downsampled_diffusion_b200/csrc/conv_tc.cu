@@ -287,6 +287,232 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
     if (et == 0) tstamp(p, 6);
 }
 
+// ---- fused GroupNorm + Mish epilogue (dd_conv_tc_gn; bf16 NHWC output, bn = 64 or 128) ----------------------------------
+// blocks.py:79-84 and :108-115 behind the convolution that feeds them: y = mish(GN(acc + bias)) [+ time bias] [+ residual].
+// The statistics of a (sample, group) span every pixel of the image, so the tiles of one image run as ONE thread-block
+// cluster (1, 2, 4 or 8 CTAs; a tile of a small map holds whole images and needs no peer):
+//   part 1  drain the accumulator from TMEM (+ bias) into an fp32 staging tile (the pipeline stages are free by then) and
+//           reduce this tile's {sum, sum of squares} per (sample of the tile, group of the N tile) into s_stat;
+//   --      cluster barrier: every tile of the image has published its partial sums;
+//   part 2  add the peers' partials through distributed shared memory (same order in every CTA: bit-identical mean / rstd),
+//           then normalise, activate, add the time bias / residual and write bf16 NHWC with coalesced 16-byte stores.
+// The normalisation reads the fp32 accumulator, not a bf16 round trip through memory: one rounding less per convolution than
+// the separate dd_gn_mish launch this replaces, no statistics atomics, no arena memset.
+// Staging layout: two fp32 planes [128 rows][bn/2 floats + 16 B]: float4 j of a row lives in plane (j & 1) at position j >> 1,
+// so both the row-per-thread writes of part 1 and the 8-channels-per-thread reads of part 2 are bank-conflict free;
+// then s_part [2 * bn/8][128], s_stat [nout][2], s_mr [nout][2] ({mean, rstd}).
+struct GnLayout { int pp, plane, off_part, off_stat, off_mr; };
+__device__ __forceinline__ GnLayout gn_layout(int bn) {
+    GnLayout L;
+    L.pp = bn * 2 + 16; L.plane = TC_BM * L.pp; L.off_part = 2 * L.plane; L.off_stat = L.off_part + bn * TC_BM; L.off_mr = L.off_stat + 1024;
+    return L;
+}
+struct GnRegs { float ga[8], be[8]; };
+
+__device__ __forceinline__ GnRegs tc_epi_gn_part1(const TcParams& p, uint32_t tmem_base, uint32_t tmem_full_bar, float* s_bias,
+                                                  uint8_t* stage, int n_tile, int n0, int warp, int lane) {
+    const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 64;
+    const int bn = p.bn, cbase = n_tile * bn;
+    const GnLayout L = gn_layout(bn);
+    const int rps_sh = p.tw_sh + p.th_sh, rps = 1 << rps_sh;
+    if (et < bn) s_bias[et] = p.bias ? p.bias[cbase + et] : 0.f;
+    // the eight channels this thread writes in part 2: their gain / offset travel in registers (fetched under the main loop)
+    GnRegs g;
+    {
+        const int c8 = (et & ((bn >> 3) - 1)) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + cbase + c8)), g1 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + cbase + c8) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + cbase + c8)), b1 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + cbase + c8) + 1);
+        g.ga[0] = g0.x; g.ga[1] = g0.y; g.ga[2] = g0.z; g.ga[3] = g0.w; g.ga[4] = g1.x; g.ga[5] = g1.y; g.ga[6] = g1.z; g.ga[7] = g1.w;
+        g.be[0] = b0.x; g.be[1] = b0.y; g.be[2] = b0.z; g.be[3] = b0.w; g.be[4] = b1.x; g.be[5] = b1.y; g.be[6] = b1.z; g.be[7] = b1.w;
+    }
+    const bool valid = (n0 + (r >> rps_sh)) < p.B && r < p.rows_valid;
+    epi_bar();
+    mbar_wait(tmem_full_bar, 0);
+    if (et == 0) tstamp(p, 5);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    float s8[16], q8[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { s8[k] = 0.f; q8[k] = 0.f; }
+    uint32_t a0[32], a1[32];
+    auto process = [&](const int c32, uint32_t (&acc)[32]) {
+        uint8_t* dst = stage + r * L.pp + c32 * 64;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+            float v[8];
+            float sa = 0.f, qa = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j] = __uint_as_float(acc[g8 * 8 + j]) + s_bias[c32 * 32 + g8 * 8 + j];
+                sa += v[j]; qa = fmaf(v[j], v[j], qa);
+            }
+            if (valid) { s8[c32 * 4 + g8] = sa; q8[c32 * 4 + g8] = qa; }
+            *reinterpret_cast<float4*>(dst + g8 * 16) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(dst + L.plane + g8 * 16) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    };
+    tmem_ld32_issue(trow, a0);
+    tmem_ld_wait();
+    tmem_ld32_issue(trow + 32u, a1);
+    process(0, a0);
+    tmem_ld_wait();
+    if (bn > 64) tmem_ld32_issue(trow + 64u, a0);
+    process(1, a1);
+    if (bn > 64) {
+        tmem_ld_wait();
+        tmem_ld32_issue(trow + 96u, a1);
+        process(2, a0);
+        tmem_ld_wait();
+        process(3, a1);
+    }
+    if (et == 0) tstamp(p, 10);
+    float* s_part = reinterpret_cast<float*>(stage + L.off_part);         // [(sub*2 + {sum,sq})][128 rows]
+    float* s_stat = reinterpret_cast<float*>(stage + L.off_stat);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (k * 8 < bn) { s_part[(2 * k) * TC_BM + r] = s8[k]; s_part[(2 * k + 1) * TC_BM + r] = q8[k]; }
+    epi_bar();
+    {
+        // (sample, group) outputs: 16 lanes each, rows of the sample split across the lanes (all sizes are powers of two)
+        const int cpg_sh = p.cpg_shift, spg = 1 << (cpg_sh - 3);           // 8-channel partials per group
+        const int ng_sh = (31 - __clz(bn)) - cpg_sh;                        // log2(groups in this tile)
+        const int nout = (1 << ng_sh) * (TC_BM >> rps_sh);
+        const int hw = et >> 4, l16 = et & 15;
+        for (int o0 = 0; o0 < nout; o0 += 8) {
+            const int o = o0 + hw;
+            const bool act = o < nout;
+            const int gl = o & ((1 << ng_sh) - 1), sl = o >> ng_sh;
+            float sa0 = 0.f, qa0 = 0.f, sa1 = 0.f, qa1 = 0.f;
+            if (act) {
+                constexpr int rs = 16;
+                const float* ps = s_part + (2 * (gl * spg)) * TC_BM + (sl << rps_sh) + l16;
+                const int cnt = rps >> 4;                                   // rows per lane (0 when rps < 16)
+                for (int k = 0; k < spg; ++k, ps += 2 * TC_BM) {
+                    if (cnt == 0) { if (l16 < rps) { sa0 += ps[0]; qa0 += ps[TC_BM]; } continue; }
+                    int i = 0;
+                    for (; i + 1 < cnt; i += 2) {
+                        sa0 += ps[rs * i]; qa0 += ps[TC_BM + rs * i];
+                        sa1 += ps[rs * i + rs]; qa1 += ps[TC_BM + rs * i + rs];
+                    }
+                    if (i < cnt) { sa0 += ps[rs * i]; qa0 += ps[TC_BM + rs * i]; }
+                }
+            }
+            float sa = sa0 + sa1, qa = qa0 + qa1;
+#pragma unroll
+            for (int d = 8; d > 0; d >>= 1) {
+                sa += __shfl_xor_sync(0xffffffffu, sa, d);
+                qa += __shfl_xor_sync(0xffffffffu, qa, d);
+            }
+            if (act && l16 == 0) { s_stat[2 * o] = sa; s_stat[2 * o + 1] = qa; }
+        }
+    }
+    if (et == 0) tstamp(p, 11);
+    return g;
+}
+
+__device__ __forceinline__ void tc_epi_gn_part2(const TcParams& p, const GnRegs& g, uint8_t* stage, int n_tile, int w0, int h0, int n0) {
+    const int et = threadIdx.x - 64, lane = threadIdx.x & 31;
+    const int bn = p.bn, cbase = n_tile * bn;
+    const GnLayout L = gn_layout(bn);
+    const int rps_sh = p.tw_sh + p.th_sh;
+    const int cpg_sh = p.cpg_shift, ng_sh = (31 - __clz(bn)) - cpg_sh;
+    const int nout = (1 << ng_sh) * (TC_BM >> rps_sh);
+    float* s_stat = reinterpret_cast<float*>(stage + L.off_stat);
+    float* s_mr = reinterpret_cast<float*>(stage + L.off_mr);
+    for (int o = et; o < nout; o += 128) {
+        float su, sq;
+        if (p.gn_cluster > 1) {
+            su = 0.f; sq = 0.f;
+            const uint32_t a = smem_u32(s_stat + 2 * o);
+            for (int rk = 0; rk < p.gn_cluster; ++rk) {
+                const uint32_t ra = mapa_u32(a, (uint32_t)rk);
+                su += ld_dsmem_f32(ra); sq += ld_dsmem_f32(ra + 4u);
+            }
+        } else { su = s_stat[2 * o]; sq = s_stat[2 * o + 1]; }
+        const float mean = su * p.gn_inv_n;
+        s_mr[2 * o] = mean;
+        s_mr[2 * o + 1] = rsqrtf(fmaxf(sq * p.gn_inv_n - mean * mean, 0.f) + p.gn_eps);
+    }
+    epi_bar();
+    // write-out: 16 bytes (8 channels) per thread, consecutive threads walk along a row
+    const int ppr_sh = 31 - __clz(bn >> 3);
+    const int pc = et & ((1 << ppr_sh) - 1), c8 = pc * 8, gl = c8 >> cpg_sh;
+    const int row_step = TC_BM >> ppr_sh;
+    const int Hh = p.H, Ww = p.W, Cout = p.Cout, rows_valid = p.rows_valid, Bn = p.B;
+    __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+    const __nv_bfloat16* resp = p.residual;
+    const unsigned gmask = (bn == 128) ? (0xFFFFu << (lane & 16)) : (0xFFu << (lane & 24));      // the lanes that share this thread's row
+    const int ntiles = Cout / bn;
+    float a8[8], b8[8], t8[8];
+    int cur_sl = -1;
+    for (int row0 = et >> ppr_sh; row0 < TC_BM; row0 += 2 * row_step) {
+        float4 lo[2], hi[2];
+        uint4 rv[2];
+        int64_t pix[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int row = row0 + u * row_step;
+            const int n = n0 + (row >> rps_sh);
+            ok[u] = row < TC_BM && row < rows_valid && n < Bn;
+            const int ww = row & (p.tw - 1), hh = (row >> p.tw_sh) & (p.th - 1);
+            pix[u] = ((int64_t)n * Hh + (h0 + hh)) * Ww + (w0 + ww);
+            if (ok[u]) {
+                lo[u] = *reinterpret_cast<const float4*>(stage + row * L.pp + pc * 16);
+                hi[u] = *reinterpret_cast<const float4*>(stage + L.plane + row * L.pp + pc * 16);
+                if (resp) rv[u] = *reinterpret_cast<const uint4*>(resp + pix[u] * Cout + cbase + c8);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!ok[u]) continue;
+            const int row = row0 + u * row_step, sl = row >> rps_sh;
+            if (sl != cur_sl) {
+                cur_sl = sl;
+                const float mean = s_mr[2 * ((sl << ng_sh) + gl)], rstd = s_mr[2 * ((sl << ng_sh) + gl) + 1];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { a8[j] = rstd * g.ga[j]; b8[j] = fmaf(-mean, a8[j], g.be[j]); t8[j] = 0.f; }
+                if (p.tbias) {
+                    const int n = n0 + sl;
+                    const int trow_i = p.trow ? p.trow[(int64_t)n * p.trow_stride] : n;
+                    const float4* tp = reinterpret_cast<const float4*>(p.tbias + (int64_t)trow_i * p.tb_stride + cbase + c8);
+                    const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+                    t8[0] = t0.x; t8[1] = t0.y; t8[2] = t0.z; t8[3] = t0.w; t8[4] = t1.x; t8[5] = t1.y; t8[6] = t1.z; t8[7] = t1.w;
+                }
+            }
+            float v[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = mish_fast(fmaf(v[j], a8[j], b8[j])) + t8[j];
+            if (resp) {
+                const uint32_t w4[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { v[2 * j] += __uint_as_float(w4[j] << 16); v[2 * j + 1] += __uint_as_float(w4[j] & 0xffff0000u); }
+            }
+            uint4 ov;
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            *reinterpret_cast<uint4*>(outp + pix[u] * Cout + cbase + c8) = ov;
+            if (p.ln_part) {
+                // channel-LayerNorm statistics of the row as the next kernel will read it (bf16-rounded): blocks.py:57-60
+                const uint32_t w4[4] = {ov.x, ov.y, ov.z, ov.w};
+                float ls = 0.f, lq = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float x0 = __uint_as_float(w4[j] << 16), x1 = __uint_as_float(w4[j] & 0xffff0000u);
+                    ls += x0 + x1; lq = fmaf(x0, x0, fmaf(x1, x1, lq));
+                }
+                for (int d = (1 << ppr_sh) >> 1; d > 0; d >>= 1) {
+                    ls += __shfl_xor_sync(gmask, ls, d);
+                    lq += __shfl_xor_sync(gmask, lq, d);
+                }
+                if (pc == 0) *reinterpret_cast<float2*>(p.ln_part + (pix[u] * ntiles + n_tile) * 2) = make_float2(ls, lq);
+            }
+        }
+    }
+    if (et == 0) tstamp(p, 6);
+}
+
 // ---- split-K partial epilogue ------------------------------------------------------------------------
 // The CTA's fp32 accumulator goes, unreduced and without bias, to ws[split][pixel][Cout].  dd_gn_mish_sum adds the
 // splits (+ bias) while it computes the GroupNorm statistics: no atomics, no counters, deterministic, and the
@@ -374,6 +600,7 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
     if (threadIdx.x == 0) tstamp(p, 1);
     pdl_sync();      // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
     if (threadIdx.x == 0) tstamp(p, 2);
+    GnRegs gnr;
 
     if (warp == 0) {
         // ===== A-operand producer: whole warp runs the (uniform) loop, one elected lane issues =====
@@ -463,12 +690,22 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
             tc_epilogue(p, tmem_base, tmem_full_bar, s_bias, m_tile, n_tile, phase, w0, h0, n0, warp, lane);
         else if constexpr (EPI == 2)
             tc_epilogue_partial(p, tmem_base, tmem_full_bar, n_tile, split, w0, h0, n0, warp, lane);
+        else if (p.gn_fuse)
+            gnr = tc_epi_gn_part1(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, n0, warp, lane);
         else
             tc_epilogue_staged(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, phase, w0, h0, n0,
                                warp, lane);
     }
+    const bool gn_cl = EPI == 0 && p.gn_fuse && p.gn_cluster > 1;
+    if (EPI == 0 && p.gn_fuse) {
+        // every tile of the image has published its partial sums (s_stat) -- the producer / MMA warps just pass through
+        if (gn_cl) cluster_sync_all();
+        else if (warp >= 2 && warp < 6) epi_bar();
+        if (warp >= 2 && warp < 6) tc_epi_gn_part2(p, gnr, smem_raw + (base - smem_u32(smem_raw)), n_tile, w0, h0, n0);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (gn_cl) cluster_sync_all();          // peers may still be reading this CTA's partial sums
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
@@ -536,6 +773,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __gri
     if (threadIdx.x == 0) tstamp(p, 1);
     pdl_sync();
     if (threadIdx.x == 0) tstamp(p, 2);
+    GnRegs gnr;
 
     if (warp == 0) {
         const uint32_t b_tx = (uint32_t)p.bn * TC_BK * 2;
@@ -615,13 +853,23 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __gri
         if (elect_one()) umma_commit(tmem_full_bar);
         __syncwarp();
     } else if (warp < 6) {
+        if (p.gn_fuse)
+            gnr = tc_epi_gn_part1(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, n0[0], warp, lane);
+        else
 #pragma unroll
         for (int s = 0; s < NT; ++s)
             tc_epilogue_staged(p, tmem_base + (uint32_t)(s * TC_TMEM_COLS), tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, 0,
                                w0[s], h0[s], n0[s], warp, lane);
     }
+    const bool gn_cl = p.gn_fuse && p.gn_cluster > 1;
+    if (p.gn_fuse) {
+        if (gn_cl) cluster_sync_all();
+        else if (warp >= 2 && warp < 6) epi_bar();
+        if (warp >= 2 && warp < 6) tc_epi_gn_part2(p, gnr, smem_raw + (base - smem_u32(smem_raw)), n_tile, w0[0], h0[0], n0[0]);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (gn_cl) cluster_sync_all();
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS * NT) : "memory");
@@ -790,10 +1038,60 @@ extern "C" int dd_conv_tc_splits(int kind, int B, int H, int W, int Cin, int Cou
     return S;
 }
 
-extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2, const void* wp, int w_rows,
-                          const float* bias, const void* residual, void* y, int out_nchw_f32, int cout_valid,
-                          float* gn_stats, int G, int B, int H, int W, int Cout, int flags,
-                          float* splitk_ws, int64_t splitk_ws_floats, int32_t* splitk_cnt, int splitk_cnt_n, void* stream) {
+namespace {
+struct GnFuse {                 // arguments of the fused GroupNorm + Mish epilogue (dd_conv_tc_gn); gamma == nullptr: not fused
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    float eps = 1e-5f;
+    const float* tbias = nullptr;
+    int tb_stride = 0;
+    const int32_t* trow = nullptr;
+    int trow_stride = 0;
+    float* ln_part = nullptr;
+};
+
+// Tile geometry of a launch (shared by dd_conv_tc and the dd_conv_tc_gn_cluster query).
+struct TcGeom { int tw, th, tn, bn, tiles_w, tiles_h, tiles_n; bool halo; };
+TcGeom tc_geometry(int kind, int B, int H, int W, int Cout, int flags, int out_nchw_f32) {
+    TcGeom g;
+    static const bool halo_off = getenv("DD_NO_HALO") != nullptr;
+    const bool wps = (flags & DD_TC_W_PER_SAMPLE) != 0;
+    g.halo = !halo_off && kind == DD_TC_CONV3x3 && H >= HALO_TH && W >= HALO_TW && Cout >= 64 && !out_nchw_f32;
+    g.tw = W < 128 ? W : 128;
+    g.th = (128 / g.tw) < H ? (128 / g.tw) : H;
+    if (g.halo) { g.tw = HALO_TW; g.th = HALO_TH; }
+    g.tn = wps ? 1 : 128 / (g.tw * g.th);      // per-sample weights: one image per tile (rows beyond it are ignored)
+    g.tiles_w = W / g.tw; g.tiles_h = H / g.th;
+    g.tiles_n = (B + g.tn - 1) / g.tn;
+    g.bn = Cout >= 128 ? 128 : Cout;
+    // low-resolution layers (at most half a wave of 128-wide tiles): halve the N tile to double the CTA count
+    const int tiles128 = g.tiles_w * g.tiles_h * g.tiles_n * ((Cout + 127) / 128);
+    if (tiles128 * 2 <= num_sms() && Cout % 64 == 0 && Cout >= 128) g.bn = 64;
+    if (flags & DD_TC_SPLITK) g.bn = 64;
+    return g;
+}
+}  // namespace
+
+// Cluster size the fused GroupNorm epilogue would use for this layer: 1 (a tile holds whole images), 2, 4 or 8 (the tiles of
+// one image form a thread-block cluster), 0 when the layer cannot take the fused epilogue (dd_conv_tc + dd_gn_mish then).
+extern "C" int dd_conv_tc_gn_cluster(int kind, int B, int H, int W, int Cout, int G) {
+    if (kind == DD_TC_UPT || kind < 0 || kind > 3 || !is_pow2(H) || !is_pow2(W) || B <= 0 || G <= 0 || Cout % G) return 0;
+    if (getenv("DD_NO_GN_FUSE")) return 0;
+    const TcGeom g = tc_geometry(kind, B, H, W, Cout, 0, 0);
+    const int cpg = Cout / G;
+    if ((g.bn != 64 && g.bn != 128) || Cout % g.bn || !is_pow2(cpg) || cpg < 8 || g.bn % cpg) return 0;
+    const int tpi = g.tiles_w * g.tiles_h;                          // tiles per image
+    if (tpi == 1) {
+        const int nsamp = g.tn, nout = nsamp * (g.bn / cpg);
+        return (g.tw * g.th >= 16 && nout <= 128) ? 1 : 0;          // s_stat / s_mr hold 128 (sample, group) pairs
+    }
+    return (tpi == 2 || tpi == 4 || tpi == 8) ? tpi : 0;
+}
+
+static int conv_tc_impl(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2, const void* wp, int w_rows,
+                        const float* bias, const void* residual, void* y, int out_nchw_f32, int cout_valid,
+                        float* gn_stats, int G, int B, int H, int W, int Cout, int flags,
+                        float* splitk_ws, int64_t splitk_ws_floats, int32_t* splitk_cnt, int splitk_cnt_n, const GnFuse& gf, void* stream) {
     DD_REQUIRE(kind >= 0 && kind <= 3, "conv_tc: bad kind %d", kind);
     DD_REQUIRE(C1 > 0 && C1 % 64 == 0 && C2 >= 0 && C2 % 64 == 0, "conv_tc: channel counts (%d,%d) must be multiples of 64", C1, C2);
     DD_REQUIRE((C2 == 0) == (x2 == nullptr), "conv_tc: x2/C2 mismatch");
@@ -822,30 +1120,34 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     TcParams p;
     memset(&p, 0, sizeof(p));
     // tile geometry over the GEMM pixel grid
-    static const bool halo_off = getenv("DD_NO_HALO") != nullptr;
-    const bool halo = !halo_off && kind == DD_TC_CONV3x3 && H >= HALO_TH && W >= HALO_TW && Cout >= 64 && !out_nchw_f32;
-    p.tw = W < 128 ? W : 128;
-    p.th = (128 / p.tw) < H ? (128 / p.tw) : H;
-    if (halo) { p.tw = HALO_TW; p.th = HALO_TH; }
-    p.tn = wps ? 1 : 128 / (p.tw * p.th);      // per-sample weights: one image per tile (rows beyond it are ignored)
+    const TcGeom geo = tc_geometry(kind, B, H, W, Cout, flags, out_nchw_f32);
+    const bool halo = geo.halo;
+    p.tw = geo.tw; p.th = geo.th; p.tn = geo.tn;
     p.rows_valid = p.tw * p.th * p.tn;
     p.tw_sh = 0; while ((1 << p.tw_sh) < p.tw) ++p.tw_sh;
     p.th_sh = 0; while ((1 << p.th_sh) < p.th) ++p.th_sh;
     p.w_per_sample = wps ? 1 : 0;
-    p.tiles_w = W / p.tw; p.tiles_h = H / p.th;
-    const int tiles_n = (B + p.tn - 1) / p.tn;
+    p.tiles_w = geo.tiles_w; p.tiles_h = geo.tiles_h;
+    const int tiles_n = geo.tiles_n;
     p.B = B; p.H = H; p.W = W;
     p.chunks0 = C1 / 64; p.chunks1 = C2 / 64;
     p.Cout = Cout; p.cout_valid = out_nchw_f32 ? cout_valid : Cout;
-    p.bn = Cout >= 128 ? 128 : Cout;
-    // low-resolution layers (at most half a wave of 128-wide tiles): halve the N tile to double the CTA count
-    const int tiles128 = p.tiles_w * p.tiles_h * tiles_n * ((Cout + 127) / 128);
-    if (tiles128 * 2 <= num_sms() && Cout % 64 == 0 && Cout >= 128) p.bn = 64;
-    if (flags & DD_TC_SPLITK) p.bn = 64;
+    p.bn = geo.bn;
     DD_REQUIRE(Cout % p.bn == 0 && (p.bn == 16 || p.bn == 32 || p.bn == 64 || p.bn == 128), "conv_tc: unsupported Cout=%d", Cout);
     p.out = y; p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.gn_stats = gn_stats; p.G = G; p.out_nchw_f32 = out_nchw_f32; p.out_mul = 1;
-    if (gn_stats) {
+    const bool fuse = gf.gamma != nullptr;
+    if (fuse) {
+        const int cl = dd_conv_tc_gn_cluster(kind, B, H, W, Cout, G);
+        DD_REQUIRE(cl > 0, "conv_tc_gn: this layer cannot take the fused GroupNorm epilogue (ask dd_conv_tc_gn_cluster first)");
+        DD_REQUIRE(gf.beta != nullptr && gn_stats == nullptr && !out_nchw_f32 && !(flags & (DD_TC_SPLITK | DD_TC_W_PER_SAMPLE | DD_TC_PAIR)),
+                   "conv_tc_gn: bad argument combination");
+        DD_REQUIRE(gf.tbias == nullptr || gf.tb_stride % 4 == 0, "conv_tc_gn: time-bias stride must be a multiple of 4 floats");
+        p.gn_fuse = 1; p.gn_cluster = cl; p.gn_eps = gf.eps; p.gn_inv_n = 1.f / ((float)H * (float)W * (float)(Cout / G));
+        p.gn_gamma = gf.gamma; p.gn_beta = gf.beta; p.tbias = gf.tbias; p.tb_stride = gf.tb_stride; p.trow = gf.trow;
+        p.trow_stride = gf.trow_stride; p.ln_part = gf.ln_part;
+    }
+    if (gn_stats || fuse) {
         DD_REQUIRE(G > 0 && Cout % G == 0 && is_pow2(Cout / G) && Cout / G >= 8, "conv_tc: GroupNorm needs power-of-two channels per group >= 8");
         const int cpg = Cout / G;
         p.cpg_mask = cpg - 1;
@@ -940,6 +1242,7 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    const int cl_x = fuse ? p.gn_cluster : 1;
     if (p.splits > 1)
         launch_pdl(conv_tc_kernel<8, 64, 1, 2>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
     else if (out_nchw_f32 || p.bn < 32)
@@ -947,16 +1250,37 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
     else if (cta_pair)
         launch_pair_pdl(conv_tc_halo2_kernel, dim3(grid.x, Cout / (p.bn * p.pair_nt), 1), dim3(TC_THREADS), HALO_SMEM, st, p);
     else if (halo)
-        launch_pdl(conv_tc_halo_kernel, dim3(grid), dim3(TC_THREADS), HALO_SMEM, st, p);
+        launch_cluster_pdl(conv_tc_halo_kernel, cl_x, dim3(grid), dim3(TC_THREADS), HALO_SMEM, st, p);
     else if (ctas > num_sms())      // more than one wave: two CTAs per SM so epilogues overlap main loops
-        launch_pdl(conv_tc_kernel<3, 128, 1, 0>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
+        launch_cluster_pdl(conv_tc_kernel<3, 128, 1, 0>, cl_x, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
     else if (p.bn <= 64 && pair)
-        launch_pdl(conv_tc_kernel<4, 64, 2, 0>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(4, 64, 2), st, p);
+        launch_cluster_pdl(conv_tc_kernel<4, 64, 2, 0>, cl_x, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(4, 64, 2), st, p);
     else if (p.bn <= 64)
-        launch_pdl(conv_tc_kernel<8, 64, 1, 0>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
+        launch_cluster_pdl(conv_tc_kernel<8, 64, 1, 0>, cl_x, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
     else if (pair)
-        launch_pdl(conv_tc_kernel<3, 128, 2, 0>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 2), st, p);
+        launch_cluster_pdl(conv_tc_kernel<3, 128, 2, 0>, cl_x, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 2), st, p);
     else
-        launch_pdl(conv_tc_kernel<6, 128, 1, 0>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(6, 128, 1), st, p);
+        launch_cluster_pdl(conv_tc_kernel<6, 128, 1, 0>, cl_x, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(6, 128, 1), st, p);
     return check_launch("conv_tc");
+}
+
+extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2, const void* wp, int w_rows,
+                          const float* bias, const void* residual, void* y, int out_nchw_f32, int cout_valid,
+                          float* gn_stats, int G, int B, int H, int W, int Cout, int flags,
+                          float* splitk_ws, int64_t splitk_ws_floats, int32_t* splitk_cnt, int splitk_cnt_n, void* stream) {
+    return conv_tc_impl(kind, x, x_pitch, x2, C1, C2, wp, w_rows, bias, residual, y, out_nchw_f32, cout_valid, gn_stats, G, B, H, W, Cout,
+                        flags, splitk_ws, splitk_ws_floats, splitk_cnt, splitk_cnt_n, GnFuse(), stream);
+}
+
+extern "C" int dd_conv_tc_gn(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2, const void* wp, int w_rows,
+                             const float* bias, void* y, int B, int H, int W, int Cout, int flags,
+                             int G, float eps, const float* gamma, const float* beta,
+                             const float* tbias, int tb_stride, const int32_t* trow, int trow_stride,
+                             const void* residual, float* ln_part, void* stream) {
+    DD_REQUIRE(gamma != nullptr && beta != nullptr, "conv_tc_gn: gamma / beta required");
+    GnFuse gf;
+    gf.gamma = gamma; gf.beta = beta; gf.eps = eps; gf.tbias = tbias; gf.tb_stride = tb_stride; gf.trow = trow; gf.trow_stride = trow_stride;
+    gf.ln_part = ln_part;
+    return conv_tc_impl(kind, x, x_pitch, x2, C1, C2, wp, w_rows, bias, residual, y, 0, 0, nullptr, G, B, H, W, Cout, flags, nullptr, 0,
+                        nullptr, 0, gf, stream);
 }

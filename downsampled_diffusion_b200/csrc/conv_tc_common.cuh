@@ -47,6 +47,17 @@ struct TcParams {
     float* out2;                // dd_conv_tc32: optional second output mish(y) (the next conv's activated input)
     const float* mgrad;         // dd_conv_tc32: optional z, the result is multiplied by mish'(z) (input gradient through a pre-activation)
     long long* dbg;             // optional per-CTA timeline (8 clock64 stamps per CTA), NULL in production
+    // ---- fused GroupNorm + Mish epilogue (dd_conv_tc_gn): y = mish(gn(acc + bias)) [+ tbias[row(n), c]] [+ residual] ----
+    int gn_fuse;                // the epilogue normalises its own tile; statistics of one image meet inside the thread-block cluster
+    int gn_cluster;             // CTAs (consecutive pixel tiles = one image) per cluster: 1 (a tile holds whole images), 2, 4 or 8
+    float gn_eps, gn_inv_n;     // inv_n = 1 / (H * W * channels per group)
+    const float* gn_gamma;
+    const float* gn_beta;
+    const float* tbias;         // time-embedding bias rows (rows, tb_stride) fp32, already offset to this layer's first column
+    int tb_stride;
+    const int32_t* trow;        // row index per sample (stride trow_stride; 0 = one shared step counter); NULL: row = n
+    int trow_stride;
+    float* ln_part;             // optional (pixels, Cout / bn, 2) fp32: per-pixel {sum, sum of squares} of the written tile row
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -132,6 +143,16 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {          // same offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t caddr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(caddr) : "memory");
+    return v;
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -295,6 +316,27 @@ static void launch_pair_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+
+// launch with an (n,1,1) thread-block cluster (n = 1: plain launch) + programmatic dependent launch
+template <typename... KArgs, typename... Args>
+static void launch_cluster_pdl(void (*kernel)(KArgs...), int cluster_x, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 extern long long* g_tc_dbg;          // optional in-kernel timeline buffer (dd_debug_set_timeline), defined in conv_tc.cu
 

@@ -136,10 +136,16 @@ class Program:
             op()
 
     # ---- convolution lowering --------------------------------------------------------------
+    FUSED = ("fused", 3)        # stats handle of a conv whose epilogue already applied GroupNorm + Mish (dd_conv_tc_gn)
+
     def conv(self, x: Act, conv: torch.nn.Module, *, x2: Act = None, kind: str = "3x3", gn: torch.nn.GroupNorm = None,
              residual: Act = None, pre_mish: bool = False, tanh: bool = False, out_nchw: torch.Tensor = None,
-             bias: bool = True) -> Tuple[Act, Optional[Tuple[torch.Tensor, int]]]:
+             bias: bool = True, fuse: dict = None) -> Tuple[Act, Optional[Tuple[torch.Tensor, int]]]:
         """Lower one nn.Conv2d / nn.ConvTranspose2d.  Returns (output Act, GroupNorm stats handle or None).
+
+        fuse (with gn, bf16 path): dict(tb_col=column of the time-bias table or None, residual=Act added after the
+             activation or None).  When the layer can take it the conv's epilogue applies GroupNorm + Mish itself
+             (dd_conv_tc_gn) and the returned handle is Program.FUSED: the output IS the activated tensor.
 
         kind: '3x3' (s1 p1), '1x1', 'down' (3x3 s2 p1), 'up' (ConvTranspose2d 4,2,1).
         gn: when given the conv feeds that GroupNorm: statistics are produced (epilogue atomics in bf16,
@@ -210,11 +216,17 @@ class Program:
                 if S > 1 and gh * gw * Cout <= 16384 and S * B * gh * gw * Cout <= self.SPLITK_WS_FLOATS:
                     flags |= L.TC_SPLITK
                     stats = (("split", S, b_t), 2)
+                elif (fuse is not None and residual is None and Cout_p == Cout and kind != "up"
+                      and int(L.lib().dd_conv_tc_gn_cluster(kcode, B, gh, gw, Cout, G)) > 0):
+                    stats = self.FUSED
                 else:
                     stats = (self._new_stats_slot(B, G), 1)
                     st_ptr = stats[0]
             taps = {"3x3": 9, "down": 9, "1x1": 1, "up": 4}[kind]
             self.conv_tc_flops.append(2.0 * B * Ho * Wo * Cout * taps * Cin)
+            if stats is self.FUSED:
+                self._add_conv_gn(kcode, src, 0, src2, x.C, x2.C if x2 is not None else 0, wp, b_t, y, B, gh, gw, Cout, flags, gn, fuse)
+                return y, stats
             self.add("dd_conv_tc", kcode, L.ptr(src), 0, L.ptr(src2) if src2 is not None else None, x.C,
                      x2.C if x2 is not None else 0, L.ptr(wp), wp.shape[0], L.ptr(b_t) if b_t is not None else None,
                      L.ptr(residual.t) if residual is not None else None,
@@ -246,6 +258,24 @@ class Program:
                 stats = (st, 0)
         return y, stats
 
+    def _add_conv_gn(self, kcode, src, pitch, src2, C1, C2, wp, b_t, y: Act, B, gh, gw, Cout, flags, gn, fuse: dict) -> None:
+        gamma, beta = self.f32(gn.weight), self.f32(gn.bias)
+        tb_col, res = fuse.get("tb_col"), fuse.get("residual")
+        self.op_names.append("dd_conv_tc")          # counted with the convolutions (bench.py's roofline replays them)
+        fn = L.lib().dd_conv_tc_gn
+        args = (kcode, L.ptr(src), pitch, L.ptr(src2) if src2 is not None else None, C1, C2, L.ptr(wp), wp.shape[0],
+                L.ptr(b_t) if b_t is not None else None, L.ptr(y.t), B, gh, gw, Cout, flags, gn.num_groups, GN_EPS,
+                L.ptr(gamma), L.ptr(beta), _TbPtr(self, tb_col) if tb_col is not None else None,
+                self.tb[0] if tb_col is not None else 0, _TrowPtr(self) if tb_col is not None else None,
+                _TrowStride(self) if tb_col is not None else 0, L.ptr(res.t) if res is not None else None, None)
+
+        def op():
+            L._Counter.n += 1
+            rc = fn(*args, L.stream())
+            if rc != 0:
+                L.check(rc, "dd_conv_tc_gn")
+        self.ops.append(op)
+
     SPLITK_WS_FLOATS = 148 * 128 * 128        # one full wave of 128x128 fp32 tiles (9.7 MB)
     SPLITK_COUNTERS = 1024
 
@@ -270,6 +300,8 @@ class Program:
             self.stats_arena = torch.zeros(total, dtype=torch.float32, device=self.device)
 
     def gn_mish(self, x: Act, stats, gn: torch.nn.GroupNorm, *, tb_col: int = None, tb=None, residual: Act = None) -> Act:
+        if stats is self.FUSED:
+            return x                                # the conv's epilogue already did it (and added tb / residual)
         y = self.act(x.H, x.W, x.C, x.B)
         st, mode = stats
         gamma, beta = self.f32(gn.weight), self.f32(gn.bias)
@@ -413,22 +445,22 @@ class UnetEngine(Program):
         has_res = not isinstance(rb.res_conv, torch.nn.Identity)
         if first and self.precision == "bf16":
             # x is the im2col'd input (B,H,W,kpad): the 3x3 conv and the 1x1 res_conv are K=kpad GEMMs
-            h, st = self._conv_im2col(x, c1, gn=g1, center_only=False)
+            h, st = self._conv_im2col(x, c1, gn=g1, center_only=False, fuse=dict(tb_col=col))
             res = self._conv_im2col(x, rb.res_conv, gn=None, center_only=True)[0] if has_res else None
             if not has_res:
                 raise ValueError("first ResnetBlock without res_conv is not supported on the tensor-core path")
         else:
-            h, st = self.conv(x, c1, x2=x2, kind="3x3", gn=g1)
+            h, st = self.conv(x, c1, x2=x2, kind="3x3", gn=g1, fuse=dict(tb_col=col))
             if has_res:
                 res, _ = self.conv(x, rb.res_conv, x2=x2, kind="1x1")
             else:
                 assert x2 is None
                 res = x
         h = self.gn_mish(h, st, g1, tb_col=col, tb=self.tb)
-        h, st = self.conv(h, c2, kind="3x3", gn=g2)
+        h, st = self.conv(h, c2, kind="3x3", gn=g2, fuse=dict(residual=res))
         return self.gn_mish(h, st, g2, residual=res)
 
-    def _conv_im2col(self, x: Act, conv, gn, center_only: bool):
+    def _conv_im2col(self, x: Act, conv, gn, center_only: bool, fuse: dict = None):
         w = conv.weight
         Cout, Cin = w.shape[0], w.shape[1]
         kpad = x.C
@@ -443,11 +475,14 @@ class UnetEngine(Program):
         b_t = self.f32(conv.bias)
         y = self.act(x.H, x.W, Cout, x.B)
         stats, st_ptr, G = None, None, 0
+        self.conv_tc_flops.append(2.0 * x.B * x.H * x.W * Cout * Cin * (1 if center_only else 9))
         if gn is not None:
             G = gn.num_groups
+            if fuse is not None and int(L.lib().dd_conv_tc_gn_cluster(L.TC_CONV1x1, x.B, x.H, x.W, Cout, G)) > 0:
+                self._add_conv_gn(L.TC_CONV1x1, x.t, 0, None, kpad, 0, wp, b_t, y, x.B, x.H, x.W, Cout, 0, gn, fuse)
+                return y, self.FUSED
             stats = (self._new_stats_slot(x.B, G), 1)
             st_ptr = stats[0]
-        self.conv_tc_flops.append(2.0 * x.B * x.H * x.W * Cout * Cin * (1 if center_only else 9))
         self.add("dd_conv_tc", L.TC_CONV1x1, L.ptr(x.t), 0, None, kpad, 0, L.ptr(wp), Cout, L.ptr(b_t), None, L.ptr(y.t),
                  0, 0, st_ptr, G, x.B, x.H, x.W, Cout, 0, *self.splitk_args())
         return y, stats
@@ -514,7 +549,7 @@ class UnetEngine(Program):
             if not isinstance(up, torch.nn.Identity):
                 x, _ = self.conv(x, up.conv, kind="up")
         blk, last = unet.final_conv[0], unet.final_conv[1]
-        h, st = self.conv(x, blk.block[0], kind="3x3", gn=blk.block[1])
+        h, st = self.conv(x, blk.block[0], kind="3x3", gn=blk.block[1], fuse=dict())
         h = self.gn_mish(h, st, blk.block[1])
         self.conv(h, last, kind="1x1", out_nchw=self.eps_out)
 

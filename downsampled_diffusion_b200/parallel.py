@@ -113,3 +113,54 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int 
         if size >= bucket_bytes:
             flush()
     flush()
+
+
+class GradReducer:
+    """Data-parallel gradient averaging overlapped with the backward pass (the reference trains on one GPU,
+    trainers/trainer_ddpm.py:219-251).
+
+    The training programs write each network's parameter gradients into ONE flat buffer at the end of that network's backward
+    (autograd.py, param_grads).  While armed, that moment launches the buffer's NCCL all-reduce (ReduceOp.AVG, in place) on a
+    side stream, so the up-/down-sampling nets' and the U-Net's collectives run under whatever is still back-propagating;
+    `finish()` makes the main stream wait for them and reduces what did not come through a flat buffer.
+
+        reducer = GradReducer(model)
+        reducer.arm(); loss.backward(); reducer.finish(); optimizer.step()
+
+    Arm only for a backward that starts from cleared gradients (`zero_grad(set_to_none=True)`, the default): autograd then
+    adopts the flat buffer's views as `.grad`, so the in-place result is what the optimizer reads.  When gradients are
+    accumulated over micro-batches (trainer_ddpm.py:35), leave it unarmed and call `allreduce_gradients` after the last backward."""
+
+    def __init__(self, model: torch.nn.Module):
+        self.params = list(model.parameters())
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        dev = self.params[0].device
+        self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self.reduced = []
+
+    def _on_flat(self, flat: torch.Tensor) -> None:
+        main = torch.cuda.current_stream(flat.device)
+        self.stream.wait_stream(main)                    # the gather launch that filled `flat` is on the main stream
+        with torch.cuda.stream(self.stream):
+            _allreduce_mean(flat, self.world)
+        flat.record_stream(self.stream)
+        self.reduced.append(flat)
+
+    def arm(self) -> None:
+        if self.world == 1 or self.stream is None:
+            return
+        from . import autograd as _ag
+        self.reduced = []
+        _ag.set_grads_ready_hook(self._on_flat)
+
+    def finish(self) -> None:
+        if self.world == 1 or self.stream is None:
+            return
+        from . import autograd as _ag
+        _ag.set_grads_ready_hook(None)
+        torch.cuda.current_stream().wait_stream(self.stream)
+        done = {f.untyped_storage().data_ptr() for f in self.reduced}
+        rest = [p for p in self.params if p.grad is not None and p.grad.untyped_storage().data_ptr() not in done]
+        if rest:
+            allreduce_gradients(rest)
+        self.reduced = []

@@ -277,6 +277,28 @@ int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int
                int B, int H, int W, int Cout, int flags,
                float* splitk_ws, int64_t splitk_ws_floats, int32_t* splitk_cnt, int splitk_cnt_n, void* stream);
 
+/* dd_conv_tc with GroupNorm + Mish (+ time-embedding bias) (+ residual) fused into its epilogue -- the `Block` of
+ * models/unet/blocks.py:73-84 as ONE launch, and the two halves of ResnetBlock.forward (:105-115):
+ *     y = mish(GroupNorm_G(conv(x|x2) + bias) * gamma + beta)  [+ tbias[row(n), c]]  [+ residual]         bf16 NHWC
+ * The statistics of a (sample, group) cover the whole image: the pixel tiles of one image are launched as one thread-block
+ * cluster of dd_conv_tc_gn_cluster(...) CTAs which exchange their partial sums through distributed shared memory (1: a tile
+ * holds whole images).  The normalisation reads the fp32 accumulator (no bf16 round trip, no statistics atomics).
+ *   tbias  : optional fp32 rows (row stride tb_stride floats), pointer already offset to this layer's first column;
+ *            row(n) = trow[n * trow_stride] (trow_stride 0: one device-side step counter for the whole batch) or n when trow == NULL
+ *   residual: optional bf16 NHWC tensor of the output geometry, added AFTER the activation (blocks.py:115)
+ *   ln_part : optional (B*H*W, Cout/bn, 2) fp32, bn = 128 (Cout >= 128, more than half a wave of tiles) else 64: per-pixel
+ *             {sum, sum of squares} over the written channels, the channel-LayerNorm statistics a following PreNorm needs
+ * dd_conv_tc_gn_cluster returns 0 for layers that cannot take this epilogue (transposed convs, images of more than 8 tiles,
+ * fewer than 8 channels per group): use dd_conv_tc with gn_stats + dd_gn_mish there.  kinds / flags as dd_conv_tc (no
+ * DD_TC_SPLITK, DD_TC_W_PER_SAMPLE, DD_TC_PAIR). */
+int dd_conv_tc_gn_cluster(int kind, int B, int H, int W, int Cout, int G);
+int dd_conv_tc_gn(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2,
+                  const void* wp, int w_rows, const float* bias, void* y,
+                  int B, int H, int W, int Cout, int flags,
+                  int G, float eps, const float* gamma, const float* beta,
+                  const float* tbias, int tb_stride, const int32_t* trow, int trow_stride,
+                  const void* residual, float* ln_part, void* stream);
+
 /* fp32 training form of the tensor-core convolution (forward AND input gradient of the 3x3 stride-1 / 1x1 convolutions
  * of blocks.py:78,103,123-124 and convblocks.py:29-67): x, x2, y, addend fp32 NHWC; wp fp32 (w_rows, taps*(C1+C2)) K-major;
  * TF32 operands (tcgen05.mma.kind::tf32), fp32 accumulate, persistent CTAs with two TMEM accumulators.

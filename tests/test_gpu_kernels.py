@@ -351,3 +351,72 @@ def test_layout_kernels(cuda):
     for py in range(2):
         for px in range(2):
             assert torch.equal(pl[py * 2 + px], xb[:, py::2, px::2])
+
+
+GN_FUSED_CASES = [
+    # kind, Cin, Cin2, Cout, H, W, B, time bias ("step": one device-side step counter, "rows": one row per sample, None), residual
+    ("3x3", 128, 0, 128, 32, 32, 2, "step", False),     # halo kernel, cluster of 8 CTAs = one image
+    ("3x3", 128, 0, 128, 32, 32, 64, None, True),       # the benchmark batch: 64 clusters
+    ("3x3", 256, 256, 128, 16, 16, 3, None, True),      # halo kernel, two sources, cluster of 2, residual after the activation
+    ("3x3", 256, 0, 256, 16, 16, 2, "rows", False),     # cluster of 2, two N tiles
+    ("3x3", 64, 0, 64, 16, 8, 1, "rows", True),         # exactly one tile, bn = 64, 8 channels per group
+    ("3x3", 256, 256, 256, 8, 8, 3, "step", True),      # two images per tile, ragged last tile, no peers
+    ("3x3", 64, 0, 128, 8, 8, 2, None, False),
+    ("3x3", 64, 0, 64, 4, 4, 5, "rows", False),         # eight images per tile, ragged
+    ("3x3", 256, 256, 256, 8, 8, 64, "step", True),     # 8x8 maps at the benchmark batch
+    ("1x1", 128, 0, 128, 32, 32, 4, "step", False),     # generic pipeline, cluster of 8 (the im2col'd first convolution)
+    ("1x1", 128, 0, 256, 16, 16, 70, None, False),      # generic pipeline, more than one wave, cluster of 2
+]
+
+
+@pytest.mark.parametrize("kind,C1,C2,Cout,H,W,B,tbmode,with_res", GN_FUSED_CASES)
+def test_conv_gn_fused_epilogue(cuda, kind, C1, C2, Cout, H, W, B, tbmode, with_res):
+    """dd_conv_tc_gn: conv + GroupNorm(8) + Mish (+ time bias) (+ residual) in one launch against the torch expression of
+    blocks.py:73-84, 105-115 on the operands the kernel consumed; per-pixel LayerNorm partial sums of the written rows."""
+    from downsampled_diffusion_b200.engine import Act, Program, ensure_lazy
+    lib = L()
+    torch.manual_seed(0)
+    Cin = C1 + C2
+    conv = torch.nn.Conv2d(Cin, Cout, 3, 1, 1) if kind == "3x3" else torch.nn.Conv2d(Cin, Cout, 1)
+    gn = torch.nn.GroupNorm(8, Cout)
+    with torch.no_grad():
+        gn.weight.add_(0.3 * tc.randn(7, Cout))
+        gn.bias.add_(0.3 * tc.randn(8, Cout))
+    holder = torch.nn.ModuleList([conv, gn]).to(cuda)
+    ensure_lazy()
+    prog = Program(holder, B, "bf16")
+    assert lib.lib().dd_conv_tc_gn_cluster(lib.TC_CONV3x3 if kind == "3x3" else lib.TC_CONV1x1, B, H, W, Cout, 8) > 0
+    J, col = Cout + 64, 64
+    if tbmode == "step":
+        table = tc.randn(11, 9, J).to(cuda)
+        prog.tb_rows, prog.trow, prog.trow_stride = table, torch.tensor([5], dtype=torch.int32, device=cuda), 0
+        tb_ref = table[5, col:col + Cout].cpu().reshape(1, Cout, 1, 1)
+    elif tbmode == "rows":
+        table = tc.randn(11, B, J).to(cuda)
+        prog.tb_rows, prog.trow, prog.trow_stride = table, None, 0
+        tb_ref = table[:, col:col + Cout].cpu().reshape(B, Cout, 1, 1)
+    else:
+        tb_ref = 0.0
+    prog.tb = (J,)
+    dt = torch.bfloat16
+    xa = Act(nhwc(tc.randn(1, B, C1, H, W), dt).to(cuda), B, H, W, C1)
+    x2a = Act(nhwc(tc.randn(2, B, C2, H, W), dt).to(cuda), B, H, W, C2) if C2 else None
+    resa = Act(nhwc(tc.randn(3, B, Cout, H, W), dt).to(cuda), B, H, W, Cout) if with_res else None
+    y, stats = prog.conv(xa, conv, x2=x2a, kind=kind, gn=gn, fuse=dict(tb_col=col if tbmode else None, residual=resa))
+    assert stats is Program.FUSED
+    prog.refresh_weights()
+    prog.run_ops()
+    first = y.t.clone()
+    prog.run_ops()                       # no state may be left behind
+    torch.cuda.synchronize()
+    assert torch.equal(first, y.t)       # and no atomics: bit-reproducible
+    xin = from_nhwc(xa.t.cpu())
+    if C2:
+        xin = torch.cat((xin, from_nhwc(x2a.t.cpu())), 1)
+    w = conv.weight.detach().cpu().bfloat16().float()
+    pre = F.conv2d(xin, w, conv.bias.detach().cpu(), padding=1 if kind == "3x3" else 0)
+    ref = F.mish(F.group_norm(pre, 8, gn.weight.detach().cpu(), gn.bias.detach().cpu(), 1e-5)) + tb_ref
+    if with_res:
+        ref = ref + from_nhwc(resa.t.cpu())
+    assert tc.rel_l2(from_nhwc(y.t.cpu()), ref) < 4e-3          # one bf16 rounding of the output
+    assert tc.max_abs(from_nhwc(y.t.cpu()), ref) < 6e-2

@@ -21,17 +21,21 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+STEPS = 10
+
+
 def _chain(m, noise, graph):
     m.use_graph = graph
     with torch.no_grad():
-        return m.p_sample_loop(tuple(noise.shape[1:]), noise=noise).clone()
+        return m.p_sample_loop(tuple(noise.shape[1:]), early_stop=m.timesteps - STEPS, noise=noise).clone()
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 3e-2)])
 @pytest.mark.parametrize("how", ["optimizer", "ema_update", "load_state_dict"])
-def test_graph_sampling_after_weight_change_matches_eager(cuda, how):
-    cfg = dict(tc.CS, T=12, precision="bf16")
+def test_graph_sampling_after_weight_change_matches_eager(cuda, how, precision, tol):
+    cfg = dict(tc.CS, T=50, precision=precision)
     m = tc.build_model(cfg, dd, "ddpm", device="cuda").to(cuda).eval()
-    noise = torch.stack([tc.randn(300 + i, 2, 8, 8, 8) for i in range(cfg["T"] + 1)]).to(cuda)
+    noise = torch.stack([tc.randn(300 + i, 2, 8, 8, 8) for i in range(STEPS + 1)]).to(cuda)
     z0 = _chain(m, noise, True)                                  # captures the graph, fills the time table
     g = torch.Generator().manual_seed(3)
     if how == "optimizer":
@@ -49,8 +53,10 @@ def test_graph_sampling_after_weight_change_matches_eager(cuda, how):
         m.load_state_dict(other.state_dict())
     z_graph = _chain(m, noise, True)
     z_eager = _chain(m, noise, False)
-    assert tc.max_abs(z_graph, z0) > 1e-3, "the weight change did not reach the chain at all"
-    assert tc.max_abs(z_graph, z_eager) < 1e-6, "graph replay read stale packed weights / time-bias table"
+    # bf16: split-K / attention partials merge in arrival order, so two runs agree to rounding only; fp32 mode is exact enough to
+    # see a single stale table row
+    assert tc.max_abs(z_graph, z0) > 3 * tol, "the weight change did not reach the chain at all"
+    assert tc.max_abs(z_graph, z_eager) < tol, "graph replay read stale packed weights / time-bias table"
     # and the table buffer did not move or multiply (one allocation per T for the life of the engine)
     eng = m.latent_model.engine(2, 8, 8)
     assert len(eng._tables) == 1

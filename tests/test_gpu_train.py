@@ -93,7 +93,9 @@ def test_dropout_training_mode_runs_and_masks(cuda):
     a = m.latent_model(x, t)
     b = m.latent_model(x, t)
     assert torch.isfinite(a).all() and not torch.equal(a, b)          # a fresh mask per call
-    a.sum().backward()
+    with pytest.raises(RuntimeError, match="overwritten"):             # b's forward reused the program's activation buffers
+        a.sum().backward()
+    b.sum().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.latent_model.parameters())
     m.eval()
     with torch.no_grad():
