@@ -48,7 +48,8 @@ SIGNATURES = {
     "dd_time_bias": [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p],
     "dd_gn_stats": [_p, _i, _i, _i, _i, _i, _f, _p, _p],
     "dd_gn_mish": [_p, _p, _i, _i, _i, _i, _i, _p, _i, _f, _p, _p, _p, _i, _p, _i, _p, _p],
-    "dd_gn_mish_sum": [_p, _i, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p, _i, _p, _p],
+    "dd_gn_mish_sum": [_p, _i, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p, _i, _p, _p, _p],
+    "dd_conv_tc_ln": [_p, _i, _p, _i, _p, _p, _p, _i, _f, _p, _i, _i, _i, _i, _p],
     "dd_layernorm_c": [_p, _p, _i, _i64, _i, _p, _p, _f, _p],
     "dd_linattn_core": [_p, _p, _i, _i, _i, _i, _i, _p, _i64, _p],
     "dd_linattn_mix": [_p, _i, _i, _i, _i, _i, _p, _i64, _p, _i, _p, _p],
@@ -77,10 +78,10 @@ SIGNATURES = {
     "dd_conv1x1_thin_wgrad": [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p],
     "dd_s2d_f32": [_p, _p, _i, _i, _i, _i, _i, _p],
     "dd_nhwc_to_chw_pad": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
-    "dd_conv_tc_gn": [_i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p, _i, _p, _p, _p],
+    "dd_conv_tc_gn": [_i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p],
     "dd_conv_tc": [_i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i64, _p, _i, _p],
 }
-PLAIN = {"dd_conv_tc_splits": (C.c_int, [_i, _i, _i, _i, _i, _i]), "dd_conv_tc_gn_cluster": (C.c_int, [_i, _i, _i, _i, _i, _i]), "dd_linattn_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_linattn_mix_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_version": (C.c_int, []), "dd_device_ok": (C.c_int, []), "dd_last_error": (C.c_char_p, [])}
+PLAIN = {"dd_conv_tc_splits": (C.c_int, [_i, _i, _i, _i, _i, _i]), "dd_conv_tc_gn_cluster": (C.c_int, [_i, _i, _i, _i, _i, _i]), "dd_gn_mish_sum_parts": (C.c_int, [_i, _i]), "dd_debug_max_clusters": (C.c_int, [_i]), "dd_conv_tc_gn_ws_floats": (C.c_int64, [_i, _i, _i, _i, _i, _i]), "dd_conv_tc_gn_ln_parts": (C.c_int, [_i, _i, _i, _i, _i, _i, _i]), "dd_conv_tc_tile_n": (C.c_int, [_i, _i, _i, _i, _i, _i]), "dd_linattn_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_linattn_mix_ws_floats": (C.c_int64, [_i, _i, _i]), "dd_version": (C.c_int, []), "dd_device_ok": (C.c_int, []), "dd_last_error": (C.c_char_p, [])}
 
 _lib: Optional[C.CDLL] = None
 

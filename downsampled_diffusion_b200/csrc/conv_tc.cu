@@ -136,6 +136,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
 //          pair each), and the tile is written out with fully coalesced 16-byte stores (+ coalesced residual
 //          reads).  The first version did both per row with warp shuffles and 16-byte scattered stores and took
 //          as long as the main loop (profiles/README.md).
+template <bool LN_FOLD>
 __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t tmem_base, uint32_t tmem_full_bar, float* s_bias,
                                                    uint8_t* stage, int n_tile, int phase, int w0, int h0, int n0, int warp,
                                                    int lane) {
@@ -146,6 +147,21 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
     if (et < bn) s_bias[et] = (p.bias && cbase + et < p.Cout) ? p.bias[cbase + et] : 0.f;
     const bool valid = (n0 + (r >> (p.tw_sh + p.th_sh))) < p.B && r < p.rows_valid;
     const bool do_stats = p.gn_stats != nullptr;
+    // channel LayerNorm of the input folded into this GEMM (dd_conv_tc_ln): per-row {1 / (std + eps), -mean / (std + eps)}
+    float* s_wsum = s_bias + 128;
+    float ln_a = 1.f, ln_b = 0.f;
+    if (LN_FOLD) {
+        if (et < bn) s_wsum[et] = p.ln_wsum[cbase + et];
+        if (valid) {
+            const int ww = r & (p.tw - 1), hh = (r >> p.tw_sh) & (p.th - 1), n = n0 + (r >> (p.tw_sh + p.th_sh));
+            const float2* lp = reinterpret_cast<const float2*>(p.ln_in) + (((int64_t)n * p.H + (h0 + hh)) * p.W + (w0 + ww)) * p.ln_in_parts;
+            float su = 0.f, sq = 0.f;
+            for (int i = 0; i < p.ln_in_parts; ++i) { const float2 v = __ldg(lp + i); su += v.x; sq += v.y; }
+            const float mean = su * p.ln_inv_c;
+            ln_a = 1.f / (sqrtf(fmaxf(sq * p.ln_inv_c - mean * mean, 0.f)) + p.ln_eps);
+            ln_b = -mean * ln_a;
+        }
+    }
     epi_bar();
     mbar_wait(tmem_full_bar, 0);
     if (et == 0) tstamp(p, 5);
@@ -163,7 +179,9 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
             float sa = 0.f, qa = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                v[j] = __uint_as_float(acc[g8 * 8 + j]) + s_bias[c32 * 32 + g8 * 8 + j];
+                const int c = c32 * 32 + g8 * 8 + j;
+                v[j] = LN_FOLD ? fmaf(__uint_as_float(acc[g8 * 8 + j]), ln_a, fmaf(ln_b, s_wsum[c], s_bias[c]))
+                               : __uint_as_float(acc[g8 * 8 + j]) + s_bias[c];
                 sa += v[j]; qa = fmaf(v[j], v[j], qa);
             }
             if (valid) { s8[c32 * 4 + g8] = sa; q8[c32 * 4 + g8] = qa; }
@@ -309,6 +327,18 @@ __device__ __forceinline__ GnLayout gn_layout(int bn) {
 }
 struct GnRegs { float ga[8], be[8]; };
 
+// gain / offset of the eight channels thread `t` writes in part 2 (t = 0 .. nthr-1 over ALL warps of the CTA: the producer and
+// MMA warps have nothing left to do once the accumulator is complete, and part 2 reads shared memory, not TMEM)
+__device__ __forceinline__ GnRegs tc_gn_load_regs(const TcParams& p, int n_tile, int t) {
+    GnRegs g;
+    const int bn = p.bn, cbase = n_tile * bn, c8 = (t & ((bn >> 3) - 1)) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + cbase + c8)), g1 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + cbase + c8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + cbase + c8)), b1 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + cbase + c8) + 1);
+    g.ga[0] = g0.x; g.ga[1] = g0.y; g.ga[2] = g0.z; g.ga[3] = g0.w; g.ga[4] = g1.x; g.ga[5] = g1.y; g.ga[6] = g1.z; g.ga[7] = g1.w;
+    g.be[0] = b0.x; g.be[1] = b0.y; g.be[2] = b0.z; g.be[3] = b0.w; g.be[4] = b1.x; g.be[5] = b1.y; g.be[6] = b1.z; g.be[7] = b1.w;
+    return g;
+}
+
 __device__ __forceinline__ GnRegs tc_epi_gn_part1(const TcParams& p, uint32_t tmem_base, uint32_t tmem_full_bar, float* s_bias,
                                                   uint8_t* stage, int n_tile, int n0, int warp, int lane) {
     const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 64;
@@ -317,14 +347,7 @@ __device__ __forceinline__ GnRegs tc_epi_gn_part1(const TcParams& p, uint32_t tm
     const int rps_sh = p.tw_sh + p.th_sh, rps = 1 << rps_sh;
     if (et < bn) s_bias[et] = p.bias ? p.bias[cbase + et] : 0.f;
     // the eight channels this thread writes in part 2: their gain / offset travel in registers (fetched under the main loop)
-    GnRegs g;
-    {
-        const int c8 = (et & ((bn >> 3) - 1)) * 8;
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + cbase + c8)), g1 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + cbase + c8) + 1);
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + cbase + c8)), b1 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + cbase + c8) + 1);
-        g.ga[0] = g0.x; g.ga[1] = g0.y; g.ga[2] = g0.z; g.ga[3] = g0.w; g.ga[4] = g1.x; g.ga[5] = g1.y; g.ga[6] = g1.z; g.ga[7] = g1.w;
-        g.be[0] = b0.x; g.be[1] = b0.y; g.be[2] = b0.z; g.be[3] = b0.w; g.be[4] = b1.x; g.be[5] = b1.y; g.be[6] = b1.z; g.be[7] = b1.w;
-    }
+    const GnRegs g = tc_gn_load_regs(p, n_tile, threadIdx.x);
     const bool valid = (n0 + (r >> rps_sh)) < p.B && r < p.rows_valid;
     epi_bar();
     mbar_wait(tmem_full_bar, 0);
@@ -366,52 +389,58 @@ __device__ __forceinline__ GnRegs tc_epi_gn_part1(const TcParams& p, uint32_t tm
         process(3, a1);
     }
     if (et == 0) tstamp(p, 10);
-    float* s_part = reinterpret_cast<float*>(stage + L.off_part);         // [(sub*2 + {sum,sq})][128 rows]
-    float* s_stat = reinterpret_cast<float*>(stage + L.off_stat);
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        if (k * 8 < bn) { s_part[(2 * k) * TC_BM + r] = s8[k]; s_part[(2 * k + 1) * TC_BM + r] = q8[k]; }
-    epi_bar();
+    // {sum, sum of squares} per (sample of the tile, group of the N tile): 8-channel slices -> groups inside the thread, rows of
+    // a sample across lanes with shuffles (a sample's rows are consecutive threads), segments of 32 rows through s_seg
     {
-        // (sample, group) outputs: 16 lanes each, rows of the sample split across the lanes (all sizes are powers of two)
-        const int cpg_sh = p.cpg_shift, spg = 1 << (cpg_sh - 3);           // 8-channel partials per group
-        const int ng_sh = (31 - __clz(bn)) - cpg_sh;                        // log2(groups in this tile)
-        const int nout = (1 << ng_sh) * (TC_BM >> rps_sh);
-        const int hw = et >> 4, l16 = et & 15;
-        for (int o0 = 0; o0 < nout; o0 += 8) {
-            const int o = o0 + hw;
-            const bool act = o < nout;
-            const int gl = o & ((1 << ng_sh) - 1), sl = o >> ng_sh;
-            float sa0 = 0.f, qa0 = 0.f, sa1 = 0.f, qa1 = 0.f;
-            if (act) {
-                constexpr int rs = 16;
-                const float* ps = s_part + (2 * (gl * spg)) * TC_BM + (sl << rps_sh) + l16;
-                const int cnt = rps >> 4;                                   // rows per lane (0 when rps < 16)
-                for (int k = 0; k < spg; ++k, ps += 2 * TC_BM) {
-                    if (cnt == 0) { if (l16 < rps) { sa0 += ps[0]; qa0 += ps[TC_BM]; } continue; }
-                    int i = 0;
-                    for (; i + 1 < cnt; i += 2) {
-                        sa0 += ps[rs * i]; qa0 += ps[TC_BM + rs * i];
-                        sa1 += ps[rs * i + rs]; qa1 += ps[TC_BM + rs * i + rs];
-                    }
-                    if (i < cnt) { sa0 += ps[rs * i]; qa0 += ps[TC_BM + rs * i]; }
+        const int cpg_sh = p.cpg_shift, spg_sh = cpg_sh - 3;                // log2(8-channel slices per group)
+        const int ng = bn >> cpg_sh;                                        // groups in this tile (<= 16)
+        const int seg_sh = rps_sh < 5 ? rps_sh : 5, seg = 1 << seg_sh;      // lanes that share a sample
+        float* s_seg = reinterpret_cast<float*>(stage + L.off_part);        // [128 / seg segments][ng][2]
+        // fold the 8-channel slices of a group (1, 2 or 4 of them) with static register indices
+        if (spg_sh >= 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s8[i] = s8[2 * i] + s8[2 * i + 1]; q8[i] = q8[2 * i] + q8[2 * i + 1]; }
+        }
+        if (spg_sh >= 2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { s8[i] = s8[2 * i] + s8[2 * i + 1]; q8[i] = q8[2 * i] + q8[2 * i + 1]; }
+        }
+#pragma unroll
+        for (int gi = 0; gi < 16; ++gi) {
+            if (gi < ng) {
+                float sa = s8[gi], qa = q8[gi];
+                for (int d = seg >> 1; d > 0; d >>= 1) {
+                    sa += __shfl_xor_sync(0xffffffffu, sa, d);
+                    qa += __shfl_xor_sync(0xffffffffu, qa, d);
+                }
+                if ((lane & (seg - 1)) == 0) {
+                    float* dst = s_seg + (((r >> seg_sh) * ng + gi) << 1);
+                    dst[0] = sa; dst[1] = qa;
                 }
             }
-            float sa = sa0 + sa1, qa = qa0 + qa1;
-#pragma unroll
-            for (int d = 8; d > 0; d >>= 1) {
-                sa += __shfl_xor_sync(0xffffffffu, sa, d);
-                qa += __shfl_xor_sync(0xffffffffu, qa, d);
+        }
+        epi_bar();
+        float* s_stat = reinterpret_cast<float*>(stage + L.off_stat);
+        const int ng_sh = (31 - __clz(bn)) - cpg_sh;
+        const int nout = ng << (7 - rps_sh);                                // (samples of the tile) x groups
+        const int sps = 1 << (rps_sh - seg_sh);                             // segments per sample
+        for (int o = et; o < nout; o += 128) {
+            const int gl = o & (ng - 1), sl = o >> ng_sh;
+            float sa = 0.f, qa = 0.f;
+            for (int i = 0; i < sps; ++i) {
+                const float* src = s_seg + (((sl * sps + i) * ng + gl) << 1);
+                sa += src[0]; qa += src[1];
             }
-            if (act && l16 == 0) { s_stat[2 * o] = sa; s_stat[2 * o + 1] = qa; }
+            s_stat[2 * o] = sa; s_stat[2 * o + 1] = qa;
         }
     }
     if (et == 0) tstamp(p, 11);
     return g;
 }
 
+// part 2 runs on every thread of the CTA (t = threadIdx.x, nthr = blockDim.x)
 __device__ __forceinline__ void tc_epi_gn_part2(const TcParams& p, const GnRegs& g, uint8_t* stage, int n_tile, int w0, int h0, int n0) {
-    const int et = threadIdx.x - 64, lane = threadIdx.x & 31;
+    const int t = threadIdx.x, nthr = blockDim.x, lane = threadIdx.x & 31;
     const int bn = p.bn, cbase = n_tile * bn;
     const GnLayout L = gn_layout(bn);
     const int rps_sh = p.tw_sh + p.th_sh;
@@ -419,25 +448,33 @@ __device__ __forceinline__ void tc_epi_gn_part2(const TcParams& p, const GnRegs&
     const int nout = (1 << ng_sh) * (TC_BM >> rps_sh);
     float* s_stat = reinterpret_cast<float*>(stage + L.off_stat);
     float* s_mr = reinterpret_cast<float*>(stage + L.off_mr);
-    for (int o = et; o < nout; o += 128) {
-        float su, sq;
+    for (int o = t; o < nout; o += nthr) {
+        float su = 0.f, sq = 0.f;
         if (p.gn_cluster > 1) {
-            su = 0.f; sq = 0.f;
+            // all loads first (each is a ~200-cycle round trip to a peer SM), then the sums, in rank order in every CTA
+            float vs[8], vq[8];
             const uint32_t a = smem_u32(s_stat + 2 * o);
-            for (int rk = 0; rk < p.gn_cluster; ++rk) {
-                const uint32_t ra = mapa_u32(a, (uint32_t)rk);
-                su += ld_dsmem_f32(ra); sq += ld_dsmem_f32(ra + 4u);
+#pragma unroll
+            for (int rk = 0; rk < 8; ++rk) {
+                vs[rk] = 0.f; vq[rk] = 0.f;
+                if (rk < p.gn_cluster) {
+                    const uint32_t ra = mapa_u32(a, (uint32_t)rk);
+                    vs[rk] = ld_dsmem_f32(ra); vq[rk] = ld_dsmem_f32(ra + 4u);
+                }
             }
+#pragma unroll
+            for (int rk = 0; rk < 8; ++rk) { su += vs[rk]; sq += vq[rk]; }
         } else { su = s_stat[2 * o]; sq = s_stat[2 * o + 1]; }
         const float mean = su * p.gn_inv_n;
         s_mr[2 * o] = mean;
         s_mr[2 * o + 1] = rsqrtf(fmaxf(sq * p.gn_inv_n - mean * mean, 0.f) + p.gn_eps);
     }
-    epi_bar();
+    __syncthreads();
+    if (t == 64) tstamp(p, 12);
     // write-out: 16 bytes (8 channels) per thread, consecutive threads walk along a row
     const int ppr_sh = 31 - __clz(bn >> 3);
-    const int pc = et & ((1 << ppr_sh) - 1), c8 = pc * 8, gl = c8 >> cpg_sh;
-    const int row_step = TC_BM >> ppr_sh;
+    const int pc = t & ((1 << ppr_sh) - 1), c8 = pc * 8, gl = c8 >> cpg_sh;
+    const int row_step = nthr >> ppr_sh;
     const int Hh = p.H, Ww = p.W, Cout = p.Cout, rows_valid = p.rows_valid, Bn = p.B;
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
     const __nv_bfloat16* resp = p.residual;
@@ -445,7 +482,7 @@ __device__ __forceinline__ void tc_epi_gn_part2(const TcParams& p, const GnRegs&
     const int ntiles = Cout / bn;
     float a8[8], b8[8], t8[8];
     int cur_sl = -1;
-    for (int row0 = et >> ppr_sh; row0 < TC_BM; row0 += 2 * row_step) {
+    for (int row0 = t >> ppr_sh; row0 < TC_BM; row0 += 2 * row_step) {
         float4 lo[2], hi[2];
         uint4 rv[2];
         int64_t pix[2];
@@ -510,7 +547,7 @@ __device__ __forceinline__ void tc_epi_gn_part2(const TcParams& p, const GnRegs&
             }
         }
     }
-    if (et == 0) tstamp(p, 6);
+    if (t == 64) tstamp(p, 6);
 }
 
 // ---- split-K partial epilogue ------------------------------------------------------------------------
@@ -692,16 +729,20 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
             tc_epilogue_partial(p, tmem_base, tmem_full_bar, n_tile, split, w0, h0, n0, warp, lane);
         else if (p.gn_fuse)
             gnr = tc_epi_gn_part1(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, n0, warp, lane);
+        else if (p.ln_in)
+            tc_epilogue_staged<true>(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, phase, w0, h0, n0,
+                                     warp, lane);
         else
-            tc_epilogue_staged(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, phase, w0, h0, n0,
-                               warp, lane);
+            tc_epilogue_staged<false>(p, tmem_base, tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, phase, w0, h0, n0,
+                                      warp, lane);
     }
     const bool gn_cl = EPI == 0 && p.gn_fuse && p.gn_cluster > 1;
     if (EPI == 0 && p.gn_fuse) {
-        // every tile of the image has published its partial sums (s_stat) -- the producer / MMA warps just pass through
+        if (warp < 2 || warp >= 6) gnr = tc_gn_load_regs(p, n_tile, threadIdx.x);      // producer / MMA warps join the write-out
+        // every tile of the image has published its partial sums (s_stat)
         if (gn_cl) cluster_sync_all();
-        else if (warp >= 2 && warp < 6) epi_bar();
-        if (warp >= 2 && warp < 6) tc_epi_gn_part2(p, gnr, smem_raw + (base - smem_u32(smem_raw)), n_tile, w0, h0, n0);
+        else __syncthreads();
+        tc_epi_gn_part2(p, gnr, smem_raw + (base - smem_u32(smem_raw)), n_tile, w0, h0, n0);
     }
     tc_fence_before();
     if (gn_cl) cluster_sync_all();          // peers may still be reading this CTA's partial sums
@@ -858,14 +899,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo_kernel(const __gri
         else
 #pragma unroll
         for (int s = 0; s < NT; ++s)
-            tc_epilogue_staged(p, tmem_base + (uint32_t)(s * TC_TMEM_COLS), tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, 0,
-                               w0[s], h0[s], n0[s], warp, lane);
+            tc_epilogue_staged<false>(p, tmem_base + (uint32_t)(s * TC_TMEM_COLS), tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)), n_tile, 0,
+                                      w0[s], h0[s], n0[s], warp, lane);
     }
     const bool gn_cl = p.gn_fuse && p.gn_cluster > 1;
     if (p.gn_fuse) {
+        if (warp < 2 || warp >= 6) gnr = tc_gn_load_regs(p, n_tile, threadIdx.x);
         if (gn_cl) cluster_sync_all();
-        else if (warp >= 2 && warp < 6) epi_bar();
-        if (warp >= 2 && warp < 6) tc_epi_gn_part2(p, gnr, smem_raw + (base - smem_u32(smem_raw)), n_tile, w0[0], h0[0], n0[0]);
+        else __syncthreads();
+        tc_epi_gn_part2(p, gnr, smem_raw + (base - smem_u32(smem_raw)), n_tile, w0[0], h0[0], n0[0]);
     }
     tc_fence_before();
     if (gn_cl) cluster_sync_all();
@@ -1000,8 +1042,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_halo2_kernel(const __gr
     } else if (warp >= 2 && warp < 6) {
         // ===== epilogue (both CTAs): own 128 rows, N2 columns in 128-wide passes =====
         for (int s = 0; s < p.pair_nt; ++s)
-            tc_epilogue_staged(p, tmem_base + (uint32_t)(s * TC_TMEM_COLS), tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)),
-                               n_pair * p.pair_nt + s, 0, w0, h0, n0, warp, lane);
+            tc_epilogue_staged<false>(p, tmem_base + (uint32_t)(s * TC_TMEM_COLS), tmem_full_bar, s_bias, smem_raw + (base - smem_u32(smem_raw)),
+                                      n_pair * p.pair_nt + s, 0, w0, h0, n0, warp, lane);
     }
     tc_fence_before();
     cluster_sync_all();                     // the peer's shared memory and TMEM stay alive until both CTAs are done
@@ -1018,6 +1060,21 @@ using namespace dd;
 
 long long* dd::g_tc_dbg = nullptr;
 extern "C" int dd_debug_set_timeline(long long* buf) { g_tc_dbg = buf; return DD_OK; }
+
+// Debug / tuning aid: how many thread-block clusters of `cluster` halo-kernel CTAs the device can keep resident
+// (cudaOccupancyMaxActiveClusters); -1 on error.
+extern "C" int dd_debug_max_clusters(int cluster) {
+    cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster * 64); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = HALO_SMEM;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = -1;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_tc_halo_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
+}
 
 extern "C" int dd_zero(void* ptr, int64_t bytes, void* stream) {
     cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream);
@@ -1048,6 +1105,12 @@ struct GnFuse {                 // arguments of the fused GroupNorm + Mish epilo
     const int32_t* trow = nullptr;
     int trow_stride = 0;
     float* ln_part = nullptr;
+    float* ws = nullptr;        // zeroed workspace of dd_conv_tc_gn_ws_floats() floats: enables the persistent kernel (statistics + arrival counters)
+    // channel LayerNorm folded into a 1x1 convolution (dd_conv_tc_ln); ln_in == nullptr: none
+    const float* ln_in = nullptr;
+    int ln_in_parts = 0;
+    const float* ln_wsum = nullptr;
+    float ln_eps = 1e-5f;
 };
 
 // Tile geometry of a launch (shared by dd_conv_tc and the dd_conv_tc_gn_cluster query).
@@ -1086,6 +1149,29 @@ extern "C" int dd_conv_tc_gn_cluster(int kind, int B, int H, int W, int Cout, in
         return (g.tw * g.th >= 16 && nout <= 128) ? 1 : 0;          // s_stat / s_mr hold 128 (sample, group) pairs
     }
     return (tpi == 2 || tpi == 4 || tpi == 8) ? tpi : 0;
+}
+
+// N tile (output channels per CTA) dd_conv_tc / dd_conv_tc_gn choose for a layer: the `parts` dimension of ln_part is Cout / it.
+extern "C" int dd_conv_tc_tile_n(int kind, int B, int H, int W, int Cout, int flags) {
+    if (kind < 0 || kind > 3 || !is_pow2(H) || !is_pow2(W) || B <= 0 || Cout <= 0) return 0;
+    return tc_geometry(kind, B, H, W, Cout, flags, 0).bn;
+}
+
+// Workspace of dd_conv_tc_gn for this layer in floats (0: none needed): per-(image, group) {sum, sum of squares} followed by
+// per-(image, 128-channel tile) arrival counters; must be ALL ZERO when the launch starts.
+extern "C" int64_t dd_conv_tc_gn_ws_floats(int kind, int B, int H, int W, int Cout, int G) {
+    if (kind != DD_TC_CONV3x3 || !is_pow2(H) || !is_pow2(W) || B <= 0 || G <= 0 || Cout % G || getenv("DD_NO_GN_FUSE")) return 0;
+    const TcGeom g = tc_geometry(kind, B, H, W, Cout, 0, 0);
+    if (!(g.halo && halo_persist_ok(kind, H, W, Cout, G))) return 0;
+    const int64_t n = (int64_t)B * G * 2 + (int64_t)B * (Cout / 128);
+    return (n + 3) / 4 * 4;
+}
+
+// `parts` dimension of dd_conv_tc_gn's ln_part output for this layer
+extern "C" int dd_conv_tc_gn_ln_parts(int kind, int B, int H, int W, int Cout, int G, int persistent) {
+    if (persistent) return dd_conv_tc_gn_ws_floats(kind, B, H, W, Cout, G) > 0 ? 2 * (Cout / 128) : 0;
+    if (dd_conv_tc_gn_cluster(kind, B, H, W, Cout, G) <= 0) return 0;
+    return Cout / tc_geometry(kind, B, H, W, Cout, 0, 0).bn;
 }
 
 static int conv_tc_impl(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2, const void* wp, int w_rows,
@@ -1137,15 +1223,24 @@ static int conv_tc_impl(int kind, const void* x, int x_pitch, const void* x2, in
     p.out = y; p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.gn_stats = gn_stats; p.G = G; p.out_nchw_f32 = out_nchw_f32; p.out_mul = 1;
     const bool fuse = gf.gamma != nullptr;
+    bool persist = false;
     if (fuse) {
-        const int cl = dd_conv_tc_gn_cluster(kind, B, H, W, Cout, G);
-        DD_REQUIRE(cl > 0, "conv_tc_gn: this layer cannot take the fused GroupNorm epilogue (ask dd_conv_tc_gn_cluster first)");
+        persist = gf.ws != nullptr && dd_conv_tc_gn_ws_floats(kind, B, H, W, Cout, G) > 0;
+        const int cl = persist ? 1 : dd_conv_tc_gn_cluster(kind, B, H, W, Cout, G);
+        DD_REQUIRE(cl > 0, "conv_tc_gn: this layer cannot take the fused GroupNorm epilogue (ask dd_conv_tc_gn_cluster / dd_conv_tc_gn_ws_floats first)");
         DD_REQUIRE(gf.beta != nullptr && gn_stats == nullptr && !out_nchw_f32 && !(flags & (DD_TC_SPLITK | DD_TC_W_PER_SAMPLE | DD_TC_PAIR)),
                    "conv_tc_gn: bad argument combination");
         DD_REQUIRE(gf.tbias == nullptr || gf.tb_stride % 4 == 0, "conv_tc_gn: time-bias stride must be a multiple of 4 floats");
         p.gn_fuse = 1; p.gn_cluster = cl; p.gn_eps = gf.eps; p.gn_inv_n = 1.f / ((float)H * (float)W * (float)(Cout / G));
         p.gn_gamma = gf.gamma; p.gn_beta = gf.beta; p.tbias = gf.tbias; p.tb_stride = gf.tb_stride; p.trow = gf.trow;
         p.trow_stride = gf.trow_stride; p.ln_part = gf.ln_part;
+        if (persist) p.gn_stats = gf.ws;
+    }
+    if (gf.ln_in) {
+        DD_REQUIRE(kind == DD_TC_CONV1x1 && C2 == 0 && !out_nchw_f32 && !fuse && gn_stats == nullptr && !(flags & (DD_TC_SPLITK | DD_TC_W_PER_SAMPLE)),
+                   "conv_tc_ln: the LayerNorm fold is for plain 1x1 convolutions");
+        DD_REQUIRE(gf.ln_wsum != nullptr && gf.ln_in_parts >= 1 && p.bn >= 32, "conv_tc_ln: bad arguments");
+        p.ln_in = gf.ln_in; p.ln_in_parts = gf.ln_in_parts; p.ln_wsum = gf.ln_wsum; p.ln_eps = gf.ln_eps; p.ln_inv_c = 1.f / (float)C1;
     }
     if (gn_stats || fuse) {
         DD_REQUIRE(G > 0 && Cout % G == 0 && is_pow2(Cout / G) && Cout / G >= 8, "conv_tc: GroupNorm needs power-of-two channels per group >= 8");
@@ -1243,6 +1338,11 @@ static int conv_tc_impl(int kind, const void* x, int x_pitch, const void* x2, in
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int cl_x = fuse ? p.gn_cluster : 1;
+    if (persist) {
+        rc = make_w_map(&p.tmB, wp, K, w_rows, 128, 0);
+        if (rc) return rc;
+        return launch_halo_persist(p, st);
+    }
     if (p.splits > 1)
         launch_pdl(conv_tc_kernel<8, 64, 1, 2>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
     else if (out_nchw_f32 || p.bn < 32)
@@ -1272,13 +1372,23 @@ extern "C" int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, 
                         flags, splitk_ws, splitk_ws_floats, splitk_cnt, splitk_cnt_n, GnFuse(), stream);
 }
 
+extern "C" int dd_conv_tc_ln(const void* x, int C, const void* wp, int w_rows, const float* bias, const float* wsum,
+                             const float* ln_in, int ln_in_parts, float ln_eps, void* y, int B, int H, int W, int Cout, void* stream) {
+    DD_REQUIRE(ln_in != nullptr && wsum != nullptr, "conv_tc_ln: statistics and weight row sums required");
+    GnFuse gf;
+    gf.ln_in = ln_in; gf.ln_in_parts = ln_in_parts; gf.ln_wsum = wsum; gf.ln_eps = ln_eps;
+    return conv_tc_impl(DD_TC_CONV1x1, x, 0, nullptr, C, 0, wp, w_rows, bias, nullptr, y, 0, 0, nullptr, 0, B, H, W, Cout, 0, nullptr, 0,
+                        nullptr, 0, gf, stream);
+}
+
 extern "C" int dd_conv_tc_gn(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2, const void* wp, int w_rows,
                              const float* bias, void* y, int B, int H, int W, int Cout, int flags,
                              int G, float eps, const float* gamma, const float* beta,
                              const float* tbias, int tb_stride, const int32_t* trow, int trow_stride,
-                             const void* residual, float* ln_part, void* stream) {
+                             const void* residual, float* ln_part, float* ws, void* stream) {
     DD_REQUIRE(gamma != nullptr && beta != nullptr, "conv_tc_gn: gamma / beta required");
     GnFuse gf;
+    gf.ws = ws;
     gf.gamma = gamma; gf.beta = beta; gf.eps = eps; gf.tbias = tbias; gf.tb_stride = tb_stride; gf.trow = trow; gf.trow_stride = trow_stride;
     gf.ln_part = ln_part;
     return conv_tc_impl(kind, x, x_pitch, x2, C1, C2, wp, w_rows, bias, residual, y, 0, 0, nullptr, G, B, H, W, Cout, flags, nullptr, 0,

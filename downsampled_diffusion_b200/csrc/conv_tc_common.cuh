@@ -16,7 +16,7 @@ constexpr int TC_THREADS = 224;      // warps: A producer, MMA, 4 x epilogue, B 
 //   <3,128>: 96 KB  -> 2 CTAs/SM, for grids that fill the GPU (epilogue of one CTA overlaps the other's loop)
 //   <6,128>: 192 KB -> 1 CTA/SM, grids of at most one wave: twice the loads in flight per CTA
 //   <8, 64>: 192 KB -> 1 CTA/SM, low-resolution layers run with bn = 64 (twice the CTAs) and 8 stages
-constexpr int tc_smem_bytes(int stages, int brows, int kch) { return stages * kch * (TC_A_BYTES + brows * TC_BK * 2) + 1024 /*align*/ + 1024 /*barriers + bias*/; }
+constexpr int tc_smem_bytes(int stages, int brows, int kch) { return stages * kch * (TC_A_BYTES + brows * TC_BK * 2) + 1024 /*align*/ + 1536 /*barriers + bias + weight row sums*/; }
 constexpr int TC_TMEM_COLS = 128;
 
 struct TcParams {
@@ -58,6 +58,11 @@ struct TcParams {
     const int32_t* trow;        // row index per sample (stride trow_stride; 0 = one shared step counter); NULL: row = n
     int trow_stride;
     float* ln_part;             // optional (pixels, Cout / bn, 2) fp32: per-pixel {sum, sum of squares} of the written tile row
+    // ---- channel LayerNorm folded into a 1x1 convolution (dd_conv_tc_ln): y = inv_p * (acc - mean_p * wsum[c]) + bias[c] ----
+    const float* ln_in;         // (pixels, ln_in_parts, 2) fp32 {sum, sum of squares} over the INPUT channels of every pixel
+    int ln_in_parts;
+    const float* ln_wsum;       // (Cout) row sums of the packed bf16 weights (the gain already folded into them)
+    float ln_eps, ln_inv_c;     // eps is added to the standard deviation (blocks.py:57-60); inv_c = 1 / input channels
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -337,6 +342,10 @@ static void launch_cluster_pdl(void (*kernel)(KArgs...), int cluster_x, dim3 gri
     cfg.attrs = attr; cfg.numAttrs = n;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// persistent halo convolution with the fused GroupNorm epilogue (conv_tc_persist.cu)
+bool halo_persist_ok(int kind, int H, int W, int Cout, int G);
+int launch_halo_persist(const TcParams& p, cudaStream_t st);
 
 extern long long* g_tc_dbg;          // optional in-kernel timeline buffer (dd_debug_set_timeline), defined in conv_tc.cu
 

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) gn_mish_sum_kernel(const float* __restric
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ tbias, int tb_stride,
                                                           const int32_t* __restrict__ trow, int trow_stride,
-                                                          const __nv_bfloat16* __restrict__ residual) {
+                                                          const __nv_bfloat16* __restrict__ residual, float* __restrict__ ln_part) {
     pdl_sync();
     extern __shared__ float4 s_x[];                        // this CTA's summed vectors: HW * (C/4) / gridDim.y
     __shared__ float s_stat[64][2];
@@ -198,6 +198,21 @@ __global__ void __launch_bounds__(256) gn_mish_sum_kernel(const float* __restric
         *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(h[0], h[1]);
         *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(h[2], h[3]);
         *reinterpret_cast<uint2*>(y + off) = o;
+        if (ln_part) {
+            // channel-LayerNorm statistics of the pixel over this CTA's channels, on the bf16 values just written: the cvp lanes
+            // of a pixel are consecutive (cvp a power of two <= 32, checked by the host)
+            const float x0 = __uint_as_float(o.x << 16), x1 = __uint_as_float(o.x & 0xffff0000u);
+            const float x2 = __uint_as_float(o.y << 16), x3 = __uint_as_float(o.y & 0xffff0000u);
+            float ls = (x0 + x1) + (x2 + x3), lq = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, x3 * x3)));
+            const unsigned lane = threadIdx.x & 31u;
+            const unsigned gm = cvp >= 32 ? 0xffffffffu : (((1u << cvp) - 1u) << (lane & ~(unsigned)(cvp - 1)));
+            for (int d = cvp >> 1; d > 0; d >>= 1) {
+                ls += __shfl_xor_sync(gm, ls, d);
+                lq += __shfl_xor_sync(gm, lq, d);
+            }
+            if ((threadIdx.x & (cvp - 1)) == 0)
+                *reinterpret_cast<float2*>(ln_part + (((int64_t)b * HW + vl / cvp) * gridDim.y + blockIdx.y) * 2) = make_float2(ls, lq);
+        }
     }
 }
 
@@ -510,9 +525,18 @@ int dd_gn_mish(const void* x, void* y, int dtype, int B, int HW, int C, int G, c
     return check_launch("gn_mish");
 }
 
+static int gn_mish_sum_parts(int C, int G) {
+    const int cv = C / 4;
+    for (int pt = 4; pt > 1; pt >>= 1)
+        if (G % pt == 0 && cv % pt == 0 && 256 % (cv / pt) == 0) return pt;
+    return 1;
+}
+
+int dd_gn_mish_sum_parts(int C, int G) { return (C > 0 && G > 0 && C % 4 == 0) ? gn_mish_sum_parts(C, G) : 0; }
+
 int dd_gn_mish_sum(const float* part, int S, const float* bias, void* y_bf16, int B, int HW, int C, int G, float eps,
                    const float* gamma, const float* beta, const float* tbias, int tb_stride, const int32_t* trow,
-                   int trow_stride, const void* residual_bf16, void* stream) {
+                   int trow_stride, const void* residual_bf16, float* ln_part, void* stream) {
     DD_REQUIRE(S >= 1 && B > 0 && HW > 0 && G > 0 && G <= 64 && C % G == 0, "gn_mish_sum: bad sizes S=%d B=%d HW=%d C=%d G=%d", S, B, HW, C, G);
     const int cv = C / 4, cpg = C / G;
     DD_REQUIRE(C % 4 == 0 && 256 % cv == 0 && cpg % 4 == 0 && cpg / 4 <= 32 && ((cpg / 4) & (cpg / 4 - 1)) == 0,
@@ -524,11 +548,11 @@ int dd_gn_mish_sum(const float* part, int S, const float* bias, void* y_bf16, in
         cudaFuncSetAttribute(gn_mish_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4);
         attr_done = true;
     }
-    int parts = 1;
-    for (int pt = 4; pt > 1; pt >>= 1)
-        if (G % pt == 0 && cv % pt == 0 && 256 % (cv / pt) == 0) { parts = pt; break; }
+    const int parts = gn_mish_sum_parts(C, G);
+    const int cvp = cv / parts;
+    DD_REQUIRE(ln_part == nullptr || (cvp <= 32 && (cvp & (cvp - 1)) == 0), "gn_mish_sum: LayerNorm partials need a power-of-two <= 32 vectors per pixel and CTA");
     launch_pdl(gn_mish_sum_kernel, dim3(B, parts), dim3(256), (size_t)HW * C * 4 / parts, (cudaStream_t)stream, part, S, (int64_t)B * HW * C, bias,
-               (__nv_bfloat16*)y_bf16, HW, C, G, eps, gamma, beta, tbias, tb_stride, trow, trow_stride, (const __nv_bfloat16*)residual_bf16);
+               (__nv_bfloat16*)y_bf16, HW, C, G, eps, gamma, beta, tbias, tb_stride, trow, trow_stride, (const __nv_bfloat16*)residual_bf16, ln_part);
     return check_launch("gn_mish_sum");
 }
 

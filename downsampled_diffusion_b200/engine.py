@@ -32,11 +32,12 @@ class EngineCache(dict):
 
 class Act:
     """An NHWC activation tensor of a program."""
-    __slots__ = ("t", "B", "H", "W", "C", "mish")
+    __slots__ = ("t", "B", "H", "W", "C", "mish", "ln")
 
     def __init__(self, t: torch.Tensor, B: int, H: int, W: int, C: int):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
         self.mish = None        # training programs: Act holding mish(t) when the producing conv's epilogue wrote it
+        self.ln = None          # (stats (B*H*W, parts, 2) fp32, parts): per-pixel channel sums the producing launch left for a PreNorm
 
 
 def _is_pow2(v: int) -> bool:
@@ -216,8 +217,7 @@ class Program:
                 if S > 1 and gh * gw * Cout <= 16384 and S * B * gh * gw * Cout <= self.SPLITK_WS_FLOATS:
                     flags |= L.TC_SPLITK
                     stats = (("split", S, b_t), 2)
-                elif (fuse is not None and residual is None and Cout_p == Cout and kind != "up"
-                      and int(L.lib().dd_conv_tc_gn_cluster(kcode, B, gh, gw, Cout, G)) > 0):
+                elif fuse is not None and residual is None and Cout_p == Cout and kind != "up" and self._gn_fusable(kcode, B, gh, gw, Cout, G):
                     stats = self.FUSED
                 else:
                     stats = (self._new_stats_slot(B, G), 1)
@@ -258,16 +258,39 @@ class Program:
                 stats = (st, 0)
         return y, stats
 
+    GN_FUSE_MAX_CLUSTER = int(os.environ.get("DD_GN_FUSE_MAX_CLUSTER", "2"))
+
+    def _gn_fusable(self, kcode, B, gh, gw, Cout, G) -> bool:
+        """The conv can apply GroupNorm + Mish itself: as the persistent kernel (statistics through a zeroed workspace), or with the
+        image's tiles as one thread-block cluster -- by default only up to 2 CTAs: clusters of 4 / 8 halve the number of resident
+        CTAs (cudaOccupancyMaxActiveClusters: 33 / 15 clusters) and lose to conv + dd_gn_mish (profiles/README.md, round 2)."""
+        lib = L.lib()
+        if int(lib.dd_conv_tc_gn_ws_floats(kcode, B, gh, gw, Cout, G)) > 0:
+            return True
+        return 0 < int(lib.dd_conv_tc_gn_cluster(kcode, B, gh, gw, Cout, G)) <= self.GN_FUSE_MAX_CLUSTER
+
     def _add_conv_gn(self, kcode, src, pitch, src2, C1, C2, wp, b_t, y: Act, B, gh, gw, Cout, flags, gn, fuse: dict) -> None:
         gamma, beta = self.f32(gn.weight), self.f32(gn.bias)
         tb_col, res = fuse.get("tb_col"), fuse.get("residual")
+        G = gn.num_groups
+        ws_floats = int(L.lib().dd_conv_tc_gn_ws_floats(kcode, B, gh, gw, Cout, G))
+        ws = None
+        if ws_floats > 0:            # persistent kernel: {sum, sumsq} per (image, group) + arrival counters, zeroed with the arena every run
+            ws = _ArenaPtr(self, sum(s_ for s_, _ in self.gn_slots))
+            self.gn_slots.append((ws_floats, G))
+        ln_buf = None
+        if fuse.get("want_ln"):
+            parts = int(L.lib().dd_conv_tc_gn_ln_parts(kcode, B, gh, gw, Cout, G, 1 if ws is not None else 0))
+            ln_buf = self.empty(B * gh * gw, parts, 2, dtype=torch.float32)
+            y.ln = (ln_buf, parts)
         self.op_names.append("dd_conv_tc")          # counted with the convolutions (bench.py's roofline replays them)
         fn = L.lib().dd_conv_tc_gn
         args = (kcode, L.ptr(src), pitch, L.ptr(src2) if src2 is not None else None, C1, C2, L.ptr(wp), wp.shape[0],
                 L.ptr(b_t) if b_t is not None else None, L.ptr(y.t), B, gh, gw, Cout, flags, gn.num_groups, GN_EPS,
                 L.ptr(gamma), L.ptr(beta), _TbPtr(self, tb_col) if tb_col is not None else None,
                 self.tb[0] if tb_col is not None else 0, _TrowPtr(self) if tb_col is not None else None,
-                _TrowStride(self) if tb_col is not None else 0, L.ptr(res.t) if res is not None else None, None)
+                _TrowStride(self) if tb_col is not None else 0, L.ptr(res.t) if res is not None else None,
+                L.ptr(ln_buf) if ln_buf is not None else None, ws)
 
         def op():
             L._Counter.n += 1
@@ -299,7 +322,8 @@ class Program:
         if total:
             self.stats_arena = torch.zeros(total, dtype=torch.float32, device=self.device)
 
-    def gn_mish(self, x: Act, stats, gn: torch.nn.GroupNorm, *, tb_col: int = None, tb=None, residual: Act = None) -> Act:
+    def gn_mish(self, x: Act, stats, gn: torch.nn.GroupNorm, *, tb_col: int = None, tb=None, residual: Act = None,
+                want_ln: bool = False) -> Act:
         if stats is self.FUSED:
             return x                                # the conv's epilogue already did it (and added tb / residual)
         y = self.act(x.H, x.W, x.C, x.B)
@@ -307,11 +331,18 @@ class Program:
         gamma, beta = self.f32(gn.weight), self.f32(gn.bias)
         if mode == 2:       # x was never written: the conv left S fp32 partials in the shared split-K workspace
             _, S, b_t = st
+            ln_buf = None
+            if want_ln and not os.environ.get("DD_NO_LN_FOLD"):
+                parts = int(L.lib().dd_gn_mish_sum_parts(x.C, gn.num_groups))
+                cvp = x.C // 4 // parts
+                if 0 < cvp <= 32 and cvp & (cvp - 1) == 0:
+                    ln_buf = self.empty(x.B * x.H * x.W, parts, 2, dtype=torch.float32)
+                    y.ln = (ln_buf, parts)
             self.add("dd_gn_mish_sum", self.splitk_args()[0], S, L.ptr(b_t) if b_t is not None else None, L.ptr(y.t), x.B, x.H * x.W,
                      x.C, gn.num_groups, GN_EPS, L.ptr(gamma), L.ptr(beta),
                      _TbPtr(self, tb_col) if tb_col is not None else None, tb[0] if tb else 0,
                      _TrowPtr(self) if tb_col is not None else None, _TrowStride(self) if tb_col is not None else 0,
-                     L.ptr(residual.t) if residual is not None else None)
+                     L.ptr(residual.t) if residual is not None else None, L.ptr(ln_buf) if ln_buf is not None else None)
             return y
         self.add("dd_gn_mish", L.ptr(x.t), L.ptr(y.t), self.dcode, x.B, x.H * x.W, x.C, gn.num_groups,
                  st if isinstance(st, _ArenaPtr) else L.ptr(st), mode, GN_EPS, L.ptr(gamma), L.ptr(beta),
@@ -438,7 +469,7 @@ class UnetEngine(Program):
         self.refresh_weights()
 
     # ---- program construction --------------------------------------------------------------
-    def _resnet(self, rb, x: Act, x2: Act = None, first: bool = False) -> Act:
+    def _resnet(self, rb, x: Act, x2: Act = None, first: bool = False, want_ln: bool = False) -> Act:
         col = self.tb_off[id(rb)]
         c1, g1 = rb.block1.block[0], rb.block1.block[1]
         c2, g2 = rb.block2.block[0], rb.block2.block[1]
@@ -457,8 +488,9 @@ class UnetEngine(Program):
                 assert x2 is None
                 res = x
         h = self.gn_mish(h, st, g1, tb_col=col, tb=self.tb)
-        h, st = self.conv(h, c2, kind="3x3", gn=g2, fuse=dict(residual=res))
-        return self.gn_mish(h, st, g2, residual=res)
+        want_ln = want_ln and self.precision == "bf16" and not os.environ.get("DD_NO_LN_FOLD")
+        h, st = self.conv(h, c2, kind="3x3", gn=g2, fuse=dict(residual=res, want_ln=want_ln))
+        return self.gn_mish(h, st, g2, residual=res, want_ln=want_ln)
 
     def _conv_im2col(self, x: Act, conv, gn, center_only: bool, fuse: dict = None):
         w = conv.weight
@@ -478,7 +510,7 @@ class UnetEngine(Program):
         self.conv_tc_flops.append(2.0 * x.B * x.H * x.W * Cout * Cin * (1 if center_only else 9))
         if gn is not None:
             G = gn.num_groups
-            if fuse is not None and int(L.lib().dd_conv_tc_gn_cluster(L.TC_CONV1x1, x.B, x.H, x.W, Cout, G)) > 0:
+            if fuse is not None and self._gn_fusable(L.TC_CONV1x1, x.B, x.H, x.W, Cout, G):
                 self._add_conv_gn(L.TC_CONV1x1, x.t, 0, None, kpad, 0, wp, b_t, y, x.B, x.H, x.W, Cout, 0, gn, fuse)
                 return y, self.FUSED
             stats = (self._new_stats_slot(x.B, G), 1)
@@ -490,12 +522,15 @@ class UnetEngine(Program):
     def _attn(self, res_mod, x: Act) -> Act:
         pre = res_mod.fn            # PreNorm
         attn = pre.fn               # LinearAttention
-        g, b = self.f32(pre.norm.g), self.f32(pre.norm.b)
-        xn = self.act(x.H, x.W, x.C, x.B)
-        self.add("dd_layernorm_c", L.ptr(x.t), L.ptr(xn.t), self.dcode, x.B * x.H * x.W, x.C, L.ptr(g), L.ptr(b),
-                 pre.norm.eps)
-        qkv, _ = self.conv(xn, attn.to_qkv, kind="1x1", bias=False)
         hid = attn.heads * attn.dim_head
+        if x.ln is not None and self.precision == "bf16" and x.C % 64 == 0:
+            qkv = self._qkv_ln_folded(pre, attn, x)
+        else:
+            g, b = self.f32(pre.norm.g), self.f32(pre.norm.b)
+            xn = self.act(x.H, x.W, x.C, x.B)
+            self.add("dd_layernorm_c", L.ptr(x.t), L.ptr(xn.t), self.dcode, x.B * x.H * x.W, x.C, L.ptr(g), L.ptr(b),
+                     pre.norm.eps)
+            qkv, _ = self.conv(xn, attn.to_qkv, kind="1x1", bias=False)
         if self.precision == "bf16":
             # fused output: per-sample matrices M_b = ctx_b . W_out^T, then ONE tensor-core GEMM q . M_b + bias + x
             C = x.C
@@ -522,6 +557,24 @@ class UnetEngine(Program):
         y, _ = self.conv(o, attn.to_out, kind="1x1", residual=x)
         return y
 
+    def _qkv_ln_folded(self, pre, attn, x: Act) -> Act:
+        """to_qkv(LayerNorm(x)) as ONE GEMM on x itself (blocks.py:57-69, 123): the gain is folded into the weights, mean and
+        1 / (std + eps) of every pixel are applied by the epilogue from the channel sums the producing launch left in x.ln."""
+        w, gvec, bvec = attn.to_qkv.weight, pre.norm.g, pre.norm.b
+        Cout, C = w.shape[0], w.shape[1]
+        wp = self.packed((Cout, C), torch.bfloat16, lambda buf: buf.copy_(w.detach().reshape(Cout, C) * gvec.detach().reshape(1, C)))
+        # row sums of the ROUNDED weights, so that a constant input cancels exactly as it does in (x - mean)
+        wsum = self.packed((Cout,), torch.float32,
+                           lambda buf: buf.copy_((w.detach().reshape(Cout, C) * gvec.detach().reshape(1, C)).to(torch.bfloat16).float().sum(1)))
+        cb = self.packed((Cout,), torch.float32, lambda buf: buf.copy_(w.detach().reshape(Cout, C) @ bvec.detach().reshape(C)))
+        stats, parts = x.ln
+        y = self.act(x.H, x.W, Cout, x.B)
+        self.conv_tc_flops.append(2.0 * x.B * x.H * x.W * Cout * C)
+        self.add("dd_conv_tc_ln", L.ptr(x.t), C, L.ptr(wp), Cout, L.ptr(cb), L.ptr(wsum), L.ptr(stats), parts, float(pre.norm.eps),
+                 L.ptr(y.t), x.B, x.H, x.W, Cout)
+        self.op_names[-1] = "dd_conv_tc"            # counted with the convolutions
+        return y
+
     def _build(self, unet) -> None:
         B, H, W, cin = self.B, self.H, self.W, unet.in_channels
         if self.precision == "bf16":
@@ -534,17 +587,17 @@ class UnetEngine(Program):
         skips: List[Act] = []
         for i, (rb1, rb2, attn, down) in enumerate(unet.downs):
             x = self._resnet(rb1, x, first=(i == 0))
-            x = self._resnet(rb2, x)
+            x = self._resnet(rb2, x, want_ln=True)
             x = self._attn(attn, x)
             skips.append(x)
             if not isinstance(down, torch.nn.Identity):
                 x, _ = self.conv(x, down.conv, kind="down")
-        x = self._resnet(unet.mid_block1, x)
+        x = self._resnet(unet.mid_block1, x, want_ln=True)
         x = self._attn(unet.mid_attn, x)
         x = self._resnet(unet.mid_block2, x)
         for rb1, rb2, attn, up in unet.ups:
             x = self._resnet(rb1, x, x2=skips.pop())        # concat-free: two K ranges (unet.py:97)
-            x = self._resnet(rb2, x)
+            x = self._resnet(rb2, x, want_ln=True)
             x = self._attn(attn, x)
             if not isinstance(up, torch.nn.Identity):
                 x, _ = self.conv(x, up.conv, kind="up")

@@ -185,7 +185,10 @@ int dd_gn_mish(const void* x, void* y, int dtype, int B, int HW, int C, int G,
 int dd_gn_mish_sum(const float* part, int S, const float* bias, void* y_bf16, int B, int HW, int C, int G, float eps,
                    const float* gamma, const float* beta,
                    const float* tbias, int tb_stride, const int32_t* trow, int trow_stride,
-                   const void* residual_bf16, void* stream);
+                   const void* residual_bf16, float* ln_part, void* stream);
+/* CTAs per image dd_gn_mish_sum uses for (C, G) = the `parts` dimension of its ln_part output: (B*HW, parts, 2) fp32 per-pixel
+ * {sum, sum of squares} over each CTA's channels of the bf16 values it wrote (channel-LayerNorm statistics for dd_conv_tc_ln). */
+int dd_gn_mish_sum_parts(int C, int G);
 
 /* Channel LayerNorm of blocks.py:50-60: (x-mean_c)/(sqrt(var_c)+eps)*g+b, per pixel. x,y NHWC (P, C). */
 int dd_layernorm_c(const void* x, void* y, int dtype, int64_t P, int C, const float* g, const float* b,
@@ -292,12 +295,28 @@ int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int
  * fewer than 8 channels per group): use dd_conv_tc with gn_stats + dd_gn_mish there.  kinds / flags as dd_conv_tc (no
  * DD_TC_SPLITK, DD_TC_W_PER_SAMPLE, DD_TC_PAIR). */
 int dd_conv_tc_gn_cluster(int kind, int B, int H, int W, int Cout, int G);
+/* output channels per CTA tile that dd_conv_tc / dd_conv_tc_gn use for this layer (ln_part has Cout / tile_n parts) */
+int dd_conv_tc_tile_n(int kind, int B, int H, int W, int Cout, int flags);
+/* 1x1 convolution of the channel-LayerNorm'd input (PreNorm + to_qkv, blocks.py:57-69, 123) without materialising the norm:
+ *     y[p, o] = inv_p * (sum_c Wg[o,c] x[p,c] - mean_p * wsum[o]) + bias[o],    inv_p = 1 / (std_p + eps)
+ * wp = bf16(W * g) (gain folded into the weights), wsum[o] = sum_c wp[o,c], bias[o] = sum_c W[o,c] b[c]; mean_p / std_p come
+ * from ln_in (B*H*W, ln_in_parts, 2) fp32 {sum, sum of squares} over the C input channels, as written by the producing launch
+ * (dd_conv_tc_gn's ln_part, dd_gn_mish_sum's ln_part).  x, y bf16 NHWC. */
+int dd_conv_tc_ln(const void* x, int C, const void* wp, int w_rows, const float* bias, const float* wsum,
+                  const float* ln_in, int ln_in_parts, float ln_eps, void* y, int B, int H, int W, int Cout, void* stream);
+/* Persistent form (3x3 stride 1 on maps of at least 16x8 pixels, Cout % 128 == 0): when dd_conv_tc_gn_ws_floats(...) > 0 and the
+ * caller passes `ws`, a ZEROED fp32 workspace of that many floats, the layer runs as one CTA per SM walking its tiles with two
+ * accumulators in TMEM -- the epilogue (statistics exchange through `ws`, normalisation, Mish, stores) of one tile under the
+ * MMAs of the next (csrc/conv_tc_persist.cu).  ws == NULL selects the cluster form above.
+ * dd_conv_tc_gn_ln_parts: the `parts` dimension of ln_part for the persistent (2 * Cout / 128) or the cluster form. */
+int64_t dd_conv_tc_gn_ws_floats(int kind, int B, int H, int W, int Cout, int G);
+int dd_conv_tc_gn_ln_parts(int kind, int B, int H, int W, int Cout, int G, int persistent);
 int dd_conv_tc_gn(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2,
                   const void* wp, int w_rows, const float* bias, void* y,
                   int B, int H, int W, int Cout, int flags,
                   int G, float eps, const float* gamma, const float* beta,
                   const float* tbias, int tb_stride, const int32_t* trow, int trow_stride,
-                  const void* residual, float* ln_part, void* stream);
+                  const void* residual, float* ln_part, float* ws, void* stream);
 
 /* fp32 training form of the tensor-core convolution (forward AND input gradient of the 3x3 stride-1 / 1x1 convolutions
  * of blocks.py:78,103,123-124 and convblocks.py:29-67): x, x2, y, addend fp32 NHWC; wp fp32 (w_rows, taps*(C1+C2)) K-major;
@@ -388,6 +407,8 @@ int dd_unpool2(const float* x, float* y, int B, int H, int W, int C, float scale
 /* Debug only: when buf != NULL every dd_conv_tc CTA writes 8 clock64() stamps (start, prologue done, dependency
  * wait done, first operands landed, last MMA issued, accumulator visible, epilogue done) to buf[cta*8 + i]. */
 int dd_debug_set_timeline(long long* buf);
+/* Tuning aid: resident thread-block clusters of `cluster` halo-convolution CTAs (cudaOccupancyMaxActiveClusters), -1 on error. */
+int dd_debug_max_clusters(int cluster);
 /* Same for dd_linattn_mix (6 stamps per CTA: start, dependency resolved, context done, warps merged, context normalised, end);
  * only instrumented builds (-DDD_ATTN_TIMELINE=1) write them. */
 int dd_debug_set_attn_timeline(long long* buf);

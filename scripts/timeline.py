@@ -22,11 +22,21 @@ for which in [int(a) for a in sys.argv[1:]] or (2, 16, 23):          # 3x3@32 (h
     L.lib().dd_debug_set_timeline(None)
     t = buf.cpu().numpy().reshape(-1, 16)
     t = t[t[:, 0] > 0]
+    if (t[:, 14] > 0).any() or (t[:, 13] > 0).any():          # persistent kernel (conv_tc_persist.cu): its own stamp set
+        d = lambda a, b: int(np.median((t[:, a] - t[:, b])[(t[:, a] > 0) & (t[:, b] > 0)])) if ((t[:, a] > 0) & (t[:, b] > 0)).any() else -1
+        print(f"conv #{which}: persistent, {len(t)} CTAs")
+        print("   start->pdl %d, pdl->first data %d, item0 MMA issue span %d, item0 MMAs issued->acc ready %d" % (d(2, 0), d(3, 2), d(4, 3), d(5, 4)))
+        print("   item0 epilogue: drain %d, stats+atomics %d, wait for the image %d, normalise+store %d" % (d(10, 5), d(11, 10), d(12, 11), d(6, 12)))
+        print("   item0 end -> item1 acc ready %d; first data -> last item's MMAs issued %d; -> last item's epilogue done %d" % (d(13, 6), d(7, 3), d(14, 3)))
+        continue
     t0 = t[:, 0].min()
     rel = t[:, :7] - t[:, [0]]
     print(f"conv #{which}: {len(t)} CTAs; kernel span {int(t[:, 6].max() - t0)} clk")
     print("   median per-CTA offsets from its own start:", {n: int(np.median(rel[:, i])) for i, n in enumerate(names)})
     print("   CTA start offsets (from first CTA): p50 %d p90 %d max %d" % tuple(np.percentile(t[:, 0] - t0, [50, 90, 100])))
     print("   epilogue split: drain+stage %d, stats %d, write-out %d" % (np.median(t[:, 10] - t[:, 5]), np.median(t[:, 11] - t[:, 10]), np.median(t[:, 6] - t[:, 11])))
+    if (t[:, 12] > 0).any():      # fused GroupNorm epilogue: stamp 12 = statistics of the image known (after the cluster barrier)
+        print("   fused GN: barrier + peer sums %d, normalise + write-out %d" % (np.median(t[:, 12] - t[:, 11]), np.median(t[:, 6] - t[:, 12])))
+    print("   CTA end offsets (from first CTA start): p10 %d p50 %d p90 %d max %d" % tuple(np.percentile(t[:, 6] - t0, [10, 50, 90, 100])))
     d = rel[:, 4] - rel[:, 3]
     print("   mainloop (first_data -> last_mma): median %d clk, epilogue (acc_ready -> done): median %d clk" % (np.median(d), np.median(rel[:, 6] - rel[:, 5])))

@@ -30,7 +30,7 @@ def _chain(m, noise, graph):
         return m.p_sample_loop(tuple(noise.shape[1:]), early_stop=m.timesteps - STEPS, noise=noise).clone()
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 3e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 1e-2)])
 @pytest.mark.parametrize("how", ["optimizer", "ema_update", "load_state_dict"])
 def test_graph_sampling_after_weight_change_matches_eager(cuda, how, precision, tol):
     cfg = dict(tc.CS, T=50, precision=precision)
@@ -55,7 +55,7 @@ def test_graph_sampling_after_weight_change_matches_eager(cuda, how, precision, 
     z_eager = _chain(m, noise, False)
     # bf16: split-K / attention partials merge in arrival order, so two runs agree to rounding only; fp32 mode is exact enough to
     # see a single stale table row
-    assert tc.max_abs(z_graph, z0) > 3 * tol, "the weight change did not reach the chain at all"
+    assert tc.max_abs(z_graph, z0) > 3e-2, "the weight change did not reach the chain at all"
     assert tc.max_abs(z_graph, z_eager) < tol, "graph replay read stale packed weights / time-bias table"
     # and the table buffer did not move or multiply (one allocation per T for the life of the engine)
     eng = m.latent_model.engine(2, 8, 8)
