@@ -23,8 +23,8 @@ namespace dd {
 
 constexpr int PS_EPI_WARPS = 8;
 constexpr int PS_THREADS = 64 + 32 * PS_EPI_WARPS;         // 320
-constexpr int PS_PAR_BYTES = 3 * 128 * 4;                  // bias, gamma, beta of the current 128-channel tile
-constexpr int ps_smem(int nh, int nb) { return nh * HALO_SLOT + nb * HALO_B_BYTES + 1024 /*align*/ + 256 /*barriers*/ + PS_PAR_BYTES; }
+constexpr int PS_PAR_BYTES = 3 * 128 * 4;                  // bias, gamma, beta of one 128-channel tile (two items in flight when one CTA per SM)
+constexpr int ps_smem(int nh, int nb) { return nh * HALO_SLOT + nb * HALO_B_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * PS_PAR_BYTES; }
 
 __device__ __forceinline__ void ps_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -60,13 +60,11 @@ __device__ __forceinline__ PsItem ps_decode(const TcParams& p, int it) {
     return i;
 }
 
-// <CPG_SH: log2(channels per GroupNorm group), NH / NB: halo / weight ring depth, MINB: CTAs per SM>
-//   <.., 2, 4, 2>: 113 KB, TWO persistent CTAs per SM.  One CTA cannot keep its tensor pipe fed: a TMA load takes ~3000 clk from
-//   issue to arrival under load, so 198 KB in flight sustain ~42 B/clk = 111 clk per MMA (profiles/README.md, round 2 pass f);
-//   two CTAs double the bytes in flight (62 clk per MMA SM-wide, the pipe rate) and their 2 x 8 epilogue warps give the
-//   activation math the thread-level parallelism it needs.  Registers: 65536 / 640 threads = 102 per thread.
-template <int CPG_SH, int PS_NH, int PS_NB, int MINB>
-__global__ void __launch_bounds__(PS_THREADS, MINB) conv_tc_halo_persist_kernel(const __grid_constant__ TcParams p) {
+// <CPG_SH: log2(channels per GroupNorm group), NH / NB: halo / weight ring depth>.  One CTA per SM.  (A two-CTAs-per-SM form
+// with 2 + 4 ring slots and 96 registers was built and measured: the occupancy calculator still grants one CTA per SM and the
+// shallower rings lose, 1.02 - 1.10 ms per step against 0.94; removed again -- profiles/README.md, round 2 passes g - k.)
+template <int CPG_SH, int PS_NH, int PS_NB>
+__global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_halo_persist_kernel(const __grid_constant__ TcParams p) {
     constexpr uint32_t DY_BYTES = (HALO_TW + 2) * 128u;                 // shared-memory bytes between filter rows of the halo
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -81,7 +79,7 @@ __global__ void __launch_bounds__(PS_THREADS, MINB) conv_tc_halo_persist_kernel(
     const uint32_t tmem_ptr_addr = bars + 8u * (2 * PS_NH + 2 * PS_NB + 4);
     static_assert(8 * (2 * PS_NH + 2 * PS_NB + 4) + 8 <= 256, "barrier block");
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
-    float* s_par = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));      // [3][128]
+    float* s_par = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));      // [2][3][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = p.chunks0 + p.chunks1, cin = nchunks * 64;
@@ -191,6 +189,9 @@ __global__ void __launch_bounds__(PS_THREADS, MINB) conv_tc_halo_persist_kernel(
         }
     } else {
         // ===== epilogue: 8 warps; thread = (pixel row r of the tile, 64-channel half) =====
+        // Software-pipelined over the CTA's items: phase 1 of item k (drain TMEM, publish the statistics) runs BEFORE phase 2 of
+        // item k - 1 (normalise, activate, store), so the other tiles of image k - 1 have had a whole main loop to arrive and the
+        // wait costs nothing; a thread carries two packed rows (2 x 32 registers).
         constexpr int NGH = 64 >> CPG_SH;                                 // GroupNorm groups inside a thread's 64 channels (1, 2, 4, 8)
         const int et = threadIdx.x - 64;                                  // 0 .. 255
         const int q = warp & 3, hsel = (warp - 2) >> 2;
@@ -198,34 +199,24 @@ __global__ void __launch_bounds__(PS_THREADS, MINB) conv_tc_halo_persist_kernel(
         const int ww = r & (HALO_TW - 1), hh = r >> 3;
         const int G = p.G;
         uint32_t* cnt_base = reinterpret_cast<uint32_t*>(p.gn_stats + (int64_t)p.B * G * 2);
-        const float* s_bias = s_par, *s_gamma = s_par + 128, *s_beta = s_par + 256;
         const int c0 = hsel * 64;
-        int k = 0;
-        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
-            const PsItem im = ps_decode(p, it);
+
+        auto phase1 = [&](const int k, const PsItem& im, uint32_t (&row)[32]) {
             const int buf = k & 1, cbase = im.n_tile * 128;
-            const int64_t pix = ((int64_t)im.img * p.H + (im.h0 + hh)) * p.W + (im.w0 + ww);
-            // parameters of this 128-channel tile -> shared memory
+            float* par = s_par + buf * 384;                               // bias, gamma, beta of this item's 128 channels
+            ps_epi_bar();                                                 // phase 2 of item k - 2 has finished reading this buffer
             if (et < 128) {
-                s_par[et] = p.bias ? p.bias[cbase + et] : 0.f;
-                s_par[256 + et] = p.gn_beta[cbase + et];
+                par[et] = p.bias ? p.bias[cbase + et] : 0.f;
+                par[256 + et] = p.gn_beta[cbase + et];
             } else {
-                s_par[et] = p.gn_gamma[cbase + et - 128];
+                par[et] = p.gn_gamma[cbase + et - 128];
             }
-            const float* tbp = nullptr;
-            if (p.tbias) {
-                const int trow_i = p.trow ? p.trow[(int64_t)im.img * p.trow_stride] : im.img;
-                tbp = p.tbias + (int64_t)trow_i * p.tb_stride + cbase + c0;
-            }
-            const __nv_bfloat16* resp = p.residual ? p.residual + pix * p.Cout + cbase + c0 : nullptr;
             ps_epi_bar();
             mbar_wait(tfull(buf), (k >> 1) & 1);
             if (et == 0) tstamp(p, k == 0 ? 5 : 13);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(buf * 128 + c0) + ((uint32_t)(q * 32) << 16);
-            // drain 64 columns, 16 at a time (the next load is in flight while the current one is processed): + bias, group
-            // statistics of the fp32 values, pack to bf16 (what the separate GroupNorm launch used to read)
-            uint32_t row[32];
+            // drain 64 columns, 16 at a time: + bias, group statistics of the fp32 values, pack to bf16
             float gs[NGH], gq[NGH];
 #pragma unroll
             for (int g = 0; g < NGH; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
@@ -236,7 +227,7 @@ __global__ void __launch_bounds__(PS_THREADS, MINB) conv_tc_halo_persist_kernel(
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int c = 16 * qd + 2 * j;                         // channel within the half (static)
-                    const float2 bi = *reinterpret_cast<const float2*>(s_bias + c0 + c);
+                    const float2 bi = *reinterpret_cast<const float2*>(par + c0 + c);
                     const float x0 = __uint_as_float(a[2 * j]) + bi.x, x1 = __uint_as_float(a[2 * j + 1]) + bi.y;
                     gs[c >> CPG_SH] += x0 + x1;
                     gq[c >> CPG_SH] = fmaf(x0, x0, fmaf(x1, x1, gq[c >> CPG_SH]));
@@ -249,8 +240,7 @@ __global__ void __launch_bounds__(PS_THREADS, MINB) conv_tc_halo_persist_kernel(
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(buf));
             if (et == 0 && k == 0) tstamp(p, 10);
-            const int gfirst = (cbase + c0) >> CPG_SH;                     // first group of this thread's channels
-            float* st = p.gn_stats + ((int64_t)im.img * G + gfirst) * 2;
+            float* st = p.gn_stats + ((int64_t)im.img * G + ((cbase + c0) >> CPG_SH)) * 2;
 #pragma unroll
             for (int g = 0; g < NGH; ++g) {
                 float sa = gs[g], qa = gq[g];
@@ -262,10 +252,24 @@ __global__ void __launch_bounds__(PS_THREADS, MINB) conv_tc_halo_persist_kernel(
                 if (lane == 0) { red_add_f32(st + 2 * g, sa); red_add_f32(st + 2 * g + 1, qa); }
             }
             ps_epi_bar();                                                  // every warp of the CTA has issued its partial sums
+            if (et == 0) red_release_add_u32(cnt_base + (im.img * ntn + im.n_tile), 1u);
             if (et == 0 && k == 0) tstamp(p, 11);
+        };
+
+        auto phase2 = [&](const int k, const PsItem& im, uint32_t (&row)[32]) {
+            const int cbase = im.n_tile * 128;
+            const float* s_gamma = s_par + (k & 1) * 384 + 128, *s_beta = s_gamma + 128;
+            const int64_t pix = ((int64_t)im.img * p.H + (im.h0 + hh)) * p.W + (im.w0 + ww);
+            const float* tbp = nullptr;
+            if (p.tbias) {
+                const int trow_i = p.trow ? p.trow[(int64_t)im.img * p.trow_stride] : im.img;
+                tbp = p.tbias + (int64_t)trow_i * p.tb_stride + cbase + c0;
+            }
+            const __nv_bfloat16* resp = p.residual ? p.residual + pix * p.Cout + cbase + c0 : nullptr;
+            uint32_t res[2][8];
+            if (resp) ldg_v8(resp, res[0]);                                // first quarter of the residual row, under the wait
             if (et == 0) {
-                uint32_t* cnt = cnt_base + (im.img * ntn + im.n_tile);
-                red_release_add_u32(cnt, 1u);
+                const uint32_t* cnt = cnt_base + (im.img * ntn + im.n_tile);
                 if (ld_acquire_u32(cnt) < (uint32_t)tpi) {
                     const long long t0 = clock64();
                     while (ld_acquire_u32(cnt) < (uint32_t)tpi) {
@@ -273,10 +277,9 @@ __global__ void __launch_bounds__(PS_THREADS, MINB) conv_tc_halo_persist_kernel(
                     }
                 }
             }
-            uint32_t res[2][8];
-            if (resp) ldg_v8(resp, res[0]);                                // first quarter of the residual row, under the wait
             ps_epi_bar();                                                  // all tiles of the image have arrived
             if (et == 0 && k == 0) tstamp(p, 12);
+            const float* st = p.gn_stats + ((int64_t)im.img * G + ((cbase + c0) >> CPG_SH)) * 2;
             float mean[NGH], rstd[NGH];
 #pragma unroll
             for (int g = 0; g < NGH; ++g) {
@@ -286,6 +289,7 @@ __global__ void __launch_bounds__(PS_THREADS, MINB) conv_tc_halo_persist_kernel(
             }
             // normalise, activate, + time bias, + residual; LayerNorm partial sums of the rounded result; 32-byte stores
             float ls = 0.f, lq = 0.f;
+            const bool want_ln = p.ln_part != nullptr;
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase + c0;
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
@@ -308,16 +312,31 @@ __global__ void __launch_bounds__(PS_THREADS, MINB) conv_tc_halo_persist_kernel(
                     __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
                     const uint32_t hv = *reinterpret_cast<uint32_t*>(&h);
                     row[8 * qd + j] = hv;
-                    const float z0 = __uint_as_float(hv << 16), z1 = __uint_as_float(hv & 0xffff0000u);
-                    ls += z0 + z1; lq = fmaf(z0, z0, fmaf(z1, z1, lq));
+                    if (want_ln) {
+                        const float z0 = __uint_as_float(hv << 16), z1 = __uint_as_float(hv & 0xffff0000u);
+                        ls += z0 + z1; lq = fmaf(z0, z0, fmaf(z1, z1, lq));
+                    }
                 }
                 asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                              ::"l"(op + 16 * qd), "r"(row[8 * qd]), "r"(row[8 * qd + 1]), "r"(row[8 * qd + 2]), "r"(row[8 * qd + 3]),
                                "r"(row[8 * qd + 4]), "r"(row[8 * qd + 5]), "r"(row[8 * qd + 6]), "r"(row[8 * qd + 7]) : "memory");
             }
-            if (p.ln_part) *reinterpret_cast<float2*>(p.ln_part + (pix * (2 * ntn) + (2 * im.n_tile + hsel)) * 2) = make_float2(ls, lq);
-            ps_epi_bar();                                                  // s_par may be overwritten for the next item
+            if (want_ln) *reinterpret_cast<float2*>(p.ln_part + (pix * (2 * ntn) + (2 * im.n_tile + hsel)) * 2) = make_float2(ls, lq);
             if (et == 0) tstamp(p, k == 0 ? 6 : 14);
+        };
+
+        uint32_t cur[32], prv[32];
+        PsItem pim = {0, 0, 0, 0};
+        int k = 0;
+        for (int it = blockIdx.x; ; it += gridDim.x, ++k) {
+            const bool has = it < n_items;
+            PsItem im = pim;
+            if (has) { im = ps_decode(p, it); phase1(k, im, cur); }
+            if (k > 0) phase2(k - 1, pim, prv);
+            if (!has) break;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) prv[j] = cur[j];
+            pim = im;
         }
     }
     tc_fence_before();
@@ -335,9 +354,9 @@ bool halo_persist_ok(int kind, int H, int W, int Cout, int G) {
     return (cpg == 8 || cpg == 16 || cpg == 32 || cpg == 64) && tpi <= num_sms();
 }
 
-template <int CPG_SH, int NH, int NB, int MINB>
+template <int CPG_SH, int NH, int NB>
 static int launch_ps(const TcParams& p, cudaStream_t st) {
-    auto kern = conv_tc_halo_persist_kernel<CPG_SH, NH, NB, MINB>;
+    auto kern = conv_tc_halo_persist_kernel<CPG_SH, NH, NB>;
     constexpr int smem = ps_smem(NH, NB);
     static int ctas_per_sm = -1;            // per template instance
     if (ctas_per_sm < 0) {
@@ -345,7 +364,7 @@ static int launch_ps(const TcParams& p, cudaStream_t st) {
         int n = 0;
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, PS_THREADS, smem);
         if (e != cudaSuccess || n < 1) { set_error("conv_tc_gn(persistent): %s (occupancy %d)", cudaGetErrorString(e), n); return DD_ERR_CUDA; }
-        ctas_per_sm = n < MINB ? n : MINB;
+        ctas_per_sm = 1;
     }
     // every CTA of the grid must be resident at once (the tiles of an image wait for each other) and the grid is a multiple of
     // the tiles per image (they then sit in the same round)
@@ -358,12 +377,11 @@ static int launch_ps(const TcParams& p, cudaStream_t st) {
 }
 
 int launch_halo_persist(const TcParams& p, cudaStream_t st) {
-    static const bool one = getenv("DD_PERSIST_ONE") != nullptr;          // A/B: one CTA per SM with deeper rings (3 halos, 8 weight tiles)
-    switch (p.cpg_shift) {
-        case 3: return one ? launch_ps<3, 3, 8, 1>(p, st) : launch_ps<3, 2, 4, 2>(p, st);
-        case 4: return one ? launch_ps<4, 3, 8, 1>(p, st) : launch_ps<4, 2, 4, 2>(p, st);
-        case 5: return one ? launch_ps<5, 3, 8, 1>(p, st) : launch_ps<5, 2, 4, 2>(p, st);
-        case 6: return one ? launch_ps<6, 3, 8, 1>(p, st) : launch_ps<6, 2, 4, 2>(p, st);
+    switch (p.cpg_shift) {          // rings: 3 halos (70.7 KB) + 8 weight tiles (128 KB)
+        case 3: return launch_ps<3, 3, 8>(p, st);
+        case 4: return launch_ps<4, 3, 8>(p, st);
+        case 5: return launch_ps<5, 3, 8>(p, st);
+        case 6: return launch_ps<6, 3, 8>(p, st);
     }
     set_error("conv_tc_gn(persistent): unsupported channels per group (shift %d)", p.cpg_shift);
     return DD_ERR_ARG;
