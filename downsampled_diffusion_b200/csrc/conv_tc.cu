@@ -1343,6 +1343,11 @@ static int conv_tc_impl(int kind, const void* x, int x_pitch, const void* x2, in
         if (rc) return rc;
         return launch_halo_persist(p, st);
     }
+    if (!fuse && !out_nchw_f32 && p.splits == 1 && gemm_persist_ok(kind, B, H, W, C1, C2, Cout, G, gn_stats != nullptr, wps)) {
+        rc = make_w_map(&p.tmB, wp, K, w_rows, 128, wps ? B : 0);
+        if (rc) return rc;
+        return launch_gemm_persist(p, x, x_pitch, C1, st);
+    }
     if (p.splits > 1)
         launch_pdl(conv_tc_kernel<8, 64, 1, 2>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
     else if (out_nchw_f32 || p.bn < 32)

@@ -346,6 +346,8 @@ static void launch_cluster_pdl(void (*kernel)(KArgs...), int cluster_x, dim3 gri
 // persistent halo convolution with the fused GroupNorm epilogue (conv_tc_persist.cu)
 bool halo_persist_ok(int kind, int H, int W, int Cout, int G);
 int launch_halo_persist(const TcParams& p, cudaStream_t st);
+bool gemm_persist_ok(int kind, int B, int H, int W, int C1, int C2, int Cout, int G, bool stats, bool wps);
+int launch_gemm_persist(TcParams& p, const void* x, int x_pitch, int C1, cudaStream_t st);
 
 extern long long* g_tc_dbg;          // optional in-kernel timeline buffer (dd_debug_set_timeline), defined in conv_tc.cu
 

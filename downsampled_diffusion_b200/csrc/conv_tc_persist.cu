@@ -387,4 +387,263 @@ int launch_halo_persist(const TcParams& p, cudaStream_t st) {
     return DD_ERR_ARG;
 }
 
+
+// =============================================================================================================================
+// Persistent GEMM for the 1x1 convolutions (to_qkv with the LayerNorm fold, the attention output with per-sample weights, the
+// ResnetBlock res_conv, the im2col'd first convolution): blocks.py:103, 123-124, unet.py:71.
+// These layers have K = 128 .. 512, i.e. 2 .. 8 k-blocks per 128 x 128 tile: as one tile per CTA they are all prologue and
+// epilogue (qkv @32x32: 1536 CTAs x (2.3 k clk set-up + 0.8 k clk of MMAs + 4.5 - 6 k clk staged epilogue) = 30 us for a 50 MB
+// output).  Here one CTA per SM walks the (row tile, 128-channel tile) items with a 6-stage operand ring running across items,
+// two accumulators in TMEM and the same 8-warp register epilogue as the halo kernel above (64 channels of one row per thread,
+// 32-byte stores), so an item costs its epilogue (~2 k clk) and nothing else.
+//   rows are the M = B*H*W pixels of the NHWC tensor (a 2-D tensor map; TMA zero-fills past M), optional per-row LayerNorm
+//   statistics (dd_conv_tc_ln), optional residual, optional GroupNorm {sum, sum of squares} atomics for a following dd_gn_mish
+//   (template CPG_SH > 0; needs H*W % 128 == 0 so that a tile lies inside one image), optional per-image weights.
+// =============================================================================================================================
+constexpr int GS_STAGES = 6;
+constexpr int GS_STAGE_BYTES = 2 * TC_A_BYTES;                     // 128 x 64 bf16 of A + 128 x 64 of B
+constexpr int GS_SMEM = GS_STAGES * GS_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 2 * 128 * 4 /*bias, weight row sums x 2 items*/;
+
+template <int CPG_SH>
+__global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + GS_STAGES * GS_STAGE_BYTES;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (GS_STAGES + s); };
+    auto tfull = [&](int s) { return bars + 8u * (2 * GS_STAGES + s); };
+    auto tempty = [&](int s) { return bars + 8u * (2 * GS_STAGES + 2 + s); };
+    const uint32_t tmem_ptr_addr = bars + 8u * (2 * GS_STAGES + 4);
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    float* s_par = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));      // [2 items][bias | wsum][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.chunks0;
+    const int HW = p.H * p.W;
+    const int64_t M = (int64_t)p.B * HW;
+    const int n_m = (int)((M + 127) >> 7), ntn = p.Cout >> 7;
+    const int n_items = n_m * ntn;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA0)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB)) : "memory");
+        for (int s = 0; s < GS_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), PS_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+    if (threadIdx.x == 0) tstamp(p, 0);
+    pdl_sync();
+    if (threadIdx.x == 0) tstamp(p, 2);
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        int st = 0, round = 0;
+        uint32_t sA = base;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const int n_tile = it % ntn, m_tile = it / ntn;
+            const int img = p.w_per_sample ? (int)(((int64_t)m_tile << 7) / HW) : 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                if (round > 0) mbar_wait(empty(st), (round - 1) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(full(st), GS_STAGE_BYTES);
+                    tma_load_2d(&p.tmA0, full(st), sA, kb * 64, m_tile * 128);
+                    if (p.w_per_sample) tma_load_3d(&p.tmB, full(st), sA + TC_A_BYTES, kb * 64, n_tile * 128, img);
+                    else tma_load_2d(&p.tmB, full(st), sA + TC_A_BYTES, kb * 64, n_tile * 128);
+                }
+                __syncwarp();
+                sA += GS_STAGE_BYTES;
+                if (++st == GS_STAGES) { st = 0; ++round; sA = base; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        int st = 0, k = 0;
+        uint32_t par = 0;
+        uint32_t sA = base;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+            const int buf = k & 1;
+            if (k >= 2) mbar_wait(tempty(buf), ((k >> 1) - 1) & 1);
+            tc_fence_after();
+            const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full(st), par);
+                if (k == 0 && kb == 0 && lane == 0) tstamp(p, 3);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t ad = umma_desc(sA), bd = umma_desc(sA + TC_A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 16; ++kk)
+                        umma_f16(dcol, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc, (kb | kk) ? 1u : 0u);
+                    umma_commit(empty(st));
+                }
+                __syncwarp();
+                sA += GS_STAGE_BYTES;
+                if (++st == GS_STAGES) { st = 0; par ^= 1u; sA = base; }
+            }
+            if (elect_one()) umma_commit(tfull(buf));
+            __syncwarp();
+            if (lane == 0) tstamp(p, k == 0 ? 4 : 7);
+        }
+    } else {
+        // ===== epilogue: 8 warps; thread = (row of the tile, 64-channel half) =====
+        constexpr int NGH = CPG_SH > 0 ? (64 >> CPG_SH) : 1;
+        const int et = threadIdx.x - 64;
+        const int q = warp & 3, hsel = (warp - 2) >> 2;
+        const int r = q * 32 + lane, c0 = hsel * 64;
+        const bool ln_fold = p.ln_in != nullptr;
+        int k = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+            const int n_tile = it % ntn, m_tile = it / ntn;
+            const int buf = k & 1, cbase = n_tile * 128;
+            const int64_t m = ((int64_t)m_tile << 7) + r;
+            const bool valid = m < M;
+            float* par = s_par + buf * 256;
+            ps_epi_bar();                                                 // the item two back has finished with this buffer
+            if (et < 128) par[et] = p.bias ? p.bias[cbase + et] : 0.f;
+            else par[et] = ln_fold ? p.ln_wsum[cbase + et - 128] : 0.f;
+            float ln_a = 1.f, ln_b = 0.f;
+            if (ln_fold && valid) {
+                const float2* lp = reinterpret_cast<const float2*>(p.ln_in) + m * p.ln_in_parts;
+                float su = 0.f, sq = 0.f;
+                for (int i = 0; i < p.ln_in_parts; ++i) { const float2 v = __ldg(lp + i); su += v.x; sq += v.y; }
+                const float mean = su * p.ln_inv_c;
+                ln_a = 1.f / (sqrtf(fmaxf(sq * p.ln_inv_c - mean * mean, 0.f)) + p.ln_eps);
+                ln_b = -mean * ln_a;
+            }
+            const __nv_bfloat16* resp = (p.residual && valid) ? p.residual + m * p.Cout + cbase + c0 : nullptr;
+            uint32_t res[2][8];
+            if (resp) ldg_v8(resp, res[0]);
+            ps_epi_bar();
+            if (et == 0 && k == 1) tstamp(p, 11);
+            mbar_wait(tfull(buf), (k >> 1) & 1);
+            if (et == 0) tstamp(p, k == 0 ? 5 : (k == 1 ? 13 : 12));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)(buf * 128 + c0) + ((uint32_t)(q * 32) << 16);
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.Cout + cbase + c0;
+            float gs[NGH], gq[NGH];
+#pragma unroll
+            for (int g = 0; g < NGH; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                uint32_t a[16];
+                tmem_ld16(taddr + (uint32_t)(16 * qd), a);
+                if (qd == 3) {                                             // every column of this thread is in registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty(buf));
+                }
+                if (resp && qd < 3) ldg_v8(resp + 16 * (qd + 1), res[(qd + 1) & 1]);
+                uint32_t ov[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + 16 * qd + 2 * j;
+                    const float2 bi = *reinterpret_cast<const float2*>(par + c);
+                    float x0 = __uint_as_float(a[2 * j]), x1 = __uint_as_float(a[2 * j + 1]);
+                    if (ln_fold) {
+                        const float2 ws = *reinterpret_cast<const float2*>(par + 128 + c);
+                        x0 = fmaf(x0, ln_a, fmaf(ln_b, ws.x, bi.x)); x1 = fmaf(x1, ln_a, fmaf(ln_b, ws.y, bi.y));
+                    } else { x0 += bi.x; x1 += bi.y; }
+                    if (CPG_SH > 0 && valid) {
+                        constexpr int SH = CPG_SH > 0 ? CPG_SH : 6;
+                        gs[(16 * qd + 2 * j) >> SH] += x0 + x1;
+                        gq[(16 * qd + 2 * j) >> SH] = fmaf(x0, x0, fmaf(x1, x1, gq[(16 * qd + 2 * j) >> SH]));
+                    }
+                    if (resp) {
+                        const uint32_t rr = res[qd & 1][j];
+                        x0 += __uint_as_float(rr << 16); x1 += __uint_as_float(rr & 0xffff0000u);
+                    }
+                    __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                    ov[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                if (valid) stg_v8(op + 16 * qd, ov);
+            }
+            if (et == 0) tstamp(p, k == 0 ? 6 : (k == 1 ? 10 : 14));
+            if (CPG_SH > 0 && p.gn_stats) {
+                // a tile lies inside one image (H*W % 128 == 0): one (image, group) target per warp and group
+                constexpr int SH = CPG_SH > 0 ? CPG_SH : 6;
+                const int img = (int)(((int64_t)m_tile << 7) / HW);
+                float* st = p.gn_stats + ((int64_t)img * p.G + ((cbase + c0) >> SH)) * 2;
+#pragma unroll
+                for (int g = 0; g < NGH; ++g) {
+                    float sa = gs[g], qa = gq[g];
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        sa += __shfl_xor_sync(0xffffffffu, sa, d);
+                        qa += __shfl_xor_sync(0xffffffffu, qa, d);
+                    }
+                    if (lane == 0) { red_add_f32(st + 2 * g, sa); red_add_f32(st + 2 * g + 1, qa); }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+    }
+}
+
+// rows x channels view of an NHWC tensor: box (64 channels, 128 rows)
+static int make_rows_map(CUtensorMap* tm, const void* ptr, int C, int pitch, int64_t M) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DD_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+    cuuint32_t box[2] = {64u, 128u};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rows C=%d M=%lld) failed: %d", C, (long long)M, (int)r); return DD_ERR_CUDA; }
+    return DD_OK;
+}
+
+// Layers worth the persistent GEMM: plain 1x1 convolutions with bf16 NHWC output, Cout % 128 == 0, at least two items per SM
+// (smaller layers are a single wave either way and keep the one-tile-per-CTA kernel, whose 96 KB let neighbours overlap).
+bool gemm_persist_ok(int kind, int B, int H, int W, int C1, int C2, int Cout, int G, bool stats, bool wps) {
+    if (getenv("DD_NO_PERSIST_GEMM") || kind != DD_TC_CONV1x1 || C2 != 0 || C1 % 64 || Cout % 128) return false;
+    const int64_t M = (int64_t)B * H * W;
+    const int64_t items = ((M + 127) / 128) * (Cout / 128);
+    if (items < 2 * num_sms()) return false;
+    if ((stats || wps) && (H * W) % 128) return false;
+    if (stats) { const int cpg = (G > 0 && Cout % G == 0) ? Cout / G : 0; if (cpg != 8 && cpg != 16 && cpg != 32) return false; }
+    return true;
+}
+
+int launch_gemm_persist(TcParams& p, const void* x, int x_pitch, int C1, cudaStream_t st) {
+    const int64_t M = (int64_t)p.B * p.H * p.W;
+    int rc = make_rows_map(&p.tmA0, x, C1, x_pitch, M);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_gemm_persist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_gemm_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_gemm_persist_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_gemm_persist_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM);
+        if (e != cudaSuccess) { set_error("conv_tc(persistent GEMM): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
+        attr_done = true;
+    }
+    const int64_t items = ((M + 127) / 128) * (p.Cout / 128);
+    const int grid = (int)(items < num_sms() ? items : num_sms());
+    const int sh = p.gn_stats ? p.cpg_shift : 0;
+    switch (sh) {
+        case 0: launch_pdl(conv_tc_gemm_persist_kernel<0>, dim3(grid), dim3(PS_THREADS), GS_SMEM, st, p); break;
+        case 3: launch_pdl(conv_tc_gemm_persist_kernel<3>, dim3(grid), dim3(PS_THREADS), GS_SMEM, st, p); break;
+        case 4: launch_pdl(conv_tc_gemm_persist_kernel<4>, dim3(grid), dim3(PS_THREADS), GS_SMEM, st, p); break;
+        case 5: launch_pdl(conv_tc_gemm_persist_kernel<5>, dim3(grid), dim3(PS_THREADS), GS_SMEM, st, p); break;
+        default: set_error("conv_tc(persistent GEMM): unsupported channels per group"); return DD_ERR_ARG;
+    }
+    return check_launch("conv_tc(persistent GEMM)");
+}
+
 }  // namespace dd

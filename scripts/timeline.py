@@ -22,6 +22,14 @@ for which in [int(a) for a in sys.argv[1:]] or (2, 16, 23):          # 3x3@32 (h
     L.lib().dd_debug_set_timeline(None)
     t = buf.cpu().numpy().reshape(-1, 16)
     t = t[t[:, 0] > 0]
+    if (t[:, 11] > 0).any() and (t[:, 10] > 0).any() and (t[:, 13] > 0).any() and not (t[:, 1] > 0).any() and (t[:, 7] > 0).any() and (t[:, 12] >= 0).all() and (t[:, 10] > t[:, 13]).all():
+        # persistent GEMM: 5 / 6 = item 0 accumulator ready / stored, 11 = item 1 parameters staged, 13 / 10 = item 1 ready / stored, 12 / 14 = last item
+        d = lambda a, b: int(np.median((t[:, a] - t[:, b])[(t[:, a] > 0) & (t[:, b] > 0)])) if ((t[:, a] > 0) & (t[:, b] > 0)).any() else -1
+        print(f"conv #{which}: persistent GEMM, {len(t)} CTAs")
+        print("   pdl->first data %d, item0: MMAs issued %d after first data, acc ready->stored %d" % (d(3, 2), d(4, 3), d(6, 5)))
+        print("   item1: item0 stored->parameters staged %d, ->acc ready %d, acc ready->stored %d" % (d(11, 6), d(13, 11), d(10, 13)))
+        print("   first data -> last item stored %d" % d(14, 3))
+        continue
     if (t[:, 14] > 0).any() or (t[:, 13] > 0).any():          # persistent kernel (conv_tc_persist.cu): its own stamp set
         d = lambda a, b: int(np.median((t[:, a] - t[:, b])[(t[:, a] > 0) & (t[:, b] > 0)])) if ((t[:, a] > 0) & (t[:, b] > 0)).any() else -1
         print(f"conv #{which}: persistent, {len(t)} CTAs")

@@ -214,6 +214,8 @@ CONV_CASES = [
     ("down", 256, 0, 256, 4, 4, 64),      # strided conv on the single-wave path
     ("1x1", 256, 0, 384, 16, 16, 2),
     ("1x1", 128, 0, 256, 2, 2, 3),
+    ("1x1", 128, 0, 384, 32, 32, 40),     # persistent GEMM (960 items on 148 SMs), residual, two k-blocks
+    ("1x1", 512, 0, 128, 16, 16, 150),    # persistent GEMM, eight k-blocks, ragged item count
     ("down", 128, 0, 128, 32, 32, 2),
     ("down", 256, 0, 256, 8, 8, 2),
     ("up", 256, 0, 256, 4, 4, 2),
@@ -436,7 +438,8 @@ def test_conv_gn_fused_epilogue(cuda, monkeypatch, kind, C1, C2, Cout, H, W, B, 
     assert tc.max_abs(from_nhwc(y.t.cpu()), ref) < 6e-2
 
 
-@pytest.mark.parametrize("C,Cout,H,W,B,parts", [(128, 384, 32, 32, 2, 1), (256, 384, 16, 16, 3, 2), (256, 384, 4, 4, 5, 4), (128, 384, 8, 8, 70, 2)])
+@pytest.mark.parametrize("C,Cout,H,W,B,parts", [(128, 384, 32, 32, 2, 1), (256, 384, 16, 16, 3, 2), (256, 384, 4, 4, 5, 4), (128, 384, 8, 8, 70, 2),
+                                                 (128, 384, 32, 32, 33, 2), (256, 384, 16, 16, 70, 4)])      # the last two: persistent GEMM
 def test_conv_ln_folded(cuda, C, Cout, H, W, B, parts):
     """dd_conv_tc_ln: to_qkv(LayerNorm(x)) (blocks.py:57-69, 123) as one GEMM on x, the norm applied by the epilogue from
     per-pixel channel sums -- against the torch expression with eps on the standard deviation."""
