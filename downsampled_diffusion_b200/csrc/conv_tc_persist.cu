@@ -23,8 +23,9 @@ namespace dd {
 
 constexpr int PS_EPI_WARPS = 8;
 constexpr int PS_THREADS = 64 + 32 * PS_EPI_WARPS;         // 320
-constexpr int PS_PAR_BYTES = 3 * 128 * 4;                  // bias, gamma, beta of one 128-channel tile (two items in flight when one CTA per SM)
-constexpr int ps_smem(int nh, int nb) { return nh * HALO_SLOT + nb * HALO_B_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * PS_PAR_BYTES; }
+constexpr int PS_MAX_COUT = 512;                           // bias, gamma, beta of the WHOLE layer are staged once per CTA
+constexpr int PS_PAR_BYTES = 3 * PS_MAX_COUT * 4;
+constexpr int ps_smem(int nh, int nb) { return nh * HALO_SLOT + nb * HALO_B_BYTES + 1024 /*align*/ + 256 /*barriers*/ + PS_PAR_BYTES; }
 
 __device__ __forceinline__ void ps_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_halo_persist_kernel(con
     const uint32_t tmem_ptr_addr = bars + 8u * (2 * PS_NH + 2 * PS_NB + 4);
     static_assert(8 * (2 * PS_NH + 2 * PS_NB + 4) + 8 <= 256, "barrier block");
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
-    float* s_par = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));      // [2][3][128]
+    float* s_par = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));      // [bias | gamma | beta][PS_MAX_COUT]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = p.chunks0 + p.chunks1, cin = nchunks * 64;
@@ -98,6 +99,12 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_halo_persist_kernel(con
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // the layer's parameters (packed before the step, not written by the preceding launch): staged under its tail
+    for (int c = threadIdx.x; c < p.Cout; c += PS_THREADS) {
+        s_par[c] = p.bias ? p.bias[c] : 0.f;
+        s_par[PS_MAX_COUT + c] = p.gn_gamma[c];
+        s_par[2 * PS_MAX_COUT + c] = p.gn_beta[c];
     }
     tc_fence_before();
     __syncthreads();
@@ -203,15 +210,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_halo_persist_kernel(con
 
         auto phase1 = [&](const int k, const PsItem& im, uint32_t (&row)[32]) {
             const int buf = k & 1, cbase = im.n_tile * 128;
-            float* par = s_par + buf * 384;                               // bias, gamma, beta of this item's 128 channels
-            ps_epi_bar();                                                 // phase 2 of item k - 2 has finished reading this buffer
-            if (et < 128) {
-                par[et] = p.bias ? p.bias[cbase + et] : 0.f;
-                par[256 + et] = p.gn_beta[cbase + et];
-            } else {
-                par[et] = p.gn_gamma[cbase + et - 128];
-            }
-            ps_epi_bar();
+            const float* par = s_par + cbase;                             // bias of this item's 128 channels
             mbar_wait(tfull(buf), (k >> 1) & 1);
             if (et == 0) tstamp(p, k == 0 ? 5 : 13);
             tc_fence_after();
@@ -258,7 +257,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_halo_persist_kernel(con
 
         auto phase2 = [&](const int k, const PsItem& im, uint32_t (&row)[32]) {
             const int cbase = im.n_tile * 128;
-            const float* s_gamma = s_par + (k & 1) * 384 + 128, *s_beta = s_gamma + 128;
+            const float* s_gamma = s_par + PS_MAX_COUT + cbase, *s_beta = s_par + 2 * PS_MAX_COUT + cbase;
             const int64_t pix = ((int64_t)im.img * p.H + (im.h0 + hh)) * p.W + (im.w0 + ww);
             const float* tbp = nullptr;
             if (p.tbias) {
@@ -349,7 +348,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_halo_persist_kernel(con
 
 bool halo_persist_ok(int kind, int H, int W, int Cout, int G) {
     const bool off = getenv("DD_NO_PERSIST") != nullptr;       // read per call: tests switch it inside one process
-    if (off || kind != DD_TC_CONV3x3 || H < HALO_TH || W < HALO_TW || Cout % 128 || G <= 0 || Cout % G) return false;
+    if (off || kind != DD_TC_CONV3x3 || H < HALO_TH || W < HALO_TW || Cout % 128 || Cout > PS_MAX_COUT || G <= 0 || Cout % G) return false;
     const int cpg = Cout / G, tpi = (H / HALO_TH) * (W / HALO_TW);
     return (cpg == 8 || cpg == 16 || cpg == 32 || cpg == 64) && tpi <= num_sms();
 }
@@ -402,7 +401,8 @@ int launch_halo_persist(const TcParams& p, cudaStream_t st) {
 // =============================================================================================================================
 constexpr int GS_STAGES = 6;
 constexpr int GS_STAGE_BYTES = 2 * TC_A_BYTES;                     // 128 x 64 bf16 of A + 128 x 64 of B
-constexpr int GS_SMEM = GS_STAGES * GS_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 2 * 128 * 4 /*bias, weight row sums x 2 items*/;
+constexpr int GS_MAX_COUT = 1024;
+constexpr int GS_SMEM = GS_STAGES * GS_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * GS_MAX_COUT * 4 /*bias, weight row sums of the layer*/;
 
 template <int CPG_SH>
 __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(const __grid_constant__ TcParams p) {
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(con
     auto tempty = [&](int s) { return bars + 8u * (2 * GS_STAGES + 2 + s); };
     const uint32_t tmem_ptr_addr = bars + 8u * (2 * GS_STAGES + 4);
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
-    float* s_par = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));      // [2 items][bias | wsum][128]
+    float* s_par = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));      // [bias | wsum][GS_MAX_COUT]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.chunks0;
@@ -435,6 +435,10 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(con
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int c = threadIdx.x; c < p.Cout; c += PS_THREADS) {       // packed before the step: safe to read before the grid dependency resolves
+        s_par[c] = p.bias ? p.bias[c] : 0.f;
+        s_par[GS_MAX_COUT + c] = p.ln_in ? p.ln_wsum[c] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -501,29 +505,33 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(con
         const int q = warp & 3, hsel = (warp - 2) >> 2;
         const int r = q * 32 + lane, c0 = hsel * 64;
         const bool ln_fold = p.ln_in != nullptr;
+        // channel sums of row m for the LayerNorm fold: {sum, sum of squares} over the parts, fetched one item ahead
+        auto ln_sums = [&](const int64_t m, float& su, float& sq) {
+            su = 0.f; sq = 0.f;
+            if (ln_fold && m < M) {
+                const float2* lp = reinterpret_cast<const float2*>(p.ln_in) + m * p.ln_in_parts;
+                for (int i = 0; i < p.ln_in_parts; ++i) { const float2 v = __ldg(lp + i); su += v.x; sq += v.y; }
+            }
+        };
+        float nsu, nsq;
+        ln_sums((((int64_t)(blockIdx.x / ntn)) << 7) + r, nsu, nsq);
         int k = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
             const int n_tile = it % ntn, m_tile = it / ntn;
             const int buf = k & 1, cbase = n_tile * 128;
             const int64_t m = ((int64_t)m_tile << 7) + r;
             const bool valid = m < M;
-            float* par = s_par + buf * 256;
-            ps_epi_bar();                                                 // the item two back has finished with this buffer
-            if (et < 128) par[et] = p.bias ? p.bias[cbase + et] : 0.f;
-            else par[et] = ln_fold ? p.ln_wsum[cbase + et - 128] : 0.f;
+            const float* par = s_par + cbase;
             float ln_a = 1.f, ln_b = 0.f;
             if (ln_fold && valid) {
-                const float2* lp = reinterpret_cast<const float2*>(p.ln_in) + m * p.ln_in_parts;
-                float su = 0.f, sq = 0.f;
-                for (int i = 0; i < p.ln_in_parts; ++i) { const float2 v = __ldg(lp + i); su += v.x; sq += v.y; }
-                const float mean = su * p.ln_inv_c;
-                ln_a = 1.f / (sqrtf(fmaxf(sq * p.ln_inv_c - mean * mean, 0.f)) + p.ln_eps);
+                const float mean = nsu * p.ln_inv_c;
+                ln_a = 1.f / (sqrtf(fmaxf(nsq * p.ln_inv_c - mean * mean, 0.f)) + p.ln_eps);
                 ln_b = -mean * ln_a;
             }
+            if (it + (int)gridDim.x < n_items) ln_sums((((int64_t)((it + (int)gridDim.x) / ntn)) << 7) + r, nsu, nsq);      // next item's rows
             const __nv_bfloat16* resp = (p.residual && valid) ? p.residual + m * p.Cout + cbase + c0 : nullptr;
             uint32_t res[2][8];
             if (resp) ldg_v8(resp, res[0]);
-            ps_epi_bar();
             if (et == 0 && k == 1) tstamp(p, 11);
             mbar_wait(tfull(buf), (k >> 1) & 1);
             if (et == 0) tstamp(p, k == 0 ? 5 : (k == 1 ? 13 : 12));
@@ -550,7 +558,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(con
                     const float2 bi = *reinterpret_cast<const float2*>(par + c);
                     float x0 = __uint_as_float(a[2 * j]), x1 = __uint_as_float(a[2 * j + 1]);
                     if (ln_fold) {
-                        const float2 ws = *reinterpret_cast<const float2*>(par + 128 + c);
+                        const float2 ws = *reinterpret_cast<const float2*>(par + GS_MAX_COUT + c);
                         x0 = fmaf(x0, ln_a, fmaf(ln_b, ws.x, bi.x)); x1 = fmaf(x1, ln_a, fmaf(ln_b, ws.y, bi.y));
                     } else { x0 += bi.x; x1 += bi.y; }
                     if (CPG_SH > 0 && valid) {
@@ -611,7 +619,7 @@ static int make_rows_map(CUtensorMap* tm, const void* ptr, int C, int pitch, int
 // Layers worth the persistent GEMM: plain 1x1 convolutions with bf16 NHWC output, Cout % 128 == 0, at least two items per SM
 // (smaller layers are a single wave either way and keep the one-tile-per-CTA kernel, whose 96 KB let neighbours overlap).
 bool gemm_persist_ok(int kind, int B, int H, int W, int C1, int C2, int Cout, int G, bool stats, bool wps) {
-    if (getenv("DD_NO_PERSIST_GEMM") || kind != DD_TC_CONV1x1 || C2 != 0 || C1 % 64 || Cout % 128) return false;
+    if (getenv("DD_NO_PERSIST_GEMM") || kind != DD_TC_CONV1x1 || C2 != 0 || C1 % 64 || Cout % 128 || Cout > GS_MAX_COUT) return false;
     const int64_t M = (int64_t)B * H * W;
     const int64_t items = ((M + 127) / 128) * (Cout / 128);
     if (items < 2 * num_sms()) return false;
