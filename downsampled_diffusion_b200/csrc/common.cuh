@@ -35,7 +35,8 @@ __device__ __forceinline__ float mish_f(float x) {
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mish_fast(float x) {
-    const float e = ex2_ftz(fminf(x, 20.f) * 1.4426950408889634f);
+    // no clamp: for large x, e (and n) overflow to +inf, rcp(inf) = +0 and the result is x; for very negative x, e flushes to 0
+    const float e = ex2_ftz(x * 1.4426950408889634f);
     const float n = e * (e + 2.f);
     return x * fmaf(-2.f, rcp_ftz(n + 2.f), 1.f);
 }

@@ -1157,19 +1157,19 @@ extern "C" int dd_conv_tc_tile_n(int kind, int B, int H, int W, int Cout, int fl
     return tc_geometry(kind, B, H, W, Cout, flags, 0).bn;
 }
 
-// Workspace of dd_conv_tc_gn for this layer in floats (0: none needed): per-(image, group) {sum, sum of squares} followed by
-// per-(image, 128-channel tile) arrival counters; must be ALL ZERO when the launch starts.
+// Workspace of dd_conv_tc_gn for this layer in floats (0: none needed): one 16-byte packet {sum, flag, sum of squares, flag} per
+// (image, 128-channel tile, pixel tile, group of the channel tile); must be ALL ZERO when the launch starts.
 extern "C" int64_t dd_conv_tc_gn_ws_floats(int kind, int B, int H, int W, int Cout, int G) {
     if (kind != DD_TC_CONV3x3 || !is_pow2(H) || !is_pow2(W) || B <= 0 || G <= 0 || Cout % G || getenv("DD_NO_GN_FUSE")) return 0;
     const TcGeom g = tc_geometry(kind, B, H, W, Cout, 0, 0);
     if (!(g.halo && halo_persist_ok(kind, H, W, Cout, G))) return 0;
-    const int64_t n = (int64_t)B * G * 2 + (int64_t)B * (Cout / 128);
-    return (n + 3) / 4 * 4;
+    const int64_t tpi = (int64_t)(H / HALO_TH) * (W / HALO_TW), groups_per_tile = 128 / (Cout / G);
+    return (int64_t)B * (Cout / 128) * tpi * groups_per_tile * 4;
 }
 
 // `parts` dimension of dd_conv_tc_gn's ln_part output for this layer
 extern "C" int dd_conv_tc_gn_ln_parts(int kind, int B, int H, int W, int Cout, int G, int persistent) {
-    if (persistent) return dd_conv_tc_gn_ws_floats(kind, B, H, W, Cout, G) > 0 ? 2 * (Cout / 128) : 0;
+    if (persistent) return dd_conv_tc_gn_ws_floats(kind, B, H, W, Cout, G) > 0 ? halo_persist_col_split() * (Cout / 128) : 0;
     if (dd_conv_tc_gn_cluster(kind, B, H, W, Cout, G) <= 0) return 0;
     return Cout / tc_geometry(kind, B, H, W, Cout, 0, 0).bn;
 }

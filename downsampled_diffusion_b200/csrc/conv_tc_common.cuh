@@ -83,6 +83,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread up to a system-dependent time limit: useless for polling two barriers)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
@@ -204,6 +214,18 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+// two 16-column loads in flight, one wait -- a single asm statement, so no use of the results can be scheduled before the wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t t0, uint32_t t1, uint32_t (&r)[16], uint32_t (&s)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8]),
+          "=r"(s[9]), "=r"(s[10]), "=r"(s[11]), "=r"(s[12]), "=r"(s[13]), "=r"(s[14]), "=r"(s[15])
+        : "r"(t0), "r"(t1) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -212,10 +234,10 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 #define DD_TC_TIMELINE 0          // build with -DDD_TC_TIMELINE=1 to record per-CTA clock64 stamps (scripts/timeline.py)
 #endif
 __device__ __forceinline__ void tstamp(const TcParams& p, int slot) {
-    if (DD_TC_TIMELINE && p.dbg) p.dbg[((int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z))) * 16 + slot] = clock64();
+    if (DD_TC_TIMELINE && p.dbg) p.dbg[((int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z))) * 32 + slot] = clock64();
 }
 __device__ __forceinline__ void tstore(const TcParams& p, int slot, long long v) {
-    if (DD_TC_TIMELINE && p.dbg) p.dbg[((int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z))) * 16 + slot] = v;
+    if (DD_TC_TIMELINE && p.dbg) p.dbg[((int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z))) * 32 + slot] = v;
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 
@@ -346,6 +368,7 @@ static void launch_cluster_pdl(void (*kernel)(KArgs...), int cluster_x, dim3 gri
 // persistent halo convolution with the fused GroupNorm epilogue (conv_tc_persist.cu)
 bool halo_persist_ok(int kind, int H, int W, int Cout, int G);
 int launch_halo_persist(const TcParams& p, cudaStream_t st);
+int halo_persist_col_split();          // ln_part blocks per 128-channel tile written by the persistent halo kernel
 bool gemm_persist_ok(int kind, int B, int H, int W, int C1, int C2, int Cout, int G, bool stats, bool wps);
 int launch_gemm_persist(TcParams& p, const void* x, int x_pitch, int C1, cudaStream_t st);
 

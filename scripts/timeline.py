@@ -9,7 +9,7 @@ m = tc.build_model(dict(tc.C3, precision="bf16"), dd, "dddpm_ae", device="cuda:0
 plan = m.sampling_plan((64, 8, 32, 32)); plan.prepare()
 eng = plan.eng
 idx = [i for i, n in enumerate(eng.op_names) if n == "dd_conv_tc"]
-buf = torch.zeros(4096 * 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(4096 * 32, dtype=torch.int64, device=dev)
 names = ["start", "prologue", "pdl_wait", "first_data", "last_mma", "acc_ready", "epi_done"]
 for which in [int(a) for a in sys.argv[1:]] or (2, 16, 23):          # 3x3@32 (halo), 3x3@8 (8x8 halo form), 3x3@4 (split-K)
     op = eng.ops[idx[which]]
@@ -20,7 +20,7 @@ for which in [int(a) for a in sys.argv[1:]] or (2, 16, 23):          # 3x3@32 (h
     op()
     torch.cuda.synchronize()
     L.lib().dd_debug_set_timeline(None)
-    t = buf.cpu().numpy().reshape(-1, 16)
+    t = buf.cpu().numpy().reshape(-1, 32)
     t = t[t[:, 0] > 0]
     if (t[:, 11] > 0).any() and (t[:, 10] > 0).any() and (t[:, 13] > 0).any() and not (t[:, 1] > 0).any() and (t[:, 7] > 0).any() and (t[:, 12] >= 0).all() and (t[:, 10] > t[:, 13]).all():
         # persistent GEMM: 5 / 6 = item 0 accumulator ready / stored, 11 = item 1 parameters staged, 13 / 10 = item 1 ready / stored, 12 / 14 = last item
@@ -36,6 +36,10 @@ for which in [int(a) for a in sys.argv[1:]] or (2, 16, 23):          # 3x3@32 (h
         print("   start->pdl %d, pdl->first data %d, item0 MMA issue span %d, item0 MMAs issued->acc ready %d" % (d(2, 0), d(3, 2), d(4, 3), d(5, 4)))
         print("   item0 epilogue: drain %d, stats+atomics %d, wait for the image %d, normalise+store %d" % (d(10, 5), d(11, 10), d(12, 11), d(6, 12)))
         print("   item0 end -> item1 acc ready %d; first data -> last item's MMAs issued %d; -> last item's epilogue done %d" % (d(13, 6), d(7, 3), d(14, 3)))
+        if (t[:, 16] > 0).any():
+            print("   statistics warp, item0, from the accumulator being ready: partial sums of all epilogue warps in %d, packet stored %d, all packets of the image seen %d, scale / shift staged + epilogue released %d" % (d(16, 5), d(17, 5), d(18, 5), d(19, 5)))
+        med = lambda c: int(np.median(t[:, c]))
+        print("   whole CTA: MMA warp waited %d clk for halos, %d for weight tiles, %d for a free accumulator; epilogue waited %d for accumulators" % (med(1), med(8), med(9), med(15)))
         continue
     t0 = t[:, 0].min()
     rel = t[:, :7] - t[:, [0]]
