@@ -18,6 +18,23 @@
 
 namespace dd {
 
+// Two MMA issuers (conv_tc_kernel<..., MW = 2>) leave two partial accumulators, 128 TMEM columns apart: every epilogue warp folds
+// the second into the first for its own 32 lanes before the epilogue proper reads it (tcgen05.ld x2, add, tcgen05.st).
+__device__ __forceinline__ void tc_fold_partials(const TcParams& p, uint32_t tmem_base, int warp) {
+    if (p.mma_parts < 2) return;
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c = 0; c < p.bn; c += 16) {
+        uint32_t a[16], b[16];
+        tmem_ld16x2(trow + (uint32_t)c, trow + (uint32_t)(TC_TMEM_COLS + c), a, b);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(b[j]));
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                     ::"r"(trow + (uint32_t)c), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]),
+                       "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // ---- epilogue shared by every pipeline variant: 4 warps, TMEM lane quadrant = warp % 4 ----
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, uint32_t tmem_full_bar, float* s_bias,
                                             int m_tile, int n_tile, int phase, int w0, int h0, int n0, int warp, int lane) {
@@ -43,6 +60,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
     mbar_wait(tmem_full_bar, 0);
     if (et == 0) tstamp(p, 5);
     tc_fence_after();
+    tc_fold_partials(p, tmem_base, warp);
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 
     const bool finisher = true;
@@ -166,6 +184,7 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcParams& p, uint32_t t
     mbar_wait(tmem_full_bar, 0);
     if (et == 0) tstamp(p, 5);
     tc_fence_after();
+    tc_fold_partials(p, tmem_base, warp);
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     float s8[16], q8[16];
 #pragma unroll
@@ -353,6 +372,7 @@ __device__ __forceinline__ GnRegs tc_epi_gn_part1(const TcParams& p, uint32_t tm
     mbar_wait(tmem_full_bar, 0);
     if (et == 0) tstamp(p, 5);
     tc_fence_after();
+    tc_fold_partials(p, tmem_base, warp);
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     float s8[16], q8[16];
 #pragma unroll
@@ -563,6 +583,7 @@ __device__ __forceinline__ void tc_epilogue_partial(const TcParams& p, uint32_t 
     float* dst = p.splitk_ws + (((int64_t)split * p.B * p.H * p.W + pix) * p.Cout + n_tile * p.bn);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    tc_fold_partials(p, tmem_base, warp);
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t a0[32], a1[32];
     tmem_ld32_issue(trow, a0);
@@ -592,8 +613,11 @@ __device__ __forceinline__ void tc_epilogue_partial(const TcParams& p, uint32_t 
 // stage, see profiles/README.md).  Warp roles: 0 = A-operand TMA producer, 6 = B-operand TMA producer,
 // 1 = MMA issuer + TMEM owner, 2..5 = epilogue.
 // ---------------------------------------------------------------------------------------------
-template <int TC_STAGES, int BROWS, int KCH, int EPI>      // EPI: 0 staged bf16, 1 legacy (fp32 NCHW / narrow), 2 split-K partial
-__global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ TcParams p) {
+// MW = 2 (the one-CTA-per-SM forms): a second MMA issuer (warp 7) takes half of the K = 16 slices of every stage into its own
+// accumulator -- ONE issuing warp needs ~430 clk of instruction latency per barrier wait + four MMAs, whatever the operand rings do
+// (433 clk per k-block measured on the 8x8 layers against 192 clk of tensor-pipe work; profiles/README.md, round 2 passes p - z).
+template <int TC_STAGES, int BROWS, int KCH, int EPI, int MW = 1>      // EPI: 0 staged bf16, 1 legacy (fp32 NCHW / narrow), 2 split-K partial
+__global__ void __launch_bounds__(TC_THREADS + 32 * (MW - 1), (TC_STAGES * KCH <= 3 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ TcParams p) {
     constexpr int CH = 64;                               // channels per 128-byte operand row (bf16)
     constexpr int B_SLOT = BROWS * TC_BK * 2;
     constexpr int TC_STAGE_BYTES = KCH * (TC_A_BYTES + B_SLOT);
@@ -621,13 +645,13 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA0)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB)) : "memory");
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), MW); }
+        mbar_init(tmem_full_bar, MW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(TC_TMEM_COLS * MW) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -693,16 +717,20 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
             sB += TC_STAGE_BYTES;
             if (++st == TC_STAGES) { st = 0; ++round; sB = base + KCH * TC_A_BYTES; }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: whole warp loops, one elected lane issues tcgen05.mma / commit =====
-        // instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128
+    } else if (warp == 1 || (MW == 2 && warp == 7)) {
+        // ===== MMA issuer(s): whole warp loops, one elected lane issues tcgen05.mma / commit =====
+        // instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128.  Issuer mw takes the K = 16 slices
+        // [mw * KK_N, (mw + 1) * KK_N) of every stage into accumulator mw (every issuer waits on every stage: all barrier phases seen).
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        constexpr int KK_N = (TC_BK / 16) / MW;
+        const int mw = warp == 1 ? 0 : 1;
+        const uint32_t dcol = tmem_base + (uint32_t)(mw * TC_TMEM_COLS);
         uint32_t sA = base;
         int st = 0;
         uint32_t par = 0;
         for (int i = 0; i < num_st; ++i) {
             mbar_wait(full_bar(st), par);
-            if (i == 0 && lane == 0) tstamp(p, 3);
+            if (mw == 0 && i == 0 && lane == 0) tstamp(p, 3);
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -710,19 +738,19 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
                     const uint64_t ad = umma_desc(sA + j * TC_A_BYTES);
                     const uint64_t bd = umma_desc(sA + KCH * TC_A_BYTES + j * B_SLOT);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k)
-                        umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | j | k) ? 1u : 0u);
+                    for (int k = 0; k < KK_N; ++k)
+                        umma_f16(dcol, ad + (uint64_t)(2 * (mw * KK_N + k)), bd + (uint64_t)(2 * (mw * KK_N + k)), idesc, (i | j | k) ? 1u : 0u);
                 }
-                umma_commit(empty_bar(st));          // frees this smem stage when the MMAs retire
+                umma_commit(empty_bar(st));          // frees this smem stage when the MMAs (of both issuers) retire
             }
             __syncwarp();
             sA += TC_STAGE_BYTES;
             if (++st == TC_STAGES) { st = 0; par ^= 1u; sA = base; }
         }
-        if (lane == 0) tstamp(p, 4);
-        if (elect_one()) umma_commit(tmem_full_bar);             // accumulator complete
+        if (mw == 0 && lane == 0) tstamp(p, 4);
+        if (elect_one()) umma_commit(tmem_full_bar);             // this issuer's accumulator complete
         __syncwarp();
-    } else {
+    } else if (warp >= 2 && warp < 6) {
         if constexpr (EPI == 1)         // fp32 NCHW output / tiles narrower than 32 channels (the final 1x1 conv)
             tc_epilogue(p, tmem_base, tmem_full_bar, s_bias, m_tile, n_tile, phase, w0, h0, n0, warp, lane);
         else if constexpr (EPI == 2)
@@ -749,7 +777,7 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_STAGES * KCH <= 3 ? 2 : 1)) co
     else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS * MW) : "memory");
     }
 }
 
@@ -1196,6 +1224,11 @@ static int conv_tc_impl(int kind, const void* x, int x_pitch, const void* x2, in
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, 64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(4, 64, 2));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 1));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<6, 128, 1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(6, 128, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64, 1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 128, 2, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(3, 128, 2));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, 64, 2, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(4, 64, 2));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8, 64, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8, 64, 1));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM);
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DD_ERR_CUDA; }
         attr_done = true;
@@ -1348,7 +1381,12 @@ static int conv_tc_impl(int kind, const void* x, int x_pitch, const void* x2, in
         if (rc) return rc;
         return launch_gemm_persist(p, x, x_pitch, C1, st);
     }
-    if (p.splits > 1)
+    static const bool one_issuer = getenv("DD_TC_ONE_ISSUER") != nullptr;
+    const dim3 blk2(TC_THREADS + 32);
+    if (!one_issuer && !(out_nchw_f32 || p.bn < 32) && !cta_pair && !halo && (p.splits > 1 || ctas <= num_sms())) p.mma_parts = 2;
+    if (p.splits > 1 && p.mma_parts == 2)
+        launch_pdl(conv_tc_kernel<8, 64, 1, 2, 2>, dim3(grid), blk2, tc_smem_bytes(8, 64, 1), st, p);
+    else if (p.splits > 1)
         launch_pdl(conv_tc_kernel<8, 64, 1, 2>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
     else if (out_nchw_f32 || p.bn < 32)
         launch_pdl(conv_tc_kernel<3, 128, 1, 1>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
@@ -1358,6 +1396,12 @@ static int conv_tc_impl(int kind, const void* x, int x_pitch, const void* x2, in
         launch_cluster_pdl(conv_tc_halo_kernel, cl_x, dim3(grid), dim3(TC_THREADS), HALO_SMEM, st, p);
     else if (ctas > num_sms())      // more than one wave: two CTAs per SM so epilogues overlap main loops
         launch_cluster_pdl(conv_tc_kernel<3, 128, 1, 0>, cl_x, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
+    else if (p.mma_parts == 2) {           // at most one wave, one CTA per SM: two MMA issuers
+        if (p.bn <= 64 && pair) launch_cluster_pdl(conv_tc_kernel<4, 64, 2, 0, 2>, cl_x, dim3(grid), blk2, tc_smem_bytes(4, 64, 2), st, p);
+        else if (p.bn <= 64) launch_cluster_pdl(conv_tc_kernel<8, 64, 1, 0, 2>, cl_x, dim3(grid), blk2, tc_smem_bytes(8, 64, 1), st, p);
+        else if (pair) launch_cluster_pdl(conv_tc_kernel<3, 128, 2, 0, 2>, cl_x, dim3(grid), blk2, tc_smem_bytes(3, 128, 2), st, p);
+        else launch_cluster_pdl(conv_tc_kernel<6, 128, 1, 0, 2>, cl_x, dim3(grid), blk2, tc_smem_bytes(6, 128, 1), st, p);
+    }
     else if (p.bn <= 64 && pair)
         launch_cluster_pdl(conv_tc_kernel<4, 64, 2, 0>, cl_x, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(4, 64, 2), st, p);
     else if (p.bn <= 64)

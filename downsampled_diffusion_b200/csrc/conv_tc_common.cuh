@@ -36,6 +36,7 @@ struct TcParams {
     int tw_sh, th_sh;           // log2(tw), log2(th): tile geometry is all powers of two
     int rows_valid;             // tw*th*tn (< 128 when one image has fewer than 128 pixels and tn is forced to 1)
     int pair_nt;                // CTA-pair halo kernel: 128-column accumulator blocks per CTA (N of the pair's MMA = bn * pair_nt)
+    int mma_parts;              // partial accumulators left by the MMA issuers (1, or 2: the epilogue folds them, tc_fold_partials)
     int w_per_sample;           // weights are (B, rows, K): every image multiplies its own matrix (fused attention output)
     int splits, kb_per_split;   // split-K over the (tap, chunk) loop; partial sums meet in splitk_ws
     void* out;
