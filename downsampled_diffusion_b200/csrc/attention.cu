@@ -21,8 +21,19 @@ constexpr int LM_SLAB = 32;              // rows per warp slab
 constexpr int LM_PITCH = 40;             // bf16 elements per smem row (80 B: conflict-free ldmatrix)
 constexpr int LM_ROWS = 8 * LM_SLAB;     // rows per CTA iteration
 
-__host__ __device__ inline int lm_chunk(int n) {           // rows per split: >= 256, at most 16 splits
-    int c = (n + 15) / 16;
+// rows per split: a multiple of 256, at least 256, at most 16 splits; the number of splits aims at `target` CTAs in all
+// (every split pays an eight-warp merge, a workspace round trip and a ticket: with 256 (b, head) pairs four splits of a 32x32 map
+// were 1024 CTAs of ONE 32-row slab per warp -- profiles/README.md, round 2)
+inline int lm_target_ctas() {
+    static int t = -1;
+    if (t < 0) { const char* e = getenv("DD_LM_TARGET_CTAS"); t = e ? atoi(e) : 148; if (t < 1) t = 1; }
+    return t;
+}
+inline int lm_chunk(int n, int bh) {
+    int S = (lm_target_ctas() + bh - 1) / bh;
+    if (S > 16) S = 16;
+    if (S < 1) S = 1;
+    int c = (n + S - 1) / S;
     c = (c + LM_ROWS - 1) / LM_ROWS * LM_ROWS;
     return c < LM_ROWS ? LM_ROWS : c;
 }
@@ -355,7 +366,7 @@ int dd_debug_set_attn_timeline(long long* buf) {
 }
 
 int64_t dd_linattn_mix_ws_floats(int B, int n, int heads) {
-    const int chunk = lm_chunk(n);
+    const int chunk = lm_chunk(n, B * heads);
     return (int64_t)B * heads * ((n + chunk - 1) / chunk) * LA_WS + (int64_t)B * heads;
 }
 
@@ -364,7 +375,7 @@ int dd_linattn_mix(const void* qkv, int dtype, int B, int n, int heads, int dh, 
     DD_REQUIRE(dtype == DD_BF16, "linattn_mix: bf16 tensor-core path only (dtype %d)", dtype);
     DD_REQUIRE(dh == 32 && heads > 0 && n > 0, "linattn_mix: dim_head must be 32 (got %d)", dh);
     DD_REQUIRE(C > 0 && C % 16 == 0, "linattn_mix: C=%d must be a multiple of 16", C);
-    const int chunk = lm_chunk(n);
+    const int chunk = lm_chunk(n, B * heads);
     const int S = (n + chunk - 1) / chunk;
     DD_REQUIRE(ws != nullptr && ws_floats >= dd_linattn_mix_ws_floats(B, n, heads), "linattn_mix: workspace too small");
     int* tickets = reinterpret_cast<int*>(ws + (int64_t)B * heads * S * LA_WS);
