@@ -659,7 +659,9 @@ __global__ void __launch_bounds__(TC_THREADS + 32 * (MW - 1), (TC_STAGES * KCH <
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
     if (threadIdx.x == 0) tstamp(p, 1);
-    pdl_sync();      // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+    // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail; the weight producer (warp 6)
+    // runs on: packed weights do not depend on the preceding launch (per-sample matrices do: it waits below)
+    if (warp != 6) pdl_sync();
     if (threadIdx.x == 0) tstamp(p, 2);
     GnRegs gnr;
 
@@ -697,6 +699,7 @@ __global__ void __launch_bounds__(TC_THREADS + 32 * (MW - 1), (TC_STAGES * KCH <
         // ===== B-operand (weights) producer =====
         const uint32_t tx = (uint32_t)KCH * p.bn * TC_BK * 2;
         const int wps = p.w_per_sample;
+        if (wps) pdl_sync();
         const int brow = wps ? n_tile * p.bn : phase * p.rows_per_phase + n_tile * p.bn;
         int kcoord = kb0 * CH;
         uint32_t sB = base + KCH * TC_A_BYTES;

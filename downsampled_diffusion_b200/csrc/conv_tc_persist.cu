@@ -43,15 +43,6 @@ __device__ __forceinline__ void ph_stats_bar_sync(int par) {
     if (par) asm volatile("bar.sync 3, %0;" ::"n"(32 * PH_EW + 32) : "memory");
     else asm volatile("bar.sync 2, %0;" ::"n"(32 * PH_EW + 32) : "memory");
 }
-#ifndef DD_PS_EXP_NOMISH
-#define DD_PS_EXP_NOMISH 0
-#endif
-#ifndef DD_PS_EXP_NOPARAM
-#define DD_PS_EXP_NOPARAM 0
-#endif
-#ifndef DD_PS_EXP_NOSTORE
-#define DD_PS_EXP_NOSTORE 0
-#endif
 #if DD_TC_TIMELINE
 #define TL_WAIT(acc, stmt) do { const long long t_ = clock64(); stmt; acc += clock64() - t_; } while (0)
 #else
@@ -160,8 +151,10 @@ __global__ void __launch_bounds__(PH_THREADS, 1) conv_tc_halo_persist_kernel(con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
     if (threadIdx.x == 0) tstamp(p, 0);
-    pdl_sync();
-    if (threadIdx.x == 0) tstamp(p, 2);
+    // the weight-tile producer runs ahead: the packed weights do not depend on the preceding launch, so its first stages are
+    // requested while the grid dependency is still pending (144 KB of the ~170 KB a CTA loads before its first MMA)
+    if (warp != PH_WARP_B) pdl_sync();
+    if (threadIdx.x == 32) tstamp(p, 2);
 
     if (warp == PH_WARP_B) {
         // ===== TMA producer: one (18 x 10)-pixel halo box per 64-channel chunk, three 128 x 64 weight tiles per (chunk, filter row);
@@ -188,9 +181,7 @@ __global__ void __launch_bounds__(PH_THREADS, 1) conv_tc_halo_persist_kernel(con
             __syncwarp();
             if (++hs == PS_NH) { hs = 0; ++hround; }
         };
-        if (total_chunks > 0) request_halo(0);
-        for (int g = 0; g < total_chunks; ++g) {
-            if (g + 1 < total_chunks) request_halo(g + 1);
+        auto weight_stages = [&](int g) {
             const int c = g % nchunks;
             const int brow = ps_decode(p, blockIdx.x + (g / nchunks) * gridDim.x).n_tile * 128;
             int kcoord = c * 64;
@@ -209,6 +200,14 @@ __global__ void __launch_bounds__(PH_THREADS, 1) conv_tc_halo_persist_kernel(con
                 sB += PS_ROW_BYTES;
                 if (++bs == PS_NB) { bs = 0; ++bround; sB = bbase; }
             }
+        };
+        static_assert(PS_NB >= 3, "the first chunk's three weight stages are requested before the grid dependency resolves");
+        if (total_chunks > 0) weight_stages(0);
+        pdl_sync();
+        if (total_chunks > 0) request_halo(0);
+        for (int g = 0; g < total_chunks; ++g) {
+            if (g + 1 < total_chunks) request_halo(g + 1);
+            if (g > 0) weight_stages(g);
         }
     } else if (warp >= PH_WARP_MMA && warp < PH_WARP_MMA + PS_MMA_WARPS) {
         // ===== MMA issuers: item k accumulates into TMEM buffer k & 1; issuer w takes its share of the K = 16 slices of every
@@ -423,46 +422,54 @@ __global__ void __launch_bounds__(PH_THREADS, 1) conv_tc_halo_persist_kernel(con
             float ls = 0.f, lq = 0.f;
             const bool want_ln = p.ln_part != nullptr;
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase + c0;
+            // The per-channel parameters come from shared memory while the tensor pipe is reading its operands from it at full rate:
+            // an LDS then takes hundreds of clocks.  They are requested one sub-block of four channels AHEAD of their use
+            // (volatile loads keep their place in the instruction stream); without this the parameter reads were 2.8 k of the
+            // 6.3 k clk this phase takes per tile (profiles/README.md, round 2 passes x - ae).
+            const uint32_t ss_a = smem_u32(ssp), tb_a = smem_u32(tbs);
+            constexpr int PSUB = 2;                                       // channel pairs per sub-block (registers: 2 x PSUB x 6)
+            float4 ssv[2][PSUB];
+            float2 tbv[2][PSUB];
+            auto ldp = [&](const int buf, const int cl0) {
 #pragma unroll
-            for (int qd = 0; qd < NQ; ++qd) {
-                if (resp && qd < NQ - 1) ldg_v8(resp + 16 * (qd + 1), res[(qd + 1) & 1]);
+                for (int j = 0; j < PSUB; ++j) {
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(ssv[buf][j].x), "=f"(ssv[buf][j].y), "=f"(ssv[buf][j].z), "=f"(ssv[buf][j].w) : "r"(ss_a + (uint32_t)((cl0 + 2 * j) * 8)));
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(tbv[buf][j].x), "=f"(tbv[buf][j].y) : "r"(tb_a + (uint32_t)((cl0 + 2 * j) * 4)));
+                }
+            };
+            ldp(0, 0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int cl = 16 * qd + 2 * j;                        // static
-#if DD_PS_EXP_NOPARAM                // timing experiment only: no shared-memory reads in the inner loop
-                    const float4 ss = make_float4(1.f, p.gn_eps, 1.f, p.gn_inv_n);
-                    const float2 tb = make_float2(p.gn_eps, p.gn_inv_n);
-#else
-                    const float4 ss = *reinterpret_cast<const float4*>(ssp + cl);      // {scale, shift} of channels cl, cl + 1
-                    const float2 tb = *reinterpret_cast<const float2*>(tbs + cl);
-#endif
-                    const uint32_t rw = row[8 * qd + j];
+            for (int sub = 0; sub < PH_CW / (2 * PSUB); ++sub) {
+                constexpr int SPQ = 8 / PSUB;                             // sub-blocks per 16-channel store
+                const int qd = sub / SPQ;
+                if (sub % SPQ == 0 && resp && qd < NQ - 1) ldg_v8(resp + 16 * (qd + 1), res[(qd + 1) & 1]);
+                if (sub + 1 < PH_CW / (2 * PSUB)) ldp((sub + 1) & 1, 2 * PSUB * (sub + 1));
+#pragma unroll
+                for (int j = 0; j < PSUB; ++j) {
+                    const int pj = PSUB * sub + j;                        // pair index within the thread's channels (static)
+                    const float4 ss = ssv[sub & 1][j];                    // {scale, shift} of channels 2 pj, 2 pj + 1
+                    const float2 tb = tbv[sub & 1][j];
+                    const uint32_t rw = row[pj];
                     const float x0 = __uint_as_float(rw << 16), x1 = __uint_as_float(rw & 0xffff0000u);
-#if DD_PS_EXP_NOMISH                 // timing experiment only (wrong results): what the activation's two MUFU per value cost
-                    float y0 = fmaf(x0, ss.x, ss.y) + tb.x;
-                    float y1 = fmaf(x1, ss.z, ss.w) + tb.y;
-#else
                     float y0 = mish_fast(fmaf(x0, ss.x, ss.y)) + tb.x;
                     float y1 = mish_fast(fmaf(x1, ss.z, ss.w)) + tb.y;
-#endif
                     if (resp) {
-                        const uint32_t rr = res[qd & 1][j];
+                        const uint32_t rr = res[qd & 1][pj & 7];
                         y0 += __uint_as_float(rr << 16); y1 += __uint_as_float(rr & 0xffff0000u);
                     }
                     __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
                     const uint32_t hv = *reinterpret_cast<uint32_t*>(&h);
-                    row[8 * qd + j] = hv;
+                    row[pj] = hv;
                     if (want_ln) {
                         const float z0 = __uint_as_float(hv << 16), z1 = __uint_as_float(hv & 0xffff0000u);
                         ls += z0 + z1; lq = fmaf(z0, z0, fmaf(z1, z1, lq));
                     }
                 }
-#if DD_PS_EXP_NOSTORE                // timing experiment only: the output stores
-                if (row[8 * qd] == 0x12345678u)
-#endif
-                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                             ::"l"(op + 16 * qd), "r"(row[8 * qd]), "r"(row[8 * qd + 1]), "r"(row[8 * qd + 2]), "r"(row[8 * qd + 3]),
-                               "r"(row[8 * qd + 4]), "r"(row[8 * qd + 5]), "r"(row[8 * qd + 6]), "r"(row[8 * qd + 7]) : "memory");
+                if (sub % SPQ == SPQ - 1)
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                                 ::"l"(op + 16 * qd), "r"(row[8 * qd]), "r"(row[8 * qd + 1]), "r"(row[8 * qd + 2]), "r"(row[8 * qd + 3]),
+                                   "r"(row[8 * qd + 4]), "r"(row[8 * qd + 5]), "r"(row[8 * qd + 6]), "r"(row[8 * qd + 7]) : "memory");
             }
             if (want_ln) *reinterpret_cast<float2*>(p.ln_part + (pix * (PH_CS * ntn) + (PH_CS * im.n_tile + csel)) * 2) = make_float2(ls, lq);
             if (et == 0) tstamp(p, k == 0 ? 6 : 14);
@@ -611,28 +618,58 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
     if (threadIdx.x == 0) tstamp(p, 0);
-    pdl_sync();
-    if (threadIdx.x == 0) tstamp(p, 2);
+    if (warp != 0) pdl_sync();            // the producer requests the weight halves of its first stages before the dependency resolves
+    if (threadIdx.x == 32) tstamp(p, 2);
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        int st = 0, round = 0;
-        uint32_t sA = base;
-        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-            const int n_tile = it % ntn, m_tile = it / ntn;
-            const int img = p.w_per_sample ? (int)(((int64_t)m_tile << 7) / HW) : 0;
-            for (int kb = 0; kb < nkb; ++kb) {
-                if (round > 0) mbar_wait(empty(st), (round - 1) & 1);
-                if (elect_one()) {
-                    mbar_expect_tx(full(st), GS_STAGE_BYTES);
-                    tma_load_2d(&p.tmA0, full(st), sA, kb * 64, m_tile * 128);
-                    if (p.w_per_sample) tma_load_3d(&p.tmB, full(st), sA + TC_A_BYTES, kb * 64, n_tile * 128, img);
-                    else tma_load_2d(&p.tmB, full(st), sA + TC_A_BYTES, kb * 64, n_tile * 128);
-                }
-                __syncwarp();
-                sA += GS_STAGE_BYTES;
-                if (++st == GS_STAGES) { st = 0; ++round; sA = base; }
+        // ===== TMA producer: stage f = (item f / nkb of this CTA, k-block f % nkb) =====
+        const int my_items = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        const int total = my_items * nkb;
+        const int early = total < GS_STAGES ? total : GS_STAGES;
+        auto coords = [&](int f, int& kb, int& n_tile, int& m_tile, int& img) {
+            const int it = blockIdx.x + (f / nkb) * gridDim.x;
+            kb = f % nkb; n_tile = it % ntn; m_tile = it / ntn;
+            img = p.w_per_sample ? (int)(((int64_t)m_tile << 7) / HW) : 0;
+        };
+        auto load_b = [&](int f, uint32_t bar, uint32_t dst) {
+            int kb, n_tile, m_tile, img; coords(f, kb, n_tile, m_tile, img);
+            if (p.w_per_sample) tma_load_3d(&p.tmB, bar, dst + TC_A_BYTES, kb * 64, n_tile * 128, img);
+            else tma_load_2d(&p.tmB, bar, dst + TC_A_BYTES, kb * 64, n_tile * 128);
+        };
+        auto load_a = [&](int f, uint32_t bar, uint32_t dst) {
+            int kb, n_tile, m_tile, img; coords(f, kb, n_tile, m_tile, img);
+            tma_load_2d(&p.tmA0, bar, dst, kb * 64, m_tile * 128);
+        };
+        // the first ring of stages: weight halves before the grid dependency resolves (unless the weights are per-sample matrices
+        // the preceding launch wrote), activation halves after
+        const bool b_early = !p.w_per_sample;
+        for (int f = 0; f < early; ++f) {
+            if (elect_one()) {
+                mbar_expect_tx(full(f), GS_STAGE_BYTES);
+                if (b_early) load_b(f, full(f), base + f * GS_STAGE_BYTES);
             }
+            __syncwarp();
+        }
+        pdl_sync();
+        for (int f = 0; f < early; ++f) {
+            if (elect_one()) {
+                if (!b_early) load_b(f, full(f), base + f * GS_STAGE_BYTES);
+                load_a(f, full(f), base + f * GS_STAGE_BYTES);
+            }
+            __syncwarp();
+        }
+        int st = 0, round = 1;
+        uint32_t sA = base;
+        for (int f = early; f < total; ++f) {
+            mbar_wait(empty(st), (round - 1) & 1);
+            if (elect_one()) {
+                mbar_expect_tx(full(st), GS_STAGE_BYTES);
+                load_a(f, full(st), sA);
+                load_b(f, full(st), sA);
+            }
+            __syncwarp();
+            sA += GS_STAGE_BYTES;
+            if (++st == GS_STAGES) { st = 0; ++round; sA = base; }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
