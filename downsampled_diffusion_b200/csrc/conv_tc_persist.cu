@@ -3,20 +3,28 @@
 //
 // Why: with one tile per CTA (conv_tc_halo_kernel) the two CTAs of an SM run in lock step -- both in their main loop, then both
 // in their epilogue -- so the tensor pipe idles during every epilogue and the activation math (2 MUFU per element) is exposed
-// (profiles/README.md, round 2: 9.0 k clk main loop + 6.1 k clk epilogue per wave, 16 - 21 k clk with the fused normalisation).
-// Here ONE CTA per SM walks the work items (pixel tile x 128-channel tile) of the layer:
-//   warp 0      TMA producer: one (18 x 10)-pixel halo box per 64-channel chunk, one 128 x 64 weight tile per (chunk, tap);
-//               the rings (3 halos, 8 weight tiles = 198 KB in flight) run across item boundaries;
-//   warp 1      MMA issuer: tcgen05.mma M128 x N128 x K16 into one of TWO accumulators in TMEM (2 x 128 columns);
-//   warps 2..9  epilogue (8 warps: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4): drain the accumulator of item i
-//               into registers (64 channels of one pixel per thread, bf16) and hand the TMEM buffer back at once, so the MMAs of
-//               item i+1 run under the statistics exchange, the normalisation / Mish / residual math and the stores of item i.
-// GroupNorm statistics of an image span several items (8 at 32x32): every CTA adds its {sum, sum of squares} per (image, group)
-// to a zeroed fp32 workspace with red.global.add, then bumps a per-(image, N tile) arrival counter (release) and waits until all
-// tiles of the image have arrived (acquire).  Items of one image are consecutive and the grid is a multiple of the tiles per
-// image, so they are in flight on co-resident CTAs in the same round: the wait cannot deadlock (and is bounded: a protocol bug
-// traps instead of hanging the GPU).  Output: bf16 NHWC, 128 contiguous bytes per thread as four 32-byte stores; no staging in
-// shared memory at all.
+// (profiles/README.md, round 2).  Here ONE CTA per SM (20 warps) walks the work items (pixel tile x 128-channel tile) of the layer:
+//   warp 0       TMA producer: one (18 x 10)-pixel halo box per 64-channel chunk (requested a chunk ahead), one weight STAGE per
+//                (chunk, filter row) = three 128 x 64 tiles, 48 KB; rings of 3 halos + 3 stages (215 KB) run across item boundaries;
+//                the first three stages are requested BEFORE griddepcontrol.wait (weights never depend on the preceding launch);
+//   warps 1, 2   MMA issuers: twelve tcgen05.mma M128 x N128 x K16 per barrier wait into one of TWO accumulator buffers in TMEM.
+//                One issuer on short-K layers; from 256 input channels on two, each taking half of the K = 16 slices of every
+//                stage into its own accumulator (one warp needs ~430 clk of instruction latency per wait + elect + descriptor
+//                arithmetic + commit, whatever the rings do: four MMAs per wait ran the pipe at 111 clk per MMA instead of 64);
+//   warp 3       statistics warp (below);
+//   warps 4..19  epilogue (16 warps: TMEM lane quadrant = warp % 4, 32-channel block = (warp - 4) / 4): drain the accumulator(s) of
+//                item i into registers (32 channels of one pixel per thread, bf16) and hand the TMEM buffer back at once, so the MMAs
+//                of item i+1 run under the statistics exchange, the normalisation / Mish / residual math and the stores of item i.
+// GroupNorm statistics of an image span several items (8 at 32x32).  Every epilogue warp leaves its {sum, sum of squares} per
+// group in shared memory and arrives on a named barrier; the statistics warp adds them, publishes one 16-byte packet
+// {sum, 1, sum of squares, 1} per (image, channel tile, pixel tile, group) in a zeroed workspace (st.relaxed.gpu.v4: value and flag
+// travel in the same 8 bytes, so neither atomics nor fences are needed -- a gpu-scope release cost 2 - 9 k clk per item here),
+// polls the packets of the image's other tiles, computes {rstd * gamma, beta - mean * rstd * gamma, time bias} for the item's 128
+// channels into shared memory and releases the epilogue through an mbarrier.  Items of one image are consecutive and the grid is
+// a multiple of the tiles per image, so they are in flight on co-resident CTAs in the same round: the wait cannot deadlock (and
+// is bounded: a protocol bug traps instead of hanging the GPU).  The epilogue probes (test_wait) "next accumulator ready" against
+// "statistics of the previous item complete" and finishes the previous item first when it can, so nothing but the last item's own
+// epilogue is left behind the last MMA.  Output: bf16 NHWC, 64 contiguous bytes per thread as two 32-byte stores; no staging.
 #include "conv_tc_common.cuh"
 
 namespace dd {

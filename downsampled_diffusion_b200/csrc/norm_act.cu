@@ -138,7 +138,6 @@ __global__ void __launch_bounds__(256) gn_mish_sum_kernel(const float* __restric
                                                           const float* __restrict__ tbias, int tb_stride,
                                                           const int32_t* __restrict__ trow, int trow_stride,
                                                           const __nv_bfloat16* __restrict__ residual, float* __restrict__ ln_part) {
-    pdl_sync();
     extern __shared__ float4 s_x[];                        // this CTA's summed vectors: HW * (C/4) / gridDim.y
     __shared__ float s_stat[64][2];
     // grid (B, parts): a CTA owns C/parts channels (whole groups) of one image -- one CTA per image left the 4x4 layers with
@@ -146,9 +145,21 @@ __global__ void __launch_bounds__(256) gn_mish_sum_kernel(const float* __restric
     const int b = blockIdx.x, cv = C >> 2, cvp = cv / gridDim.y, nloc = HW * cvp;
     const int c4 = blockIdx.y * cvp + threadIdx.x % cvp, c = c4 * 4, cpg = C / G, g = c / cpg;
     if (threadIdx.x < 2 * G) (&s_stat[0][0])[threadIdx.x] = 0.f;
-    __syncthreads();
+    // Only the split-K partials come from the preceding launch: the parameters, the time bias (its row index was written at the end
+    // of the previous step) and the residual (an earlier launch's output) are fetched while the grid dependency is still pending.
     const float4* src = reinterpret_cast<const float4*>(part) + (int64_t)b * HW * cv;
     const float4 bi = bias ? __ldg(reinterpret_cast<const float4*>(bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4), be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 tb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tbias) {
+        const int row = trow ? trow[(int64_t)b * trow_stride] : b;
+        tb = __ldg(reinterpret_cast<const float4*>(tbias + (int64_t)row * tb_stride) + c4);
+    }
+    uint2 res0 = make_uint2(0u, 0u);                        // residual of the thread's first vector (the only one on the 4x4 maps)
+    if (residual && threadIdx.x < nloc)
+        res0 = *reinterpret_cast<const uint2*>(residual + ((int64_t)b * HW * cv + (threadIdx.x / cvp) * cv + c4) * 4);
+    __syncthreads();
+    pdl_sync();
     float sum = 0.f, sq = 0.f;
     for (int vl = threadIdx.x; vl < nloc; vl += 256) {
         const int v = (vl / cvp) * cv + c4;                 // vector index inside the image
@@ -172,12 +183,6 @@ __global__ void __launch_bounds__(256) gn_mish_sum_kernel(const float* __restric
     const float inv_n = 1.f / ((float)HW * (float)cpg);
     const float mean = s_stat[g][0] * inv_n;
     const float rstd = rsqrtf(fmaxf(s_stat[g][1] * inv_n - mean * mean, 0.f) + eps);
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4), be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
-    float4 tb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tbias) {
-        const int row = trow ? trow[(int64_t)b * trow_stride] : b;
-        tb = __ldg(reinterpret_cast<const float4*>(tbias + (int64_t)row * tb_stride) + c4);
-    }
     const float sc[4] = {ga.x * rstd, ga.y * rstd, ga.z * rstd, ga.w * rstd};
     const float sh[4] = {be.x - mean * sc[0], be.y - mean * sc[1], be.z - mean * sc[2], be.w - mean * sc[3]};
     const float tbv[4] = {tb.x, tb.y, tb.z, tb.w};
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(256) gn_mish_sum_kernel(const float* __restric
         for (int j = 0; j < 4; ++j) h[j] = mish_fast(fmaf(xin[j], sc[j], sh[j])) + tbv[j];
         const int64_t off = ((int64_t)b * HW * cv + v) * 4;
         if (residual) {
-            const uint2 rr = *reinterpret_cast<const uint2*>(residual + off);
+            const uint2 rr = vl == (int)threadIdx.x ? res0 : *reinterpret_cast<const uint2*>(residual + off);
             h[0] += __uint_as_float(rr.x << 16); h[1] += __uint_as_float(rr.x & 0xffff0000u);
             h[2] += __uint_as_float(rr.y << 16); h[3] += __uint_as_float(rr.y & 0xffff0000u);
         }

@@ -272,6 +272,13 @@ int dd_space_to_depth2(const void* x, void* y, int B, int H, int W, int C, void*
 /* DD_TC_STRIDED_IN (DD_TC_DOWN only): x is the plain NHWC input (B, 2H, 2W, C) instead of its four space-to-depth parity
  * planes; the kernel reads every other pixel through a stride-2 tensor map (TMA elementStrides), no copy. */
 #define DD_TC_STRIDED_IN 8
+/* Stream ordering of the PARAMETER operands (wp, bias, gamma / beta, wsum): the launches are chained by programmatic dependent
+ * launch, and the weight producer of dd_conv_tc / dd_conv_tc_gn / dd_conv_tc_ln requests its first tiles BEFORE the dependency on
+ * the preceding launch in the stream resolves (they never depend on it inside a step).  A caller that writes these buffers must
+ * therefore not make the writing kernel the IMMEDIATELY preceding launch in the same stream (any launch in between, an event or a
+ * synchronisation restores the order; the Python layer packs weights before the step's graph is launched).  Activations, residuals,
+ * statistics and DD_TC_W_PER_SAMPLE weight matrices are ordered as usual.  DD_NO_PDL=1 in the environment turns the programmatic
+ * launches (and with them this relaxation) off. */
 int dd_conv_tc_splits(int kind, int B, int H, int W, int Cin, int Cout);
 int dd_conv_tc(int kind, const void* x, int x_pitch, const void* x2, int C1, int C2,
                const void* wp, int w_rows, const float* bias, const void* residual,

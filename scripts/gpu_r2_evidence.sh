@@ -12,6 +12,7 @@ timeout 900 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$ta
 timeout 300 python scripts/step_n.py 64 3 > gpurun_out/plain_$tag.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$tag.csv python scripts/step_n.py 64 3 > gpurun_out/ncu_list_$tag.log 2>&1
 python scripts/ncu_list.py gpurun_out/launches_$tag.csv x > gpurun_out/launches_${tag}_summary.txt 2>&1; head -24 gpurun_out/launches_${tag}_summary.txt
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:conv_tc --csv --log-file gpurun_out/conv_dram_$tag.csv python scripts/step_n.py 64 2 > gpurun_out/ncu_dram_$tag.log 2>&1; echo "dram exit $?"
 # one full capture per kernel class of the sampling step: "<regex>:<skip>:<name>"
 # (-k matches the base name only: the skip counts pick the template instance / layer, see profiles/launches_*_summary.txt)
 for spec in "conv_tc_halo_persist_kernel:1:persist32" "conv_tc_halo_persist_kernel:4:persist16" "conv_tc_halo_persist_kernel:7:persist_2src" \
