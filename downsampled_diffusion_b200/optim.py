@@ -25,7 +25,14 @@ class Adam(torch.optim.Optimizer):
     """Adam(lr, betas, eps) with optional fused gradient clipping (`max_grad_norm`) and EMA (`attach_ema`).
 
     Same update as torch.optim.Adam (no weight decay / amsgrad -- the reference uses neither).  All parameters must be
-    contiguous fp32 CUDA tensors; anything else raises (no CPU fallback)."""
+    contiguous fp32 CUDA tensors; anything else raises (no CPU fallback).
+
+    Differences from `clip_grad_norm_` + `torch.optim.Adam` a caller can observe (none matters to the reference's loop):
+      * the clip coefficient is applied inside the fused pass: `p.grad` itself is NOT scaled, so with `zero_grad=False` the
+        gradients left behind are the unclipped ones;
+      * the step count is kept per parameter GROUP: a parameter whose first gradient arrives in a later step gets the bias
+        correction of the group's step count, not of its own first step (torch counts per parameter);
+      * `opt.grad_norm` is a view of a device buffer that the next `step()` overwrites -- clone it to keep a value."""
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, max_grad_norm: Optional[float] = None):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
