@@ -323,6 +323,33 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict_
     }
 }
 
+// C = 8 (the dDDPM latent): output vector g of a pixel is exactly tap g's eight channels (k = 8 g + c), so a thread gathers its
+// 16 bytes straight from the eight NCHW planes (2 MB input: L2-resident, reads coalesced along w) -- no shared memory, no barrier,
+// one 16-byte store per thread, consecutive threads consecutive vectors.  Columns 72 .. kpad-1 are written as zeros.
+__global__ void __launch_bounds__(256) im2col3x3_c8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int H, int W, int kpad,
+                                                           int64_t total_vec) {
+    pdl_sync();
+    const int groups = kpad >> 3, HW = H * W;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(v % groups);
+        const int64_t pixg = v / groups;                    // b * HW + h * W + w
+        const int w = (int)(pixg % W), h = (int)((pixg / W) % H);
+        const int64_t b = pixg / HW;
+        Vec<__nv_bfloat16> o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
+        if (g < 9) {
+            const int hh = h + g / 3 - 1, ww = w + g % 3 - 1;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                const float* src = x + (b * 8) * HW + hh * W + ww;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o.v[c] = __ldg(src + (int64_t)c * HW);
+            }
+        }
+        o.store(y + v * 8);
+    }
+}
+
 template <typename T>
 __global__ void avgpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, int64_t total_vec) {
     pdl_sync();
@@ -491,7 +518,11 @@ int dd_im2col3x3_nchw(const float* x, void* y, int B, int C, int H, int W, int k
     DD_REQUIRE(C > 0 && C <= 64, "im2col3x3: C=%d out of range (1..64)", C);
     dim3 grid((unsigned)(H * ((W + IM2COL_TW - 1) / IM2COL_TW)), B);
     const size_t smem = (size_t)C * 3 * (IM2COL_TW + 2) * sizeof(float);
-    if (C == 8) launch_pdl(im2col3x3_kernel<8>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, x, (__nv_bfloat16*)y, C, H, W, kpad);
+    if (C == 8 && !getenv("DD_IM2COL_STAGED")) {
+        const int64_t total = (int64_t)B * H * W * (kpad >> 3);
+        launch_pdl(im2col3x3_c8_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, H, W, kpad, total);
+    }
+    else if (C == 8) launch_pdl(im2col3x3_kernel<8>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, x, (__nv_bfloat16*)y, C, H, W, kpad);
     else launch_pdl(im2col3x3_kernel<0>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, x, (__nv_bfloat16*)y, C, H, W, kpad);
     return check_launch("im2col3x3");
 }
