@@ -110,24 +110,37 @@ __global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloa
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
 
-    __nv_bfloat16 (*sk)[LM_PITCH] = s_kv[warp][0];
-    __nv_bfloat16 (*sv)[LM_PITCH] = s_kv[warp][1];
-    for (int r0 = n_lo + warp * LM_SLAB; r0 < n_hi; r0 += LM_ROWS) {
-        // ---- slab load: 32 rows x (64 B of k + 64 B of v), 8 x 16-byte vectors per lane, all issued before use
-        uint4 ld[8];
+    // The slabs are double-buffered with cp.async: the loads of slab i + 1 are in flight while slab i is processed (one L2 round
+    // trip per slab was exposed: 26 k clk for the four slabs per warp of a 32x32 map, scripts/timeline_attn.py).  Buffer 0 is the
+    // warp's static slab, buffer 1 sits behind the weight slice in dynamic shared memory.
+    __nv_bfloat16* kvb[2] = {&s_kv[warp][0][0][0],
+                             reinterpret_cast<__nv_bfloat16*>(s_dyn) + (size_t)C * LM_PITCH + (size_t)warp * 2 * LM_SLAB * LM_PITCH};
+    auto issue_slab = [&](const int r0, __nv_bfloat16* dstb) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int idx = lane + 32 * u, isv = idx >> 7, r = (idx & 127) >> 2, c16 = idx & 3;
-            if (r0 + r < n_hi) ld[u] = __ldg(reinterpret_cast<const uint4*>(kb + (int64_t)(r0 + r) * C3 + isv * HD) + c16);
-            else ld[u] = isv ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);  // k = -inf
+            __nv_bfloat16* d = dstb + (isv * LM_SLAB + r) * LM_PITCH + c16 * 8;
+            if (r0 + r < n_hi) {
+                const uint32_t da = (uint32_t)__cvta_generic_to_shared(d);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(kb + (int64_t)(r0 + r) * C3 + isv * HD + c16 * 8) : "memory");
+            } else {
+                *reinterpret_cast<uint4*>(d) = isv ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);  // k = -inf
+            }
         }
-        __syncwarp();                     // previous slab's ldmatrix reads are done
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int idx = lane + 32 * u, isv = idx >> 7, r = (idx & 127) >> 2, c16 = idx & 3;
-            *reinterpret_cast<uint4*>(&s_kv[warp][isv][r][c16 * 8]) = ld[u];
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int cur = 0;
+    if (n_lo + warp * LM_SLAB < n_hi) issue_slab(n_lo + warp * LM_SLAB, kvb[0]);
+    for (int r0 = n_lo + warp * LM_SLAB; r0 < n_hi; r0 += LM_ROWS, cur ^= 1) {
+        if (r0 + LM_ROWS < n_hi) {
+            issue_slab(r0 + LM_ROWS, kvb[cur ^ 1]);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncwarp();
+        __nv_bfloat16 (*sk)[LM_PITCH] = reinterpret_cast<__nv_bfloat16 (*)[LM_PITCH]>(kvb[cur]);
+        __nv_bfloat16 (*sv)[LM_PITCH] = reinterpret_cast<__nv_bfloat16 (*)[LM_PITCH]>(kvb[cur] + LM_SLAB * LM_PITCH);
         // ---- A = exp(k - m)^T fragments (d x n): ldmatrix.trans of the [n][d] slab
         uint32_t a[2][2][4];
         const int mi = lane >> 3, li = lane & 7;
@@ -188,6 +201,7 @@ __global__ void __launch_bounds__(256, 3) linattn_ctxmix_kernel(const __nv_bfloa
                     mma_bf16(acc[mt][np * 2 + 1], a[mt][ks], bb[2], bb[3]);
                 }
             }
+        __syncwarp();                     // this buffer is refilled by the next iteration's cp.async
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -379,8 +393,9 @@ int dd_linattn_mix(const void* qkv, int dtype, int B, int n, int heads, int dh, 
     const int S = (n + chunk - 1) / chunk;
     DD_REQUIRE(ws != nullptr && ws_floats >= dd_linattn_mix_ws_floats(B, n, heads), "linattn_mix: workspace too small");
     int* tickets = reinterpret_cast<int*>(ws + (int64_t)B * heads * S * LA_WS);
-    const size_t dyn = (size_t)C * LM_PITCH * sizeof(__nv_bfloat16);          // this head's (C x 32) projection slice, 80-byte rows
-    DD_REQUIRE(dyn <= 96 * 1024, "linattn_mix: C=%d too large for the shared-memory weight slice", C);
+    // this head's (C x 32) projection slice, 80-byte rows + the second k / v slab of every warp
+    const size_t dyn = (size_t)C * LM_PITCH * sizeof(__nv_bfloat16) + (size_t)8 * 2 * LM_SLAB * LM_PITCH * sizeof(__nv_bfloat16);
+    DD_REQUIRE(dyn <= 136 * 1024, "linattn_mix: C=%d too large for the shared-memory weight slice", C);
     static size_t dyn_set = 0;
     if (dyn > dyn_set) {
         cudaError_t e = cudaFuncSetAttribute(linattn_ctxmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
