@@ -123,3 +123,26 @@ def test_dp_check_two_gpus_nccl():
            "--master-port", "29541", os.path.join(ROOT, "scripts", "dp_check.py")]
     r = subprocess.run(cmd, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("batch", [64, 8, 3])
+def test_step_replays_at_benchmarked_batches_do_not_fault(cuda, batch):
+    """Round 2: with two MMA issuers taking ALTERNATE stages of a three-slot weight ring, an issuer could see a barrier two phases
+    on and take it for ready -- a launch failure that only showed after a few graph replays of the C3 step at 64 samples (every
+    kernel-level test was green).  Replay the captured step at the benchmarked batch sizes (and an odd one) and compare two
+    replays from the same state: same launches, same inputs -> the persistent kernels' deterministic parts must agree."""
+    m = tc.build_model(dict(tc.C3, precision="bf16"), dd, "dddpm_ae", device="cuda").to(cuda).eval()
+    plan = m.sampling_plan((batch, 8, 32, 32))
+    plan.prepare()
+    x0 = tc.randn(11, batch, 8, 32, 32).to(cuda)
+    plan.noise.normal_()
+    outs = []
+    for _ in range(2):
+        plan.eng.x_in.copy_(x0)
+        plan.t_dev.fill_(plan.T - 1)
+        for _ in range(25):
+            plan.graph.replay()
+        torch.cuda.synchronize()                                  # a trapped launch surfaces here
+        outs.append(plan.eng.x_in.clone())
+    assert torch.isfinite(outs[0]).all()
+    assert tc.max_abs(outs[0], outs[1]) < 5e-2                   # bf16: split-K / attention partials merge in arrival order
