@@ -43,6 +43,7 @@ SIGNATURES = {
     "dd_prior_kl": [_p, _f, _f, _p, _i, _i64, _p],
     "dd_fix_samples": [_p, _p, _i, _i, _i, _i, _p],
     "dd_nchw_to_nhwc": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "dd_nchw_to_nhwc_pad": [_p, _p, _i, _i, _i, _i, _i, _p],
     "dd_nhwc_to_nchw": [_p, _i, _p, _i, _i, _i, _i, _p],
     "dd_im2col3x3_nchw": [_p, _p, _i, _i, _i, _i, _i, _p],
     "dd_time_bias": [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p],

@@ -191,6 +191,28 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__
     for (int c = 0; c < C; ++c) yb[c] = from_f<T>(xb[(int64_t)c * HW]);
 }
 
+// NCHW fp32 (C <= Cp channels) -> NHWC bf16 with the channels zero-padded to Cp (a multiple of 8): the U-Net's input as an
+// ordinary 64-channel activation, so that its first convolution is a regular 3x3 tensor-core layer with the fused GroupNorm
+// epilogue (one 16-byte store per thread, consecutive threads consecutive channel groups of a pixel).
+__global__ void __launch_bounds__(256) nchw_to_nhwc_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int HW, int Cp,
+                                                               int64_t total_vec) {
+    pdl_sync();
+    const int groups = Cp >> 3;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(v % groups);
+        const int64_t pixg = v / groups;                    // b * HW + pixel
+        const int64_t b = pixg / HW;
+        const int pix = (int)(pixg - b * HW);
+        Vec<__nv_bfloat16> o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            o.v[j] = c < C ? __ldg(x + (b * C + c) * HW + pix) : 0.f;
+        }
+        o.store(y + v * 8);
+    }
+}
+
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int C, int HW) {
     pdl_sync();
@@ -488,6 +510,13 @@ int dd_nchw_to_nhwc(const float* x, void* y, int dtype, int B, int C, int H, int
     dim3 grid((H * W + 127) / 128, B);
     DD_DISPATCH_DTYPE(dtype, T, (launch_pdl(nchw_to_nhwc_kernel<T>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, x, (T*)y, C, H * W)));
     return check_launch("nchw_to_nhwc");
+}
+
+int dd_nchw_to_nhwc_pad(const float* x, void* y_bf16, int B, int C, int H, int W, int Cp, void* stream) {
+    DD_REQUIRE(B > 0 && C > 0 && Cp >= C && Cp % 8 == 0, "nchw_to_nhwc_pad: C=%d, Cp=%d (Cp must be a multiple of 8 >= C)", C, Cp);
+    const int64_t total = (int64_t)B * H * W * (Cp >> 3);
+    launch_pdl(nchw_to_nhwc_pad_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y_bf16, C, H * W, Cp, total);
+    return check_launch("nchw_to_nhwc_pad");
 }
 
 int dd_nhwc_to_nchw(const void* x, int dtype, float* y, int B, int C, int H, int W, void* stream) {

@@ -32,10 +32,11 @@ class EngineCache(dict):
 
 class Act:
     """An NHWC activation tensor of a program."""
-    __slots__ = ("t", "B", "H", "W", "C", "mish", "ln")
+    __slots__ = ("t", "B", "H", "W", "C", "mish", "ln", "c_real")
 
     def __init__(self, t: torch.Tensor, B: int, H: int, W: int, C: int):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+        self.c_real = C         # logical channels when the tensor is zero-padded to C (the U-Net input on the tensor-core path)
         self.mish = None        # training programs: Act holding mish(t) when the producing conv's epilogue wrote it
         self.ln = None          # (stats (B*H*W, parts, 2) fp32, parts): per-pixel channel sums the producing launch left for a PreNorm
 
@@ -177,14 +178,24 @@ class Program:
                 raise ValueError(f"unsupported Cout={Cout} for the tensor-core path")
             if b_t is not None and Cout_p != Cout:
                 b_t = self.f32(conv.bias, pad_to=Cout_p)
+            cr = x.c_real                   # < x.C: the input carries zero pad channels, the packed weights zero columns for them
+            if cr != x.C and (x2 is not None or kind not in ("3x3", "1x1") or w.shape[1] != cr):
+                raise ValueError("a zero-padded input feeds plain 3x3 / 1x1 convolutions only")
             if kind in ("3x3", "down"):
                 K = 9 * Cin
-                wp = self.packed((rows, K), torch.bfloat16,
-                                 lambda buf: buf[:Cout].copy_(w.detach().permute(0, 2, 3, 1).reshape(Cout, K)))
+                if cr != x.C:
+                    wp = self.packed((rows, K), torch.bfloat16, lambda buf: buf.view(rows, 9, Cin)[:Cout, :, :cr].copy_(
+                        w.detach().permute(0, 2, 3, 1).reshape(Cout, 9, cr)))
+                else:
+                    wp = self.packed((rows, K), torch.bfloat16,
+                                     lambda buf: buf[:Cout].copy_(w.detach().permute(0, 2, 3, 1).reshape(Cout, K)))
                 kcode = L.TC_CONV3x3 if kind == "3x3" else L.TC_DOWN
             elif kind == "1x1":
                 K = Cin
-                wp = self.packed((rows, K), torch.bfloat16, lambda buf: buf[:Cout].copy_(w.detach().reshape(Cout, K)))
+                if cr != x.C:
+                    wp = self.packed((rows, K), torch.bfloat16, lambda buf: buf[:Cout, :cr].copy_(w.detach().reshape(Cout, cr)))
+                else:
+                    wp = self.packed((rows, K), torch.bfloat16, lambda buf: buf[:Cout].copy_(w.detach().reshape(Cout, K)))
                 kcode = L.TC_CONV1x1
             else:   # 'up': ConvTranspose2d weight (Cin, Cout, 4, 4) -> 4 sub-pixel phase matrices
                 K = 4 * Cin
@@ -223,7 +234,7 @@ class Program:
                     stats = (self._new_stats_slot(B, G), 1)
                     st_ptr = stats[0]
             taps = {"3x3": 9, "down": 9, "1x1": 1, "up": 4}[kind]
-            self.conv_tc_flops.append(2.0 * B * Ho * Wo * Cout * taps * Cin)
+            self.conv_tc_flops.append(2.0 * B * Ho * Wo * Cout * taps * (Cin if x.c_real == x.C else x.c_real))     # algorithmic: no pad channels
             if stats is self.FUSED:
                 self._add_conv_gn(kcode, src, 0, src2, x.C, x2.C if x2 is not None else 0, wp, b_t, y, B, gh, gw, Cout, flags, gn, fuse)
                 return y, stats
@@ -474,13 +485,15 @@ class UnetEngine(Program):
         c1, g1 = rb.block1.block[0], rb.block1.block[1]
         c2, g2 = rb.block2.block[0], rb.block2.block[1]
         has_res = not isinstance(rb.res_conv, torch.nn.Identity)
-        if first and self.precision == "bf16":
+        if first and self.precision == "bf16" and x.c_real == x.C:
             # x is the im2col'd input (B,H,W,kpad): the 3x3 conv and the 1x1 res_conv are K=kpad GEMMs
             h, st = self._conv_im2col(x, c1, gn=g1, center_only=False, fuse=dict(tb_col=col))
             res = self._conv_im2col(x, rb.res_conv, gn=None, center_only=True)[0] if has_res else None
             if not has_res:
                 raise ValueError("first ResnetBlock without res_conv is not supported on the tensor-core path")
         else:
+            if x.c_real != x.C and not has_res:
+                raise ValueError("first ResnetBlock without res_conv is not supported on the tensor-core path")
             h, st = self.conv(x, c1, x2=x2, kind="3x3", gn=g1, fuse=dict(tb_col=col))
             if has_res:
                 res, _ = self.conv(x, rb.res_conv, x2=x2, kind="1x1")
@@ -577,7 +590,14 @@ class UnetEngine(Program):
 
     def _build(self, unet) -> None:
         B, H, W, cin = self.B, self.H, self.W, unet.in_channels
-        if self.precision == "bf16":
+        if self.precision == "bf16" and cin <= 64 and not os.environ.get("DD_FIRST_IM2COL"):
+            # the input as an ordinary activation, zero-padded to 64 channels: the first ResnetBlock is then lowered like every other
+            # (3x3 convolution with the fused GroupNorm + Mish epilogue, 1x1 res_conv); K = 9 * 64 instead of the im2col GEMM's 128,
+            # but no separate dd_gn_mish pass and 8 MB instead of 17 MB of input copy (profiles/README.md, round 2 pass ap)
+            x = self.act(H, W, 64)
+            x.c_real = cin
+            self.add("dd_nchw_to_nhwc_pad", L.ptr(self.x_in), L.ptr(x.t), B, cin, H, W, 64)
+        elif self.precision == "bf16":
             kpad = (9 * cin + 63) // 64 * 64
             x = self.act(H, W, kpad)
             self.add("dd_im2col3x3_nchw", L.ptr(self.x_in), L.ptr(x.t), B, cin, H, W, kpad)

@@ -151,6 +151,9 @@ int dd_fix_samples(const float* x, float* y, int B, int C, int H, int W, void* s
 
 /* NCHW fp32 -> NHWC dtype (input staging for unet.py:74). */
 int dd_nchw_to_nhwc(const float* x, void* y, int dtype, int B, int C, int H, int W, void* stream);
+/* the same into bf16 NHWC with the channel dimension zero-padded to Cp (a multiple of 8, >= C): the U-Net input (unet.py:81) as a
+ * regular 64-channel activation for the tensor-core path (pack the first convolution's weights with zeros for the pad channels) */
+int dd_nchw_to_nhwc_pad(const float* x, void* y_bf16, int B, int C, int H, int W, int Cp, void* stream);
 /* NHWC dtype -> NCHW fp32. */
 int dd_nhwc_to_nchw(const void* x, int dtype, float* y, int B, int C, int H, int W, void* stream);
 /* NCHW fp32 -> bf16 im2col rows (B*H*W, kpad): column tap*C+c holds x[b,c,h+dy,w+dx] (3x3, zero pad 1),

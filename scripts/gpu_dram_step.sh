@@ -19,7 +19,7 @@ for r in rows:
     else:
         d["us"]= v/1000 if u.startswith("n") else v
 ids=list(per)
-ims=[i for i in ids if "im2col" in per[i]["name"]]
+ims=[i for i in ids if "im2col" in per[i]["name"] or "nchw_to_nhwc_pad" in per[i]["name"]]
 step=ids[ids.index(ims[-2]):ids.index(ims[-1])]
 rd=sum(per[i].get("rd",0) for i in step); wr=sum(per[i].get("wr",0) for i in step); us=sum(per[i].get("us",0) for i in step)
 print(f"one step: {len(step)} launches, DRAM read {rd/1e6:.1f} MB, write {wr/1e6:.1f} MB, kernel time (serialised) {us:.1f} us -> {(rd+wr)/1e6/ (us/1e6) /1e6:.2f} TB/s")

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, pass ad: staged tile written out by all 256 threads of the two-issuer CTAs; im2col with four rows per CTA
+# round 2, pass ap: U-Net input as a zero-padded 64-channel activation, first ResnetBlock through the regular fused 3x3 path
 cd "$(dirname "$0")/.."
 tag=${1:-r02_ad}
 mkdir -p gpurun_out
@@ -10,3 +10,5 @@ for b in 64 8; do
 done
 timeout 600 python scripts/op_times.py 64 > gpurun_out/op_times_$tag.txt 2>&1; tail -8 gpurun_out/op_times_$tag.txt
 timeout 600 python scripts/op_times.py 8 > gpurun_out/op_times_${tag}_b8.txt 2>&1; tail -8 gpurun_out/op_times_${tag}_b8.txt
+echo "with the im2col first block:"; for b in 64 8; do DD_FIRST_IM2COL=1 timeout 300 python scripts/step_n.py $b 50 2>&1 | tail -1; done
+timeout 900 python -m pytest tests/test_gpu_chain_full.py -m gpu -q -s --timeout 600 -p no:cacheprovider -k "bf16_vs_reference" > gpurun_out/pytest_c_$tag.log 2>&1; echo "chain tests exit $?"; grep -E "full chain|passed|failed" gpurun_out/pytest_c_$tag.log

@@ -15,7 +15,7 @@ print(f"launches {len(rows)} total {tot:.1f} us")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{k[:48]:48s} n={v[0]:4d} sum={v[1]:9.1f} avg={v[1] / v[0]:7.2f} share={100 * v[1] / tot:5.1f}%")
 if len(sys.argv) > 2:
-    idx = [i for i, r in enumerate(rows) if "im2col" in r["Kernel Name"]]
+    idx = [i for i, r in enumerate(rows) if "im2col" in r["Kernel Name"] or "nchw_to_nhwc_pad" in r["Kernel Name"]]
     if len(idx) >= 2:
         for r in rows[idx[-2]:idx[-1]]:
             print(f"{nm(r)[:30]:30s} grid={r['Grid Size']:>16s} {us(r):8.2f} us")

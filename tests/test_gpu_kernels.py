@@ -347,6 +347,10 @@ def test_layout_kernels(cuda):
     lib.call("dd_im2col3x3_nchw", lib.ptr(x), lib.ptr(col), 3, 8, 16, 16, 128, lib.stream())
     ref = F.unfold(x, 3, padding=1).reshape(3, 8, 9, 256).permute(0, 3, 2, 1).reshape(3 * 256, 72)   # (pixel, tap, c)
     assert torch.equal(col[:, :72], ref.to(torch.bfloat16)) and float(col[:, 72:].abs().max()) == 0.0
+    # the same input as a zero-padded 64-channel NHWC activation (the first ResnetBlock as a regular 3x3 layer)
+    pad = torch.full((3, 16, 16, 64), 7.0, dtype=torch.bfloat16, device=cuda)
+    lib.call("dd_nchw_to_nhwc_pad", lib.ptr(x), lib.ptr(pad), 3, 8, 16, 16, 64, lib.stream())
+    assert torch.equal(pad[..., :8], x.permute(0, 2, 3, 1).to(torch.bfloat16)) and float(pad[..., 8:].abs().max()) == 0.0
     xb = torch.randn(2, 8, 8, 64, device=cuda).to(torch.bfloat16)
     pl = torch.empty(4, 2, 4, 4, 64, dtype=torch.bfloat16, device=cuda)
     lib.call("dd_space_to_depth2", lib.ptr(xb), lib.ptr(pl), 2, 8, 8, 64, lib.stream())
