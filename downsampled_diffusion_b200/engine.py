@@ -125,6 +125,29 @@ class Program:
                 L.check(rc, name)
         self.ops.append(op)
 
+    def _fork(self, branch: List[Callable[[], None]], names: List[str]) -> Callable[[], None]:
+        """Append ONE op that runs `branch` on the program's side stream after everything issued so far; returns the op that makes
+        the main stream wait for it.  Under graph capture the pair becomes a fork / join of the captured graph."""
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        side = self._side
+        ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+
+        def fork():
+            main = torch.cuda.current_stream(self.device)
+            ev_fork.record(main)
+            side.wait_event(ev_fork)
+            with torch.cuda.stream(side):
+                for op in branch:
+                    op()
+                ev_join.record(side)
+
+        def join():
+            torch.cuda.current_stream(self.device).wait_event(ev_join)
+        self.ops.append(fork)
+        assert len(names) >= 1
+        return join
+
     def run_ops(self) -> None:
         if os.environ.get("DD_DEBUG"):
             for i, op in enumerate(self.ops):        # synchronise after every launch to localise a fault
@@ -485,6 +508,7 @@ class UnetEngine(Program):
         c1, g1 = rb.block1.block[0], rb.block1.block[1]
         c2, g2 = rb.block2.block[0], rb.block2.block[1]
         has_res = not isinstance(rb.res_conv, torch.nn.Identity)
+        join = None
         if first and self.precision == "bf16" and x.c_real == x.C:
             # x is the im2col'd input (B,H,W,kpad): the 3x3 conv and the 1x1 res_conv are K=kpad GEMMs
             h, st = self._conv_im2col(x, c1, gn=g1, center_only=False, fuse=dict(tb_col=col))
@@ -494,13 +518,31 @@ class UnetEngine(Program):
         else:
             if x.c_real != x.C and not has_res:
                 raise ValueError("first ResnetBlock without res_conv is not supported on the tensor-core path")
-            h, st = self.conv(x, c1, x2=x2, kind="3x3", gn=g1, fuse=dict(tb_col=col))
-            if has_res:
+            # all blocks or none (measured, pass ar): at 64 samples x 32x32 the second branch only gets in the persistent kernels' way
+            # (+0.15 %; forking the low-resolution blocks alone +0.8 %), from 32 samples down it is worth 2 % of the step
+            fork_rows = int(os.environ.get("DD_FORK_MAX_ROWS", "32768"))
+            if has_res and self.precision == "bf16" and self.B * self.H * self.W <= fork_rows and not os.environ.get("DD_NO_FORK"):
+                # The 1x1 res_conv reads only the block's input and is needed only by the second convolution's epilogue: it is issued
+                # FIRST, on a side stream (a parallel branch of the captured graph), and runs next to the first convolution instead
+                # of between the two.  (Without the res_conv launches at all a step is 29 us shorter: profiles/README.md, pass ar.)
+                n0 = len(self.ops)
                 res, _ = self.conv(x, rb.res_conv, x2=x2, kind="1x1")
+                branch = self.ops[n0:]
+                del self.ops[n0:]
+                join = self._fork(branch, self.op_names[n0:])
+                del self.op_names[n0 + 1:]
+                h, st = self.conv(x, c1, x2=x2, kind="3x3", gn=g1, fuse=dict(tb_col=col))
             else:
-                assert x2 is None
-                res = x
+                h, st = self.conv(x, c1, x2=x2, kind="3x3", gn=g1, fuse=dict(tb_col=col))
+                if has_res:
+                    res, _ = self.conv(x, rb.res_conv, x2=x2, kind="1x1")
+                else:
+                    assert x2 is None
+                    res = x
         h = self.gn_mish(h, st, g1, tb_col=col, tb=self.tb)
+        if join is not None:
+            self.ops.append(join)
+            self.op_names.append("join")
         want_ln = want_ln and self.precision == "bf16" and not os.environ.get("DD_NO_LN_FOLD")
         h, st = self.conv(h, c2, kind="3x3", gn=g2, fuse=dict(residual=res, want_ln=want_ln))
         return self.gn_mish(h, st, g2, residual=res, want_ln=want_ln)
