@@ -1,6 +1,7 @@
 """Warm per-op GPU time of the C3 step program: each op is captured 10x into its own CUDA graph and replayed,
 so CPU launch overhead is excluded and operands are L2-resident like in the real step."""
 import os, sys, collections, torch
+os.environ.setdefault("DD_NO_FORK", "1")          # per-op replays: keep every launch on one stream
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import downsampled_diffusion_b200 as dd
 from tests import common as tc

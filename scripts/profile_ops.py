@@ -1,5 +1,6 @@
 """Per-op CUDA-event timing of the C3 U-Net step program (eager launches, warm L2): where the step time goes."""
 import os, sys, collections, torch
+os.environ.setdefault("DD_NO_FORK", "1")          # per-op replays: keep every launch on one stream
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import downsampled_diffusion_b200 as dd
 from tests import common as tc

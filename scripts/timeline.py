@@ -1,5 +1,6 @@
 """In-kernel timeline of single conv_tc launches (clock64 stamps per CTA)."""
 import os, sys, torch, numpy as np
+os.environ.setdefault("DD_NO_FORK", "1")          # per-op replays: keep every launch on one stream
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import downsampled_diffusion_b200 as dd
 from downsampled_diffusion_b200 import _lib as L
