@@ -15,7 +15,7 @@ python scripts/ncu_list.py gpurun_out/launches_$tag.csv x > gpurun_out/launches_
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:conv_tc --csv --log-file gpurun_out/conv_dram_$tag.csv python scripts/step_n.py 64 2 > gpurun_out/ncu_dram_$tag.log 2>&1; echo "dram exit $?"
 # one full capture per kernel class of the sampling step: "<regex>:<skip>:<name>"
 # (-k matches the base name only: the skip counts pick the template instance / layer, see profiles/launches_*_summary.txt)
-for spec in "conv_tc_halo_persist_kernel:1:persist32" "conv_tc_halo_persist_kernel:4:persist16" "conv_tc_halo_persist_kernel:7:persist_2src" \
+for spec in "conv_tc_halo_persist_kernel:1:persist32" "conv_tc_halo_persist_kernel:4:persist16_128to256" "conv_tc_halo_persist_kernel:7:persist16_256to256" \
             "conv_tc_kernel:3:gen8x8" "conv_tc_kernel:11:splitk4x4" "conv_tc_kernel:0:gen_1x1" "conv_tc_gemm_persist_kernel:1:gemm_qkv32" \
             "linattn_ctxmix_kernel:0:linattn32" "gn_mish_sum_kernel:0:gnsum4x4"; do
   IFS=: read -r rx skip name <<< "$spec"
