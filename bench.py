@@ -158,12 +158,14 @@ def conv_roofline(model, plan, pk):
     from downsampled_diffusion_b200 import _lib as L
 
     def conv_ops():
-        # the persistent convolutions exchange GroupNorm sums through a workspace that must start out zero (in a real step the
-        # posterior launch of the step before clears it): the memset is part of every replay here, so the waits are real
+        # the persistent convolutions exchange GroupNorm sums through a workspace that must start out zero (a real step begins
+        # with the same memset): it is part of every replay here, so the waits for the other tiles of an image are real
         if eng.stats_arena is not None:
             L.call("dd_zero", eng.stats_arena.data_ptr(), eng.stats_arena.numel() * 4, L.stream())
-        for i in idx:
+        for i in idx_run:
             eng.ops[i]()
+    # a res_conv on a side stream (per-GPU batches of 32 and less) is a fork op named like a convolution; its join must be replayed too
+    idx_run = [i for i, n in enumerate(eng.op_names) if n in ("dd_conv_tc", "join")]
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):

@@ -146,3 +146,29 @@ def test_step_replays_at_benchmarked_batches_do_not_fault(cuda, batch):
         outs.append(plan.eng.x_in.clone())
     assert torch.isfinite(outs[0]).all()
     assert tc.max_abs(outs[0], outs[1]) < 5e-2                   # bf16: split-K / attention partials merge in arrival order
+
+
+def test_convolution_only_replay_with_the_forked_res_conv(cuda):
+    """bench.py's roofline leg replays the step's convolution launches alone from their own graph.  With the res_conv of a
+    ResnetBlock on a side stream (per-GPU batches of 32 and less) a replay without the matching joins ends the capture with
+    unjoined work -- found by the 4-GPU run of round 2.  The fork op is named like a convolution, its join "join"."""
+    m = tc.build_model(dict(tc.C3, precision="bf16"), dd, "dddpm_ae", device="cuda").to(cuda).eval()
+    plan = m.sampling_plan((8, 8, 32, 32))
+    plan.prepare()
+    eng = plan.eng
+    assert "join" in eng.op_names, "batch 8 x 32x32 is expected to fork its res_convs"
+    assert eng.op_names.count("dd_conv_tc") == len(eng.conv_tc_flops)
+    idx = [i for i, n in enumerate(eng.op_names) if n in ("dd_conv_tc", "join")]
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for i in idx:
+            eng.ops[i]()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in idx:
+            eng.ops[i]()
+    g.replay()
+    torch.cuda.synchronize()
