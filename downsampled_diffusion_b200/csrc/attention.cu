@@ -30,7 +30,9 @@ inline int lm_target_ctas() {
     return t;
 }
 inline int lm_chunk(int n, int bh) {
-    int S = (lm_target_ctas() + bh - 1) / bh;
+    // one CTA per (b, head) once those alone fill the SMs; below that three CTAs per SM's worth of splits (sweep: profiles/README.md)
+    const int target = bh >= lm_target_ctas() ? lm_target_ctas() : 3 * lm_target_ctas();
+    int S = (target + bh - 1) / bh;
     if (S > 16) S = 16;
     if (S < 1) S = 1;
     int c = (n + S - 1) / S;
