@@ -62,17 +62,8 @@ constexpr int PS_ROW_BYTES = 3 * HALO_B_BYTES;            // one weight stage: t
 constexpr int PS_XCH_BYTES = 2 * PH_EW * 16 * 4 /*per-warp partial sums, double buffered*/ + 2 * 128 * 3 * 4 /*scale, shift, time bias per channel of the item, double buffered*/;
 constexpr int ps_smem(int nh, int nb) { return nh * HALO_SLOT + nb * PS_ROW_BYTES + 1024 /*align*/ + 256 /*barriers*/ + PS_PAR_BYTES + PS_XCH_BYTES; }
 
-__device__ __forceinline__ void ps_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
     asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
