@@ -238,7 +238,7 @@ class DDPM(nn.Module):
             base = done % plan.period
             if noise is None:
                 for j in range(chunk):
-                    plan.noise[base + j].copy_(torch.randn(shape, device=dev))
+                    torch.randn(shape, out=plan.noise[base + j])      # same Philox draws as a fresh tensor, no copy launch
             elif isinstance(noise, torch.Tensor) and not noise.is_cuda and chunk > HOST_NOISE_BLOCK:
                 # host noise: blocks of HOST_NOISE_BLOCK steps go up on a side stream while earlier blocks are consumed
                 # (2.1 GB per C3 chain = ~40 ms of PCIe time that would otherwise sit in front of the first step)
@@ -340,7 +340,7 @@ class DDPM(nn.Module):
             chunk = min(plan.period - base, T - done)
             if noise is None:
                 for j in range(chunk):
-                    plan.noise[base + j].copy_(torch.randn(shape, device=dev))
+                    torch.randn(shape, out=plan.noise[base + j])      # same Philox draws as a fresh tensor, no copy launch
             elif isinstance(noise, torch.Tensor):
                 plan.noise[base:base + chunk].copy_(noise[done:done + chunk], non_blocking=True)
             else:
