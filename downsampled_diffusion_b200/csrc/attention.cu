@@ -9,8 +9,8 @@
 // contraction runs on mma.sync.m16n8k16 because a 32x32 output per (b, head) is far too small for a tcgen05 tile.
 //
 // CTA (b, head, split) = 8 warps; a warp owns 32-row slabs of the split's pixel range, keeps an online softmax
-// (running max per d, rescaled fp32 accumulators) in registers, operands via ldmatrix.trans from a warp-private
-// shared-memory slab.  Warps merge through shared memory, splits through a workspace + self-resetting arrival
+// (running max per d, rescaled fp32 accumulators) in registers, operands via ldmatrix.trans from warp-private
+// shared-memory slabs, double-buffered with cp.async (the loads of slab i + 1 are in flight under slab i).  Warps merge through shared memory, splits through a workspace + self-resetting arrival
 // ticket: the last CTA of a (b, head) normalises the context and does the projection fold, also on mma.sync.
 #include "common.cuh"
 
