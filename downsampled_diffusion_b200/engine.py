@@ -32,10 +32,12 @@ class EngineCache(dict):
 
 class Act:
     """An NHWC activation tensor of a program."""
-    __slots__ = ("t", "B", "H", "W", "C", "mish", "ln", "c_real")
+    __slots__ = ("t", "B", "H", "W", "C", "mish", "ln", "c_real", "released", "pinned")
 
     def __init__(self, t: torch.Tensor, B: int, H: int, W: int, C: int):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+        self.released = False   # its buffer went back to the program's pool (Program.release)
+        self.pinned = False     # still needed later in the program (a skip connection): release() leaves it alone
         self.c_real = C         # logical channels when the tensor is zero-padded to C (the U-Net input on the tensor-core path)
         self.mish = None        # training programs: Act holding mish(t) when the producing conv's epilogue wrote it
         self.ln = None          # (stats (B*H*W, parts, 2) fp32, parts): per-pixel channel sums the producing launch left for a PreNorm
@@ -77,6 +79,11 @@ class Program:
         self.tc_flags = 0                           # extra dd_conv_tc flags for every conv of the program (tests: L.TC_PAIR)
         self.gn_slots: List[Tuple[int, int]] = []   # (B*G*2 offset, G) per GroupNorm of a bf16 program
         self.stats_arena: Optional[torch.Tensor] = None
+        # Inference programs hand the buffers of dead activations to later layers of the same shape: the ~1.5 GB of per-op outputs
+        # of a C3 step otherwise all end up written back to HBM (417 MB per step, profiles/README.md), and a 50 MB output burst
+        # stalls on the write-back of somebody else's dirty lines.  A reused buffer is still L2-resident from its last life.
+        self.pooling = precision == "bf16" and not os.environ.get("DD_NO_POOL")
+        self._pool: Dict[tuple, List[torch.Tensor]] = {}
 
     # ---- helpers ---------------------------------------------------------------------------
     def empty(self, *shape, dtype=None) -> torch.Tensor:
@@ -87,7 +94,16 @@ class Program:
 
     def act(self, H: int, W: int, C: int, B: int = None) -> Act:
         B = B or self.B
-        return Act(self.empty(B, H, W, C), B, H, W, C)
+        free = self._pool.get((B, H, W, C, self.adt)) if self.pooling else None
+        return Act(free.pop() if free else self.empty(B, H, W, C), B, H, W, C)
+
+    def release(self, a: Optional[Act]) -> None:
+        """The activation is dead from here on in launch order: its buffer may be the output of any LATER launch (every launch
+        writes only after the grid dependency on its predecessors has resolved, side-stream launches after their fork event)."""
+        if not self.pooling or a is None or a.released or a.pinned or a.t.dtype != self.adt or a.t.dim() != 4:
+            return
+        a.released = True
+        self._pool.setdefault((a.B, a.H, a.W, a.C, self.adt), []).append(a.t)
 
     def packed(self, shape, dtype, fill: Callable[[torch.Tensor], None]) -> torch.Tensor:
         """A derived weight buffer: allocated once, (re)filled from the fp32 master parameters."""
@@ -539,13 +555,21 @@ class UnetEngine(Program):
                 else:
                     assert x2 is None
                     res = x
-        h = self.gn_mish(h, st, g1, tb_col=col, tb=self.tb)
+        h1 = self.gn_mish(h, st, g1, tb_col=col, tb=self.tb)
+        if h1 is not h:
+            self.release(h)
         if join is not None:
             self.ops.append(join)
             self.op_names.append("join")
         want_ln = want_ln and self.precision == "bf16" and not os.environ.get("DD_NO_LN_FOLD")
-        h, st = self.conv(h, c2, kind="3x3", gn=g2, fuse=dict(residual=res, want_ln=want_ln))
-        return self.gn_mish(h, st, g2, residual=res, want_ln=want_ln)
+        h2, st = self.conv(h1, c2, kind="3x3", gn=g2, fuse=dict(residual=res, want_ln=want_ln))
+        out = self.gn_mish(h2, st, g2, residual=res, want_ln=want_ln)
+        if out is not h2:
+            self.release(h2)
+        self.release(h1)
+        if has_res:
+            self.release(res)
+        return out
 
     def _conv_im2col(self, x: Act, conv, gn, center_only: bool, fuse: dict = None):
         w = conv.weight
@@ -578,6 +602,7 @@ class UnetEngine(Program):
         pre = res_mod.fn            # PreNorm
         attn = pre.fn               # LinearAttention
         hid = attn.heads * attn.dim_head
+        xn = None
         if x.ln is not None and self.precision == "bf16" and x.C % 64 == 0:
             qkv = self._qkv_ln_folded(pre, attn, x)
         else:
@@ -603,6 +628,8 @@ class UnetEngine(Program):
             self.conv_tc_flops.append(2.0 * x.B * x.H * x.W * C * hid)
             self.add("dd_conv_tc", L.TC_CONV1x1, L.ptr(qkv.t), qkv.C, None, hid, 0, L.ptr(mb), C, L.ptr(b_t), L.ptr(x.t),
                      L.ptr(y.t), 0, 0, None, 0, x.B, x.H, x.W, C, L.TC_W_PER_SAMPLE, *self.splitk_args())
+            self.release(qkv)
+            self.release(xn)
             return y
         o = self.act(x.H, x.W, hid, x.B)
         need = int(L.lib().dd_linattn_ws_floats(x.B, x.H * x.W, attn.heads))
@@ -647,26 +674,40 @@ class UnetEngine(Program):
             x = self.act(H, W, cin)
             self.add("dd_nchw_to_nhwc", L.ptr(self.x_in), L.ptr(x.t), self.dcode, B, cin, H, W)
         skips: List[Act] = []
+
+        def step(fn, x, **kw):
+            """x -> fn(x): the input is dead afterwards (unless it is pinned as a skip connection)"""
+            y = fn(x, **kw)
+            self.release(x)
+            return y
         for i, (rb1, rb2, attn, down) in enumerate(unet.downs):
-            x = self._resnet(rb1, x, first=(i == 0))
-            x = self._resnet(rb2, x, want_ln=True)
-            x = self._attn(attn, x)
+            x = step(lambda a, **kw: self._resnet(rb1, a, **kw), x, first=(i == 0))
+            x = step(lambda a, **kw: self._resnet(rb2, a, **kw), x, want_ln=True)
+            x = step(lambda a: self._attn(attn, a), x)
+            x.pinned = True                                 # read again by the matching block of the up path
             skips.append(x)
             if not isinstance(down, torch.nn.Identity):
                 x, _ = self.conv(x, down.conv, kind="down")
-        x = self._resnet(unet.mid_block1, x, want_ln=True)
-        x = self._attn(unet.mid_attn, x)
-        x = self._resnet(unet.mid_block2, x)
+        x = step(lambda a, **kw: self._resnet(unet.mid_block1, a, **kw), x, want_ln=True)
+        x = step(lambda a: self._attn(unet.mid_attn, a), x)
+        x = step(lambda a: self._resnet(unet.mid_block2, a), x)
         for rb1, rb2, attn, up in unet.ups:
-            x = self._resnet(rb1, x, x2=skips.pop())        # concat-free: two K ranges (unet.py:97)
-            x = self._resnet(rb2, x, want_ln=True)
-            x = self._attn(attn, x)
+            skip = skips.pop()
+            x = step(lambda a: self._resnet(rb1, a, x2=skip), x)        # concat-free: two K ranges (unet.py:97)
+            skip.pinned = False
+            self.release(skip)
+            x = step(lambda a, **kw: self._resnet(rb2, a, **kw), x, want_ln=True)
+            x = step(lambda a: self._attn(attn, a), x)
             if not isinstance(up, torch.nn.Identity):
-                x, _ = self.conv(x, up.conv, kind="up")
+                x = step(lambda a: self.conv(a, up.conv, kind="up")[0], x)
         blk, last = unet.final_conv[0], unet.final_conv[1]
         h, st = self.conv(x, blk.block[0], kind="3x3", gn=blk.block[1], fuse=dict())
-        h = self.gn_mish(h, st, blk.block[1])
-        self.conv(h, last, kind="1x1", out_nchw=self.eps_out)
+        h2 = self.gn_mish(h, st, blk.block[1])
+        if h2 is not h:
+            self.release(h)
+        self.release(x)
+        self.conv(h2, last, kind="1x1", out_nchw=self.eps_out)
+        self.release(h2)
 
     # ---- execution -------------------------------------------------------------------------
     def run(self) -> None:
