@@ -325,7 +325,7 @@ class Program:
         G = gn.num_groups
         ws_floats = int(L.lib().dd_conv_tc_gn_ws_floats(kcode, B, gh, gw, Cout, G))
         ws = None
-        if ws_floats > 0:            # persistent kernel: {sum, sumsq} per (image, group) + arrival counters, zeroed with the arena every run
+        if ws_floats > 0:            # persistent kernel: flagged {sum, 1, sumsq, 1} packets per (image, channel tile, pixel tile, group), zeroed with the arena every run
             ws = _ArenaPtr(self, sum(s_ for s_, _ in self.gn_slots))
             self.gn_slots.append((ws_floats, G))
         ln_buf = None
