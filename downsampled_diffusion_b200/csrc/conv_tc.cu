@@ -43,7 +43,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
     const int r = q * 32 + lane;
     const int ww = r % p.tw, hh = (r / p.tw) % p.th, nl = r / (p.tw * p.th);
     const int n = n0 + nl;
-    const bool valid = n < p.B && r < p.rows_valid;
+    const bool valid = n < p.B && r < p.rows_valid && h0 + hh < p.H && w0 + ww < p.W;     // tiles may hang over the edge of a ragged map
     const int mul = p.out_mul;
     const int Ho = p.H * mul, Wo = p.W * mul;
     const int oh = (h0 + hh) * mul + (phase >> 1), ow = (w0 + ww) * mul + (phase & 1);
@@ -1117,7 +1117,7 @@ extern "C" int dd_zero(void* ptr, int64_t bytes, void* stream) {
 // third of the SMs.  Each CTA streams its whole K range through one SM's L2 port (~64 B/clk), so 32 CTAs take ~7 us
 // for 27 MB of operands while 116 SMs idle; S splits cut that stream S-fold.  Returns S (>= 2) or 1.
 extern "C" int dd_conv_tc_splits(int kind, int B, int H, int W, int Cin, int Cout) {
-    if (kind != DD_TC_CONV3x3 || H * W > 16 || Cout < 128 || Cout % 64 || Cin % 64 || getenv("DD_NO_SPLITK")) return 1;
+    if (kind != DD_TC_CONV3x3 || H * W > 16 || !is_pow2(H) || !is_pow2(W) || Cout < 128 || Cout % 64 || Cin % 64 || getenv("DD_NO_SPLITK")) return 1;
     const int rows = B * H * W, tiles = (rows + 127) / 128 * (Cout / 64), num_kb = 9 * (Cin / 64);
     if (tiles * 3 > dd::num_sms()) return 1;
     int S = dd::num_sms() / tiles;
@@ -1145,17 +1145,23 @@ struct GnFuse {                 // arguments of the fused GroupNorm + Mish epilo
 };
 
 // Tile geometry of a launch (shared by dd_conv_tc and the dd_conv_tc_gn_cluster query).
-struct TcGeom { int tw, th, tn, bn, tiles_w, tiles_h, tiles_n; bool halo; };
+// Maps whose sides are not powers of two (28x28 -> 14x14 -> 7x7 of the MNIST-shaped DDPM) are tiled as
+// if padded to the next power of two: the TMA boxes hang over the right / bottom edge (out-of-bounds elements arrive as zeros,
+// which is also the convolution's padding) and the epilogue skips the rows of a tile that lie outside the image.
+struct TcGeom { int tw, th, tn, bn, tiles_w, tiles_h, tiles_n; bool halo, ragged; };
+static int next_pow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 TcGeom tc_geometry(int kind, int B, int H, int W, int Cout, int flags, int out_nchw_f32) {
     TcGeom g;
     static const bool halo_off = getenv("DD_NO_HALO") != nullptr;
     const bool wps = (flags & DD_TC_W_PER_SAMPLE) != 0;
-    g.halo = !halo_off && kind == DD_TC_CONV3x3 && H >= HALO_TH && W >= HALO_TW && Cout >= 64 && !out_nchw_f32;
-    g.tw = W < 128 ? W : 128;
-    g.th = (128 / g.tw) < H ? (128 / g.tw) : H;
+    g.ragged = !is_pow2(H) || !is_pow2(W);
+    const int Wp = next_pow2(W), Hp = next_pow2(H);
+    g.halo = !g.ragged && !halo_off && kind == DD_TC_CONV3x3 && H >= HALO_TH && W >= HALO_TW && Cout >= 64 && !out_nchw_f32;
+    g.tw = Wp < 128 ? Wp : 128;
+    g.th = (128 / g.tw) < Hp ? (128 / g.tw) : Hp;
     if (g.halo) { g.tw = HALO_TW; g.th = HALO_TH; }
     g.tn = wps ? 1 : 128 / (g.tw * g.th);      // per-sample weights: one image per tile (rows beyond it are ignored)
-    g.tiles_w = W / g.tw; g.tiles_h = H / g.th;
+    g.tiles_w = (W + g.tw - 1) / g.tw; g.tiles_h = (H + g.th - 1) / g.th;
     g.tiles_n = (B + g.tn - 1) / g.tn;
     g.bn = Cout >= 128 ? 128 : Cout;
     // low-resolution layers (at most half a wave of 128-wide tiles): halve the N tile to double the CTA count
@@ -1184,7 +1190,7 @@ extern "C" int dd_conv_tc_gn_cluster(int kind, int B, int H, int W, int Cout, in
 
 // N tile (output channels per CTA) dd_conv_tc / dd_conv_tc_gn choose for a layer: the `parts` dimension of ln_part is Cout / it.
 extern "C" int dd_conv_tc_tile_n(int kind, int B, int H, int W, int Cout, int flags) {
-    if (kind < 0 || kind > 3 || !is_pow2(H) || !is_pow2(W) || B <= 0 || Cout <= 0) return 0;
+    if (kind < 0 || kind > 3 || H <= 0 || W <= 0 || B <= 0 || Cout <= 0) return 0;
     return tc_geometry(kind, B, H, W, Cout, flags, 0).bn;
 }
 
@@ -1212,7 +1218,7 @@ static int conv_tc_impl(int kind, const void* x, int x_pitch, const void* x2, in
     DD_REQUIRE(kind >= 0 && kind <= 3, "conv_tc: bad kind %d", kind);
     DD_REQUIRE(C1 > 0 && C1 % 64 == 0 && C2 >= 0 && C2 % 64 == 0, "conv_tc: channel counts (%d,%d) must be multiples of 64", C1, C2);
     DD_REQUIRE((C2 == 0) == (x2 == nullptr), "conv_tc: x2/C2 mismatch");
-    DD_REQUIRE(is_pow2(H) && is_pow2(W) && B > 0, "conv_tc: H=%d, W=%d must be powers of two (use the direct kernel otherwise)", H, W);
+    DD_REQUIRE(H > 0 && W > 0 && B > 0, "conv_tc: bad sizes B=%d H=%d W=%d", B, H, W);
     DD_REQUIRE(Cout > 0 && Cout % 16 == 0 && w_rows >= Cout, "conv_tc: Cout=%d must be a multiple of 16 (pad the weights)", Cout);
     DD_REQUIRE(!out_nchw_f32 || (residual == nullptr && gn_stats == nullptr && cout_valid > 0 && cout_valid <= Cout),
                "conv_tc: fp32 NCHW output takes no residual / GroupNorm statistics");
@@ -1243,7 +1249,9 @@ static int conv_tc_impl(int kind, const void* x, int x_pitch, const void* x2, in
     memset(&p, 0, sizeof(p));
     // tile geometry over the GEMM pixel grid
     const TcGeom geo = tc_geometry(kind, B, H, W, Cout, flags, out_nchw_f32);
-    const bool halo = geo.halo;
+    const bool halo = geo.halo, ragged = geo.ragged;
+    DD_REQUIRE(!ragged || (gf.gamma == nullptr && gf.ln_in == nullptr && !(flags & (DD_TC_SPLITK | DD_TC_PAIR))),
+               "conv_tc: maps that are not powers of two (%dx%d) take the plain epilogue only (no fused GroupNorm, LayerNorm fold, split-K)", H, W);
     p.tw = geo.tw; p.th = geo.th; p.tn = geo.tn;
     p.rows_valid = p.tw * p.th * p.tn;
     p.tw_sh = 0; while ((1 << p.tw_sh) < p.tw) ++p.tw_sh;
@@ -1379,19 +1387,19 @@ static int conv_tc_impl(int kind, const void* x, int x_pitch, const void* x2, in
         if (rc) return rc;
         return launch_halo_persist(p, st);
     }
-    if (!fuse && !out_nchw_f32 && p.splits == 1 && gemm_persist_ok(kind, B, H, W, C1, C2, Cout, G, gn_stats != nullptr, wps)) {
+    if (!ragged && !fuse && !out_nchw_f32 && p.splits == 1 && gemm_persist_ok(kind, B, H, W, C1, C2, Cout, G, gn_stats != nullptr, wps)) {
         rc = make_w_map(&p.tmB, wp, K, w_rows, 128, wps ? B : 0);
         if (rc) return rc;
         return launch_gemm_persist(p, x, x_pitch, C1, st);
     }
     static const bool one_issuer = getenv("DD_TC_ONE_ISSUER") != nullptr;
     const dim3 blk2(TC_THREADS + 32);
-    if (!one_issuer && !(out_nchw_f32 || p.bn < 32) && !cta_pair && !halo && (p.splits > 1 || ctas <= num_sms())) p.mma_parts = 2;
+    if (!one_issuer && !(out_nchw_f32 || p.bn < 32) && !cta_pair && !halo && !ragged && (p.splits > 1 || ctas <= num_sms())) p.mma_parts = 2;
     if (p.splits > 1 && p.mma_parts == 2)
         launch_pdl(conv_tc_kernel<8, 64, 1, 2, 2>, dim3(grid), blk2, tc_smem_bytes(8, 64, 1), st, p);
     else if (p.splits > 1)
         launch_pdl(conv_tc_kernel<8, 64, 1, 2>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(8, 64, 1), st, p);
-    else if (out_nchw_f32 || p.bn < 32)
+    else if (out_nchw_f32 || p.bn < 32 || ragged)        // per-row epilogue: the only one that masks rows outside the image
         launch_pdl(conv_tc_kernel<3, 128, 1, 1>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(3, 128, 1), st, p);
     else if (cta_pair)
         launch_pair_pdl(conv_tc_halo2_kernel, dim3(grid.x, Cout / (p.bn * p.pair_nt), 1), dim3(TC_THREADS), HALO_SMEM, st, p);

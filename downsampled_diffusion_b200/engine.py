@@ -207,8 +207,8 @@ class Program:
 
         use_tc = self.precision == "bf16" and not pre_mish and not tanh
         if use_tc:
-            if not (_is_pow2(Ho if kind != "up" else H) and _is_pow2(Wo if kind != "up" else W)):
-                raise ValueError(f"bf16 tensor-core path needs power-of-two feature maps, got {H}x{W}; use precision='fp32'")
+            # maps that are not powers of two (28 -> 14 -> 7) run the same tcgen05 kernel on tiles padded to the next power of two
+            # (TMA zero-fills what hangs over the edge); the library keeps them on the plain epilogue: GroupNorm + Mish as dd_gn_mish
             if x.C % 64 or (x2 is not None and x2.C % 64):
                 raise ValueError(f"bf16 tensor-core path needs channel counts that are multiples of 64, got {x.C}")
             Cout_p = Cout if Cout % 16 == 0 else (Cout + 15) // 16 * 16

@@ -250,7 +250,10 @@ int dd_space_to_depth2(const void* x, void* y, int B, int H, int W, int C, void*
  *                        K = 4 taps * C; output (B,2H,2W,Cout)
  * x_pitch: channels per pixel of the tensor x points into (0 = C1); lets a conv read the first C1 channels of a
  * wider tensor (q out of qkv).  x2 (optional, same geometry, C2 channels) is the skip tensor of unet.py:97 (concat-free).
- * C1, C2 multiples of 64; H, W powers of two; Wp (rows, K) bf16 K-major, rows padded to bn.
+ * C1, C2 multiples of 64; Wp (rows, K) bf16 K-major, rows padded to bn.  H, W: any size -- maps that are not powers of two
+ * (28 -> 14 -> 7) are tiled as if padded to the next power of two (TMA zero fill over the edge, rows outside the image skipped
+ * by the epilogue) and take this plain entry point only: dd_conv_tc_gn_cluster / dd_conv_tc_gn_ws_floats return 0 and
+ * dd_conv_tc_splits returns 1 for them, DD_TC_SPLITK / DD_TC_PAIR are rejected.
  * Epilogue: + bias, GroupNorm {sum,sumsq} atomics into gn_stats (B, G, 2) when non-NULL (stats of the
  * fp32 accumulator + bias), + residual (bf16 NHWC, output geometry), store bf16 NHWC or fp32 NCHW
  * (out_nchw_f32, only the first cout_valid channels).

@@ -72,7 +72,8 @@ def max_abs(a: torch.Tensor, b: torch.Tensor) -> float:
 
 # ---- full T-step chains at the BASELINE sizes (tests/test_gpu_chain_full.py, oracle/make_golden_chain.py) ----------
 CHAIN_ROWS = 3                                   # rows of the benchmarked batch that the CPU side follows
-CHAIN_SEEDS = {"c2": 7102, "c3": 7103}
+CHAIN_SEEDS = {"c1": 7101, "c2": 7102, "c3": 7103}
+C1_CHAIN_BATCH = 16          # BASELINE configs[0]: the standard DDPM on 1x28x28, T = 1000, batch 16
 
 
 def chain_noise(tag: str, T: int, rows: int, C: int, H: int, W: int) -> torch.Tensor:

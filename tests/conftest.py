@@ -16,7 +16,7 @@ def pytest_configure(config):
 def golden():
     import numpy as np
     out = {}
-    for name in ("golden_v1.npz", "golden_v2.npz", "golden_v3.npz"):     # oracle/make_golden{,_eval,_chain}.py
+    for name in ("golden_v1.npz", "golden_v2.npz", "golden_v3.npz", "golden_v4.npz"):     # oracle/make_golden{,_eval,_chain,_c1}.py
         with np.load(os.path.join(ROOT, "tests", "golden", name)) as z:
             out.update({k: z[k] for k in z.files})
     return out

@@ -69,6 +69,22 @@ def test_c2_full_chain_fp32_mode_vs_reference(cuda, golden):
     _check(golden, "c2", x, z, FP32_BOTH, FP32_BOTH, "fp32 mode")
 
 
+@pytest.mark.parametrize("precision,bar", [("bf16", BF16_LATENT), ("fp32", FP32_BOTH)])
+def test_c1_full_chain_batch16_vs_reference(cuda, golden, precision, bar):
+    """BASELINE configs[0] as written: the standard DDPM (no resampling nets) on 1x28x28, T = 1000, batch 16 -- all sixteen final
+    images against the unmodified reference's (golden_v4.npz).  The chain state IS the image, so the latent bar applies.  In bf16
+    the 28 -> 14 -> 7 maps run on the tcgen05 kernel with tiles padded to the next power of two."""
+    cfg, B = tc.C1, tc.C1_CHAIN_BATCH
+    m = tc.build_model(dict(cfg, precision=precision), dd, "ddpm", device="cuda").to(cuda).eval()
+    noise = tc.chain_noise("c1", cfg["T"], B, 1, 28, 28).to(cuda)
+    with torch.no_grad():
+        x = m.sample(B, noise=noise)
+    xr = torch.from_numpy(np.asarray(golden["fullchain.c1.x"]))
+    err = tc.max_abs(x.cpu(), xr)
+    print(f"full chain c1 {precision} B={B}: image max-abs {err:.3e} (bar {bar}), rel-L2 {tc.rel_l2(x.cpu(), xr):.3e}")
+    assert x.shape == (B, 1, 28, 28) and err <= bar
+
+
 @pytest.mark.parametrize("precision,tol_obj,tol_norm,tol_grad", [("fp32", 1e-4, 2e-3, 5e-4), ("bf16", 2e-3, 3e-2, 2e-2)])
 def test_c4_size_training_step_vs_reference_autograd(cuda, golden, precision, tol_obj, tol_norm, tol_grad):
     """256x256 training objective + all parameter-gradient norms + three gradients against the reference's autograd

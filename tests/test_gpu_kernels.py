@@ -220,6 +220,17 @@ CONV_CASES = [
     ("down", 256, 0, 256, 8, 8, 2),
     ("up", 256, 0, 256, 4, 4, 2),
     ("up", 128, 0, 128, 16, 16, 2),
+    # maps that are not powers of two (C1: 28 -> 14 -> 7): tiles padded to the next power of two, TMA zero fill over the edge
+    ("3x3", 64, 0, 64, 28, 28, 2),        # 32x4 tiles, four columns of every row outside the image
+    ("3x3", 128, 128, 128, 14, 14, 3),    # 16x8 tiles, the second tile of an image has two rows outside; two sources
+    ("3x3", 128, 0, 128, 7, 7, 5),        # 8x8 tiles holding two images each, odd batch
+    ("3x3", 64, 0, 64, 12, 20, 2),        # rectangular, both sides ragged
+    ("down", 64, 0, 128, 28, 28, 2),      # stride-2 tensor map onto a 14x14 output
+    ("down", 128, 0, 128, 14, 14, 3),
+    ("up", 128, 0, 128, 7, 7, 3),
+    ("up", 128, 0, 64, 14, 14, 2),
+    ("1x1", 128, 0, 384, 14, 14, 2),      # residual read masked like the store
+    ("1x1", 64, 0, 128, 28, 28, 2),
 ]
 
 
@@ -320,9 +331,13 @@ def test_conv_tc_rejects_unsupported(cuda):
     x = torch.zeros(1, 28, 28, 64, dtype=torch.bfloat16, device=cuda)
     w = torch.zeros(64, 9 * 64, dtype=torch.bfloat16, device=cuda)
     y = torch.zeros(1, 28, 28, 64, dtype=torch.bfloat16, device=cuda)
-    with pytest.raises(RuntimeError, match="powers of two"):
-        lib.call("dd_conv_tc", lib.TC_CONV3x3, lib.ptr(x), 0, None, 64, 0, lib.ptr(w), 64, None, None, lib.ptr(y), 0, 0, None, 0,
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        lib.call("dd_conv_tc", lib.TC_CONV3x3, lib.ptr(x), 0, None, 48, 0, lib.ptr(w), 64, None, None, lib.ptr(y), 0, 0, None, 0,
                  1, 28, 28, 64, 0, None, 0, None, 0, lib.stream())
+    # ragged maps take the plain epilogue only: the fused-GroupNorm and split-K queries say so instead of failing at launch
+    assert lib.lib().dd_conv_tc_gn_cluster(lib.TC_CONV3x3, 2, 28, 28, 64, 8) == 0
+    assert lib.lib().dd_conv_tc_gn_ws_floats(lib.TC_CONV3x3, 2, 28, 28, 64, 8) == 0
+    assert lib.lib().dd_conv_tc_splits(lib.TC_CONV3x3, 2, 3, 3, 256, 256) == 1
 
 
 def test_layout_kernels(cuda):

@@ -38,7 +38,8 @@ def test_unet_eps_fp32(cuda, golden, tag, cfg, hw, seed):
         assert tc.rel_l2(eps, G(golden, f"unet.{tag}.eps{j}")) < 1e-4
 
 
-@pytest.mark.parametrize("tag,cfg,hw,seed", [("c3", tc.C3, 32, 11), ("c2", tc.C2, 16, 14), ("cs", tc.CS, 8, 13)])
+@pytest.mark.parametrize("tag,cfg,hw,seed", [("c3", tc.C3, 32, 11), ("c2", tc.C2, 16, 14), ("cs", tc.CS, 8, 13),
+                                             ("c1", tc.C1, 28, 12)])       # c1: 28 -> 14 -> 7 maps on padded tensor-core tiles
 def test_unet_eps_bf16(cuda, golden, tag, cfg, hw, seed):
     net = tc.build_model(dict(cfg, precision="bf16"), dd, "unet").to(cuda).eval()
     x = tc.randn(seed, 2, cfg["unet_in"], hw, hw).to(cuda)
@@ -51,9 +52,10 @@ def test_unet_eps_bf16(cuda, golden, tag, cfg, hw, seed):
 
 
 def test_bf16_rejects_untileable_shapes(cuda):
-    net = tc.build_model(dict(tc.C1, precision="bf16"), dd, "unet").to(cuda).eval()
-    with pytest.raises((ValueError, RuntimeError)):
+    net = tc.build_model(dict(tc.C1, unet_chan=48, precision="bf16"), dd, "unet").to(cuda).eval()
+    with pytest.raises((ValueError, RuntimeError)):                   # 48-channel operands have no 128-byte K rows
         net(torch.zeros(2, 1, 28, 28, device=cuda), torch.zeros(2, dtype=torch.long, device=cuda))
+    net = tc.build_model(dict(tc.C1, precision="bf16"), dd, "unet").to(cuda).eval()
     with pytest.raises(RuntimeError, match="CUDA"):
         net(torch.zeros(2, 1, 28, 28), torch.zeros(2, dtype=torch.long))
     with pytest.raises(ValueError, match="divisible"):

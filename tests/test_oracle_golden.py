@@ -242,6 +242,18 @@ def test_full_chain_oracle_vs_reference(golden, tag, cfg, hw, rows):
     assert tc.max_abs(z, zr) < 2e-4 and tc.max_abs(x, xr) < 2e-4
 
 
+def test_c1_full_chain_oracle_vs_reference(golden):
+    """BASELINE configs[0] (standard DDPM, 1x28x28, T = 1000, batch 16; golden_v4.npz, oracle/make_golden_c1.py): the oracle's
+    loop on the first two rows against the unmodified reference's `sample()`."""
+    cfg, rows = tc.C1, 2
+    sd = sd_of(cfg, "ddpm")
+    buf = O.schedule_buffers("linear", cfg["T"])
+    noise = tc.chain_noise("c1", cfg["T"], tc.C1_CHAIN_BATCH, 1, 28, 28)[:, :rows]
+    with torch.no_grad():
+        x = O.p_sample_loop(sd, cfg, buf, list(noise))
+    assert tc.max_abs(x, T(golden["fullchain.c1.x"])[:rows]) < 2e-4
+
+
 def test_full_size_training_objective_oracle_vs_reference(golden):
     cfg = tc.C3
     model = tc.build_model(cfg, ours, "dddpm_ae")
