@@ -55,7 +55,8 @@ def test_vlb_terms_kernel_vs_oracle_and_golden(cuda, golden):
 
 
 @pytest.mark.parametrize("tag,cfg,kind,shape,seed,xseed,precision,rtol", [
-    ("c1", tc.C1, "ddpm", (2, 1, 28, 28), 9, 73, "fp32", 2e-4),          # 28x28 maps have no bf16 tensor-core tiling (fp32 mode only)
+    ("c1", tc.C1, "ddpm", (2, 1, 28, 28), 9, 73, "fp32", 2e-4),
+    ("c1", tc.C1, "ddpm", (2, 1, 28, 28), 9, 73, "bf16", 6e-2),          # 28 -> 14 -> 7 maps on padded tensor-core tiles
     ("cs", tc.CS, "dddpm_ae", (2, 3, 32, 32), 10, 74, "fp32", 2e-4),
     ("cs", tc.CS, "dddpm_ae", (2, 3, 32, 32), 10, 74, "bf16", 6e-2)])
 def test_evaluation_chain_vs_reference(cuda, golden, tag, cfg, kind, shape, seed, xseed, precision, rtol):

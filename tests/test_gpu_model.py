@@ -81,6 +81,16 @@ def test_p_sample_and_chains_c1_fp32(cuda, golden):
     assert torch.equal(eager, full)
 
 
+def test_chain_c1_bf16(cuda, golden):
+    """The 50-step C1 chains of the fp32 test above on the bf16 tensor-core path (ragged 28 / 14 / 7 maps): bar 5e-2."""
+    m = tc.build_model(dict(tc.C1, T=50, precision="bf16"), dd, "ddpm", device="cuda").to(cuda).eval()
+    full = m.sample(2, noise=chain_noise(5, (2, 1, 28, 28), 50).to(cuda))
+    early = m.sample(2, early_stop=40, noise=chain_noise(6, (2, 1, 28, 28), 10).to(cuda))
+    e1, e2 = tc.max_abs(full, G(golden, "chain.c1.x")), tc.max_abs(early, G(golden, "chain.c1.early"))
+    print(f"bf16 c1 chains: full max-abs {e1:.3e}, early-stop max-abs {e2:.3e}")
+    assert e1 < 5e-2 and e2 < 5e-2
+
+
 @pytest.mark.parametrize("precision,tol_z,tol_x", [("fp32", 1e-3, 1e-3), ("bf16", 5e-2, 2e-2)])
 def test_dddpm_chain_cs(cuda, golden, precision, tol_z, tol_x):
     cfg = dict(tc.CS, T=50, precision=precision)
