@@ -231,6 +231,9 @@ CONV_CASES = [
     ("up", 128, 0, 64, 14, 14, 2),
     ("1x1", 128, 0, 384, 14, 14, 2),      # residual read masked like the store
     ("1x1", 64, 0, 128, 28, 28, 2),
+    ("3x3", 64, 0, 64, 5, 160, 1),        # wider than one tile: two 128-pixel tiles per row, the second 32 valid pixels
+    ("3x3", 64, 64, 128, 24, 32, 2),      # only the height ragged
+    ("up", 64, 0, 64, 3, 5, 9),           # tiny odd map, 4 images per tile, odd batch
 ]
 
 
