@@ -676,13 +676,14 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(con
         int st = 0, k = 0;
         uint32_t par = 0;
         uint32_t sA = base;
+        long long w_full = 0, w_tempty = 0;               // timeline builds: clocks this warp waited for operand stages / a free accumulator
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
             const int buf = k & 1;
-            if (k >= 2) mbar_wait(tempty(buf), ((k >> 1) - 1) & 1);
+            if (k >= 2) TL_WAIT(w_tempty, mbar_wait(tempty(buf), ((k >> 1) - 1) & 1));
             tc_fence_after();
             const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
             for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(full(st), par);
+                TL_WAIT(w_full, mbar_wait(full(st), par));
                 if (k == 0 && kb == 0 && lane == 0) tstamp(p, 3);
                 tc_fence_after();
                 if (elect_one()) {
@@ -700,6 +701,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(con
             __syncwarp();
             if (lane == 0) tstamp(p, k == 0 ? 4 : 7);
         }
+        if (lane == 0) { tstore(p, 8, w_full); tstore(p, 9, w_tempty); }
     } else {
         // ===== epilogue: 8 warps; thread = (row of the tile, 64-channel half) =====
         constexpr int NGH = CPG_SH > 0 ? (64 >> CPG_SH) : 1;
@@ -707,17 +709,27 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(con
         const int q = warp & 3, hsel = (warp - 2) >> 2;
         const int r = q * 32 + lane, c0 = hsel * 64;
         const bool ln_fold = p.ln_in != nullptr;
-        // channel sums of row m for the LayerNorm fold: {sum, sum of squares} over the parts, fetched one item ahead
-        auto ln_sums = [&](const int64_t m, float& su, float& sq) {
-            su = 0.f; sq = 0.f;
+        // channel sums of row m for the LayerNorm fold: {sum, sum of squares} over the parts, fetched one item ahead.  The loads are
+        // only ISSUED here; the raw values stay in registers and are summed when the next item starts (the empty asm below keeps the
+        // compiler from hoisting the adds back up to the loads): summing in the fetch loop made every add wait for its load and the
+        // next load for the add -- 4 (8) dependent L2 round trips = 0.9 k (1.3 k) clk per item on the warp that bounds the item
+        // rate (scripts/timeline.py: the MMA warp waits for a free accumulator, profiles/timeline_gemm_r02_aw2.txt)
+        constexpr int LN_MAXP = 8;
+        float2 lnv[LN_MAXP];
+        auto ln_fetch = [&](const int64_t m) {
+#pragma unroll
+            for (int i = 0; i < LN_MAXP; ++i) lnv[i] = make_float2(0.f, 0.f);
             if (ln_fold && m < M) {
                 const float2* lp = reinterpret_cast<const float2*>(p.ln_in) + m * p.ln_in_parts;
-                for (int i = 0; i < p.ln_in_parts; ++i) { const float2 v = __ldg(lp + i); su += v.x; sq += v.y; }
+#pragma unroll
+                for (int i = 0; i < LN_MAXP; ++i)
+                    if (i < p.ln_in_parts) lnv[i] = __ldg(lp + i);
+                for (int i = LN_MAXP; i < p.ln_in_parts; ++i) { const float2 v = __ldg(lp + i); lnv[0].x += v.x; lnv[0].y += v.y; }
             }
         };
-        float nsu, nsq;
-        ln_sums((((int64_t)(blockIdx.x / ntn)) << 7) + r, nsu, nsq);
+        ln_fetch((((int64_t)(blockIdx.x / ntn)) << 7) + r);
         int k = 0;
+        long long w_tfull = 0;                            // timeline builds: clocks this warp waited for accumulators
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
             const int n_tile = it % ntn, m_tile = it / ntn;
             const int buf = k & 1, cbase = n_tile * 128;
@@ -725,17 +737,24 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(con
             const bool valid = m < M;
             const float* par = s_par + cbase;
             float ln_a = 1.f, ln_b = 0.f;
+            if (ln_fold) {
+#pragma unroll
+                for (int i = 0; i < LN_MAXP; ++i) asm volatile("" : "+f"(lnv[i].x), "+f"(lnv[i].y));      // consumed here, not earlier
+            }
             if (ln_fold && valid) {
+                float nsu = 0.f, nsq = 0.f;
+#pragma unroll
+                for (int i = 0; i < LN_MAXP; ++i) { nsu += lnv[i].x; nsq += lnv[i].y; }
                 const float mean = nsu * p.ln_inv_c;
                 ln_a = 1.f / (sqrtf(fmaxf(nsq * p.ln_inv_c - mean * mean, 0.f)) + p.ln_eps);
                 ln_b = -mean * ln_a;
             }
-            if (it + (int)gridDim.x < n_items) ln_sums((((int64_t)((it + (int)gridDim.x) / ntn)) << 7) + r, nsu, nsq);      // next item's rows
+            if (it + (int)gridDim.x < n_items) ln_fetch((((int64_t)((it + (int)gridDim.x) / ntn)) << 7) + r);      // next item's rows
             const __nv_bfloat16* resp = (p.residual && valid) ? p.residual + m * p.Cout + cbase + c0 : nullptr;
             uint32_t res[2][8];
             if (resp) ldg_v8(resp, res[0]);
             if (et == 0 && k == 1) tstamp(p, 11);
-            mbar_wait(tfull(buf), (k >> 1) & 1);
+            TL_WAIT(w_tfull, mbar_wait(tfull(buf), (k >> 1) & 1));
             if (et == 0) tstamp(p, k == 0 ? 5 : (k == 1 ? 13 : 12));
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(buf * 128 + c0) + ((uint32_t)(q * 32) << 16);
@@ -775,7 +794,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(con
                     __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
                     ov[j] = *reinterpret_cast<uint32_t*>(&h);
                 }
-                if (valid) stg_v8(op + 16 * qd, ov);
+                if (valid) stg_v8(op + 16 * qd, ov);       // (holding the four pieces back to store the 128-byte line at once was slower)
             }
             if (et == 0) tstamp(p, k == 0 ? 6 : (k == 1 ? 10 : 14));
             if (CPG_SH > 0 && p.gn_stats) {
@@ -795,6 +814,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) conv_tc_gemm_persist_kernel(con
                 }
             }
         }
+        if (et == 0) { tstore(p, 15, w_tfull); tstore(p, 20, (long long)k); }
     }
     tc_fence_before();
     __syncthreads();

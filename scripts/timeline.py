@@ -30,6 +30,8 @@ for which in [int(a) for a in sys.argv[1:]] or (2, 16, 23):          # 3x3@32 (h
         print("   pdl->first data %d, item0: MMAs issued %d after first data, acc ready->stored %d" % (d(3, 2), d(4, 3), d(6, 5)))
         print("   item1: item0 stored->parameters staged %d, ->acc ready %d, acc ready->stored %d" % (d(11, 6), d(13, 11), d(10, 13)))
         print("   first data -> last item stored %d" % d(14, 3))
+        med = lambda c: int(np.median(t[:, c]))
+        print("   whole CTA (%d items): MMA warp waited %d clk for operand stages, %d for a free accumulator; epilogue warp waited %d for accumulators" % (med(20), med(8), med(9), med(15)))
         continue
     if (t[:, 14] > 0).any() or (t[:, 13] > 0).any():          # persistent kernel (conv_tc_persist.cu): its own stamp set
         d = lambda a, b: int(np.median((t[:, a] - t[:, b])[(t[:, a] > 0) & (t[:, b] > 0)])) if ((t[:, a] > 0) & (t[:, b] > 0)).any() else -1
