@@ -35,6 +35,16 @@ def test_error_reporting_without_gpu():
     assert rc == -1 and b"multiple of 4" in lib.dd_last_error()
 
 
+def test_ragged_maps_are_kept_on_the_plain_convolution_epilogue():
+    """Host-side tiling queries (no device needed for these shapes): maps that are not powers of two take neither the fused GroupNorm
+    epilogue nor split-K; dd_conv_tc pads their tile grid to the next power of two instead (conv_tc_kernel)."""
+    lib = _lib.lib()
+    for h, w in ((28, 28), (14, 14), (7, 7), (12, 20), (3, 3)):
+        assert lib.dd_conv_tc_gn_cluster(_lib.TC_CONV3x3, 2, h, w, 128, 8) == 0
+        assert lib.dd_conv_tc_gn_ws_floats(_lib.TC_CONV3x3, 2, h, w, 128, 8) == 0
+        assert lib.dd_conv_tc_splits(_lib.TC_CONV3x3, 2, h, w, 256, 256) == 1
+
+
 def test_module_tree_matches_reference_names():
     m = tc.build_model(tc.C2, dd, "dddpm_ae")
     sd = m.state_dict()
